@@ -1,0 +1,916 @@
+// celt_parse.cuh -- CELT entropy stage: one thread decodes one (stream, frame).
+//
+// Covers SURVEY section 8 rows a1 (range decoder, rangedec.cuh), a2 (energy symbols), a3 (tf, caps,
+// dynalloc, allocation), a4 (quant_all_bands / quant_band / quant_partition / compute_theta control
+// flow) and the serial half of a5 (PVQ index -> pulses -> normalised, spread-rotated leaf vector).
+// Reference order of symbols: celt_decode_with_ec, src/celt.cpp:2162-2367.
+//
+// Output per frame: a CeltFrameHdr, a list of BandOps for the warp-parallel band kernel, and the
+// coded leaves of X (int16, unit-norm Q14) written straight to the frame's X buffer in HBM.
+#pragma once
+#include "celt_script.cuh"
+#include "celt_tables.cuh"
+#include "rangedec.cuh"
+
+namespace opusb200 {
+
+// Thread-private leaf buffer. On the GPU it is a column of a shared-memory tile (stride = block
+// size) so that the serial PVQ / rotation passes never touch HBM.
+struct LeafBuf {
+    int16_t* p;
+    int stride;
+    OPUS_HD int16_t& operator[](int j) const { return p[j * stride]; }
+};
+
+struct ParseCtx {
+    RangeDec rd;
+    // frame constants
+    int C, LM, start, end, disable_inv;
+    // band loop state (ref band_ctx_t, src/celt.h:125)
+    int band, intensity, spread, tf_change, remaining_bits;
+    // outputs
+    BandOp* ops;
+    int n_ops, ops_cap, overflow;
+    uint32_t lcg_steps;
+    int16_t* Xg;  // frame's X buffer in global memory: [C][N]
+    LeafBuf leaf;
+};
+
+OPUS_HD void emit_op(ParseCtx& p, uint8_t code, int a, int off, int off2, int n, int g, int g2) {
+    if (p.n_ops >= p.ops_cap) { p.overflow = 1; return; }
+    BandOp o;
+    o.code = code; o.a = (uint8_t)a; o.off = (uint16_t)off; o.off2 = (uint16_t)off2; o.n = (uint16_t)n;
+    o.g = (int16_t)g; o.g2 = (int16_t)g2;
+    p.ops[p.n_ops++] = o;
+}
+
+// ---- pulse cache helpers (ref src/celt.h:533-569) ----
+OPUS_HD int get_pulses(int i) { return i < 8 ? i : (8 + (i & 7)) << ((i >> 3) - 1); }
+OPUS_HD const uint8_t* pulse_cache(int band, int LM) { return kCacheBits + kCacheIndex[(LM + 1) * kNbEBands + band]; }
+OPUS_HD int bits2pulses(int band, int LM, int bits) {
+    const uint8_t* cache = pulse_cache(band, LM);
+    int lo = 0, hi = cache[0];
+    bits--;
+    for (int i = 0; i < 6; i++) {
+        int mid = (lo + hi + 1) >> 1;
+        if ((int)cache[mid] >= bits) hi = mid; else lo = mid;
+    }
+    if (bits - (lo == 0 ? -1 : (int)cache[lo]) <= (int)cache[hi] - bits) return lo;
+    return hi;
+}
+OPUS_HD int pulses2bits(int band, int LM, int pulses) {
+    return pulses == 0 ? 0 : pulse_cache(band, LM)[pulses] + 1;
+}
+
+// ---- PVQ codebook size and index decode (ref src/celt.cpp:653-660, 2545) ----
+OPUS_HD u32 pvq_u(int n, int k) { return n < k ? kPvqU[kPvqRow[n] + k] : kPvqU[kPvqRow[k] + n]; }
+OPUS_HD u32 pvq_v(int n, int k) { return pvq_u(n, k) + pvq_u(n, k + 1); }
+
+// index -> signed pulse vector y[0..n), returns sum y^2 (ref cwrsi)
+OPUS_HD s32 pvq_decode_index(int n, int k, u32 i, const LeafBuf& y) {
+    u32 p;
+    int s, k0, pos = 0;
+    s32 yy = 0;
+    while (n > 2) {
+        u32 q;
+        if (k >= n) {  // lots of pulses
+            const u32* row = kPvqU + kPvqRow[n];
+            p = row[k + 1];
+            s = -(int)(i >= p);
+            i -= p & (u32)s;
+            k0 = k;
+            q = row[n];
+            if (q > i) {
+                k = n;
+                do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
+            } else {
+                for (p = row[k]; p > i; p = row[k]) k--;
+            }
+            i -= p;
+            s16 val = (s16)((k0 - k + s) ^ s);
+            y[pos++] = val;
+            yy += mul16(val, val);
+        } else {  // lots of dimensions
+            p = kPvqU[kPvqRow[k] + n];
+            q = kPvqU[kPvqRow[k + 1] + n];
+            if (p <= i && i < q) {
+                i -= p;
+                y[pos++] = 0;
+            } else {
+                s = -(int)(i >= q);
+                i -= q & (u32)s;
+                k0 = k;
+                do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
+                i -= p;
+                s16 val = (s16)((k0 - k + s) ^ s);
+                y[pos++] = val;
+                yy += mul16(val, val);
+            }
+        }
+        n--;
+    }
+    // n == 2
+    p = 2 * (u32)k + 1;
+    s = -(int)(i >= p);
+    i -= p & (u32)s;
+    k0 = k;
+    k = (int)((i + 1) >> 1);
+    if (k) i -= 2 * (u32)k - 1;
+    s16 val = (s16)((k0 - k + s) ^ s);
+    y[pos++] = val;
+    yy += mul16(val, val);
+    // n == 1
+    s = -(int)i;
+    val = (s16)((k + s) ^ s);
+    y[pos] = val;
+    yy += mul16(val, val);
+    return yy;
+}
+
+// ref exp_rotation1 / exp_rotation (src/celt.cpp:684, 707), decoder direction only (dir = -1)
+OPUS_HD void leaf_rotate1(const LeafBuf& X, int base, int len, int stride, s16 c, s16 s) {
+    s16 ms = (s16)(-(s32)s);
+    for (int i = 0; i < len - stride; i++) {
+        s16 x1 = X[base + i], x2 = X[base + i + stride];
+        X[base + i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
+        X[base + i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
+    }
+    for (int i = len - 2 * stride - 1; i >= 0; i--) {
+        s16 x1 = X[base + i], x2 = X[base + i + stride];
+        X[base + i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
+        X[base + i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
+    }
+}
+OPUS_HD void leaf_rotate(const LeafBuf& X, int len, int stride, int K, int spread) {
+    if (2 * K >= len || spread == 0) return;
+    const int factor = spread == 1 ? 15 : (spread == 2 ? 10 : 5);
+    s16 gain = (s16)mul32_q31((s32)mul16(32767, len), rcp_q(len + factor * K));  // celt_div
+    s16 theta = (s16)(mul16_q15(gain, gain) >> 1);
+    s16 c = cos_norm((s32)theta);
+    s16 s = cos_norm((s32)sub16(32767, theta));
+    int stride2 = 0;
+    if (len >= 8 * stride) {
+        stride2 = 1;
+        while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+    }
+    len = (int)((u32)len / (u32)stride);
+    for (int i = 0; i < stride; i++) {
+        if (stride2) leaf_rotate1(X, i * len, len, stride2, s, c);
+        leaf_rotate1(X, i * len, len, 1, c, s);
+    }
+}
+
+// ref alg_unquant (src/celt.cpp:782): decode_pulses + normalise_residual + exp_rotation + collapse mask
+OPUS_HD u32 leaf_unquant(ParseCtx& p, int xoff, int N, int K, int B, s16 gain) {
+    const LeafBuf& y = p.leaf;
+    s32 Ryy = pvq_decode_index(N, K, rd_uint(p.rd, pvq_v(N, K)), y);
+    // extract_collapse_mask (ref :760) -- taken from the pulses before they are scaled in place
+    u32 cm;
+    if (B <= 1) cm = 1;
+    else {
+        int N0 = (int)((u32)N / (u32)B);
+        cm = 0;
+        for (int i = 0; i < B; i++) {
+            int any = 0;
+            for (int j = 0; j < N0; j++) any |= y[i * N0 + j];
+            cm |= (u32)(any != 0) << i;
+        }
+    }
+    // normalise_residual (ref :745)
+    int k = ilog2p(Ryy) >> 1;
+    s32 t = vshr32(Ryy, 2 * (k - 7));
+    s16 g = (s16)mul16_p15(rsqrt_norm(t), gain);
+    for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
+    leaf_rotate(y, N, B, K, p.spread);
+    for (int i = 0; i < N; i++) p.Xg[xoff + i] = y[i];
+    return cm;
+}
+
+struct ThetaOut { int inv, imid, iside, delta, itheta, qalloc; };
+
+// ref compute_qn (src/celt.cpp:1215)
+OPUS_HD int compute_qn(int N, int b, int offset, int pulse_cap, int stereo) {
+    const s16 exp2_table8[8] = {16384, 17866, 19483, 21247, 23170, 25267, 27554, 30048};
+    int N2 = 2 * N - 1;
+    if (stereo && N == 2) N2--;
+    int qb = (b + N2 * offset) / N2;
+    qb = imin(b - pulse_cap - (4 << 3), qb);
+    qb = imin(8 << 3, qb);
+    int qn;
+    if (qb < (1 << 3 >> 1)) qn = 1;
+    else {
+        qn = exp2_table8[qb & 0x7] >> (14 - (qb >> 3));
+        qn = (qn + 1) >> 1 << 1;
+    }
+    return qn;
+}
+
+// ref compute_theta (src/celt.cpp:1241), decoder side
+OPUS_HD void decode_theta(ParseCtx& p, ThetaOut& o, int N, int* b, int B, int B0, int LM, int stereo, int* fill) {
+    int itheta = 0, inv = 0;
+    const int i = p.band;
+    int pulse_cap = kLogN400[i] + LM * (1 << 3);
+    int offset = (pulse_cap >> 1) - (stereo && N == 2 ? 16 : 4);
+    int qn = compute_qn(N, *b, offset, pulse_cap, stereo);
+    if (stereo && i >= p.intensity) qn = 1;
+    int tell = (int)rd_tell_frac(p.rd);
+    if (qn != 1) {
+        if (stereo && N > 2) {
+            const int p0 = 3;
+            int x0 = qn / 2;
+            u32 ft = (u32)(p0 * (x0 + 1) + x0);
+            int fs = (int)rd_decode(p.rd, ft);
+            int x;
+            if (fs < (x0 + 1) * p0) x = fs / p0;
+            else x = x0 + 1 + (fs - (x0 + 1) * p0);
+            rd_update(p.rd, (u32)(x <= x0 ? p0 * x : (x - 1 - x0) + (x0 + 1) * p0),
+                      (u32)(x <= x0 ? p0 * (x + 1) : (x - x0) + (x0 + 1) * p0), ft);
+            itheta = x;
+        } else if (B0 > 1 || stereo) {
+            itheta = (int)rd_uint(p.rd, (u32)qn + 1);
+        } else {
+            int fs = 1, fl = 0;
+            int ft = ((qn >> 1) + 1) * ((qn >> 1) + 1);
+            int fm = (int)rd_decode(p.rd, (u32)ft);
+            if (fm < ((qn >> 1) * ((qn >> 1) + 1) >> 1)) {
+                itheta = (int)((isqrt32(8 * (u32)fm + 1) - 1) >> 1);
+                fs = itheta + 1;
+                fl = itheta * (itheta + 1) >> 1;
+            } else {
+                itheta = (int)((2 * (u32)(qn + 1) - isqrt32(8 * (u32)(ft - fm - 1) + 1)) >> 1);
+                fs = qn + 1 - itheta;
+                fl = ft - ((qn + 1 - itheta) * (qn + 2 - itheta) >> 1);
+            }
+            rd_update(p.rd, (u32)fl, (u32)(fl + fs), (u32)ft);
+        }
+        itheta = (int)((u32)(itheta * 16384) / (u32)qn);
+    } else if (stereo) {
+        if (*b > 2 << 3 && p.remaining_bits > 2 << 3) inv = rd_bit_logp(p.rd, 2);
+        else inv = 0;
+        if (p.disable_inv) inv = 0;
+        itheta = 0;
+    }
+    int qalloc = (int)rd_tell_frac(p.rd) - tell;
+    *b -= qalloc;
+    int imid, iside, delta;
+    if (itheta == 0) {
+        imid = 32767; iside = 0;
+        *fill &= (1 << B) - 1;
+        delta = -16384;
+    } else if (itheta == 16384) {
+        imid = 0; iside = 32767;
+        *fill &= ((1 << B) - 1) << B;
+        delta = 16384;
+    } else {
+        imid = bitexact_cos((s16)itheta);
+        iside = bitexact_cos((s16)(16384 - itheta));
+        delta = frac_mul16((N - 1) << 7, bitexact_log2tan(iside, imid));
+    }
+    o.inv = inv; o.imid = imid; o.iside = iside; o.delta = delta; o.itheta = itheta; o.qalloc = qalloc;
+}
+
+// ref quant_band_n1 (src/celt.cpp:1357). xoff/yoff index X (yoff < 0: mono), out = lowband_out offset or -1.
+OPUS_HD u32 band_n1(ParseCtx& p, int xoff, int yoff, int out) {
+    int x0 = 0;
+    for (int c = 0; c < 1 + (yoff >= 0); c++) {
+        int sign = 0;
+        if (p.remaining_bits >= 1 << 3) {
+            sign = (int)rd_bits(p.rd, 1);
+            p.remaining_bits -= 1 << 3;
+        }
+        int v = sign ? -16384 : 16384;
+        p.Xg[c ? yoff : xoff] = (s16)v;
+        if (c == 0) x0 = v;
+    }
+    if (out >= 0) emit_op(p, OP_SETW, 0, out, 0, 1, x0 >> 4, 0);
+    return 1;
+}
+
+// ref quant_partition (src/celt.cpp:1382). Offsets index the W workspace; lowband < 0 means NULL.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, s16 gain, int fill) {
+    const int i = p.band;
+    const uint8_t* cache = pulse_cache(i, LM);
+    u32 cm = 0;
+    const int B0 = B;
+    if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
+        ThetaOut t;
+        N >>= 1;
+        const int yoff = xoff + N;
+        LM -= 1;
+        if (B == 1) fill = (fill & 1) | (fill << 1);
+        B = (B + 1) >> 1;
+        decode_theta(p, t, N, &b, B, B0, LM, 0, &fill);
+        s16 mid = (s16)t.imid, side = (s16)t.iside;
+        int delta = t.delta;
+        const int itheta = t.itheta;
+        if (B0 > 1 && (itheta & 0x3fff)) {
+            if (itheta > 8192) delta -= delta >> (4 - LM);
+            else delta = imin(0, delta + (N << 3 >> (5 - LM)));
+        }
+        int mbits = imax(0, imin(b, (b - delta) / 2));
+        int sbits = b - mbits;
+        p.remaining_bits -= t.qalloc;
+        const int lowband2 = lowband >= 0 ? lowband + N : -1;
+        int rebalance = p.remaining_bits;
+        if (mbits >= sbits) {
+            cm = partition(p, xoff, N, mbits, B, lowband, LM, (s16)mul16_p15(gain, mid), fill);
+            rebalance = mbits - (rebalance - p.remaining_bits);
+            if (rebalance > 3 << 3 && itheta != 0) sbits += rebalance - (3 << 3);
+            cm |= partition(p, yoff, N, sbits, B, lowband2, LM, (s16)mul16_p15(gain, side), fill >> B) << (B0 >> 1);
+        } else {
+            cm = partition(p, yoff, N, sbits, B, lowband2, LM, (s16)mul16_p15(gain, side), fill >> B) << (B0 >> 1);
+            rebalance = sbits - (rebalance - p.remaining_bits);
+            if (rebalance > 3 << 3 && itheta != 16384) mbits += rebalance - (3 << 3);
+            cm |= partition(p, xoff, N, mbits, B, lowband, LM, (s16)mul16_p15(gain, mid), fill);
+        }
+    } else {
+        int q = bits2pulses(i, LM, b);
+        int curr_bits = pulses2bits(i, LM, q);
+        p.remaining_bits -= curr_bits;
+        while (p.remaining_bits < 0 && q > 0) {
+            p.remaining_bits += curr_bits;
+            q--;
+            curr_bits = pulses2bits(i, LM, q);
+            p.remaining_bits -= curr_bits;
+        }
+        if (q != 0) {
+            cm = leaf_unquant(p, xoff, N, get_pulses(q), B, gain);
+        } else {
+            u32 cm_mask = (u32)(1UL << B) - 1;
+            fill &= (int)cm_mask;
+            if (!fill) {
+                for (int j = 0; j < N; j++) p.Xg[xoff + j] = 0;
+            } else if (lowband < 0) {
+                emit_op(p, OP_NOISE, 0, xoff, 0, N, gain, 0);
+                p.lcg_steps += (u32)N;
+                cm = cm_mask;
+            } else {
+                emit_op(p, OP_FOLD, 0, xoff, lowband, N, gain, 0);
+                p.lcg_steps += (u32)N;
+                cm = (u32)fill;
+            }
+        }
+    }
+    return cm;
+}
+
+// ref quant_band (src/celt.cpp:1526)
+OPUS_HD u32 band_mono(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, int lowband_out, s16 gain,
+                      int scratch, int fill) {
+    const int N0 = N;
+    int N_B = (int)((u32)N / (u32)B);
+    int B0 = B, time_divide = 0, recombine = 0;
+    int tf_change = p.tf_change;
+    const int longBlocks = B0 == 1;
+    if (N == 1) return band_n1(p, xoff, -1, lowband_out);
+    if (tf_change > 0) recombine = tf_change;
+    if (scratch >= 0 && lowband >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
+        emit_op(p, OP_COPY, 0, scratch, lowband, N, 0, 0);
+        lowband = scratch;
+    }
+    for (int k = 0; k < recombine; k++) {
+        const uint8_t bit_interleave[16] = {0, 1, 1, 1, 2, 3, 3, 3, 2, 3, 3, 3, 2, 3, 3, 3};
+        if (lowband >= 0) emit_op(p, OP_HAAR, 1 << k, lowband, 0, N >> k, 0, 0);
+        fill = bit_interleave[fill & 0xF] | bit_interleave[fill >> 4] << 2;
+    }
+    B >>= recombine;
+    N_B <<= recombine;
+    while ((N_B & 1) == 0 && tf_change < 0) {
+        if (lowband >= 0) emit_op(p, OP_HAAR, B, lowband, 0, N_B, 0, 0);
+        fill |= fill << B;
+        B <<= 1;
+        N_B >>= 1;
+        time_divide++;
+        tf_change++;
+    }
+    B0 = B;
+    const int N_B0 = N_B;
+    if (B0 > 1 && lowband >= 0) emit_op(p, OP_DEINT, B0 << recombine, lowband, 0, N_B >> recombine, longBlocks, 0);
+
+    u32 cm = partition(p, xoff, N, b, B, lowband, LM, gain, fill);
+
+    if (B0 > 1) emit_op(p, OP_INT, B0 << recombine, xoff, 0, N_B >> recombine, longBlocks, 0);
+    N_B = N_B0;
+    B = B0;
+    for (int k = 0; k < time_divide; k++) {
+        B >>= 1;
+        N_B <<= 1;
+        cm |= cm >> B;
+        emit_op(p, OP_HAAR, B, xoff, 0, N_B, 0, 0);
+    }
+    for (int k = 0; k < recombine; k++) {
+        const uint8_t bit_deinterleave[16] = {0x00, 0x03, 0x0C, 0x0F, 0x30, 0x33, 0x3C, 0x3F,
+                                              0xC0, 0xC3, 0xCC, 0xCF, 0xF0, 0xF3, 0xFC, 0xFF};
+        cm = bit_deinterleave[cm];
+        emit_op(p, OP_HAAR, 1 << k, xoff, 0, N0 >> k, 0, 0);
+    }
+    B <<= recombine;
+    if (lowband_out >= 0) emit_op(p, OP_SCALE_OUT, 0, xoff, lowband_out, N0, sqrt_q(shl32(N0, 22)), 0);
+    cm &= (u32)((1 << B) - 1);
+    return cm;
+}
+
+// ref quant_band_stereo (src/celt.cpp:1628)
+OPUS_HD u32 band_stereo(ParseCtx& p, int xoff, int yoff, int N, int b, int B, int lowband, int LM, int lowband_out,
+                        int scratch, int fill) {
+    if (N == 1) return band_n1(p, xoff, yoff, lowband_out);
+    const int orig_fill = fill;
+    ThetaOut t;
+    decode_theta(p, t, N, &b, B, B, LM, 1, &fill);
+    const s16 mid = (s16)t.imid, side = (s16)t.iside;
+    const int itheta = t.itheta;
+    u32 cm;
+    if (N == 2) {
+        int mbits = b, sbits = 0;
+        if (itheta != 0 && itheta != 16384) sbits = 1 << 3;
+        mbits -= sbits;
+        const int c = itheta > 8192;
+        p.remaining_bits -= t.qalloc + sbits;
+        const int x2 = c ? yoff : xoff, y2 = c ? xoff : yoff;
+        int sign = 0;
+        if (sbits) sign = (int)rd_bits(p.rd, 1);
+        cm = band_mono(p, x2, N, mbits, B, lowband, LM, lowband_out, 32767, scratch, orig_fill);
+        emit_op(p, OP_N2, sign | (c << 1), x2, y2, 2, mid, side);
+    } else {
+        int mbits = imax(0, imin(b, (b - t.delta) / 2));
+        int sbits = b - mbits;
+        p.remaining_bits -= t.qalloc;
+        int rebalance = p.remaining_bits;
+        if (mbits >= sbits) {
+            cm = band_mono(p, xoff, N, mbits, B, lowband, LM, lowband_out, 32767, scratch, fill);
+            rebalance = mbits - (rebalance - p.remaining_bits);
+            if (rebalance > 3 << 3 && itheta != 0) sbits += rebalance - (3 << 3);
+            cm |= band_mono(p, yoff, N, sbits, B, -1, LM, -1, side, -1, fill >> B);
+        } else {
+            cm = band_mono(p, yoff, N, sbits, B, -1, LM, -1, side, -1, fill >> B);
+            rebalance = sbits - (rebalance - p.remaining_bits);
+            if (rebalance > 3 << 3 && itheta != 16384) mbits += rebalance - (3 << 3);
+            cm |= band_mono(p, xoff, N, mbits, B, lowband, LM, lowband_out, 32767, scratch, fill);
+        }
+        emit_op(p, OP_MERGE, 0, xoff, yoff, N, mid, 0);
+    }
+    if (t.inv) emit_op(p, OP_NEG, 0, yoff, 0, N, 0, 0);
+    return cm;
+}
+
+// ref quant_all_bands (src/celt.cpp:1754)
+OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int shortBlocks, int dual_stereo, int intensity,
+                       const int* tf_res, int total_bits, int balance, int codedBands) {
+    const int LM = p.LM, C = p.C, start = p.start, end = p.end;
+    const int M = 1 << LM;
+    const int N = M * kShortMdct;
+    const int B = shortBlocks ? M : 1;
+    const int norm_offset = M * kEBands[start];
+    int lowband_offset = 0, update_lowband = 1;
+    p.intensity = intensity;
+    for (int i = start; i < end; i++) {
+        p.band = i;
+        const int last = (i == end - 1);
+        const int xoff = M * kEBands[i];
+        const int yoff = C == 2 ? N + xoff : -1;
+        const int Nb = M * kEBands[i + 1] - M * kEBands[i];
+        const int tell = (int)rd_tell_frac(p.rd);
+        if (i != start) balance -= tell;
+        const int remaining = total_bits - tell - 1;
+        p.remaining_bits = remaining;
+        int b;
+        if (i <= codedBands - 1) {
+            int curr_balance = balance / imin(3, codedBands - i);
+            b = imax(0, imin(16383, imin(remaining + 1, pulses[i] + curr_balance)));
+        } else {
+            b = 0;
+        }
+        if ((M * kEBands[i] - Nb >= M * kEBands[start] || i == start + 1) && (update_lowband || lowband_offset == 0))
+            lowband_offset = i;
+        if (i == start + 1) {  // special_hybrid_folding (ref :1743)
+            int n1 = M * (kEBands[start + 1] - kEBands[start]);
+            int n2 = M * (kEBands[start + 2] - kEBands[start + 1]);
+            if (n2 > n1) {
+                emit_op(p, OP_COPY, 0, W_NORM + n1, W_NORM + 2 * n1 - n2, n2 - n1, 0, 0);
+                if (dual_stereo) emit_op(p, OP_COPY, 0, W_NORM2 + n1, W_NORM2 + 2 * n1 - n2, n2 - n1, 0, 0);
+            }
+        }
+        const int tf_change = tf_res[i];
+        p.tf_change = tf_change;
+        int scratch = last ? -1 : W_SCRATCH;
+        int effective_lowband = -1;
+        u32 x_cm, y_cm;
+        if (lowband_offset != 0 && (p.spread != 3 || B > 1 || tf_change < 0)) {
+            effective_lowband = imax(0, M * kEBands[lowband_offset] - norm_offset - Nb);
+            int fold_start = lowband_offset;
+            while (M * kEBands[--fold_start] > effective_lowband + norm_offset) {}
+            int fold_end = lowband_offset - 1;
+            while (++fold_end < i && M * kEBands[fold_end] < effective_lowband + norm_offset + Nb) {}
+            x_cm = y_cm = 0;
+            int fold_i = fold_start;
+            do {
+                x_cm |= cmask[fold_i * C + 0];
+                y_cm |= cmask[fold_i * C + C - 1];
+            } while (++fold_i < fold_end);
+        } else {
+            x_cm = y_cm = (u32)((1 << B) - 1);
+        }
+        if (dual_stereo && i == intensity) {
+            dual_stereo = 0;
+            int n = M * kEBands[i] - norm_offset;
+            if (n > 0) emit_op(p, OP_AVG, 0, W_NORM, W_NORM2, n, 0, 0);
+        }
+        const int lb = effective_lowband != -1 ? W_NORM + effective_lowband : -1;
+        const int lb2 = effective_lowband != -1 ? W_NORM2 + effective_lowband : -1;
+        const int out = last ? -1 : W_NORM + M * kEBands[i] - norm_offset;
+        const int out2 = last ? -1 : W_NORM2 + M * kEBands[i] - norm_offset;
+        if (dual_stereo) {
+            x_cm = band_mono(p, xoff, Nb, b / 2, B, lb, LM, out, 32767, scratch, (int)x_cm);
+            y_cm = band_mono(p, yoff, Nb, b / 2, B, lb2, LM, out2, 32767, scratch, (int)y_cm);
+        } else {
+            if (yoff >= 0) x_cm = band_stereo(p, xoff, yoff, Nb, b, B, lb, LM, out, scratch, (int)(x_cm | y_cm));
+            else x_cm = band_mono(p, xoff, Nb, b, B, lb, LM, out, 32767, scratch, (int)(x_cm | y_cm));
+            y_cm = x_cm;
+        }
+        cmask[i * C + 0] = (uint8_t)x_cm;
+        cmask[i * C + C - 1] = (uint8_t)y_cm;
+        balance += pulses[i] + tell;
+        update_lowband = b > (Nb << 3);
+    }
+}
+
+// ref interp_bits2pulses (src/celt.cpp:3298), decoder side
+OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start, const int* bits1, const int* bits2,
+                               const int* thresh, const int* cap, int total, int* balance_out, int skip_rsv, int* intensity,
+                               int intensity_rsv, int* dual_stereo, int dual_stereo_rsv, int* bits, int* ebits,
+                               int* fine_priority, int C, int LM) {
+    const int alloc_floor = C << 3;
+    const int stereo = C > 1;
+    const int logM = LM << 3;
+    int lo = 0, hi = 1 << 6, psum, done, j;
+    for (int it = 0; it < 6; it++) {
+        int mid = (lo + hi) >> 1;
+        psum = 0; done = 0;
+        for (j = end; j-- > start;) {
+            int tmp = bits1[j] + (mid * bits2[j] >> 6);
+            if (tmp >= thresh[j] || done) { done = 1; psum += imin(tmp, cap[j]); }
+            else if (tmp >= alloc_floor) psum += alloc_floor;
+        }
+        if (psum > total) hi = mid; else lo = mid;
+    }
+    psum = 0; done = 0;
+    for (j = end; j-- > start;) {
+        int tmp = bits1[j] + (lo * bits2[j] >> 6);
+        if (tmp < thresh[j] && !done) tmp = tmp >= alloc_floor ? alloc_floor : 0;
+        else done = 1;
+        tmp = imin(tmp, cap[j]);
+        bits[j] = tmp;
+        psum += tmp;
+    }
+    int codedBands, left, percoeff;
+    for (codedBands = end;; codedBands--) {
+        j = codedBands - 1;
+        if (j <= skip_start) { total += skip_rsv; break; }
+        left = total - psum;
+        percoeff = (int)((u32)left / (u32)(kEBands[codedBands] - kEBands[start]));
+        left -= (kEBands[codedBands] - kEBands[start]) * percoeff;
+        int rem = imax(left - (kEBands[j] - kEBands[start]), 0);
+        int band_width = kEBands[codedBands] - kEBands[j];
+        int band_bits = bits[j] + percoeff * band_width + rem;
+        if (band_bits >= imax(thresh[j], alloc_floor + (1 << 3))) {
+            if (rd_bit_logp(rd, 1)) break;
+            psum += 1 << 3;
+            band_bits -= 1 << 3;
+        }
+        psum -= bits[j] + intensity_rsv;
+        if (intensity_rsv > 0) intensity_rsv = kLog2Frac[j - start];
+        psum += intensity_rsv;
+        if (band_bits >= alloc_floor) { psum += alloc_floor; bits[j] = alloc_floor; }
+        else bits[j] = 0;
+    }
+    if (intensity_rsv > 0) *intensity = start + (int)rd_uint(rd, (u32)(codedBands + 1 - start));
+    else *intensity = 0;
+    if (*intensity <= start) { total += dual_stereo_rsv; dual_stereo_rsv = 0; }
+    if (dual_stereo_rsv > 0) *dual_stereo = rd_bit_logp(rd, 1);
+    else *dual_stereo = 0;
+
+    left = total - psum;
+    percoeff = (int)((u32)left / (u32)(kEBands[codedBands] - kEBands[start]));
+    left -= (kEBands[codedBands] - kEBands[start]) * percoeff;
+    for (j = start; j < codedBands; j++) bits[j] += percoeff * (kEBands[j + 1] - kEBands[j]);
+    for (j = start; j < codedBands; j++) {
+        int tmp = imin(left, kEBands[j + 1] - kEBands[j]);
+        bits[j] += tmp;
+        left -= tmp;
+    }
+    int balance = 0;
+    for (j = start; j < codedBands; j++) {
+        int N0 = kEBands[j + 1] - kEBands[j];
+        int N = N0 << LM;
+        int bit = bits[j] + balance;
+        int excess;
+        if (N > 1) {
+            excess = imax(bit - cap[j], 0);
+            bits[j] = bit - excess;
+            int den = C * N + ((C == 2 && N > 2 && !*dual_stereo && j < *intensity) ? 1 : 0);
+            int NClogN = den * (kLogN400[j] + logM);
+            int offset = (NClogN >> 1) - den * 21;
+            if (N == 2) offset += den << 3 >> 2;
+            if (bits[j] + offset < den * 2 << 3) offset += NClogN >> 2;
+            else if (bits[j] + offset < den * 3 << 3) offset += NClogN >> 3;
+            ebits[j] = imax(0, bits[j] + offset + (den << 2));
+            ebits[j] = (int)((u32)ebits[j] / (u32)den) >> 3;
+            if (C * ebits[j] > (bits[j] >> 3)) ebits[j] = bits[j] >> stereo >> 3;
+            ebits[j] = imin(ebits[j], 8);
+            fine_priority[j] = ebits[j] * (den << 3) >= bits[j] + offset;
+            bits[j] -= C * ebits[j] << 3;
+        } else {
+            excess = imax(0, bit - (C << 3));
+            bits[j] = bit - excess;
+            ebits[j] = 0;
+            fine_priority[j] = 1;
+        }
+        if (excess > 0) {
+            int extra_fine = imin(excess >> (stereo + 3), 8 - ebits[j]);
+            ebits[j] += extra_fine;
+            int extra_bits = extra_fine * C << 3;
+            fine_priority[j] = extra_bits >= excess - balance;
+            excess -= extra_bits;
+        }
+        balance = excess;
+    }
+    *balance_out = balance;
+    for (; j < end; j++) {
+        ebits[j] = bits[j] >> stereo >> 3;
+        bits[j] = 0;
+        fine_priority[j] = ebits[j] < 1;
+    }
+    return codedBands;
+}
+
+// ref clt_compute_allocation (src/celt.cpp:3523), decoder side
+OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offsets, const int* cap, int alloc_trim,
+                               int* intensity, int* dual_stereo, int total, int* balance, int* pulses, int* ebits,
+                               int* fine_priority, int C, int LM) {
+    total = imax(total, 0);
+    const int len = kNbEBands;
+    int skip_start = start;
+    int skip_rsv = total >= 1 << 3 ? 1 << 3 : 0;
+    total -= skip_rsv;
+    int intensity_rsv = 0, dual_stereo_rsv = 0;
+    if (C == 2) {
+        intensity_rsv = kLog2Frac[end - start];
+        if (intensity_rsv > total) intensity_rsv = 0;
+        else {
+            total -= intensity_rsv;
+            dual_stereo_rsv = total >= 1 << 3 ? 1 << 3 : 0;
+            total -= dual_stereo_rsv;
+        }
+    }
+    int bits1[kNbEBands], bits2[kNbEBands], thresh[kNbEBands], trim_offset[kNbEBands];
+    for (int j = start; j < end; j++) {
+        int w = kEBands[j + 1] - kEBands[j];
+        thresh[j] = imax(C << 3, (3 * w << LM << 3) >> 4);
+        trim_offset[j] = C * w * (alloc_trim - 5 - LM) * (end - j - 1) * (1 << (LM + 3)) >> 6;
+        if (w << LM == 1) trim_offset[j] -= C << 3;
+    }
+    int lo = 1, hi = 11 - 1;
+    do {
+        int done = 0, psum = 0;
+        int mid = (lo + hi) >> 1;
+        for (int j = end; j-- > start;) {
+            int w = kEBands[j + 1] - kEBands[j];
+            int bitsj = C * w * kBandAlloc[mid * len + j] << LM >> 2;
+            if (bitsj > 0) bitsj = imax(0, bitsj + trim_offset[j]);
+            bitsj += offsets[j];
+            if (bitsj >= thresh[j] || done) { done = 1; psum += imin(bitsj, cap[j]); }
+            else if (bitsj >= C << 3) psum += C << 3;
+        }
+        if (psum > total) hi = mid - 1; else lo = mid + 1;
+    } while (lo <= hi);
+    hi = lo--;
+    for (int j = start; j < end; j++) {
+        int w = kEBands[j + 1] - kEBands[j];
+        int bits1j = C * w * kBandAlloc[lo * len + j] << LM >> 2;
+        int bits2j = hi >= 11 ? cap[j] : C * w * kBandAlloc[hi * len + j] << LM >> 2;
+        if (bits1j > 0) bits1j = imax(0, bits1j + trim_offset[j]);
+        if (bits2j > 0) bits2j = imax(0, bits2j + trim_offset[j]);
+        if (lo > 0) bits1j += offsets[j];
+        bits2j += offsets[j];
+        if (offsets[j] > 0) skip_start = j;
+        bits2j = imax(0, bits2j - bits1j);
+        bits1[j] = bits1j;
+        bits2[j] = bits2j;
+    }
+    return interp_bits2pulses(rd, start, end, skip_start, bits1, bits2, thresh, cap, total, balance, skip_rsv, intensity,
+                              intensity_rsv, dual_stereo, dual_stereo_rsv, pulses, ebits, fine_priority, C, LM);
+}
+
+// One CELT frame: every symbol of celt_decode_with_ec (ref src/celt.cpp:2239-2367) in bitstream order.
+// `p.rd` must already be initialised on the frame (and, for hybrid, advanced past the SILK layer).
+// frame_size = 120 << LM.  Returns the status also stored in hdr.
+OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
+    RangeDec& rd = p.rd;
+    const int C = p.C, LM = p.LM, start = p.start, end = p.end;
+    const int M = 1 << LM;
+    hdr.LM = (uint8_t)LM; hdr.C = (uint8_t)C; hdr.start = (uint8_t)start; hdr.end = (uint8_t)end;
+    hdr.n_ops = 0; hdr.lcg_steps = 0; hdr.flags = 0; hdr.pf_pitch = 0; hdr.pf_gain = 0; hdr.pf_tapset = 0;
+    hdr.final_rng = 0;
+    if (rd.storage > (u32)kMaxPacket || rd.storage <= 1) {  // ref :2216, :2225
+        hdr.status = OPUSB_CELT_BAD_ARG;
+        return hdr.status;
+    }
+    p.n_ops = 0; p.overflow = 0; p.lcg_steps = 0;
+
+    int total_bits = (int)rd.storage * 8;
+    int tell = rd_tell(rd);
+    int silence;
+    if (tell >= total_bits) silence = 1;
+    else if (tell == 1) silence = rd_bit_logp(rd, 15);
+    else silence = 0;
+    if (silence) {
+        tell = (int)rd.storage * 8;
+        rd.nbits_total += tell - rd_tell(rd);
+    }
+    int pf_gain = 0, pf_pitch = 0, pf_tapset = 0, flags = 0;
+    if (start == 0 && tell + 16 <= total_bits) {
+        if (rd_bit_logp(rd, 1)) {
+            int octave = (int)rd_uint(rd, 6);
+            pf_pitch = (16 << octave) + (int)rd_bits(rd, 4 + (u32)octave) - 1;
+            int qg = (int)rd_bits(rd, 3);
+            if (rd_tell(rd) + 2 <= total_bits) {
+                const uint8_t tapset_icdf[3] = {2, 1, 0};
+                pf_tapset = rd_icdf(rd, tapset_icdf, 2);
+            }
+            pf_gain = 3072 * (qg + 1);  // QCONST16(.09375, 15)
+            flags |= FF_POSTFILTER;
+        }
+        tell = rd_tell(rd);
+    }
+    int isTransient = 0;
+    if (LM > 0 && tell + 3 <= total_bits) {
+        isTransient = rd_bit_logp(rd, 3);
+        tell = rd_tell(rd);
+    }
+    const int shortBlocks = isTransient ? M : 0;
+    const int intra = tell + 3 <= total_bits ? rd_bit_logp(rd, 3) : 0;
+
+    // ---- coarse energy symbols (ref unquant_coarse_energy :3613): only the bitstream-dependent part;
+    // the prediction from the previous frame is applied by the energy kernel.
+    {
+        const uint8_t* prob = kEProb + (LM * 2 + intra) * 42;
+        const s16 beta = intra ? (s16)4915 : (LM == 0 ? (s16)30147 : LM == 1 ? (s16)22282 : LM == 2 ? (s16)12124 : (s16)6554);
+        s32 prev[2] = {0, 0};
+        const int budget = (int)rd.storage * 8;
+        for (int i = start; i < end; i++) {
+            for (int c = 0; c < C; c++) {
+                int qi;
+                int t = rd_tell(rd);
+                if (budget - t >= 15) {
+                    int pi = 2 * imin(i, 20);
+                    qi = rd_laplace(rd, (u32)prob[pi] << 7, (int)prob[pi + 1] << 6);
+                } else if (budget - t >= 2) {
+                    const uint8_t small_icdf[3] = {2, 1, 0};
+                    qi = rd_icdf(rd, small_icdf, 2);
+                    qi = (qi >> 1) ^ -(qi & 1);
+                } else if (budget - t >= 1) {
+                    qi = -rd_bit_logp(rd, 1);
+                } else {
+                    qi = -1;
+                }
+                s32 q = shl32(qi, 10);
+                hdr.pq[c][i] = prev[c] + shl32(q, 7);
+                prev[c] = prev[c] + shl32(q, 7) - mul16(beta, pshr32(q, 8));
+            }
+        }
+    }
+
+    // ---- tf_decode (ref :2128)
+    int tf_res[kNbEBands];
+    {
+        u32 budget = rd.storage * 8;
+        u32 t = (u32)rd_tell(rd);
+        int logp = isTransient ? 2 : 4;
+        int tf_select_rsv = LM > 0 && t + (u32)logp + 1 <= budget;
+        budget -= (u32)tf_select_rsv;
+        int tf_changed = 0, curr = 0;
+        for (int i = start; i < end; i++) {
+            if (t + (u32)logp <= budget) {
+                curr ^= rd_bit_logp(rd, (u32)logp);
+                t = (u32)rd_tell(rd);
+                tf_changed |= curr;
+            }
+            tf_res[i] = curr;
+            logp = isTransient ? 4 : 5;
+        }
+        int tf_select = 0;
+        if (tf_select_rsv && kTfSelect[LM * 8 + 4 * isTransient + 0 + tf_changed] != kTfSelect[LM * 8 + 4 * isTransient + 2 + tf_changed])
+            tf_select = rd_bit_logp(rd, 1);
+        for (int i = start; i < end; i++) tf_res[i] = kTfSelect[LM * 8 + 4 * isTransient + 2 * tf_select + tf_res[i]];
+    }
+
+    tell = rd_tell(rd);
+    int spread = 2;  // SPREAD_NORMAL
+    if (tell + 4 <= total_bits) spread = rd_icdf(rd, kSpreadIcdf, 5);
+    p.spread = spread;
+
+    // ---- caps + dynalloc (ref :911, :2301-2328)
+    int cap[kNbEBands], offsets[kNbEBands];
+    for (int i = 0; i < kNbEBands; i++) {
+        int N = (kEBands[i + 1] - kEBands[i]) << LM;
+        cap[i] = (kCacheCaps[kNbEBands * (2 * LM + C - 1) + i] + 64) * C * N >> 2;
+        offsets[i] = 0;
+    }
+    int dynalloc_logp = 6;
+    total_bits <<= 3;
+    tell = (int)rd_tell_frac(rd);
+    for (int i = start; i < end; i++) {
+        int width = C * (kEBands[i + 1] - kEBands[i]) << LM;
+        int quanta = imin(width << 3, imax(6 << 3, width));
+        int loop_logp = dynalloc_logp;
+        int boost = 0;
+        while (tell + (loop_logp << 3) < total_bits && boost < cap[i]) {
+            int flag = rd_bit_logp(rd, (u32)loop_logp);
+            tell = (int)rd_tell_frac(rd);
+            if (!flag) break;
+            boost += quanta;
+            total_bits -= quanta;
+            loop_logp = 1;
+        }
+        offsets[i] = boost;
+        if (boost > 0) dynalloc_logp = imax(2, dynalloc_logp - 1);
+    }
+    const int alloc_trim = tell + (6 << 3) <= total_bits ? rd_icdf(rd, kTrimIcdf, 7) : 5;
+
+    int bits = (((int)rd.storage * 8) << 3) - (int)rd_tell_frac(rd) - 1;
+    const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << 3) ? (1 << 3) : 0;
+    bits -= anti_collapse_rsv;
+
+    int pulses[kNbEBands], fine_quant[kNbEBands], fine_priority[kNbEBands];
+    for (int i = 0; i < kNbEBands; i++) { pulses[i] = 0; fine_quant[i] = 0; fine_priority[i] = 0; }
+    int intensity = 0, dual_stereo = 0, balance = 0;
+    const int codedBands = compute_allocation(rd, start, end, offsets, cap, alloc_trim, &intensity, &dual_stereo, bits, &balance,
+                                              pulses, fine_quant, fine_priority, C, LM);
+
+    // ---- fine energy (ref unquant_fine_energy :3664)
+    s32 fine_acc[2][kNbEBands];
+    for (int c = 0; c < 2; c++) for (int i = 0; i < kNbEBands; i++) fine_acc[c][i] = 0;
+    for (int i = start; i < end; i++) {
+        if (fine_quant[i] <= 0) continue;
+        for (int c = 0; c < C; c++) {
+            s32 q2 = (s32)rd_bits(rd, (u32)fine_quant[i]);
+            s32 offset = sub16((shl32(q2, 10) + 512) >> fine_quant[i], 512);
+            fine_acc[c][i] += (s16)offset;
+        }
+    }
+
+    // ---- PVQ / band structure (ref quant_all_bands :1754)
+    uint8_t cmask[2 * kNbEBands];
+    for (int i = 0; i < 2 * kNbEBands; i++) cmask[i] = 0;
+    all_bands(p, cmask, pulses, shortBlocks, dual_stereo, intensity, tf_res,
+              (int)rd.storage * (8 << 3) - anti_collapse_rsv, balance, codedBands);
+
+    int anti_collapse_on = 0;
+    if (anti_collapse_rsv > 0) anti_collapse_on = (int)rd_bits(rd, 1);
+
+    // ---- final energy bits (ref unquant_energy_finalise :3681)
+    {
+        int bits_left = (int)rd.storage * 8 - rd_tell(rd);
+        for (int prio = 0; prio < 2; prio++) {
+            for (int i = start; i < end && bits_left >= C; i++) {
+                if (fine_quant[i] >= 8 || fine_priority[i] != prio) continue;
+                for (int c = 0; c < C; c++) {
+                    s32 q2 = (s32)rd_bits(rd, 1);
+                    s32 offset = ((s32)shl16(q2, 10) - 512) >> (fine_quant[i] + 1);
+                    fine_acc[c][i] += (s16)offset;
+                    bits_left--;
+                }
+            }
+        }
+    }
+
+    for (int c = 0; c < 2; c++)
+        for (int i = 0; i < kNbEBands; i++) {
+            hdr.fine[c][i] = (int16_t)fine_acc[c][i];
+            if (c >= C || i < start || i >= end) hdr.pq[c][i] = 0;
+        }
+    for (int i = 0; i < kNbEBands; i++) hdr.pulses[i] = (int16_t)pulses[i];
+    for (int i = 0; i < 2 * kNbEBands; i++) hdr.cmask[i] = cmask[i];
+    if (silence) flags |= FF_SILENCE;
+    if (isTransient) flags |= FF_TRANSIENT;
+    if (intra) flags |= FF_INTRA;
+    if (anti_collapse_on) flags |= FF_ANTICOLLAPSE;
+    if (rd.error) flags |= FF_EC_ERROR;
+    hdr.flags = (uint8_t)flags;
+    hdr.pf_pitch = (int16_t)pf_pitch;
+    hdr.pf_gain = (int16_t)pf_gain;
+    hdr.pf_tapset = (uint8_t)pf_tapset;
+    hdr.n_ops = (uint16_t)p.n_ops;
+    hdr.lcg_steps = p.lcg_steps;
+    hdr.final_rng = rd.rng;
+    int status = kShortMdct << LM;
+    if (rd_tell(rd) > 8 * (int)rd.storage) status = OPUSB_INTERNAL_ERROR;  // ref :2441
+    if (p.overflow) status = OPUSB_SCRIPT_OVERFLOW;
+    hdr.status = status;
+    return status;
+}
+
+}  // namespace opusb200
