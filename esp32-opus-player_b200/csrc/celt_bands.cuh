@@ -1,0 +1,240 @@
+// celt_bands.cuh -- band reconstruction stage: one warp replays one frame's BandOp script.
+//
+// SURVEY section 8 rows a4 (folding / noise fill), a5 (renormalise_vector), a6 (stereo_merge, haar1,
+// (de)interleave_hadamard) and a7 (anti_collapse).  All operands live in the warp's int16 workspace W
+// in shared memory (layout in celt_script.cuh); lanes stride over the vector, reductions are warp
+// reductions, the LCG noise sequence is generated with jump-ahead so that lane j owns draw j.
+#pragma once
+#include "celt_script.cuh"
+#include "celt_tables.cuh"
+#include "lanes.cuh"
+
+namespace opusb200 {
+
+struct FrameEnergy {
+    int16_t E[2][kNbEBands];     // band log-energy after this frame's coarse+fine+final (ref oldBandE)
+    int16_t pmin[2][kNbEBands];  // min(oldLogE, oldLogE2) before this frame (anti_collapse input, ref :1044-1050)
+};
+
+// advance the LCG by cnt (1..kLanes) draws
+OPUS_HD u32 lcg_jump(u32 seed, int cnt) { return kLcgMul[cnt - 1] * seed + kLcgAdd[cnt - 1]; }
+
+// ref renormalise_vector (src/celt.cpp:797)
+OPUS_HD void w_renormalise(const Lanes& L, int16_t* X, int N, s16 gain) {
+    s32 acc = 0;
+    for (int j = L.lane; j < N; j += kLanes) acc = add_w(acc, mul16(X[j], X[j]));
+    s32 E = add_w(1, L.sum(acc));
+    int k = ilog2p(E) >> 1;
+    s32 t = vshr32(E, 2 * (k - 7));
+    s16 g = (s16)mul16_p15(rsqrt_norm(t), gain);
+    for (int j = L.lane; j < N; j += kLanes) X[j] = (s16)pshr32(mul16(g, X[j]), k + 1);
+    L.sync();
+}
+
+// ref haar1 (src/celt.cpp:1202)
+OPUS_HD void w_haar(const Lanes& L, int16_t* X, int N0, int stride) {
+    const int pairs = (N0 >> 1) * stride;
+    for (int t = L.lane; t < pairs; t += kLanes) {
+        int i = t % stride, j = t / stride;
+        int ia = stride * 2 * j + i, ib = stride * (2 * j + 1) + i;
+        s32 t1 = mul16(23170, X[ia]), t2 = mul16(23170, X[ib]);
+        X[ia] = (s16)pshr32(t1 + t2, 15);
+        X[ib] = (s16)pshr32(t1 - t2, 15);
+    }
+    L.sync();
+}
+
+// ref deinterleave_hadamard / interleave_hadamard (src/celt.cpp:1162, 1183): a permutation of N0*stride values
+OPUS_HD void w_hadamard_perm(const Lanes& L, int16_t* X, int N0, int stride, int hadamard, int inverse) {
+    const int N = N0 * stride;
+    const uint8_t* ordery = kOrdery + stride - 2;
+    enum { kPer = (kMaxLeaf + kLanes - 1) / kLanes };
+    s16 tmp[kPer];
+    // destination index d -> source index
+    int q = 0;
+    for (int d = L.lane; d < N; d += kLanes, q++) {
+        int src;
+        if (!inverse) {  // tmp[ord(i)*N0 + j] = X[j*stride + i]
+            int oi = d / N0, j = d % N0;
+            int i = oi;
+            if (hadamard) { for (i = 0; i < stride; i++) if (ordery[i] == oi) break; }
+            src = j * stride + i;
+        } else {         // tmp[j*stride + i] = X[ord(i)*N0 + j]
+            int j = d / stride, i = d % stride;
+            src = (hadamard ? ordery[i] : i) * N0 + j;
+        }
+        tmp[q] = X[src];
+    }
+    L.sync();
+    q = 0;
+    for (int d = L.lane; d < N; d += kLanes, q++) X[d] = tmp[q];
+    L.sync();
+}
+
+// ref stereo_merge (src/celt.cpp:1113)
+OPUS_HD void w_stereo_merge(const Lanes& L, int16_t* X, int16_t* Y, s16 mid, int N) {
+    s32 a = 0, b = 0;
+    for (int j = L.lane; j < N; j += kLanes) {
+        a = add_w(a, mul16(Y[j], X[j]));
+        b = add_w(b, mul16(Y[j], Y[j]));
+    }
+    s32 xp = L.sum(a), side = L.sum(b);
+    xp = mul16x32_q15(mid, xp);
+    s16 mid2 = (s16)(mid >> 1);
+    s32 El = mul16(mid2, mid2) + side - 2 * xp;
+    s32 Er = mul16(mid2, mid2) + side + 2 * xp;
+    if (Er < 161061 || El < 161061) {  // QCONST32(6e-4f, 28)
+        for (int j = L.lane; j < N; j += kLanes) Y[j] = X[j];
+        L.sync();
+        return;
+    }
+    int kl = ilog2p(El) >> 1, kr = ilog2p(Er) >> 1;
+    s32 lgain = rsqrt_norm(vshr32(El, (kl - 7) << 1));
+    s32 rgain = rsqrt_norm(vshr32(Er, (kr - 7) << 1));
+    if (kl < 7) kl = 7;
+    if (kr < 7) kr = 7;
+    for (int j = L.lane; j < N; j += kLanes) {
+        s16 l = (s16)mul16_p15(mid, X[j]);
+        s16 r = Y[j];
+        X[j] = (s16)pshr32(mul16(lgain, sub16(l, r)), kl + 1);
+        Y[j] = (s16)pshr32(mul16(rgain, add16(l, r)), kr + 1);
+    }
+    L.sync();
+}
+
+// Replays the script of one frame.  `seed` = noise seed at frame start (= previous frame's final range).
+// Returns the seed after all fills (input of anti_collapse, ref src/celt.cpp:2371).
+OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_ops, u32 seed) {
+    for (int k = 0; k < n_ops; k++) {
+        const BandOp o = ops[k];
+        int16_t* X = W + o.off;
+        const int n = o.n;
+        switch (o.code) {
+            case OP_NOISE:
+                for (int j0 = 0; j0 < n; j0 += kLanes) {
+                    int cnt = imin(kLanes, n - j0);
+                    if (L.lane < cnt) {
+                        u32 s = lcg_jump(seed, L.lane + 1);
+                        X[j0 + L.lane] = (s16)((s32)s >> 20);
+                    }
+                    seed = lcg_jump(seed, cnt);
+                }
+                L.sync();
+                w_renormalise(L, X, n, o.g);
+                break;
+            case OP_FOLD: {
+                const int16_t* lb = W + o.off2;
+                for (int j0 = 0; j0 < n; j0 += kLanes) {
+                    int cnt = imin(kLanes, n - j0);
+                    if (L.lane < cnt) {
+                        u32 s = lcg_jump(seed, L.lane + 1);
+                        s32 tmp = (s & 0x8000u) ? 4 : -4;  // QCONST16(1/256, 10)
+                        X[j0 + L.lane] = (s16)(lb[j0 + L.lane] + tmp);
+                    }
+                    seed = lcg_jump(seed, cnt);
+                }
+                L.sync();
+                w_renormalise(L, X, n, o.g);
+            } break;
+            case OP_COPY: {
+                const int16_t* src = W + o.off2;
+                for (int j = L.lane; j < n; j += kLanes) X[j] = src[j];
+                L.sync();
+            } break;
+            case OP_HAAR: w_haar(L, X, n, o.a); break;
+            case OP_DEINT: w_hadamard_perm(L, X, n, o.a, o.g, 0); break;
+            case OP_INT: w_hadamard_perm(L, X, n, o.a, o.g, 1); break;
+            case OP_SCALE_OUT: {
+                int16_t* dst = W + o.off2;
+                for (int j = L.lane; j < n; j += kLanes) dst[j] = (s16)mul16_q15(o.g, X[j]);
+                L.sync();
+            } break;
+            case OP_SETW:
+                if (L.lane == 0) X[0] = o.g;
+                L.sync();
+                break;
+            case OP_MERGE: w_stereo_merge(L, X, W + o.off2, o.g, n); break;
+            case OP_NEG:
+                for (int j = L.lane; j < n; j += kLanes) X[j] = (s16)(-(s32)X[j]);
+                L.sync();
+                break;
+            case OP_N2: {
+                if (L.lane == 0) {
+                    int16_t* x2 = X;
+                    int16_t* y2 = W + o.off2;
+                    const int sign = 1 - 2 * (o.a & 1);
+                    y2[0] = (s16)(-sign * x2[1]);
+                    y2[1] = (s16)(sign * x2[0]);
+                    int16_t* Xc = (o.a & 2) ? y2 : x2;  // channel 0
+                    int16_t* Yc = (o.a & 2) ? x2 : y2;  // channel 1
+                    Xc[0] = (s16)mul16_q15(o.g, Xc[0]);
+                    Xc[1] = (s16)mul16_q15(o.g, Xc[1]);
+                    Yc[0] = (s16)mul16_q15(o.g2, Yc[0]);
+                    Yc[1] = (s16)mul16_q15(o.g2, Yc[1]);
+                    s16 tmp = Xc[0];
+                    Xc[0] = (s16)sub16(tmp, Yc[0]);
+                    Yc[0] = add16(tmp, Yc[0]);
+                    tmp = Xc[1];
+                    Xc[1] = (s16)sub16(tmp, Yc[1]);
+                    Yc[1] = add16(tmp, Yc[1]);
+                }
+                L.sync();
+            } break;
+            case OP_AVG: {
+                const int16_t* src = W + o.off2;
+                for (int j = L.lane; j < n; j += kLanes) X[j] = (s16)(((s32)X[j] + (s32)src[j]) >> 1);
+                L.sync();
+            } break;
+            default: break;
+        }
+    }
+    return seed;
+}
+
+// ref anti_collapse (src/celt.cpp:1010).  X = W + W_XY holds [C][N].
+OPUS_HD void band_stage_anti_collapse(const Lanes& L, int16_t* W, const CeltFrameHdr& h, const FrameEnergy& fe, u32 seed) {
+    const int LM = h.LM, C = h.C, size = kShortMdct << LM;
+    for (int i = h.start; i < h.end; i++) {
+        const int N0 = kEBands[i + 1] - kEBands[i];
+        const int depth = (int)((u32)(1 + h.pulses[i]) / (u32)N0) >> LM;
+        s32 thresh32 = exp2_q((s16)(-(s32)shl16(depth, 10 - 3))) >> 1;
+        s16 thresh = (s16)mul16x32_q15(16384, imin(32767, thresh32));
+        s32 t = N0 << LM;
+        const int shift = ilog2p(t) >> 1;
+        t = shl32(t, (7 - shift) << 1);
+        const s16 sqrt_1 = rsqrt_norm(t);
+        for (int c = 0; c < C; c++) {
+            s32 Ediff = (s32)fe.E[c][i] - (s32)fe.pmin[c][i];
+            Ediff = imax(0, Ediff);
+            s16 r;
+            if (Ediff < 16384) {
+                s32 r32 = exp2_q((s16)(-(s32)(s16)Ediff)) >> 1;
+                r = (s16)(2 * imin(16383, r32));
+            } else {
+                r = 0;
+            }
+            if (LM == 3) r = (s16)mul16_q14(23170, imin(23169, r));
+            r = (s16)(imin(thresh, r) >> 1);
+            r = (s16)(mul16_q15(sqrt_1, r) >> shift);
+            int16_t* X = W + W_XY + c * size + (kEBands[i] << LM);
+            int renorm = 0;
+            for (int k = 0; k < (1 << LM); k++) {
+                if (!(h.cmask[i * C + c] & (1 << k))) {
+                    for (int j0 = 0; j0 < N0; j0 += kLanes) {
+                        int cnt = imin(kLanes, N0 - j0);
+                        if (L.lane < cnt) {
+                            u32 s = lcg_jump(seed, L.lane + 1);
+                            X[((j0 + L.lane) << LM) + k] = (s & 0x8000u) ? r : (s16)(-(s32)r);
+                        }
+                        seed = lcg_jump(seed, cnt);
+                    }
+                    renorm = 1;
+                }
+            }
+            L.sync();
+            if (renorm) w_renormalise(L, X, N0 << LM, 32767);
+        }
+    }
+}
+
+}  // namespace opusb200

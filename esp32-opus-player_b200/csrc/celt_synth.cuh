@@ -1,0 +1,359 @@
+// celt_synth.cuh -- energy recurrence, denormalisation, inverse MDCT, TDAC overlap-add, comb
+// post-filter and de-emphasis stage bodies.
+#pragma once
+#include "celt_bands.cuh"
+
+namespace opusb200 {
+
+// ---------------------------------------------------------------------------------------------
+// Per-stream CELT state carried between frames.  Plain POD in HBM.
+// ---------------------------------------------------------------------------------------------
+enum { kCombHist = 1024 + 4 };  // post-filter reaches back T+2 <= 1024 samples (ref src/celt.cpp:874-884)
+
+struct CeltBandState {   // one per (stream, band): both channels
+    int16_t oldE[2], logE[2], logE2[2];
+};
+
+struct CeltStreamState {
+    uint32_t rng;                 // previous frame's final range = noise seed (ref :2437)
+    int32_t pf_period, pf_period_old;
+    int32_t pf_gain, pf_gain_old;
+    int32_t pf_tapset, pf_tapset_old;
+    int32_t preemph_mem[2];       // de-emphasis IIR memory (ref :1972-1985)
+    int32_t tail[2][kOverlap / 2];  // raw IMDCT tail awaiting the next frame's TDAC (ref :2349, 3281)
+    int32_t hist[2][kCombHist];     // last post-filtered samples, oldest first (ref decode_mem)
+    CeltBandState band[kNbEBands];
+};
+
+// ---- energy recurrence: one lane per band, frames in order (ref :2234-2237, 3613-3662, 2373-2436) ----
+OPUS_HD void energy_step(CeltBandState& s, int i, const CeltFrameHdr& h, FrameEnergy& out) {
+    const int C = h.C, LM = h.LM;
+    const int intra = (h.flags & FF_INTRA) != 0;
+    if (C == 1) s.oldE[0] = (int16_t)imax(s.oldE[0], s.oldE[1]);
+    if (i >= h.start && i < h.end) {
+        const s16 coef = intra ? (s16)0 : (LM == 0 ? (s16)29440 : LM == 1 ? (s16)26112 : LM == 2 ? (s16)21248 : (s16)16384);
+        for (int c = 0; c < C; c++) {
+            s32 old = imax(-9216, s.oldE[c]);
+            s32 tmp = pshr32(mul16(coef, old), 8) + h.pq[c][i];
+            tmp = imax(-(28 << 17), tmp);
+            s16 e = (s16)pshr32(tmp, 7);
+            s.oldE[c] = (s16)(e + h.fine[c][i]);
+        }
+    }
+    for (int c = 0; c < 2; c++) {
+        s16 p1 = s.logE[c], p2 = s.logE2[c];
+        if (C == 1) { p1 = (s16)imax(p1, s.logE[1]); p2 = (s16)imax(p2, s.logE2[1]); }
+        out.pmin[c][i] = (s16)imin(p1, p2);
+    }
+    // anti_collapse reads the energies before the silence override; silence never co-occurs with it.
+    if (h.flags & FF_SILENCE) for (int c = 0; c < C; c++) s.oldE[c] = -(28 << 10);
+    out.E[0][i] = s.oldE[0];
+    out.E[1][i] = s.oldE[1];
+    if (C == 1) s.oldE[1] = s.oldE[0];
+    if (!(h.flags & FF_TRANSIENT)) {
+        for (int c = 0; c < 2; c++) { s.logE2[c] = s.logE[c]; s.logE[c] = s.oldE[c]; }
+    } else {
+        for (int c = 0; c < 2; c++) s.logE[c] = (s16)imin(s.logE[c], s.oldE[c]);
+    }
+    if (i < h.start || i >= h.end) {
+        for (int c = 0; c < 2; c++) { s.oldE[c] = 0; s.logE[c] = s.logE2[c] = -(28 << 10); }
+    }
+}
+
+// ---- denormalise_bands (ref src/celt.cpp:948): freq[j] = X[j] * 2^(E+eMeans) ----
+OPUS_HD void denormalise(const Lanes& L, const int16_t* X, int32_t* freq, const int16_t* bandLogE, int start, int end, int M,
+                         int silence) {
+    const int N = M * kShortMdct;
+    int bound = M * kEBands[end];
+    if (silence) { bound = 0; start = end = 0; }
+    for (int j = L.lane; j < M * kEBands[start]; j += kLanes) freq[j] = 0;
+    for (int i = start; i < end; i++) {
+        const int j0 = M * kEBands[i], j1 = M * kEBands[i + 1];
+        s16 lg = sat16((s32)bandLogE[i] + shl32((s32)kEMeans[i], 6));
+        int shift = 16 - (lg >> 10);
+        s16 g;
+        if (shift > 31) { shift = 0; g = 0; }
+        else g = (s16)exp2_frac((s16)(lg & 1023));
+        if (shift < 0) {
+            if (shift <= -2) { g = 16384; shift = -2; }
+            for (int j = j0 + L.lane; j < j1; j += kLanes) freq[j] = shl32(mul16(X[j], g), -shift);
+        } else {
+            for (int j = j0 + L.lane; j < j1; j += kLanes) freq[j] = mul16(X[j], g) >> shift;
+        }
+    }
+    for (int j = bound + L.lane; j < N; j += kLanes) freq[j] = 0;
+    L.sync();
+}
+
+// ---- fixed-point FFT butterflies (ref kf_bfly2/3/4/5, src/celt.cpp:2794-2995) ----
+struct Cpx { s32 r, i; };
+OPUS_HD s32 smul(s32 a, s16 b) { return mul16x32_q15(b, a); }  // ref S_MUL(a,b), src/celt.h:192
+OPUS_HD Cpx cmul(Cpx a, int tw) {                                // ref C_MUL with twiddle index tw
+    const s16 br = kFftTwRe[tw], bi = kFftTwIm[tw];
+    Cpx m;
+    m.r = sub_w(smul(a.r, br), smul(a.i, bi));
+    m.i = add_w(smul(a.r, bi), smul(a.i, br));
+    return m;
+}
+OPUS_HD Cpx cadd(Cpx a, Cpx b) { Cpx c; c.r = add_w(a.r, b.r); c.i = add_w(a.i, b.i); return c; }
+OPUS_HD Cpx csub(Cpx a, Cpx b) { Cpx c; c.r = sub_w(a.r, b.r); c.i = sub_w(a.i, b.i); return c; }
+
+struct FftStage { uint8_t radix, m, N, fstride, mm; };
+
+// radix-4, unit t in [0, N*m)
+OPUS_HD void bfly4(Cpx* f, int t, const FftStage& s) {
+    const int m = s.m;
+    if (m == 1) {
+        Cpx* F = f + 4 * t;
+        Cpx a0 = F[0], a1 = F[1], a2 = F[2], a3 = F[3];
+        Cpx s0 = csub(a0, a2);
+        a0 = cadd(a0, a2);
+        Cpx s1 = cadd(a1, a3);
+        F[2] = csub(a0, s1);
+        F[0] = cadd(a0, s1);
+        s1 = csub(a1, a3);
+        F[1].r = add_w(s0.r, s1.i); F[1].i = sub_w(s0.i, s1.r);
+        F[3].r = sub_w(s0.r, s1.i); F[3].i = add_w(s0.i, s1.r);
+    } else {
+        const int i = t / m, j = t % m;
+        Cpx* F = f + i * s.mm + j;
+        Cpx c0 = cmul(F[m], j * s.fstride);
+        Cpx c1 = cmul(F[2 * m], 2 * j * s.fstride);
+        Cpx c2 = cmul(F[3 * m], 3 * j * s.fstride);
+        Cpx a0 = F[0];
+        Cpx c5 = csub(a0, c1);
+        a0 = cadd(a0, c1);
+        Cpx c3 = cadd(c0, c2);
+        Cpx c4 = csub(c0, c2);
+        F[2 * m] = csub(a0, c3);
+        F[0] = cadd(a0, c3);
+        F[m].r = add_w(c5.r, c4.i); F[m].i = sub_w(c5.i, c4.r);
+        F[3 * m].r = sub_w(c5.r, c4.i); F[3 * m].i = add_w(c5.i, c4.r);
+    }
+}
+// radix-2 (always m == 4), unit t in [0, N*4)
+OPUS_HD void bfly2(Cpx* f, int t) {
+    const int i = t >> 2, k = t & 3;
+    Cpx* F = f + 8 * i + k;
+    Cpx a = F[0], b = F[4], tt;
+    const s16 tw = 23170;
+    if (k == 0) tt = b;
+    else if (k == 1) { tt.r = smul(add_w(b.r, b.i), tw); tt.i = smul(sub_w(b.i, b.r), tw); }
+    else if (k == 2) { tt.r = b.i; tt.i = neg_w(b.r); }
+    else { tt.r = smul(sub_w(b.i, b.r), tw); tt.i = smul(neg_w(add_w(b.i, b.r)), tw); }
+    F[4] = csub(a, tt);
+    F[0] = cadd(a, tt);
+}
+// radix-3, unit t in [0, N*m)
+OPUS_HD void bfly3(Cpx* f, int t, const FftStage& s) {
+    const int m = s.m, i = t / m, j = t % m;
+    Cpx* F = f + i * s.mm + j;
+    Cpx c1 = cmul(F[m], j * s.fstride);
+    Cpx c2 = cmul(F[2 * m], 2 * j * s.fstride);
+    Cpx c3 = cadd(c1, c2);
+    Cpx c0 = csub(c1, c2);
+    Cpx a0 = F[0], fm;
+    fm.r = sub_w(a0.r, c3.r >> 1);
+    fm.i = sub_w(a0.i, c3.i >> 1);
+    c0.r = smul(c0.r, -28378);
+    c0.i = smul(c0.i, -28378);
+    F[0] = cadd(a0, c3);
+    F[2 * m].r = add_w(fm.r, c0.i); F[2 * m].i = sub_w(fm.i, c0.r);
+    F[m].r = sub_w(fm.r, c0.i);     F[m].i = add_w(fm.i, c0.r);
+}
+// radix-5, unit t in [0, N*m)
+OPUS_HD void bfly5(Cpx* f, int t, const FftStage& s) {
+    const int m = s.m, i = t / m, u = t % m;
+    Cpx* F = f + i * s.mm + u;
+    const s16 yar = 10126, yai = -31164, ybr = -26510, ybi = -19261;
+    Cpx s0 = F[0];
+    Cpx s1 = cmul(F[m], u * s.fstride);
+    Cpx s2 = cmul(F[2 * m], 2 * u * s.fstride);
+    Cpx s3 = cmul(F[3 * m], 3 * u * s.fstride);
+    Cpx s4 = cmul(F[4 * m], 4 * u * s.fstride);
+    Cpx s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
+    F[0].r = add_w(s0.r, add_w(s7.r, s8.r));
+    F[0].i = add_w(s0.i, add_w(s7.i, s8.i));
+    Cpx s5, s6, s11, s12;
+    s5.r = add_w(s0.r, add_w(smul(s7.r, yar), smul(s8.r, ybr)));
+    s5.i = add_w(s0.i, add_w(smul(s7.i, yar), smul(s8.i, ybr)));
+    s6.r = add_w(smul(s10.i, yai), smul(s9.i, ybi));
+    s6.i = neg_w(add_w(smul(s10.r, yai), smul(s9.r, ybi)));
+    F[m] = csub(s5, s6);
+    F[4 * m] = cadd(s5, s6);
+    s11.r = add_w(s0.r, add_w(smul(s7.r, ybr), smul(s8.r, yar)));
+    s11.i = add_w(s0.i, add_w(smul(s7.i, ybr), smul(s8.i, yar)));
+    s12.r = sub_w(smul(s9.i, yai), smul(s10.i, ybi));
+    s12.i = sub_w(smul(s10.r, ybi), smul(s9.r, yai));
+    F[2 * m] = cadd(s11, s12);
+    F[3 * m] = csub(s11, s12);
+}
+
+// FFT plans for nfft = 480, 240, 120, 60 (shift 0..3), in execution order (ref opus_fft_impl :2997 with the
+// factor lists of fft_state48000_960_{0..3}, :589-626).  fstride already includes << shift.
+OPUS_HD int fft_plan(int shift, FftStage* st) {
+    int n = 0;
+    if (shift == 0) {
+        st[n++] = FftStage{4, 1, 120, 120, 4};
+        st[n++] = FftStage{2, 4, 60, 0, 0};
+        st[n++] = FftStage{4, 8, 15, 15, 32};
+        st[n++] = FftStage{3, 32, 5, 5, 96};
+        st[n++] = FftStage{5, 96, 1, 1, 1};
+    } else if (shift == 1) {
+        st[n++] = FftStage{4, 1, 60, 120, 4};
+        st[n++] = FftStage{4, 4, 15, 30, 16};
+        st[n++] = FftStage{3, 16, 5, 10, 48};
+        st[n++] = FftStage{5, 48, 1, 2, 1};
+    } else if (shift == 2) {
+        st[n++] = FftStage{4, 1, 30, 120, 4};
+        st[n++] = FftStage{2, 4, 15, 0, 0};
+        st[n++] = FftStage{3, 8, 5, 20, 24};
+        st[n++] = FftStage{5, 24, 1, 4, 1};
+    } else {
+        st[n++] = FftStage{4, 1, 15, 120, 4};
+        st[n++] = FftStage{3, 4, 5, 40, 12};
+        st[n++] = FftStage{5, 12, 1, 8, 1};
+    }
+    return n;
+}
+
+// Inverse MDCT of `nblk` interleaved blocks (ref clt_mdct_backward :3204 without the TDAC mirror, which
+// needs the previous block and is done by tdac_* below).  freq: N coefficients, block b at freq[b + k*nblk].
+// work: N int32 (nblk FFTs of N4 complex points).  On return work[b*N2 + k] = raw post-rotated y_b[k].
+OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int shift, int nblk) {
+    const int Nm = 1920 >> shift, N2 = Nm >> 1, N4 = Nm >> 2;
+    const int16_t* trig = kMdctTrig + (shift == 0 ? 0 : shift == 1 ? 960 : shift == 2 ? 1440 : 1680);
+    const int16_t* bitrev = shift == 0 ? kBitrev480 : shift == 1 ? kBitrev240 : shift == 2 ? kBitrev120 : kBitrev60;
+    // pre-rotation into bit-reversed order (ref :3219-3239)
+    for (int t = L.lane; t < nblk * N4; t += kLanes) {
+        const int b = t / N4, i = t % N4;
+        const int32_t* in = freq + b;
+        s32 x1 = in[2 * i * nblk], x2 = in[nblk * (N2 - 1 - 2 * i)];
+        s16 t0 = trig[i], t1 = trig[N4 + i];
+        s32 yr = add_w(smul(x2, t0), smul(x1, t1));
+        s32 yi = sub_w(smul(x1, t0), smul(x2, t1));
+        int rev = bitrev[i];
+        work[b * N2 + 2 * rev + 1] = yr;
+        work[b * N2 + 2 * rev] = yi;
+    }
+    L.sync();
+    FftStage st[5];
+    const int ns = fft_plan(shift, st);
+    for (int s = 0; s < ns; s++) {
+        const FftStage g = st[s];
+        const int units = (g.radix == 2 ? g.N * 4 : g.N * g.m);
+        for (int t = L.lane; t < nblk * units; t += kLanes) {
+            Cpx* f = (Cpx*)(work + (t / units) * N2);
+            const int u = t % units;
+            if (g.radix == 4) bfly4(f, u, g);
+            else if (g.radix == 2) bfly2(f, u);
+            else if (g.radix == 3) bfly3(f, u, g);
+            else bfly5(f, u, g);
+        }
+        L.sync();
+    }
+    // post-rotation, in place from both ends (ref :3244-3277)
+    const int half = (N4 + 1) >> 1;
+    for (int t = L.lane; t < nblk * half; t += kLanes) {
+        const int b = t / half, i = t % half;
+        int32_t* yp0 = work + b * N2 + 2 * i;
+        int32_t* yp1 = work + b * N2 + N2 - 2 - 2 * i;
+        s32 re = yp0[1], im = yp0[0];
+        s16 t0 = trig[i], t1 = trig[N4 + i];
+        s32 yr = add_w(smul(re, t0), smul(im, t1));
+        s32 yi = sub_w(smul(re, t1), smul(im, t0));
+        re = yp1[1];
+        im = yp1[0];
+        yp0[0] = yr;
+        yp1[1] = yi;
+        t0 = trig[N4 - i - 1];
+        t1 = trig[N2 - i - 1];
+        yr = add_w(smul(re, t0), smul(im, t1));
+        yi = sub_w(smul(re, t1), smul(im, t0));
+        yp1[0] = yr;
+        yp0[1] = yi;
+    }
+    L.sync();
+}
+
+// TDAC mirror + window for one frame (ref :3279-3295 applied block by block, then SATURATE :2121-2125).
+// raw: this frame's nblk * N2 raw values; tail: previous block's last overlap/2 raw values (in/out).
+// out[0..N) receives the frame's time-domain signal (before the post-filter).
+OPUS_HD void tdac_frame(const Lanes& L, const int32_t* raw, int32_t* tail, int32_t* out, int N2, int nblk) {
+    const int N = N2 * nblk;
+    for (int n = L.lane; n < N; n += kLanes) {
+        const int b = n / N2, k = n % N2;
+        s32 v;
+        if (k < kOverlap) {
+            const int i = k < kOverlap / 2 ? k : kOverlap - 1 - k;
+            s32 x2 = b == 0 ? tail[i] : raw[(b - 1) * N2 + N2 - kOverlap / 2 + i];  // previous block, un-windowed
+            s32 x1 = raw[b * N2 + kOverlap / 2 - 1 - i];
+            s16 w1 = kWindow120[i], w2 = kWindow120[kOverlap - 1 - i];
+            if (k < kOverlap / 2) v = sub_w(mul16x32_q15(w2, x2), mul16x32_q15(w1, x1));
+            else v = add_w(mul16x32_q15(w1, x2), mul16x32_q15(w2, x1));
+        } else {
+            v = raw[b * N2 + k - kOverlap / 2];
+        }
+        out[n] = sat_sym(v, 300000000);
+    }
+    L.sync();
+    for (int i = L.lane; i < kOverlap / 2; i += kLanes) tail[i] = raw[(nblk - 1) * N2 + N2 - kOverlap / 2 + i];
+    L.sync();
+}
+
+// ---- comb post-filter (ref comb_filter :848, comb_filter_const_c :830), in place on a history ring ----
+// x points at the first sample to filter inside a buffer that holds >= T+2 valid earlier samples.
+// In-place IIR: y[i] depends on y[i-T+2 .. i-T-2], T >= 15, so `chunk` = min(T0,T1)-2 >= 13 samples
+// are independent and are computed by the lanes in parallel.
+OPUS_HD void comb_filter_inplace(const Lanes& L, int32_t* x, int T0, int T1, int N, s16 g0, s16 g1, int tapset0, int tapset1) {
+    if (g0 == 0 && g1 == 0) return;
+    const s16 gains[3][3] = {{10048, 7112, 4248}, {15200, 8784, 0}, {26208, 3280, 0}};
+    T0 = imax(T0, 15);
+    T1 = imax(T1, 15);
+    const s16 g00 = (s16)mul16_p15(g0, gains[tapset0][0]), g01 = (s16)mul16_p15(g0, gains[tapset0][1]),
+              g02 = (s16)mul16_p15(g0, gains[tapset0][2]);
+    const s16 g10 = (s16)mul16_p15(g1, gains[tapset1][0]), g11 = (s16)mul16_p15(g1, gains[tapset1][1]),
+              g12 = (s16)mul16_p15(g1, gains[tapset1][2]);
+    int overlap = kOverlap;
+    if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
+    if (overlap > N) overlap = N;
+    const int chunk = imin(imin(T0, T1) - 2, kLanes);
+    int i0 = 0;
+    for (; i0 < overlap; i0 += chunk) {
+        const int i = i0 + L.lane;
+        if (L.lane < chunk && i < overlap) {
+            s16 f = (s16)mul16_q15(kWindow120[i], kWindow120[i]);
+            s16 nf = (s16)(32767 - f);
+            s32 v = x[i]
+                + mul16x32_q15(mul16_q15(nf, g00), x[i - T0])
+                + mul16x32_q15(mul16_q15(nf, g01), x[i - T0 + 1] + x[i - T0 - 1])
+                + mul16x32_q15(mul16_q15(nf, g02), x[i - T0 + 2] + x[i - T0 - 2])
+                + mul16x32_q15(mul16_q15(f, g10), x[i - T1])
+                + mul16x32_q15(mul16_q15(f, g11), x[i - T1 + 1] + x[i - T1 - 1])
+                + mul16x32_q15(mul16_q15(f, g12), x[i - T1 + 2] + x[i - T1 - 2]);
+            x[i] = sat_sym(v, 300000000);
+        }
+        L.sync();
+    }
+    if (g1 == 0) return;
+    const int chunk1 = imin(T1 - 2, kLanes);
+    for (i0 = overlap; i0 < N; i0 += chunk1) {
+        const int i = i0 + L.lane;
+        if (L.lane < chunk1 && i < N) {
+            s32 v = x[i] + mul16x32_q15(g10, x[i - T1]) + mul16x32_q15(g11, x[i - T1 + 1] + x[i - T1 - 1])
+                  + mul16x32_q15(g12, x[i - T1 + 2] + x[i - T1 - 2]);
+            x[i] = sat_sym(v, 300000000);
+        }
+        L.sync();
+    }
+}
+
+// ---- de-emphasis + int16 conversion, strictly serial per channel (ref deemphasis :1988, sig2word16 :413) ----
+OPUS_HD s32 deemph_sample(s32 x, s32& mem) {
+    s32 tmp = x + mem;
+    mem = mul16x32_q15(27853, tmp);
+    s32 v = pshr32(tmp, 12);
+    return v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
+}
+
+}  // namespace opusb200

@@ -23,3 +23,78 @@ int hs_sizeof_hdr() { return (int)sizeof(CeltFrameHdr); }
 int hs_sizeof_op() { return (int)sizeof(BandOp); }
 
 }
+
+// ---- whole CELT frame through the stage bodies, serially (lanes = 1) ----
+#include "../../esp32-opus-player_b200/csrc/celt_synth.cuh"
+
+struct HsCelt {
+    CeltStreamState st;
+    int CC;
+};
+
+extern "C" {
+
+void* hs_celt_new(int channels) {
+    HsCelt* d = (HsCelt*)calloc(1, sizeof(HsCelt));
+    d->CC = channels;
+    for (int i = 0; i < kNbEBands; i++)
+        for (int c = 0; c < 2; c++) d->st.band[i].logE[c] = d->st.band[i].logE2[c] = -(28 << 10);
+    return d;
+}
+void hs_celt_free(void* d) { free(d); }
+
+// decode one CELT frame; C = coded channels, frame_size in {120,240,480,960}; pcm gets frame_size*CC
+int hs_celt_decode(void* dv, const uint8_t* pkt, int len, int C, int frame_size, int start, int16_t* pcm, int32_t* dbg_mem) {
+    HsCelt* d = (HsCelt*)dv;
+    CeltStreamState& st = d->st;
+    const int CC = d->CC;
+    int LM = frame_size == 120 ? 0 : frame_size == 240 ? 1 : frame_size == 480 ? 2 : frame_size == 960 ? 3 : -1;
+    if (LM < 0) return OPUSB_CELT_BAD_ARG;
+    static CeltFrameHdr hdr;
+    static BandOp ops[kMaxOps];
+    static int16_t Xg[2 * kMaxFrame];
+    static int16_t W[W_SIZE];
+    int status = hs_celt_parse(pkt, len, C, LM, start, CC == 1, &hdr, ops, Xg);
+    if (status == OPUSB_CELT_BAD_ARG) return status;
+    const int N = frame_size, M = 1 << LM;
+    Lanes L;
+    FrameEnergy fe;
+    for (int i = 0; i < kNbEBands; i++) energy_step(st.band[i], i, hdr, fe);
+    memcpy(W + W_XY, Xg, sizeof(int16_t) * C * N);
+    u32 seed = band_stage_ops(L, W, ops, hdr.n_ops, st.rng);
+    if (hdr.flags & FF_ANTICOLLAPSE) band_stage_anti_collapse(L, W, hdr, fe, seed);
+    const int transient = (hdr.flags & FF_TRANSIENT) != 0, silence = (hdr.flags & FF_SILENCE) != 0;
+    const int nblk = transient ? M : 1, shift = transient ? 3 : 3 - LM, N2 = N / nblk;
+    static int32_t freq[kMaxFrame], freq2[kMaxFrame], work[kMaxFrame], buf[kCombHist + kMaxFrame];
+    for (int c = 0; c < CC; c++) {
+        if (CC == 2 && C == 1) {
+            denormalise(L, W + W_XY, freq, fe.E[0], hdr.start, hdr.end, M, silence);
+        } else if (CC == 1 && C == 2) {
+            denormalise(L, W + W_XY, freq, fe.E[0], hdr.start, hdr.end, M, silence);
+            denormalise(L, W + W_XY + N, freq2, fe.E[1], hdr.start, hdr.end, M, silence);
+            for (int i = 0; i < N; i++) freq[i] = (freq[i] >> 1) + (freq2[i] >> 1);
+        } else {
+            denormalise(L, W + W_XY + c * N, freq, fe.E[c], hdr.start, hdr.end, M, silence);
+        }
+        imdct_raw(L, freq, work, shift, nblk);
+        memcpy(buf, st.hist[c], sizeof(int32_t) * kCombHist);
+        tdac_frame(L, work, st.tail[c], buf + kCombHist, N2, nblk);
+        comb_filter_inplace(L, buf + kCombHist, st.pf_period_old, st.pf_period, kShortMdct, (s16)st.pf_gain_old, (s16)st.pf_gain,
+                            st.pf_tapset_old, st.pf_tapset);
+        if (LM != 0)
+            comb_filter_inplace(L, buf + kCombHist + kShortMdct, st.pf_period, hdr.pf_pitch, N - kShortMdct, (s16)st.pf_gain,
+                                hdr.pf_gain, st.pf_tapset, hdr.pf_tapset);
+        memcpy(st.hist[c], buf + N, sizeof(int32_t) * kCombHist);
+        if (dbg_mem) memcpy(dbg_mem + c * kMaxFrame, buf + kCombHist, sizeof(int32_t) * N);
+        s32 mem = st.preemph_mem[c];
+        for (int j = 0; j < N; j++) pcm[j * CC + c] = (int16_t)deemph_sample(buf[kCombHist + j], mem);
+        st.preemph_mem[c] = mem;
+    }
+    st.pf_period_old = st.pf_period; st.pf_gain_old = st.pf_gain; st.pf_tapset_old = st.pf_tapset;
+    st.pf_period = hdr.pf_pitch; st.pf_gain = hdr.pf_gain; st.pf_tapset = hdr.pf_tapset;
+    if (LM != 0) { st.pf_period_old = st.pf_period; st.pf_gain_old = st.pf_gain; st.pf_tapset_old = st.pf_tapset; }
+    st.rng = hdr.final_rng;
+    return status;
+}
+
+}
