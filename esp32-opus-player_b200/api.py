@@ -1,0 +1,270 @@
+"""ctypes binding of the C ABI in include/opus_b200.h.
+
+Names follow the reference's packet API (src/opus_decoder.h:165-176): opus_decode, opus_packet_get_*;
+`BatchDecoder.decode_many` is the batched call the reference lacks.  Errors are the reference's
+negative ints; this layer raises only for misuse (wrong array shapes) and for a missing library.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .build import LIB, build
+
+DM_MODE_OPUS = 0
+DM_MODE_CELT_RAW = 1
+
+FRAME_DTYPE = np.dtype([("offset", "<u4"), ("len", "<u2"), ("toc", "u1"), ("flags", "u1")])
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [("n_frames", _I), ("mode", _I), ("frame_size", _I), ("coded_channels", _I), ("start_band", _I),
+                ("bytes", _P), ("n_bytes", ctypes.c_size_t), ("frames", _P)]
+
+
+class _Out(ctypes.Structure):
+    _fields_ = [("pcm", _P), ("status", _P)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libopusb200.so (building it if needed). Fails loudly if it cannot be built or loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        build()
+    L = ctypes.CDLL(LIB)
+    L.dm_create.argtypes = [ctypes.POINTER(_P), _I, _I, _I, _I]
+    L.dm_destroy.argtypes = [_P]
+    L.dm_reset.argtypes = [_P, _P, _I]
+    L.decode_many.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out)]
+    L.dm_decode_device.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), _P]
+    L.dm_host_alloc.restype = _P
+    L.dm_host_alloc.argtypes = [ctypes.c_size_t]
+    L.dm_host_free.argtypes = [_P]
+    L.dm_launch_count.restype = ctypes.c_longlong
+    L.dm_launch_count.argtypes = [_P]
+    L.dm_device_bytes.restype = ctypes.c_size_t
+    L.dm_device_bytes.argtypes = [_P]
+    L.dm_stage_times.argtypes = [_P, _P, _I]
+    L.dm_stage_name.restype = ctypes.c_char_p
+    L.dm_stage_name.argtypes = [_I]
+    L.dm_get_stream_state.argtypes = [_P, _I, _P, ctypes.c_size_t]
+    L.dm_stream_state_size.restype = ctypes.c_size_t
+    L.dm_synth_bytes.restype = ctypes.c_size_t
+    L.dm_synth_bytes.argtypes = [_I, _I, _I]
+    L.dm_synth_fill.argtypes = [_P, _P, _I, _I, _I, _I, ctypes.c_uint64, _I]
+    for fn in ("opusb_packet_get_mode", "opusb_packet_get_bandwidth", "opusb_packet_get_nb_channels"):
+        getattr(L, fn).argtypes = [_P]
+    L.opusb_packet_get_samples_per_frame.argtypes = [_P, ctypes.c_int32]
+    L.opusb_packet_get_nb_frames.argtypes = [_P, ctypes.c_int32]
+    L.opusb_packet_get_nb_samples.argtypes = [_P, ctypes.c_int32, ctypes.c_int32]
+    L.opusb_packet_parse.argtypes = [_P, ctypes.c_int32, _P, _P, _P, _P]
+    L.opusb_decoder_create.restype = _P
+    L.opusb_decoder_create.argtypes = [ctypes.c_int32, _I, ctypes.POINTER(_I)]
+    L.opusb_decoder_destroy.argtypes = [_P]
+    L.opusb_decoder_init.argtypes = [_P, ctypes.c_int32, _I]
+    L.opusb_decode.argtypes = [_P, _P, ctypes.c_int32, _P, _I]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (dm_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = lib().dm_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise MemoryError("dm_host_alloc(%d) failed" % self.nbytes)
+        buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().dm_host_free(self.ptr)
+            self.ptr = None
+
+
+def make_frames(n_streams, n_frames):
+    return np.zeros((n_streams, n_frames), dtype=FRAME_DTYPE)
+
+
+def synth_corpus(n_streams, n_frames, payload_len, toc, seed_base=0x9E3779B97F4A7C15, first_stream=0, bytes_out=None, frames_out=None):
+    """SURVEY 8c/8d synthetic streams: stream i = xorshift64(seed_base ^ i) payload bytes behind `toc`."""
+    L = lib()
+    nb = L.dm_synth_bytes(n_streams, n_frames, payload_len)
+    b = bytes_out if bytes_out is not None else np.empty(nb, np.uint8)
+    f = frames_out if frames_out is not None else make_frames(n_streams, n_frames)
+    L.dm_synth_fill(_ptr(b), _ptr(f), n_streams, n_frames, payload_len, toc, ctypes.c_uint64(seed_base), first_stream)
+    return b, f
+
+
+class BatchDecoder:
+    """n_streams independent decoders on one GPU (dm_ctx)."""
+
+    def __init__(self, n_streams, max_frames, channels=2, device=0):
+        self.n_streams, self.max_frames, self.channels, self.device = n_streams, max_frames, channels, device
+        self._ctx = _P()
+        rc = lib().dm_create(ctypes.byref(self._ctx), n_streams, max_frames, channels, device)
+        if rc != 0:
+            raise RuntimeError("dm_create failed: %d (no CUDA device => no decode path)" % rc)
+
+    def close(self):
+        if self._ctx:
+            lib().dm_destroy(self._ctx)
+            self._ctx = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, stream_ids=None):
+        if stream_ids is None:
+            return lib().dm_reset(self._ctx, None, 0)
+        ids = np.ascontiguousarray(stream_ids, np.int32)
+        return lib().dm_reset(self._ctx, ids.ctypes.data, len(ids))
+
+    def _batch(self, bytes_ptr, n_bytes, frames_ptr, n_frames, mode, frame_size, coded_channels, start_band):
+        b = _Batch()
+        b.n_frames, b.mode, b.frame_size, b.coded_channels, b.start_band = n_frames, mode, frame_size, coded_channels, start_band
+        b.bytes, b.n_bytes, b.frames = bytes_ptr, n_bytes, frames_ptr
+        return b
+
+    def decode_many(self, data, frames, mode=DM_MODE_OPUS, frame_size=960, coded_channels=2, start_band=0, pcm=None, status=None):
+        """Host buffers in, host buffers out. data: uint8[n]; frames: FRAME_DTYPE[n_streams][n_frames].
+        Returns (rc, pcm int16[n_streams][n_frames][frame_size][channels], status int32[n_streams][n_frames])."""
+        frames = np.ascontiguousarray(frames)
+        assert frames.dtype == FRAME_DTYPE and frames.shape[0] == self.n_streams
+        n_frames = frames.shape[1]
+        fs = frame_size if mode == DM_MODE_CELT_RAW else 960
+        if pcm is None:
+            pcm = np.zeros((self.n_streams, n_frames, fs, self.channels), np.int16)
+        if status is None:
+            status = np.zeros((self.n_streams, n_frames), np.int32)
+        data = np.ascontiguousarray(data, np.uint8)
+        b = self._batch(_ptr(data), data.size, _ptr(frames), n_frames, mode, frame_size, coded_channels, start_band)
+        o = _Out(_ptr(pcm), _ptr(status))
+        rc = lib().decode_many(self._ctx, ctypes.byref(b), ctypes.byref(o))
+        return rc, pcm, status
+
+    def decode_device(self, d_bytes, n_bytes, d_frames, n_frames, d_pcm, d_status, cuda_stream=0, mode=DM_MODE_OPUS, frame_size=960,
+                      coded_channels=2, start_band=0):
+        """Device pointers (ints), enqueued on cuda_stream; no synchronisation."""
+        b = self._batch(d_bytes, n_bytes, d_frames, n_frames, mode, frame_size, coded_channels, start_band)
+        o = _Out(d_pcm, d_status)
+        return lib().dm_decode_device(self._ctx, ctypes.byref(b), ctypes.byref(o), cuda_stream)
+
+    def stage_times(self):
+        ms = (ctypes.c_float * 16)()
+        n = lib().dm_stage_times(self._ctx, ctypes.cast(ms, _P), 16)
+        return {lib().dm_stage_name(i).decode(): float(ms[i]) for i in range(n)}
+
+    @property
+    def launch_count(self):
+        return int(lib().dm_launch_count(self._ctx))
+
+    @property
+    def device_bytes(self):
+        return int(lib().dm_device_bytes(self._ctx))
+
+    def stream_state(self, stream):
+        n = lib().dm_stream_state_size()
+        buf = np.zeros(n, np.uint8)
+        rc = lib().dm_get_stream_state(self._ctx, stream, buf.ctypes.data, n)
+        if rc:
+            raise RuntimeError("dm_get_stream_state: %d" % rc)
+        return buf
+
+
+# ---- packet helpers with the reference's names (src/opus_decoder.h:169-176) ----
+def _pkt(data):
+    return np.ascontiguousarray(np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else data, np.uint8)
+
+
+def opus_packet_get_mode(data):
+    return lib().opusb_packet_get_mode(_pkt(data).ctypes.data)
+
+
+def opus_packet_get_bandwidth(data):
+    return lib().opusb_packet_get_bandwidth(_pkt(data).ctypes.data)
+
+
+def opus_packet_get_nb_channels(data):
+    return lib().opusb_packet_get_nb_channels(_pkt(data).ctypes.data)
+
+
+def opus_packet_get_samples_per_frame(data, Fs=48000):
+    return lib().opusb_packet_get_samples_per_frame(_pkt(data).ctypes.data, Fs)
+
+
+def opus_packet_get_nb_frames(data):
+    p = _pkt(data)
+    return lib().opusb_packet_get_nb_frames(p.ctypes.data, p.size)
+
+
+def opus_packet_get_nb_samples(data, Fs=48000):
+    p = _pkt(data)
+    return lib().opusb_packet_get_nb_samples(p.ctypes.data, p.size, Fs)
+
+
+def opus_packet_parse(data):
+    """Returns (count or negative error, toc, [(offset, size)...])."""
+    p = _pkt(data)
+    toc = ctypes.c_uint8(0)
+    sizes = (ctypes.c_int16 * 48)()
+    frames = (_P * 48)()
+    off = _I(0)
+    n = lib().opusb_packet_parse(p.ctypes.data, p.size, ctypes.cast(ctypes.byref(toc), _P), ctypes.cast(frames, _P), ctypes.cast(sizes, _P),
+                                 ctypes.cast(ctypes.byref(off), _P))
+    if n < 0:
+        return n, 0, []
+    base = p.ctypes.data
+    return n, toc.value, [((frames[i] or base) - base, sizes[i]) for i in range(n)]
+
+
+class OpusDecoder:
+    """Single-stream drop-in for the reference's opus_decoder_init/opus_decode (src/opus_decoder.cpp:82, 351)."""
+
+    def __init__(self, Fs=48000, channels=2):
+        err = _I(0)
+        self._st = lib().opusb_decoder_create(Fs, channels, ctypes.byref(err))
+        self.channels = channels
+        if not self._st:
+            raise RuntimeError("opus_decoder_create failed: %d" % err.value)
+
+    def init(self, Fs=48000, channels=None):
+        return lib().opusb_decoder_init(self._st, Fs, channels or self.channels)
+
+    def decode(self, data, frame_size=5760):
+        """Returns (samples per channel or negative error, pcm int16[samples][channels])."""
+        p = _pkt(data)
+        pcm = np.zeros((frame_size, self.channels), np.int16)
+        n = lib().opusb_decode(self._st, p.ctypes.data, p.size, pcm.ctypes.data, frame_size)
+        return n, pcm[: max(n, 0)]
+
+    def close(self):
+        if self._st:
+            lib().opusb_decoder_destroy(self._st)
+            self._st = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,27 @@
+"""Build libopusb200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "lib", "libopusb200.so")
+SRCS = [os.path.join(HERE, "csrc", "opus_b200.cu"), os.path.join(HERE, "csrc", "host_api.cpp")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _newest_source_mtime():
+    m = 0.0
+    for root in (os.path.join(HERE, "csrc"), os.path.join(HERE, "..", "include")):
+        for fn in os.listdir(root):
+            m = max(m, os.path.getmtime(os.path.join(root, fn)))
+    return m
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library if it is missing or older than its sources. Returns the .so path."""
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRCS
+    subprocess.run(cmd, check=True)
+    return LIB

@@ -11,9 +11,16 @@
 
 namespace opusb200 {
 
+// Output of the per-stream sequencer for one frame: everything a frame needs from its predecessors.
 struct FrameEnergy {
     int16_t E[2][kNbEBands];     // band log-energy after this frame's coarse+fine+final (ref oldBandE)
     int16_t pmin[2][kNbEBands];  // min(oldLogE, oldLogE2) before this frame (anti_collapse input, ref :1044-1050)
+    uint32_t seed;               // noise seed entering the frame = previous frame's final range (ref :2359, 2437)
+    int16_t pf_period, pf_period_old;  // post-filter state entering the frame (ref :2381-2402)
+    int16_t pf_gain, pf_gain_old;
+    uint8_t pf_tapset, pf_tapset_old;
+    uint8_t skip;                // frame failed before touching state (bad length / unsupported): no output
+    uint8_t pad;
 };
 
 // advance the LCG by cnt (1..kLanes) draws

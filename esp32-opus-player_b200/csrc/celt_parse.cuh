@@ -288,7 +288,7 @@ OPUS_HD u32 band_n1(ParseCtx& p, int xoff, int yoff, int out) {
 
 // ref quant_partition (src/celt.cpp:1382). Offsets index the W workspace; lowband < 0 means NULL.
 #if defined(__CUDACC__)
-__host__ __device__
+__device__
 #endif
 inline u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, s16 gain, int fill) {
     const int i = p.band;

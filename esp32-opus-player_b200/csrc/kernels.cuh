@@ -1,0 +1,299 @@
+// kernels.cuh -- the CUDA kernels of the decode path (sm_100a), one per subsystem.
+//
+//   k_entropy   thread per (stream, frame)   range decoder + allocation + PVQ leaves -> script     [a1-a5]
+//   k_sequence  warp   per stream            energy recurrence, noise seed, post-filter history    [a2,a12]
+//   k_bands     warp   per (stream, frame)   folding, Haar/Hadamard, stereo merge, anti-collapse   [a4-a7]
+//   k_imdct     warp   per (stream, frame, ch) denormalise + inverse MDCT (radix 2/3/4/5 FFT)      [a8,a9]
+//   k_postfilter warp  per (stream, ch)      TDAC overlap-add + comb filter, frames in order       [a9,a10]
+//   k_deemph    thread per (stream, ch)      1-pole IIR + int16 PCM, coalesced through smem tiles   [a11]
+//
+// Frames are indexed t = stream * n_frames + frame.  All intermediates live in HBM between kernels
+// (<= 36 KB per frame; the traffic is three orders of magnitude under the HBM roofline -- the path is
+// issue bound), per-stream state is a POD blob in HBM (CeltStreamState).
+#pragma once
+#include "celt_parse.cuh"
+#include "celt_synth.cuh"
+
+namespace opusb200 {
+
+struct FrameDesc {  // mirrors dm_frame in include/opus_b200.h
+    uint32_t offset;
+    uint16_t len;
+    uint8_t toc;
+    uint8_t flags;
+};
+
+struct DevParams {
+    int n_streams, n_frames;
+    int mode;            // 0 Opus frames (TOC), 1 raw CELT
+    int frame_size;      // samples per frame per channel in the output layout
+    int coded_channels;  // raw CELT only
+    int start_band;      // raw CELT only
+    int CC;              // decoder (output) channels
+    int first_stream, n_sel;  // stream range handled by this launch
+};
+
+enum { K1_THREADS = 128, KW_WARPS = 4 };
+
+__device__ __forceinline__ bool frame_skipped(int status) {
+    return status == OPUSB_CELT_BAD_ARG || status == OPUSB_UNIMPLEMENTED || status == OPUSB_BAD_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1_THREADS)
+k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
+          BandOp* __restrict__ ops, int16_t* __restrict__ X) {
+    extern __shared__ int16_t leaf_tile[];  // [kMaxLeaf][K1_THREADS]: one private column per thread
+    const int local = blockIdx.x * K1_THREADS + threadIdx.x;
+    if (local >= P.n_sel * P.n_frames) return;
+    const size_t t = (size_t)P.first_stream * P.n_frames + local;
+    const FrameDesc d = fr[t];
+    CeltFrameHdr& h = hdr[t];
+    int C, LM, start;
+    if (P.mode == 1) {
+        C = P.coded_channels;
+        LM = P.frame_size == 120 ? 0 : P.frame_size == 240 ? 1 : P.frame_size == 480 ? 2 : 3;
+        start = P.start_band;
+    } else {
+        if (!(d.toc & 0x80)) {  // SILK / hybrid frames are not handled by this kernel
+            h.status = OPUSB_UNIMPLEMENTED; h.flags = 0; h.n_ops = 0; h.LM = 3; h.C = 1; h.start = 0; h.end = kNbEBands;
+            return;
+        }
+        C = (d.toc & 0x4) ? 2 : 1;
+        LM = 3;  // the reference decodes every Opus frame as 960 samples (src/opus_decoder.cpp:161,259)
+        start = 0;
+    }
+    ParseCtx p;
+    rd_init(p.rd, bytes + d.offset, d.len);
+    p.C = C; p.LM = LM; p.start = start; p.end = kNbEBands; p.disable_inv = (P.CC == 1);
+    p.band = 0; p.intensity = 0; p.spread = 0; p.tf_change = 0; p.remaining_bits = 0;
+    p.ops = ops + t * kMaxOps; p.n_ops = 0; p.ops_cap = kMaxOps; p.overflow = 0; p.lcg_steps = 0;
+    p.Xg = X + t * (2 * kMaxFrame);
+    p.leaf.p = leaf_tile + threadIdx.x;
+    p.leaf.stride = K1_THREADS;
+    celt_parse_frame(p, h);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * KW_WARPS)
+k_sequence(const CeltFrameHdr* __restrict__ hdr, FrameEnergy* __restrict__ fe, CeltStreamState* __restrict__ st, DevParams P) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= P.n_sel) return;
+    const int s = P.first_stream + w;
+    CeltStreamState& S = st[s];
+    CeltBandState b;
+    if (lane < kNbEBands) b = S.band[lane];
+    u32 rng = S.rng;
+    int pfp = S.pf_period, pfpo = S.pf_period_old, pfg = S.pf_gain, pfgo = S.pf_gain_old, pft = S.pf_tapset, pfto = S.pf_tapset_old;
+    for (int f = 0; f < P.n_frames; f++) {
+        const size_t t = (size_t)s * P.n_frames + f;
+        const CeltFrameHdr& h = hdr[t];
+        FrameEnergy& o = fe[t];
+        const bool skip = frame_skipped(h.status);
+        if (lane == 0) {
+            o.skip = skip;
+            o.seed = rng;
+            o.pf_period = (int16_t)pfp; o.pf_period_old = (int16_t)pfpo;
+            o.pf_gain = (int16_t)pfg; o.pf_gain_old = (int16_t)pfgo;
+            o.pf_tapset = (uint8_t)pft; o.pf_tapset_old = (uint8_t)pfto;
+        }
+        if (skip) continue;
+        if (lane < kNbEBands) energy_step(b, lane, h, o);
+        rng = h.final_rng;
+        // post-filter history (ref src/celt.cpp:2392-2402)
+        pfpo = pfp; pfgo = pfg; pfto = pft;
+        pfp = h.pf_pitch; pfg = h.pf_gain; pft = h.pf_tapset;
+        if (h.LM != 0) { pfpo = pfp; pfgo = pfg; pfto = pft; }
+    }
+    if (lane < kNbEBands) S.band[lane] = b;
+    if (lane == 0) {
+        S.rng = rng;
+        S.pf_period = pfp; S.pf_period_old = pfpo; S.pf_gain = pfg; S.pf_gain_old = pfgo; S.pf_tapset = pft; S.pf_tapset_old = pfto;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * KW_WARPS)
+k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, const FrameEnergy* __restrict__ fe,
+        int16_t* __restrict__ X, DevParams P) {
+    __shared__ __align__(16) int16_t Wsm[KW_WARPS][W_SIZE];
+    const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (local >= P.n_sel * P.n_frames) return;
+    const size_t t = (size_t)P.first_stream * P.n_frames + local;
+    const CeltFrameHdr& h = hdr[t];
+    const FrameEnergy& e = fe[t];
+    if (e.skip) return;
+    Lanes L;
+    int16_t* W = Wsm[threadIdx.x >> 5];
+    const int words = (h.C * (kShortMdct << h.LM)) >> 1;
+    int32_t* Xw = reinterpret_cast<int32_t*>(X + t * (2 * kMaxFrame));
+    int32_t* Ww = reinterpret_cast<int32_t*>(W);
+    for (int j = L.lane; j < words; j += 32) Ww[j] = Xw[j];
+    L.sync();
+    u32 seed = band_stage_ops(L, W, ops + t * kMaxOps, h.n_ops, e.seed);
+    if (h.flags & FF_ANTICOLLAPSE) band_stage_anti_collapse(L, W, h, e, seed);
+    L.sync();
+    for (int j = L.lane; j < words; j += 32) Xw[j] = Ww[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * KW_WARPS)
+k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int16_t* __restrict__ X,
+        int32_t* __restrict__ raw, DevParams P) {
+    __shared__ int32_t fsm[KW_WARPS][2][kMaxFrame];
+    const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (local >= P.n_sel * P.n_frames * P.CC) return;
+    const int c = local % P.CC;
+    const size_t t = (size_t)P.first_stream * P.n_frames + local / P.CC;
+    const CeltFrameHdr& h = hdr[t];
+    const FrameEnergy& e = fe[t];
+    if (e.skip) return;
+    Lanes L;
+    int32_t* freq = fsm[threadIdx.x >> 5][0];
+    int32_t* work = fsm[threadIdx.x >> 5][1];
+    const int LM = h.LM, M = 1 << LM, N = kShortMdct << LM, C = h.C, CC = P.CC;
+    const int transient = (h.flags & FF_TRANSIENT) != 0, silence = (h.flags & FF_SILENCE) != 0;
+    const int16_t* Xf = X + t * (2 * kMaxFrame);
+    if (CC == 2 && C == 1) {
+        denormalise(L, Xf, freq, e.E[0], h.start, h.end, M, silence);
+    } else if (CC == 1 && C == 2) {
+        denormalise(L, Xf, freq, e.E[0], h.start, h.end, M, silence);
+        denormalise(L, Xf + N, work, e.E[1], h.start, h.end, M, silence);
+        for (int i = L.lane; i < N; i += 32) freq[i] = (freq[i] >> 1) + (work[i] >> 1);
+        L.sync();
+    } else {
+        denormalise(L, Xf + c * N, freq, e.E[c], h.start, h.end, M, silence);
+    }
+    imdct_raw(L, freq, work, transient ? 3 : 3 - LM, transient ? M : 1);
+    int32_t* out = raw + (t * CC + c) * kMaxFrame;
+    for (int i = L.lane; i < N; i += 32) out[i] = work[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * KW_WARPS)
+k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ raw,
+             int32_t* __restrict__ syn, CeltStreamState* __restrict__ st, DevParams P) {
+    __shared__ int32_t bsm[KW_WARPS][kCombHist + kMaxFrame];
+    __shared__ int32_t tsm[KW_WARPS][kOverlap / 2];
+    const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (local >= P.n_sel * P.CC) return;
+    const int c = local % P.CC, s = P.first_stream + local / P.CC;
+    Lanes L;
+    int32_t* buf = bsm[threadIdx.x >> 5];
+    int32_t* tail = tsm[threadIdx.x >> 5];
+    CeltStreamState& S = st[s];
+    for (int i = L.lane; i < kCombHist; i += 32) buf[i] = S.hist[c][i];
+    for (int i = L.lane; i < kOverlap / 2; i += 32) tail[i] = S.tail[c][i];
+    L.sync();
+    for (int f = 0; f < P.n_frames; f++) {
+        const size_t t = (size_t)s * P.n_frames + f;
+        const FrameEnergy& e = fe[t];
+        if (e.skip) continue;
+        const CeltFrameHdr& h = hdr[t];
+        const int LM = h.LM, N = kShortMdct << LM;
+        const int nblk = (h.flags & FF_TRANSIENT) ? (1 << LM) : 1;
+        int32_t* x = buf + kCombHist;
+        tdac_frame(L, raw + (t * P.CC + c) * kMaxFrame, tail, x, N / nblk, nblk);
+        comb_filter_inplace(L, x, e.pf_period_old, e.pf_period, kShortMdct, e.pf_gain_old, e.pf_gain, e.pf_tapset_old, e.pf_tapset);
+        if (LM != 0)
+            comb_filter_inplace(L, x + kShortMdct, e.pf_period, h.pf_pitch, N - kShortMdct, e.pf_gain, h.pf_gain, e.pf_tapset,
+                                h.pf_tapset);
+        L.sync();
+        int32_t* out = syn + (t * P.CC + c) * kMaxFrame;
+        for (int i = L.lane; i < N; i += 32) out[i] = x[i];
+        // slide the history window: buf[k] = buf[N + k]; ascending order is hazard free because N > 32
+        for (int k0 = 0; k0 < kCombHist; k0 += 32) {
+            const int k = k0 + L.lane;
+            int32_t v = 0;
+            if (k < kCombHist) v = buf[N + k];
+            L.sync();
+            if (k < kCombHist) buf[k] = v;
+        }
+        L.sync();
+    }
+    for (int i = L.lane; i < kCombHist; i += 32) S.hist[c][i] = buf[i];
+    for (int i = L.lane; i < kOverlap / 2; i += 32) S.tail[c][i] = tail[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// De-emphasis is a strictly serial 1-pole IIR with per-step truncation (ref src/celt.cpp:1977-1982):
+// one lane owns one (stream, channel) chain.  A warp owns 32 chains and moves 32x32 tiles through
+// shared memory so that every global access is a full 128 B line (loads) or int16x8 vectors (stores).
+enum { DE_TW = 32, DE_IN_STRIDE = 33, DE_OUT_STRIDE = 36 };
+
+__global__ void __launch_bounds__(32)
+k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hdr, const int32_t* __restrict__ syn,
+         int16_t* __restrict__ pcm, int32_t* __restrict__ status, CeltStreamState* __restrict__ st, DevParams P) {
+    __shared__ int32_t tin[32 * DE_IN_STRIDE];
+    __shared__ __align__(16) uint32_t tout[32 * DE_OUT_STRIDE];
+    const int lane = threadIdx.x;
+    const int CC = P.CC;
+    const int chain0 = blockIdx.x * 32;              // chains are (stream - first_stream) * CC + c
+    const int n_chains = P.n_sel * CC;
+    const int my = chain0 + lane;
+    const bool live = my < n_chains;
+    const int my_s = P.first_stream + (live ? my / CC : 0), my_c = live ? my % CC : 0;
+    s32 mem = live ? st[my_s].preemph_mem[my_c] : 0;
+    const int N = P.frame_size;
+    int16_t* tout16 = reinterpret_cast<int16_t*>(tout);
+    for (int f = 0; f < P.n_frames; f++) {
+        const size_t my_t = (size_t)my_s * P.n_frames + f;
+        const bool my_skip = live ? (fe[my_t].skip != 0) : true;
+        if (live && my_c == 0) status[my_t] = hdr[my_t].status;
+        for (int j0 = 0; j0 < N; j0 += DE_TW) {
+            const int w = min(DE_TW, N - j0);
+            // load: row r = chain r, 128 B per row
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+                const int q = chain0 + r;
+                int32_t v = 0;
+                if (q < n_chains && lane < w) {
+                    const size_t t = (size_t)(P.first_stream + q / CC) * P.n_frames + f;
+                    v = syn[(t * CC + (q % CC)) * kMaxFrame + j0 + lane];
+                }
+                tin[r * DE_IN_STRIDE + lane] = v;
+            }
+            __syncwarp();
+            // serial recurrence, one chain per lane
+            if (CC == 2) {
+                const int q = lane >> 1;
+                for (int j = 0; j < w; j++) {
+                    s32 v = my_skip ? 0 : deemph_sample(tin[lane * DE_IN_STRIDE + j], mem);
+                    tout16[(q * DE_OUT_STRIDE + j) * 2 + (lane & 1)] = (int16_t)v;
+                }
+            } else {
+                for (int j = 0; j < w; j++) {
+                    s32 v = my_skip ? 0 : deemph_sample(tin[lane * DE_IN_STRIDE + j], mem);
+                    tout16[lane * DE_OUT_STRIDE * 2 + j] = (int16_t)v;
+                }
+            }
+            __syncwarp();
+            // store: interleaved PCM rows, 16 B per lane
+            if (CC == 2) {
+                for (int it = 0; it < 4; it++) {
+                    const int q = it * 4 + (lane >> 3), chunk = lane & 7;  // stream within the warp, 4 samples per chunk
+                    const int sl = chain0 / 2 + q;                          // stream index relative to first_stream
+                    if (sl < P.n_sel && chunk * 4 < w) {
+                        const size_t t = (size_t)(P.first_stream + sl) * P.n_frames + f;
+                        uint4 v = *reinterpret_cast<const uint4*>(&tout[q * DE_OUT_STRIDE + chunk * 4]);
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(pcm) + (t * N + j0 + chunk * 4);
+                        if (chunk * 4 + 4 <= w) *reinterpret_cast<uint4*>(dst) = v;
+                        else { const uint32_t vv[4] = {v.x, v.y, v.z, v.w}; for (int k = 0; k < w - chunk * 4; k++) dst[k] = vv[k]; }
+                    }
+                }
+            } else {
+                for (int r = 0; r < 32; r++) {
+                    const int sl = chain0 + r;
+                    if (sl < P.n_sel && lane < w) {
+                        const size_t t = (size_t)(P.first_stream + sl) * P.n_frames + f;
+                        pcm[t * N + j0 + lane] = tout16[r * DE_OUT_STRIDE * 2 + lane];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (live) st[my_s].preemph_mem[my_c] = mem;
+}
+
+}  // namespace opusb200

@@ -8,7 +8,7 @@
 
 namespace opusb200 {
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 enum { kLanes = 32 };
 struct Lanes {
     int lane;

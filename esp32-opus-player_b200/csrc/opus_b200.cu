@@ -1,0 +1,256 @@
+// opus_b200.cu -- host side of libopusb200.so: context, launch sequence, pinned-buffer pipeline and
+// the C ABI declared in include/opus_b200.h.  Build: nvcc -gencode arch=compute_100a,code=sm_100a.
+// There is no CPU decode path in this library: without a CUDA device every decode call fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/opus_b200.h"
+#include "kernels.cuh"
+
+using namespace opusb200;
+
+static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
+static_assert(sizeof(BandOp) == 12, "BandOp layout");
+
+enum { kStages = 6, kMaxChunks = 4 };
+static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph"};
+
+struct dm_ctx {
+    int n_streams, max_frames, channels, device;
+    // per-stream state
+    CeltStreamState* d_state;
+    // per-frame intermediates
+    CeltFrameHdr* d_hdr;
+    BandOp* d_ops;
+    int16_t* d_X;
+    FrameEnergy* d_fe;
+    int32_t* d_raw;
+    int32_t* d_syn;
+    // staging for the host-buffer path
+    uint8_t* d_bytes;
+    size_t d_bytes_cap;
+    FrameDesc* d_frames;
+    int16_t* d_pcm;
+    int32_t* d_status;
+    cudaStream_t streams[kMaxChunks];
+    cudaEvent_t bytes_ready;
+    cudaEvent_t ev[kStages + 1];
+    long long launches;
+    size_t dev_bytes;
+    int last_cuda_error;
+};
+
+#define CU_TRY(ctx, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            if (ctx) (ctx)->last_cuda_error = (int)e__;                                     \
+            fprintf(stderr, "opusb200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return e__ == cudaErrorMemoryAllocation ? DM_ERR_NOMEM : DM_ERR_CUDA;           \
+        }                                                                                   \
+    } while (0)
+
+template <class T>
+static int dev_alloc(dm_ctx* c, T** p, size_t n) {
+    CU_TRY(c, cudaMalloc((void**)p, n * sizeof(T)));
+    c->dev_bytes += n * sizeof(T);
+    return 0;
+}
+
+static void init_state_host(CeltStreamState& s) {
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < kNbEBands; i++)
+        for (int c = 0; c < 2; c++) s.band[i].logE[c] = s.band[i].logE2[c] = -(28 << 10);  // ref src/celt.cpp:2496
+}
+
+extern "C" {
+
+int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int device) {
+    if (!out || n_streams < 1 || max_frames < 1 || (channels != 1 && channels != 2)) return OPUSB_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "opusb200: no usable CUDA device (this library has no CPU path)\n");
+        return DM_ERR_NO_DEVICE;
+    }
+    dm_ctx* c = new (std::nothrow) dm_ctx();
+    if (!c) return DM_ERR_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
+    CU_TRY(c, cudaSetDevice(device));
+    // quant_partition recursion (<= 5 levels) + per-thread allocation arrays live on the local stack
+    CU_TRY(c, cudaDeviceSetLimit(cudaLimitStackSize, 6 * 1024));
+    const size_t nfr = (size_t)n_streams * max_frames;
+    int r;
+    if ((r = dev_alloc(c, &c->d_state, (size_t)n_streams))) return r;
+    if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
+    if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &c->d_fe, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_raw, nfr * channels * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &c->d_syn, nfr * channels * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &c->d_frames, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_pcm, nfr * channels * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &c->d_status, nfr))) return r;
+    for (int i = 0; i < kMaxChunks; i++) CU_TRY(c, cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    CU_TRY(c, cudaEventCreateWithFlags(&c->bytes_ready, cudaEventDisableTiming));
+    for (int i = 0; i <= kStages; i++) CU_TRY(c, cudaEventCreate(&c->ev[i]));
+    CU_TRY(c, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLeaf * K1_THREADS * 2));
+    *out = c;
+    return dm_reset(c, nullptr, 0);
+}
+
+void dm_destroy(dm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_state); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
+    cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes); cudaFree(c->d_frames); cudaFree(c->d_pcm);
+    cudaFree(c->d_status);
+    for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->bytes_ready) cudaEventDestroy(c->bytes_ready);
+    for (int i = 0; i <= kStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+}
+
+int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
+    if (!c) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CeltStreamState* init = (CeltStreamState*)malloc(sizeof(CeltStreamState));
+    if (!init) return DM_ERR_NOMEM;
+    init_state_host(*init);
+    int rc = 0;
+    if (!ids) {
+        std::vector<CeltStreamState> all((size_t)c->n_streams, *init);
+        cudaError_t e = cudaMemcpy(c->d_state, all.data(), all.size() * sizeof(CeltStreamState), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = DM_ERR_CUDA;
+    } else {
+        for (int i = 0; i < n && !rc; i++) {
+            if (ids[i] < 0 || ids[i] >= c->n_streams) { rc = OPUSB_BAD_ARG; break; }
+            if (cudaMemcpy(c->d_state + ids[i], init, sizeof(CeltStreamState), cudaMemcpyHostToDevice) != cudaSuccess) rc = DM_ERR_CUDA;
+        }
+    }
+    free(init);
+    return rc;
+}
+
+static int check_batch(const dm_ctx* c, const dm_batch* in) {
+    if (!c || !in || !in->frames || (!in->bytes && in->n_bytes)) return OPUSB_BAD_ARG;
+    if (in->n_frames < 1 || in->n_frames > c->max_frames) return DM_ERR_CAPACITY;
+    if (in->mode == DM_MODE_CELT_RAW) {
+        if (in->frame_size != 120 && in->frame_size != 240 && in->frame_size != 480 && in->frame_size != 960) return OPUSB_BAD_ARG;
+        if (in->coded_channels != 1 && in->coded_channels != 2) return OPUSB_BAD_ARG;
+        if (in->start_band < 0 || in->start_band >= kNbEBands) return OPUSB_BAD_ARG;
+    } else if (in->mode != DM_MODE_OPUS) {
+        return OPUSB_BAD_ARG;
+    }
+    return 0;
+}
+
+// Enqueue the six kernels for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
+static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
+                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed) {
+    DevParams P;
+    P.n_streams = c->n_streams; P.n_frames = in->n_frames; P.mode = in->mode;
+    P.frame_size = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
+    P.coded_channels = in->coded_channels; P.start_band = in->start_band; P.CC = c->channels;
+    P.first_stream = first; P.n_sel = n_sel;
+    const int nfr = n_sel * in->n_frames;
+    const int wb = 32 * KW_WARPS;
+    if (timed) cudaEventRecord(c->ev[0], s);
+    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, kMaxLeaf * K1_THREADS * 2, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_X);
+    if (timed) cudaEventRecord(c->ev[1], s);
+    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_state, P);
+    if (timed) cudaEventRecord(c->ev[2], s);
+    k_bands<<<(nfr + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, P);
+    if (timed) cudaEventRecord(c->ev[3], s);
+    k_imdct<<<(nfr * P.CC + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
+    if (timed) cudaEventRecord(c->ev[4], s);
+    k_postfilter<<<(n_sel * P.CC + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
+    if (timed) cudaEventRecord(c->ev[5], s);
+    k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
+    if (timed) cudaEventRecord(c->ev[6], s);
+    c->launches += kStages;
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int dm_decode_device(dm_ctx* c, const dm_batch* in, dm_out* out, void* cuda_stream) {
+    int r = check_batch(c, in);
+    if (r) return r;
+    if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    return launch_pipeline(c, in, in->bytes, (const FrameDesc*)in->frames, out->pcm, out->status, 0, c->n_streams,
+                           (cudaStream_t)cuda_stream, true);
+}
+
+int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
+    int r = check_batch(c, in);
+    if (r) return r;
+    if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (in->n_bytes > c->d_bytes_cap) {
+        if (c->d_bytes) { cudaFree(c->d_bytes); c->dev_bytes -= c->d_bytes_cap; }
+        c->d_bytes = nullptr; c->d_bytes_cap = 0;
+        size_t cap = in->n_bytes + in->n_bytes / 4 + 4096;
+        CU_TRY(c, cudaMalloc((void**)&c->d_bytes, cap));
+        c->d_bytes_cap = cap; c->dev_bytes += cap;
+    }
+    const int nf = in->n_frames, CC = c->channels;
+    const int fs = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
+    // packets are small: one copy on stream 0, the other chunk streams wait for it
+    CU_TRY(c, cudaMemcpyAsync(c->d_bytes, in->bytes, in->n_bytes, cudaMemcpyHostToDevice, c->streams[0]));
+    CU_TRY(c, cudaEventRecord(c->bytes_ready, c->streams[0]));
+    // stream ranges are pipelined so that the PCM read-back of one range overlaps the kernels of the next
+    int n_chunks = c->n_streams >= 64 * kMaxChunks ? kMaxChunks : 1;
+    for (int k = 0; k < n_chunks; k++) {
+        const int first = (int)((long long)c->n_streams * k / n_chunks), last = (int)((long long)c->n_streams * (k + 1) / n_chunks);
+        const int n_sel = last - first;
+        if (n_sel <= 0) continue;
+        cudaStream_t s = c->streams[k];
+        const size_t f0 = (size_t)first * nf, fn = (size_t)n_sel * nf;
+        if (k) CU_TRY(c, cudaStreamWaitEvent(s, c->bytes_ready, 0));
+        CU_TRY(c, cudaMemcpyAsync(c->d_frames + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
+        r = launch_pipeline(c, in, c->d_bytes, c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false);
+        if (r) return r;
+        CU_TRY(c, cudaMemcpyAsync(out->pcm + f0 * fs * CC, c->d_pcm + f0 * fs * CC, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaMemcpyAsync(out->status + f0, c->d_status + f0, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < n_chunks; k++) CU_TRY(c, cudaStreamSynchronize(c->streams[k]));
+    return 0;
+}
+
+void* dm_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void dm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+long long dm_launch_count(const dm_ctx* c) { return c ? c->launches : 0; }
+size_t dm_device_bytes(const dm_ctx* c) { return c ? c->dev_bytes : 0; }
+const char* dm_stage_name(int i) { return (i >= 0 && i < kStages) ? kStageNames[i] : ""; }
+int dm_stage_times(dm_ctx* c, float* ms, int cap) {
+    if (!c || !ms) return 0;
+    int n = cap < kStages ? cap : kStages;
+    for (int i = 0; i < n; i++) {
+        ms[i] = 0.f;
+        if (cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]) != cudaSuccess) ms[i] = -1.f;
+    }
+    return n;
+}
+size_t dm_stream_state_size(void) { return sizeof(CeltStreamState); }
+int dm_get_stream_state(dm_ctx* c, int stream, void* dst, size_t cap) {
+    if (!c || !dst || stream < 0 || stream >= c->n_streams || cap < sizeof(CeltStreamState)) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    CU_TRY(c, cudaMemcpy(dst, c->d_state + stream, sizeof(CeltStreamState), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

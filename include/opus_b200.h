@@ -1,0 +1,136 @@
+/* opus_b200.h -- C ABI of the B200 batched Opus decoder (libopusb200.so).
+ *
+ * Drop-in boundary for the hot path "Opus packet -> int16 PCM" of schreibfaul1/ESP32-Opus-Player
+ * (opus_decode_frame and everything below it, src/opus_decoder.cpp:154), plus the batched
+ * decode_many() call the reference lacks.  Every entry point states the reference interface it
+ * replaces (file:line under /root/reference).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Errors are the reference's negative ints (src/opus_decoder.h:40-77): OPUS_BAD_ARG -1,
+ * OPUS_BUFFER_TOO_SMALL -2, OPUS_INTERNAL_ERROR -3, OPUS_INVALID_PACKET -4, OPUS_UNIMPLEMENTED -5,
+ * ERR_OPUS_CELT_BAD_ARG -18 ..., plus DM_ERR_* (<= -2000) for CUDA/runtime failures of this library.
+ * There is NO CPU fallback: without a usable CUDA device every decode entry point fails with
+ * DM_ERR_NO_DEVICE.
+ */
+#ifndef OPUS_B200_H
+#define OPUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_ERR_NO_DEVICE (-2000)
+#define DM_ERR_CUDA (-2001)
+#define DM_ERR_NOMEM (-2002)
+#define DM_ERR_CAPACITY (-2003)
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched decoder.  One context owns the decoder state of n_streams independent streams on one GPU
+ * (the reference keeps exactly one such state in process-wide singletons, src/celt.cpp:36-39,
+ * src/silk.cpp:18-29, src/opus_decoder.cpp:40-59).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dm_ctx dm_ctx;
+
+/* Replaces opus_decoder_get_size + opus_decoder_init (src/opus_decoder.cpp:66, 82) for n_streams
+ * decoders at once: Fs is fixed at 48000 (the only rate the reference ever uses, src/opusfile.cpp:693),
+ * `channels` (1|2) is the output channel count of every stream.  max_frames = frames per stream that
+ * one decode call may carry.  device = CUDA ordinal. */
+int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int device);
+void dm_destroy(dm_ctx* ctx);
+
+/* opus_decoder_init / OPUS_RESET_STATE for a subset of streams (src/opus_decoder.cpp:82, 361):
+ * stream_ids == NULL resets all. */
+int dm_reset(dm_ctx* ctx, const int32_t* stream_ids, int n);
+
+/* How frames are interpreted. */
+#define DM_MODE_OPUS 0     /* frames are Opus frames; toc[] gives mode/bandwidth/channels (player-level
+                              semantics of opus_decode_frame: 20 ms only) */
+#define DM_MODE_CELT_RAW 1 /* frames are raw CELT frames for celt_decode_with_ec (src/celt.cpp:2162):
+                              frame_size 120/240/480/960, coded_channels, start_band given explicitly */
+
+typedef struct dm_frame {  /* one coded frame of one stream */
+    uint32_t offset;       /* byte offset of the frame payload inside `bytes` (TOC already stripped) */
+    uint16_t len;          /* payload bytes (<= 1275) */
+    uint8_t toc;           /* the packet's TOC byte (DM_MODE_OPUS) */
+    uint8_t flags;         /* reserved, 0 */
+} dm_frame;
+
+typedef struct dm_batch {
+    int n_frames;             /* frames per stream in this call (<= max_frames) */
+    int mode;                 /* DM_MODE_* */
+    int frame_size;           /* DM_MODE_CELT_RAW: samples per frame; DM_MODE_OPUS: ignored (960) */
+    int coded_channels;       /* DM_MODE_CELT_RAW: channels coded in the frames (1|2) */
+    int start_band;           /* DM_MODE_CELT_RAW: 0, or 17 for the hybrid high band */
+    const uint8_t* bytes;     /* all payload bytes */
+    size_t n_bytes;
+    const dm_frame* frames;   /* [n_streams][n_frames], stream-major */
+} dm_batch;
+
+typedef struct dm_out {
+    int16_t* pcm;             /* [n_streams][n_frames][frame_size][channels] interleaved */
+    int32_t* status;          /* [n_streams][n_frames]: samples per channel, or a negative error */
+} dm_out;
+
+/* Batched replacement of opus_decode() (src/opus_decoder.cpp:351) / celt_decode_with_ec()
+ * (src/celt.cpp:2162) with HOST buffers: copies the batch to the GPU, runs the kernels, copies PCM
+ * and status back, returns when they are in host memory.  Pinned buffers (dm_host_alloc) make the
+ * copies asynchronous and pipelined. */
+int decode_many(dm_ctx* ctx, const dm_batch* in, dm_out* out);
+
+/* Same with every pointer in DEVICE memory, enqueued on `cuda_stream` (a cudaStream_t, NULL = the
+ * legacy default stream), no synchronisation: the kernel-only path. */
+int dm_decode_device(dm_ctx* ctx, const dm_batch* in_dev, dm_out* out_dev, void* cuda_stream);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+void* dm_host_alloc(size_t bytes);
+void dm_host_free(void* p);
+
+/* Number of kernel launches issued by this library since dm_create (bench evidence). */
+long long dm_launch_count(const dm_ctx* ctx);
+/* Bytes of device memory held by the context. */
+size_t dm_device_bytes(const dm_ctx* ctx);
+/* Device time in ms of each pipeline stage of the most recent dm_decode_device call, measured with
+ * CUDA events on the launching stream; valid after that stream was synchronised.  Returns the number
+ * of stages written (names via dm_stage_name). */
+int dm_stage_times(dm_ctx* ctx, float* ms, int cap);
+const char* dm_stage_name(int i);
+/* Debug/test access: copies one stream's CELT state blob to host (checkpoint). */
+int dm_get_stream_state(dm_ctx* ctx, int stream, void* dst, size_t cap);
+size_t dm_stream_state_size(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic corpus: stream i, frame f payload = xorshift64 bytes seeded
+ * seed_base ^ i, behind a fixed TOC.  Fills `bytes`/`frames` on the host.
+ * ---------------------------------------------------------------------------------------------- */
+size_t dm_synth_bytes(int n_streams, int n_frames, int payload_len);
+void dm_synth_fill(uint8_t* bytes, dm_frame* frames, int n_streams, int n_frames, int payload_len, int toc,
+                   uint64_t seed_base, int first_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packet helpers with the reference's semantics (src/opus_decoder.cpp:135, 460-680).
+ * ---------------------------------------------------------------------------------------------- */
+int opusb_packet_get_mode(const uint8_t* data);                 /* 1000 SILK, 1001 hybrid, 1002 CELT */
+int opusb_packet_get_bandwidth(const uint8_t* data);            /* 1101..1105 */
+int opusb_packet_get_samples_per_frame(const uint8_t* data, int32_t Fs);
+int opusb_packet_get_nb_channels(const uint8_t* data);
+int opusb_packet_get_nb_frames(const uint8_t* packet, int32_t len);
+int opusb_packet_get_nb_samples(const uint8_t* packet, int32_t len, int32_t Fs);
+int opusb_packet_parse(const uint8_t* data, int32_t len, uint8_t* out_toc, const uint8_t* frames[48], int16_t size[48],
+                       int* payload_offset);
+
+/* ------------------------------------------------------------------------------------------------
+ * Single-stream drop-in (same argument meaning as the reference's packet API, src/opus_decoder.h:165-168).
+ * The OpusDecoder blob is opaque; it holds a one-stream dm_ctx.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OpusB200Decoder OpusB200Decoder;
+OpusB200Decoder* opusb_decoder_create(int32_t Fs, int channels, int* error);
+void opusb_decoder_destroy(OpusB200Decoder* st);
+int opusb_decoder_init(OpusB200Decoder* st, int32_t Fs, int channels);
+int opusb_decode(OpusB200Decoder* st, const uint8_t* data, int32_t len, int16_t* pcm, int frame_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPUS_B200_H */

@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracle (the unmodified reference)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "survey_hashes.json")))
+
+
+def xorshift_bytes(seed, n):
+    s, out, M = seed, np.empty(n, np.uint8), (1 << 64) - 1
+    for i in range(n):
+        s ^= (s << 13) & M
+        s ^= s >> 7
+        s ^= (s << 17) & M
+        out[i] = (s >> 11) & 0xFF
+    return out
+
+
+def test_golden_fixture_through_c_abi(pkg):
+    fx = np.load(os.path.join(HERE, "golden", "celt_fb_stereo.npz"))
+    data = fx["payload"].reshape(-1).copy()
+    frames = pkg.make_frames(1, 4)
+    for f in range(4):
+        frames[0, f] = (f * 159, 159, int(fx["toc"]), 0)
+    dec = pkg.BatchDecoder(1, 4, channels=2)
+    rc, pcm, status = dec.decode_many(data, frames)
+    assert rc == 0 and (status == 960).all()
+    assert np.array_equal(pcm.reshape(-1, 2), fx["pcm"])
+    dec.close()
+
+
+def test_golden_short_frames(pkg):
+    fx = np.load(os.path.join(HERE, "golden", "celt_short.npz"))
+    for fs, ch in [(120, 1), (120, 2), (240, 2), (480, 1), (480, 2)]:
+        fr = fx["f_%d_%d" % (fs, ch)]
+        n, ln = fr.shape
+        frames = pkg.make_frames(1, n)
+        for f in range(n):
+            frames[0, f] = (f * ln, ln, 0, 0)
+        dec = pkg.BatchDecoder(1, n, channels=ch)
+        rc, pcm, status = dec.decode_many(fr.reshape(-1).copy(), frames, mode=pkg.DM_MODE_CELT_RAW, frame_size=fs, coded_channels=ch)
+        assert rc == 0 and (status == fs).all()
+        assert np.array_equal(pcm.reshape(-1, ch), fx["p_%d_%d" % (fs, ch)]), (fs, ch)
+        dec.close()
+
+
+def test_config2_streams_bit_exact(pkg, ref):
+    """BASELINE config 2 shape at a size the oracle finishes in seconds: 96 streams x 50 frames, 160 B packets."""
+    n_streams, n_frames = 96, 50
+    data, frames = pkg.synth_corpus(n_streams, n_frames, 159, 0xFC)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+    rc, pcm, status = dec.decode_many(data, frames)
+    assert rc == 0 and (status == 960).all()
+    for s in range(n_streams):
+        h, want, err = ref.decode_synth_stream(0xFC, 160, 2, n_frames, seed=ref.SEED ^ s)
+        assert err == 0
+        assert np.array_equal(pcm[s].reshape(-1, 2), want), "stream %d" % s
+    assert dec.launch_count > 0
+    dec.close()
+
+
+def test_survey_hash_celt_fb_stereo_500_frames(pkg, ref):
+    e = GOLD["packet_level"][0]
+    data, frames = pkg.synth_corpus(1, 500, e["len"] - 1, e["toc"])
+    dec = pkg.BatchDecoder(1, 500, channels=2)
+    rc, pcm, status = dec.decode_many(data, frames)
+    assert rc == 0
+    assert "%016x" % ref.fnv_hash(pcm, 2) == e["hash"]
+    dec.close()
+
+
+def test_state_carries_across_calls(pkg, ref):
+    """3000-frame stream decoded as 60 calls of 50 frames == the reference's single pass (state carry)."""
+    n_calls, per = 12, 50
+    data, frames = pkg.synth_corpus(2, n_calls * per, 159, 0xFC)
+    dec = pkg.BatchDecoder(2, per, channels=2)
+    out = []
+    for k in range(n_calls):
+        fr = np.ascontiguousarray(frames[:, k * per:(k + 1) * per])
+        rc, pcm, status = dec.decode_many(data, fr)
+        assert rc == 0 and (status == 960).all()
+        out.append(pcm.copy())
+    got = np.concatenate(out, axis=1)
+    for s in range(2):
+        _, want, _ = ref.decode_synth_stream(0xFC, 160, 2, n_calls * per, seed=ref.SEED ^ s)
+        assert np.array_equal(got[s].reshape(-1, 2), want)
+    dec.close()
+
+
+@pytest.mark.parametrize("fs,ch,C,ln", [(960, 2, 2, 160), (960, 1, 1, 100), (480, 2, 2, 80), (240, 2, 2, 40), (120, 1, 1, 20),
+                                        (120, 2, 2, 2), (960, 2, 2, 8), (960, 2, 2, 1275), (960, 2, 1, 90), (960, 1, 2, 90),
+                                        (240, 2, 1, 50), (480, 1, 2, 60), (960, 2, 2, 0)])
+def test_celt_layer_all_sizes(pkg, ref, fs, ch, C, ln):
+    """CELT-layer parity: every frame size, mono/stereo and mono<->stereo coded/decoded mixes,
+    smallest and largest frames, ragged lengths (ln == 0)."""
+    n_streams, n_frames = 5, 30
+    rng = np.random.default_rng(fs + 10 * ch + C + ln)
+    lens = np.full((n_streams, n_frames), ln) if ln else rng.integers(2, 600, (n_streams, n_frames))
+    frames = pkg.make_frames(n_streams, n_frames)
+    chunks, pos = [], 0
+    for s in range(n_streams):
+        for f in range(n_frames):
+            b = rng.integers(0, 256, int(lens[s, f]), dtype=np.uint8)
+            chunks.append(b)
+            frames[s, f] = (pos, len(b), 0, 0)
+            pos += len(b)
+    data = np.concatenate(chunks)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=ch)
+    rc, pcm, status = dec.decode_many(data, frames, mode=pkg.DM_MODE_CELT_RAW, frame_size=fs, coded_channels=C)
+    assert rc == 0
+    for s in range(n_streams):
+        layer = ref.CeltLayer(ch, C)
+        for f in range(n_frames):
+            fr = frames[s, f]
+            n, want = layer.decode(data[fr["offset"]:fr["offset"] + fr["len"]], fs)
+            assert status[s, f] == n
+            assert np.array_equal(pcm[s, f], want), (s, f)
+    dec.close()
+
+
+def test_bad_frames_do_not_poison_the_batch(pkg, ref):
+    """len <= 1 fails like the reference (ERR_OPUS_CELT_BAD_ARG, src/celt.cpp:2225) and leaves the stream's
+    state untouched; neighbouring streams are unaffected."""
+    n_streams, n_frames = 4, 6
+    data, frames = pkg.synth_corpus(n_streams, n_frames, 159, 0xFC)
+    frames[1, 2]["len"] = 1
+    frames[2, 0]["len"] = 0
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+    rc, pcm, status = dec.decode_many(data, frames, mode=pkg.DM_MODE_CELT_RAW, frame_size=960, coded_channels=2)
+    assert rc == 0
+    assert status[1, 2] == -18 and status[2, 0] == -18
+    for s in range(n_streams):
+        layer = ref.CeltLayer(2, 2)
+        for f in range(n_frames):
+            fr = frames[s, f]
+            n, want = layer.decode(data[fr["offset"]:fr["offset"] + fr["len"]], 960)
+            assert status[s, f] == n
+            if n > 0:
+                assert np.array_equal(pcm[s, f], want), (s, f)
+    dec.close()
+
+
+def test_chunked_pipeline_and_determinism(pkg, ref):
+    """>= 256 streams takes the multi-stream (4 CUDA streams) host pipeline; run twice, identical, and
+    spot-check against the oracle."""
+    n_streams, n_frames = 320, 8
+    data, frames = pkg.synth_corpus(n_streams, n_frames, 159, 0xFC)
+    outs = []
+    for _ in range(2):
+        dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+        rc, pcm, status = dec.decode_many(data, frames)
+        assert rc == 0 and (status == 960).all()
+        outs.append(pcm.copy())
+        dec.close()
+    assert np.array_equal(outs[0], outs[1])
+    for s in (0, 79, 80, 159, 160, 239, 240, 319):
+        _, want, _ = ref.decode_synth_stream(0xFC, 160, 2, n_frames, seed=ref.SEED ^ s)
+        assert np.array_equal(outs[0][s].reshape(-1, 2), want), s
+
+
+def test_reset_subset(pkg, ref):
+    data, frames = pkg.synth_corpus(3, 5, 159, 0xFC)
+    dec = pkg.BatchDecoder(3, 5, channels=2)
+    rc, first, _ = dec.decode_many(data, frames)
+    dec.reset([1])
+    rc, second, _ = dec.decode_many(data, frames)
+    assert np.array_equal(second[1], first[1])          # stream 1 restarted from a fresh decoder
+    assert not np.array_equal(second[0], first[0])      # stream 0 kept its state
+    dec.close()
+
+
+def test_single_stream_drop_in(pkg, ref):
+    """opus_decode() mirror: packet in, 960 samples out, same PCM as the reference's opus_decode."""
+    dec = pkg.OpusDecoder(48000, 2)
+    rdec = ref.PacketDecoder(2)
+    payload = xorshift_bytes(ref.SEED, 6 * 159).reshape(6, 159)
+    for f in range(6):
+        pkt = np.concatenate([[0xFC], payload[f]]).astype(np.uint8)
+        n, pcm = dec.decode(pkt)
+        rn, rpcm = rdec.decode(pkt)
+        assert n == rn == 960
+        assert np.array_equal(pcm, rpcm)
+    assert dec.decode(np.zeros(0, np.uint8))[0] == -1
+    dec.close()
+    rdec.close()
+
+
+def test_device_resident_path(pkg, ref):
+    import torch
+
+    n_streams, n_frames = 16, 10
+    data, frames = pkg.synth_corpus(n_streams, n_frames, 159, 0xFC)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+    d_bytes = torch.from_numpy(data).cuda()
+    d_frames = torch.from_numpy(frames.view(np.uint8).reshape(-1)).cuda()
+    d_pcm = torch.zeros(n_streams * n_frames * 960 * 2, dtype=torch.int16, device="cuda")
+    d_status = torch.zeros(n_streams * n_frames, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = dec.decode_device(d_bytes.data_ptr(), data.size, d_frames.data_ptr(), n_frames, d_pcm.data_ptr(), d_status.data_ptr(), stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    pcm = d_pcm.cpu().numpy().reshape(n_streams, n_frames * 960, 2)
+    assert (d_status.cpu().numpy() == 960).all()
+    for s in range(n_streams):
+        _, want, _ = ref.decode_synth_stream(0xFC, 160, 2, n_frames, seed=ref.SEED ^ s)
+        assert np.array_equal(pcm[s], want)
+    times = dec.stage_times()
+    assert set(times) >= {"entropy", "bands", "imdct", "postfilter", "deemph"} and all(v >= 0 for v in times.values())
+    dec.close()
