@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded audio-seconds per second (x realtime) of the batched Opus decode path.
+
+Workload (BASELINE.json configs[1]): 4096 concurrent CELT-only fullband stereo 20 ms streams per GPU,
+160-byte packets (TOC 0xFC + 159 xorshift payload bytes, stream i seeded 0x9E3779B97F4A7C15 ^ i).
+A "step" decodes `--frames` (default 50 = 1 s of audio) consecutive packets of every stream; decoder
+state carries from step to step, so W+K steps are W+K consecutive seconds of every stream.
+
+  value      kernel path, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        decode_many() through the C ABI with pinned HOST buffers: H2D packets + kernels + D2H PCM
+  roofline   dominant kernel, algorithmic bytes (4000 B/frame) / measured kernel time vs measured HBM peak
+             (the path is issue bound, not HBM bound: see roofline.issue and DESIGN.md)
+  cpu_baseline  the unmodified reference (oracle/_ref) forked one worker per host core on a bounded sample
+
+`--impl reference` times that CPU reference alone and prints the same JSON line with "impl": "reference".
+Multi-GPU: one process per GPU (torchrun), streams sharded round-robin, no collective on the data path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoded audio-sec/sec (x realtime), 4096 CELT FB streams, 1/2/4/8 B200"
+UNIT = "audio-s/s"
+TOC, PAYLOAD = 0xFC, 159          # 160-byte packets
+BYTES_PER_FRAME_ALGO = 160 + 3840  # packet in + int16 stereo PCM out
+OPS_PER_FRAME = 5.35e5            # reference x86-64 instructions per frame
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(n_frames, target_s, jobs=None):
+    """The reference's own CPU decoder on all host cores, bounded sample. Returns dict."""
+    from oracle import ref
+
+    cores = jobs or os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref.decode_synth_stream(TOC, PAYLOAD + 1, 2, 250, want_pcm=False)
+    rate1 = 250 * 0.02 / max(time.perf_counter() - t0, 1e-6)  # x realtime on one core
+    per_core = max(1, int(round(target_s * rate1 / (n_frames * 0.02))))
+    n_streams = cores * per_core
+    wall, hashes = ref.bench_fork(TOC, PAYLOAD + 1, 2, n_streams, n_frames, jobs=cores)
+    audio = n_streams * n_frames * 0.02
+    return {"value": audio / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%d streams x %d frames (%.0f audio-s) of the same corpus, one forked reference decoder per core, %.1f s wall"
+                      % (n_streams, n_frames, audio, wall), "wall_s": wall, "audio_s": audio}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = []
+    for _ in range(args.warmup):
+        cpu_reference(args.frames * 10, 1.0)
+    t_total, a_total, last = 0.0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_reference(args.frames * 10, 3.0)
+        t_total += last["wall_s"]
+        a_total += last["audio_s"]
+        steps.append(last["wall_s"])
+    v = a_total / t_total
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed-point",
+            "data": "synthetic", "config": {"workload": "CELT FB stereo 20 ms, 160 B packets, reference CPU decoder (oracle/_ref) forked per core",
+                                            "frames_per_stream_per_step": args.frames * 10},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "reference", "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=50, help="frames per stream per step (50 = 1 s of audio)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    S, F, K, W = args.streams, args.frames, args.steps, args.warmup
+    n_steps = W + K
+    CC = 2
+
+    # ---- synthetic corpus: global stream g = rank + world * s (round-robin shard), n_steps*F frames each
+    lib = pkg.lib()
+    nb_step = S * F * PAYLOAD
+    h_bytes = [pkg.api.PinnedArray(nb_step, np.uint8) for _ in range(n_steps)]
+    h_frames = [pkg.api.PinnedArray((S, F), pkg.FRAME_DTYPE) for _ in range(n_steps)]
+    full = np.empty(S * n_steps * F * PAYLOAD, np.uint8)
+    fr_full = pkg.make_frames(S, n_steps * F)
+    for s in range(S):  # stream ids are interleaved across ranks, so fill one stream at a time
+        pkg.synth_corpus(1, n_steps * F, PAYLOAD, TOC, first_stream=rank + world * s,
+                         bytes_out=full[s * n_steps * F * PAYLOAD:(s + 1) * n_steps * F * PAYLOAD], frames_out=fr_full[s:s + 1])
+    full = full.reshape(S, n_steps, F * PAYLOAD)
+    for k in range(n_steps):
+        h_bytes[k].array[:] = full[:, k, :].reshape(-1)
+        fr = h_frames[k].array
+        fr["offset"] = (np.arange(S * F, dtype=np.uint32) * PAYLOAD).reshape(S, F)
+        fr["len"] = PAYLOAD
+        fr["toc"] = TOC
+        fr["flags"] = 0
+    del full, fr_full
+    h_pcm = pkg.api.PinnedArray((S, F, 960, CC), np.int16)
+    h_status = pkg.api.PinnedArray((S, F), np.int32)
+
+    dec = pkg.BatchDecoder(S, F, channels=CC, device=local_rank)
+    d_bytes = [torch.from_numpy(h_bytes[k].array).cuda() for k in range(n_steps)]
+    d_frames = [torch.from_numpy(h_frames[k].array.view(np.uint8).reshape(-1)).cuda() for k in range(n_steps)]
+    d_pcm = torch.empty(S * F * 960 * CC, dtype=torch.int16, device="cuda")
+    d_status = torch.empty(S * F, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(k):
+        rc = dec.decode_device(d_bytes[k].data_ptr(), nb_step, d_frames[k].data_ptr(), F, d_pcm.data_ptr(), d_status.data_ptr(), stream)
+        if rc:
+            raise RuntimeError("dm_decode_device rc=%d" % rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, CUDA events
+    for k in range(W):
+        step_device(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = dec.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_acc = {}
+    ev0.record()
+    for k in range(W, n_steps):
+        step_device(k)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = dec.launch_count - launches0
+    st_status = d_status.cpu().numpy()
+    assert (st_status == 960).all(), "decode errors in the timed region"
+    # per-stage times of the last step (events recorded inside the library on the same stream)
+    stage_acc = dec.stage_times()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    audio_per_step = S * F * 0.02
+    value = world * K * audio_per_step / (ms_max * 1e-3)
+
+    # ---- e2e: C ABI with pinned host buffers (fresh decoder so that the same packets are legal input)
+    e2e = None
+    if not args.no_e2e:
+        dec2 = pkg.BatchDecoder(S, F, channels=CC, device=local_rank)
+        for k in range(W):
+            rc, _, _ = dec2.decode_many(h_bytes[k].array, h_frames[k].array, pcm=h_pcm.array, status=h_status.array)
+            assert rc == 0
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(W, n_steps):
+            rc, _, _ = dec2.decode_many(h_bytes[k].array, h_frames[k].array, pcm=h_pcm.array, status=h_status.array)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert rc == 0 and (h_status.array == 960).all()
+        # the two legs decode the same stream positions: their last step must agree bit for bit
+        same = bool(np.array_equal(h_pcm.array.reshape(-1), d_pcm.cpu().numpy()))
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * K * audio_per_step / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(nb_step + S * F * 8), "d2h_bytes_per_step": int(S * F * 960 * CC * 2 + S * F * 4),
+               "ms_per_step": 1e3 * float(t.item()) / K, "matches_device_leg": same}
+        dec2.close()
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = peaks()
+        top = max(stage_acc, key=lambda n: stage_acc[n]) if stage_acc else None
+        top_ms = stage_acc.get(top, 0.0) if top else 0.0
+        algo_bytes = S * F * BYTES_PER_FRAME_ALGO
+        achieved = algo_bytes / (top_ms * 1e-3) / 1e9 if top_ms > 0 else None
+        sm_clock = (clocks.get("sm_mhz") or sm_max) * 1e6
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        issue_peak = n_sm * 4 * sm_max * 1e6 * 32  # lane-ops/s at max clock
+        step_s = ms_max * 1e-3 / K
+        roof = {"bound": "hbm", "kernel": "k_" + str(top), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": top_ms, "stage_ms": stage_acc,
+                "issue": {"note": "the path is issue bound (SURVEY 8d): algorithmic integer ops vs SM issue peak over the whole step",
+                          "achieved_lane_ops_per_s": S * F * OPS_PER_FRAME / step_s, "peak_lane_ops_per_s": issue_peak,
+                          "frac": S * F * OPS_PER_FRAME / step_s / issue_peak, "sm_clock_hz_under_load": sm_clock}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed-point", "data": "synthetic",
+                "config": {"workload": "configs[1]: %d concurrent CELT-only FB stereo 20 ms streams per GPU, 160 B packets, %d frames (%.1f s) per stream per step"
+                                       % (S, F, F * 0.02), "streams_per_gpu": S, "frames_per_step": F, "sharding": "stream i -> GPU i mod N, no collective",
+                           "l2": "inputs and intermediates per step (%.1f GB) exceed L2; every step decodes new packets" % (dec.device_bytes / 1e9)},
+                "clocks": clocks, "roofline": roof, "gpu_launches": int(launches)}
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            cb = cpu_reference(3000 if F * n_steps >= 3000 else F * n_steps, 10.0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    dec.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
