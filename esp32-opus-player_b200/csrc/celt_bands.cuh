@@ -109,6 +109,120 @@ OPUS_HD void w_stereo_merge(const Lanes& L, int16_t* X, int16_t* Y, s16 mid, int
     L.sync();
 }
 
+// ---- coded PVQ leaves: one lane expands one leaf (index -> pulses -> unit-norm rotated vector) ----
+// ref cwrsi (src/celt.cpp:2545): codeword index -> signed pulses y[0..n), returns sum y^2
+OPUS_HD s32 pvq_expand(int n, int k, u32 i, int16_t* y) {
+    u32 p;
+    int s, k0;
+    s32 yy = 0;
+    while (n > 2) {
+        u32 q;
+        s16 val;
+        if (k >= n) {  // lots of pulses
+            const u32* row = kPvqU + kPvqRow[n];
+            p = row[k + 1];
+            s = -(int)(i >= p);
+            i -= p & (u32)s;
+            k0 = k;
+            q = row[n];
+            if (q > i) {
+                k = n;
+                do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
+            } else {
+                for (p = row[k]; p > i; p = row[k]) k--;
+            }
+            i -= p;
+            val = (s16)((k0 - k + s) ^ s);
+        } else {  // lots of dimensions
+            p = kPvqU[kPvqRow[k] + n];
+            q = kPvqU[kPvqRow[k + 1] + n];
+            if (p <= i && i < q) {
+                i -= p;
+                val = 0;
+            } else {
+                s = -(int)(i >= q);
+                i -= q & (u32)s;
+                k0 = k;
+                do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
+                i -= p;
+                val = (s16)((k0 - k + s) ^ s);
+            }
+        }
+        *y++ = val;
+        yy += mul16(val, val);
+        n--;
+    }
+    p = 2 * (u32)k + 1;
+    s = -(int)(i >= p);
+    i -= p & (u32)s;
+    k0 = k;
+    k = (int)((i + 1) >> 1);
+    if (k) i -= 2 * (u32)k - 1;
+    s16 val = (s16)((k0 - k + s) ^ s);
+    *y++ = val;
+    yy += mul16(val, val);
+    s = -(int)i;
+    val = (s16)((k + s) ^ s);
+    *y = val;
+    yy += mul16(val, val);
+    return yy;
+}
+
+// ref exp_rotation1 / exp_rotation (src/celt.cpp:684, 707), decoder direction (dir = -1).  Each pass is a
+// recurrence with per-step rounding: serial along the vector, so a lane keeps the carried value in a register.
+OPUS_HD void leaf_rotate1(int16_t* X, int len, int stride, s16 c, s16 s) {
+    const s16 ms = (s16)(-(s32)s);
+    for (int i = 0; i < len - stride; i++) {
+        s16 x1 = X[i], x2 = X[i + stride];
+        X[i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
+        X[i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
+    }
+    for (int i = len - 2 * stride - 1; i >= 0; i--) {
+        s16 x1 = X[i], x2 = X[i + stride];
+        X[i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
+        X[i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
+    }
+}
+OPUS_HD void leaf_rotate(int16_t* X, int len, int stride, int K, int spread) {
+    if (2 * K >= len || spread == 0) return;
+    const int factor = spread == 1 ? 15 : (spread == 2 ? 10 : 5);
+    s16 gain = (s16)mul32_q31((s32)mul16(32767, len), rcp_q(len + factor * K));  // celt_div
+    s16 theta = (s16)(mul16_q15(gain, gain) >> 1);
+    s16 c = cos_norm((s32)theta);
+    s16 s = cos_norm((s32)sub16(32767, theta));
+    int stride2 = 0;
+    if (len >= 8 * stride) {
+        stride2 = 1;
+        while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+    }
+    len = (int)((u32)len / (u32)stride);
+    for (int i = 0; i < stride; i++) {
+        if (stride2) leaf_rotate1(X + i * len, len, stride2, s, c);
+        leaf_rotate1(X + i * len, len, 1, c, s);
+    }
+}
+
+// ref alg_unquant (src/celt.cpp:782) for every coded leaf of the frame.  `last` points at the first leaf
+// record (leaves are stored downwards from the end of the frame's op buffer).
+OPUS_HD void leaf_stage(const Lanes& L, int16_t* W, const BandOp* last, int n_leaves, int spread) {
+    for (int l0 = 0; l0 < n_leaves; l0 += kLanes) {
+        const int l = l0 + L.lane;
+        if (l < n_leaves) {
+            const BandOp o = last[-l];
+            int16_t* y = W + o.off;
+            const int N = o.n, K = o.off2, B = o.a;
+            const s32 Ryy = pvq_expand(N, K, o.aux, y);
+            // normalise_residual (ref :745)
+            const int k = ilog2p(Ryy) >> 1;
+            const s32 t = vshr32(Ryy, 2 * (k - 7));
+            const s16 g = (s16)mul16_p15(rsqrt_norm(t), o.g);
+            for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
+            leaf_rotate(y, N, B, K, spread);
+        }
+    }
+    L.sync();
+}
+
 // Replays the script of one frame.  `seed` = noise seed at frame start (= previous frame's final range).
 // Returns the seed after all fills (input of anti_collapse, ref src/celt.cpp:2371).
 OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_ops, u32 seed) {
@@ -187,6 +301,10 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
                 }
                 L.sync();
             } break;
+            case OP_ZERO:
+                for (int j = L.lane; j < n; j += kLanes) X[j] = 0;
+                L.sync();
+                break;
             case OP_AVG: {
                 const int16_t* src = W + o.off2;
                 for (int j = L.lane; j < n; j += kLanes) X[j] = (s16)(((s32)X[j] + (s32)src[j]) >> 1);

@@ -14,14 +14,6 @@
 
 namespace opusb200 {
 
-// Thread-private leaf buffer. On the GPU it is a column of a shared-memory tile (stride = block
-// size) so that the serial PVQ / rotation passes never touch HBM.
-struct LeafBuf {
-    int16_t* p;
-    int stride;
-    OPUS_HD int16_t& operator[](int j) const { return p[j * stride]; }
-};
-
 struct ParseCtx {
     RangeDec rd;
     // frame constants
@@ -29,19 +21,24 @@ struct ParseCtx {
     // band loop state (ref band_ctx_t, src/celt.h:125)
     int band, intensity, spread, tf_change, remaining_bits;
     // outputs
-    BandOp* ops;
-    int n_ops, ops_cap, overflow;
+    BandOp* ops;      // transform ops from the front, leaf records from the back
+    int n_ops, n_leaves, ops_cap, overflow;
     uint32_t lcg_steps;
-    int16_t* Xg;  // frame's X buffer in global memory: [C][N]
-    LeafBuf leaf;
 };
 
 OPUS_HD void emit_op(ParseCtx& p, uint8_t code, int a, int off, int off2, int n, int g, int g2) {
-    if (p.n_ops >= p.ops_cap) { p.overflow = 1; return; }
+    if (p.n_ops + p.n_leaves >= p.ops_cap) { p.overflow = 1; return; }
     BandOp o;
     o.code = code; o.a = (uint8_t)a; o.off = (uint16_t)off; o.off2 = (uint16_t)off2; o.n = (uint16_t)n;
-    o.g = (int16_t)g; o.g2 = (int16_t)g2;
+    o.g = (int16_t)g; o.g2 = (int16_t)g2; o.aux = 0;
     p.ops[p.n_ops++] = o;
+}
+OPUS_HD void emit_leaf(ParseCtx& p, int B, int off, int K, int n, int gain, u32 index) {
+    if (p.n_ops + p.n_leaves >= p.ops_cap) { p.overflow = 1; return; }
+    BandOp o;
+    o.code = OP_LEAF; o.a = (uint8_t)B; o.off = (uint16_t)off; o.off2 = (uint16_t)K; o.n = (uint16_t)n;
+    o.g = (int16_t)gain; o.g2 = 0; o.aux = index;
+    p.ops[p.ops_cap - 1 - p.n_leaves++] = o;
 }
 
 // ---- pulse cache helpers (ref src/celt.h:533-569) ----
@@ -66,14 +63,17 @@ OPUS_HD int pulses2bits(int band, int LM, int pulses) {
 OPUS_HD u32 pvq_u(int n, int k) { return n < k ? kPvqU[kPvqRow[n] + k] : kPvqU[kPvqRow[k] + n]; }
 OPUS_HD u32 pvq_v(int n, int k) { return pvq_u(n, k) + pvq_u(n, k + 1); }
 
-// index -> signed pulse vector y[0..n), returns sum y^2 (ref cwrsi)
-OPUS_HD s32 pvq_decode_index(int n, int k, u32 i, const LeafBuf& y) {
-    u32 p;
+// Walks a PVQ codeword index (ref cwrsi, src/celt.cpp:2545) only far enough to know which of the B
+// interleaved blocks receive a pulse: the collapse mask (ref extract_collapse_mask :760) steers later
+// folding decisions, so the entropy thread needs it; the pulses themselves are expanded by the band kernel.
+OPUS_HD u32 pvq_index_mask(int n, int k, u32 i, int B) {
+    const int N0 = (int)((u32)n / (u32)B);
+    u32 p, cm = 0;
     int s, k0, pos = 0;
-    s32 yy = 0;
     while (n > 2) {
         u32 q;
-        if (k >= n) {  // lots of pulses
+        int val;
+        if (k >= n) {
             const u32* row = kPvqU + kPvqRow[n];
             p = row[k + 1];
             s = -(int)(i >= p);
@@ -87,103 +87,43 @@ OPUS_HD s32 pvq_decode_index(int n, int k, u32 i, const LeafBuf& y) {
                 for (p = row[k]; p > i; p = row[k]) k--;
             }
             i -= p;
-            s16 val = (s16)((k0 - k + s) ^ s);
-            y[pos++] = val;
-            yy += mul16(val, val);
-        } else {  // lots of dimensions
+            val = k0 - k;
+        } else {
             p = kPvqU[kPvqRow[k] + n];
             q = kPvqU[kPvqRow[k + 1] + n];
             if (p <= i && i < q) {
                 i -= p;
-                y[pos++] = 0;
+                val = 0;
             } else {
                 s = -(int)(i >= q);
                 i -= q & (u32)s;
                 k0 = k;
                 do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
                 i -= p;
-                s16 val = (s16)((k0 - k + s) ^ s);
-                y[pos++] = val;
-                yy += mul16(val, val);
+                val = k0 - k;
             }
         }
+        if (val) cm |= 1u << (pos / N0);
+        pos++;
         n--;
+        if (k == 0) return cm;  // no pulses left: the remaining coefficients are zero
     }
-    // n == 2
     p = 2 * (u32)k + 1;
     s = -(int)(i >= p);
     i -= p & (u32)s;
     k0 = k;
     k = (int)((i + 1) >> 1);
-    if (k) i -= 2 * (u32)k - 1;
-    s16 val = (s16)((k0 - k + s) ^ s);
-    y[pos++] = val;
-    yy += mul16(val, val);
-    // n == 1
-    s = -(int)i;
-    val = (s16)((k + s) ^ s);
-    y[pos] = val;
-    yy += mul16(val, val);
-    return yy;
-}
-
-// ref exp_rotation1 / exp_rotation (src/celt.cpp:684, 707), decoder direction only (dir = -1)
-OPUS_HD void leaf_rotate1(const LeafBuf& X, int base, int len, int stride, s16 c, s16 s) {
-    s16 ms = (s16)(-(s32)s);
-    for (int i = 0; i < len - stride; i++) {
-        s16 x1 = X[base + i], x2 = X[base + i + stride];
-        X[base + i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
-        X[base + i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
-    }
-    for (int i = len - 2 * stride - 1; i >= 0; i--) {
-        s16 x1 = X[base + i], x2 = X[base + i + stride];
-        X[base + i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
-        X[base + i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
-    }
-}
-OPUS_HD void leaf_rotate(const LeafBuf& X, int len, int stride, int K, int spread) {
-    if (2 * K >= len || spread == 0) return;
-    const int factor = spread == 1 ? 15 : (spread == 2 ? 10 : 5);
-    s16 gain = (s16)mul32_q31((s32)mul16(32767, len), rcp_q(len + factor * K));  // celt_div
-    s16 theta = (s16)(mul16_q15(gain, gain) >> 1);
-    s16 c = cos_norm((s32)theta);
-    s16 s = cos_norm((s32)sub16(32767, theta));
-    int stride2 = 0;
-    if (len >= 8 * stride) {
-        stride2 = 1;
-        while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
-    }
-    len = (int)((u32)len / (u32)stride);
-    for (int i = 0; i < stride; i++) {
-        if (stride2) leaf_rotate1(X, i * len, len, stride2, s, c);
-        leaf_rotate1(X, i * len, len, 1, c, s);
-    }
-}
-
-// ref alg_unquant (src/celt.cpp:782): decode_pulses + normalise_residual + exp_rotation + collapse mask
-OPUS_HD u32 leaf_unquant(ParseCtx& p, int xoff, int N, int K, int B, s16 gain) {
-    const LeafBuf& y = p.leaf;
-    s32 Ryy = pvq_decode_index(N, K, rd_uint(p.rd, pvq_v(N, K)), y);
-    // extract_collapse_mask (ref :760) -- taken from the pulses before they are scaled in place
-    u32 cm;
-    if (B <= 1) cm = 1;
-    else {
-        int N0 = (int)((u32)N / (u32)B);
-        cm = 0;
-        for (int i = 0; i < B; i++) {
-            int any = 0;
-            for (int j = 0; j < N0; j++) any |= y[i * N0 + j];
-            cm |= (u32)(any != 0) << i;
-        }
-    }
-    // normalise_residual (ref :745)
-    int k = ilog2p(Ryy) >> 1;
-    s32 t = vshr32(Ryy, 2 * (k - 7));
-    s16 g = (s16)mul16_p15(rsqrt_norm(t), gain);
-    for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
-    leaf_rotate(y, N, B, K, p.spread);
-    for (int i = 0; i < N; i++) p.Xg[xoff + i] = y[i];
+    if (k0 - k) cm |= 1u << (pos / N0);
+    pos++;
+    if (k) cm |= 1u << (pos / N0);
     return cm;
+}
+
+// ref alg_unquant (src/celt.cpp:782), entropy half: read the codeword index, record the leaf.
+OPUS_HD u32 leaf_unquant(ParseCtx& p, int xoff, int N, int K, int B, s16 gain) {
+    const u32 index = rd_uint(p.rd, pvq_v(N, K));
+    emit_leaf(p, B, xoff, K, N, gain, index);
+    return B <= 1 ? 1u : pvq_index_mask(N, K, index, B);
 }
 
 struct ThetaOut { int inv, imid, iside, delta, itheta, qalloc; };
@@ -279,7 +219,7 @@ OPUS_HD u32 band_n1(ParseCtx& p, int xoff, int yoff, int out) {
             p.remaining_bits -= 1 << 3;
         }
         int v = sign ? -16384 : 16384;
-        p.Xg[c ? yoff : xoff] = (s16)v;
+        emit_op(p, OP_SETW, 0, c ? yoff : xoff, 0, 1, v, 0);
         if (c == 0) x0 = v;
     }
     if (out >= 0) emit_op(p, OP_SETW, 0, out, 0, 1, x0 >> 4, 0);
@@ -342,7 +282,7 @@ inline u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, in
             u32 cm_mask = (u32)(1UL << B) - 1;
             fill &= (int)cm_mask;
             if (!fill) {
-                for (int j = 0; j < N; j++) p.Xg[xoff + j] = 0;
+                emit_op(p, OP_ZERO, 0, xoff, 0, N, 0, 0);
             } else if (lowband < 0) {
                 emit_op(p, OP_NOISE, 0, xoff, 0, N, gain, 0);
                 p.lcg_steps += (u32)N;
@@ -712,13 +652,13 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     const int C = p.C, LM = p.LM, start = p.start, end = p.end;
     const int M = 1 << LM;
     hdr.LM = (uint8_t)LM; hdr.C = (uint8_t)C; hdr.start = (uint8_t)start; hdr.end = (uint8_t)end;
-    hdr.n_ops = 0; hdr.lcg_steps = 0; hdr.flags = 0; hdr.pf_pitch = 0; hdr.pf_gain = 0; hdr.pf_tapset = 0;
+    hdr.n_ops = 0; hdr.n_leaves = 0; hdr.spread = 2; hdr.pad0 = 0; hdr.lcg_steps = 0; hdr.flags = 0; hdr.pf_pitch = 0; hdr.pf_gain = 0; hdr.pf_tapset = 0;
     hdr.final_rng = 0;
     if (rd.storage > (u32)kMaxPacket || rd.storage <= 1) {  // ref :2216, :2225
         hdr.status = OPUSB_CELT_BAD_ARG;
         return hdr.status;
     }
-    p.n_ops = 0; p.overflow = 0; p.lcg_steps = 0;
+    p.n_ops = 0; p.n_leaves = 0; p.overflow = 0; p.lcg_steps = 0;
 
     int total_bits = (int)rd.storage * 8;
     int tell = rd_tell(rd);
@@ -904,6 +844,8 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     hdr.pf_gain = (int16_t)pf_gain;
     hdr.pf_tapset = (uint8_t)pf_tapset;
     hdr.n_ops = (uint16_t)p.n_ops;
+    hdr.n_leaves = (uint16_t)p.n_leaves;
+    hdr.spread = (uint8_t)spread;
     hdr.lcg_steps = p.lcg_steps;
     hdr.final_rng = rd.rng;
     int status = kShortMdct << LM;

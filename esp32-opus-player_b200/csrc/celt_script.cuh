@@ -46,9 +46,11 @@ enum BandOpCode : uint8_t {
     OP_NEG,        // W[off..+n) = -W[..]                                  (ref :1733-1738)
     OP_N2,         // N=2 stereo special case: x2=off, y2=off2, a=sign bit(0/1), g=mid, g2=side (ref :1682-1696)
     OP_AVG,        // W[off+j] = (W[off+j] + W[off2+j]) >> 1, j<n  (dual stereo -> intensity) (ref :1888-1889)
+    OP_ZERO,       // W[off..+n) = 0                                       (ref :1493)
+    OP_LEAF,       // coded PVQ leaf: W[off..+n) = alg_unquant(index=aux, N=n, K=off2, B=a, gain=g) (ref :782)
 };
 
-struct BandOp {  // 12 bytes
+struct BandOp {  // 16 bytes, one 128-bit access
     uint8_t code;
     uint8_t a;
     uint16_t off;
@@ -56,8 +58,11 @@ struct BandOp {  // 12 bytes
     uint16_t n;
     int16_t g;
     int16_t g2;
+    uint32_t aux;
 };
 
+// One op buffer per frame: transform ops grow from the front in bitstream order, coded-leaf records
+// (OP_LEAF) grow from the back -- they are independent of everything else and are expanded first.
 enum {
     kMaxOps = 1360,  // worst case: 21 bands x 2 channels x (16 leaves + ~16 transforms)
 };
@@ -92,7 +97,10 @@ struct CeltFrameHdr {
     uint8_t start;
     uint8_t end;
     uint8_t pf_tapset;
+    uint8_t spread;
+    uint8_t pad0;
     uint16_t n_ops;
+    uint16_t n_leaves;
     int16_t pf_pitch;
     int16_t pf_gain;
     uint32_t lcg_steps;  // LCG draws consumed by noise/fold fills (anti-collapse seed = seed advanced by this)

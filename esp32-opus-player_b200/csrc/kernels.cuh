@@ -11,6 +11,8 @@
 // (<= 36 KB per frame; the traffic is three orders of magnitude under the HBM roofline -- the path is
 // issue bound), per-stream state is a POD blob in HBM (CeltStreamState).
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "celt_parse.cuh"
 #include "celt_synth.cuh"
 
@@ -42,8 +44,7 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1_THREADS)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
-          BandOp* __restrict__ ops, int16_t* __restrict__ X) {
-    extern __shared__ int16_t leaf_tile[];  // [kMaxLeaf][K1_THREADS]: one private column per thread
+          BandOp* __restrict__ ops) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
     if (local >= P.n_sel * P.n_frames) return;
     const size_t t = (size_t)P.first_stream * P.n_frames + local;
@@ -56,7 +57,7 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
         start = P.start_band;
     } else {
         if (!(d.toc & 0x80)) {  // SILK / hybrid frames are not handled by this kernel
-            h.status = OPUSB_UNIMPLEMENTED; h.flags = 0; h.n_ops = 0; h.LM = 3; h.C = 1; h.start = 0; h.end = kNbEBands;
+            h.status = OPUSB_UNIMPLEMENTED; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1; h.start = 0; h.end = kNbEBands;
             return;
         }
         C = (d.toc & 0x4) ? 2 : 1;
@@ -67,10 +68,7 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     rd_init(p.rd, bytes + d.offset, d.len);
     p.C = C; p.LM = LM; p.start = start; p.end = kNbEBands; p.disable_inv = (P.CC == 1);
     p.band = 0; p.intensity = 0; p.spread = 0; p.tf_change = 0; p.remaining_bits = 0;
-    p.ops = ops + t * kMaxOps; p.n_ops = 0; p.ops_cap = kMaxOps; p.overflow = 0; p.lcg_steps = 0;
-    p.Xg = X + t * (2 * kMaxFrame);
-    p.leaf.p = leaf_tile + threadIdx.x;
-    p.leaf.stride = K1_THREADS;
+    p.ops = ops + t * kMaxOps; p.n_ops = 0; p.n_leaves = 0; p.ops_cap = kMaxOps; p.overflow = 0; p.lcg_steps = 0;
     celt_parse_frame(p, h);
 }
 
@@ -128,9 +126,9 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
     const int words = (h.C * (kShortMdct << h.LM)) >> 1;
     int32_t* Xw = reinterpret_cast<int32_t*>(X + t * (2 * kMaxFrame));
     int32_t* Ww = reinterpret_cast<int32_t*>(W);
-    for (int j = L.lane; j < words; j += 32) Ww[j] = Xw[j];
-    L.sync();
-    u32 seed = band_stage_ops(L, W, ops + t * kMaxOps, h.n_ops, e.seed);
+    const BandOp* fops = ops + t * kMaxOps;
+    leaf_stage(L, W, fops + kMaxOps - 1, h.n_leaves, h.spread);
+    u32 seed = band_stage_ops(L, W, fops, h.n_ops, e.seed);
     if (h.flags & FF_ANTICOLLAPSE) band_stage_anti_collapse(L, W, h, e, seed);
     L.sync();
     for (int j = L.lane; j < words; j += 32) Xw[j] = Ww[j];
@@ -219,12 +217,15 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
 // De-emphasis is a strictly serial 1-pole IIR with per-step truncation (ref src/celt.cpp:1977-1982):
 // one lane owns one (stream, channel) chain.  A warp owns 32 chains and moves 32x32 tiles through
 // shared memory so that every global access is a full 128 B line (loads) or int16x8 vectors (stores).
-enum { DE_TW = 32, DE_IN_STRIDE = 33, DE_OUT_STRIDE = 36 };
+// The next tiles are prefetched with cp.async (LDGSTS) into a 4-deep shared-memory ring while the
+// lanes run the recurrence on the current one: with only one warp of work per 32 chains there is no
+// other way to hide HBM latency.
+enum { DE_TW = 32, DE_IN_STRIDE = 33, DE_OUT_STRIDE = 36, DE_STAGES = 4 };
 
 __global__ void __launch_bounds__(32)
 k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hdr, const int32_t* __restrict__ syn,
          int16_t* __restrict__ pcm, int32_t* __restrict__ status, CeltStreamState* __restrict__ st, DevParams P) {
-    __shared__ int32_t tin[32 * DE_IN_STRIDE];
+    __shared__ int32_t tin[DE_STAGES][32 * DE_IN_STRIDE];
     __shared__ __align__(16) uint32_t tout[32 * DE_OUT_STRIDE];
     const int lane = threadIdx.x;
     const int CC = P.CC;
@@ -235,63 +236,78 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     const int my_s = P.first_stream + (live ? my / CC : 0), my_c = live ? my % CC : 0;
     s32 mem = live ? st[my_s].preemph_mem[my_c] : 0;
     const int N = P.frame_size;
+    const int tpf = (N + DE_TW - 1) / DE_TW, T = tpf * P.n_frames;
+    const int rows = min(32, n_chains - chain0);
     int16_t* tout16 = reinterpret_cast<int16_t*>(tout);
-    for (int f = 0; f < P.n_frames; f++) {
-        const size_t my_t = (size_t)my_s * P.n_frames + f;
-        const bool my_skip = live ? (fe[my_t].skip != 0) : true;
-        if (live && my_c == 0) status[my_t] = hdr[my_t].status;
-        for (int j0 = 0; j0 < N; j0 += DE_TW) {
-            const int w = min(DE_TW, N - j0);
-            // load: row r = chain r, 128 B per row
-#pragma unroll 8
-            for (int r = 0; r < 32; r++) {
-                const int q = chain0 + r;
-                int32_t v = 0;
-                if (q < n_chains && lane < w) {
-                    const size_t t = (size_t)(P.first_stream + q / CC) * P.n_frames + f;
-                    v = syn[(t * CC + (q % CC)) * kMaxFrame + j0 + lane];
-                }
-                tin[r * DE_IN_STRIDE + lane] = v;
-            }
-            __syncwarp();
-            // serial recurrence, one chain per lane
-            if (CC == 2) {
-                const int q = lane >> 1;
-                for (int j = 0; j < w; j++) {
-                    s32 v = my_skip ? 0 : deemph_sample(tin[lane * DE_IN_STRIDE + j], mem);
-                    tout16[(q * DE_OUT_STRIDE + j) * 2 + (lane & 1)] = (int16_t)v;
-                }
-            } else {
-                for (int j = 0; j < w; j++) {
-                    s32 v = my_skip ? 0 : deemph_sample(tin[lane * DE_IN_STRIDE + j], mem);
-                    tout16[lane * DE_OUT_STRIDE * 2 + j] = (int16_t)v;
+
+    auto prefetch = [&](int q) {
+        if (q < T) {
+            const int f = q / tpf, j0 = (q % tpf) * DE_TW;
+            int32_t* dst = tin[q % DE_STAGES];
+            if (j0 + lane < N) {
+#pragma unroll 4
+                for (int r = 0; r < rows; r++) {
+                    const int qc = chain0 + r;
+                    const size_t t = (size_t)(P.first_stream + qc / CC) * P.n_frames + f;
+                    __pipeline_memcpy_async(&dst[r * DE_IN_STRIDE + lane], &syn[(t * CC + (qc % CC)) * kMaxFrame + j0 + lane], 4);
                 }
             }
-            __syncwarp();
-            // store: interleaved PCM rows, 16 B per lane
-            if (CC == 2) {
-                for (int it = 0; it < 4; it++) {
-                    const int q = it * 4 + (lane >> 3), chunk = lane & 7;  // stream within the warp, 4 samples per chunk
-                    const int sl = chain0 / 2 + q;                          // stream index relative to first_stream
-                    if (sl < P.n_sel && chunk * 4 < w) {
-                        const size_t t = (size_t)(P.first_stream + sl) * P.n_frames + f;
-                        uint4 v = *reinterpret_cast<const uint4*>(&tout[q * DE_OUT_STRIDE + chunk * 4]);
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(pcm) + (t * N + j0 + chunk * 4);
-                        if (chunk * 4 + 4 <= w) *reinterpret_cast<uint4*>(dst) = v;
-                        else { const uint32_t vv[4] = {v.x, v.y, v.z, v.w}; for (int k = 0; k < w - chunk * 4; k++) dst[k] = vv[k]; }
-                    }
-                }
-            } else {
-                for (int r = 0; r < 32; r++) {
-                    const int sl = chain0 + r;
-                    if (sl < P.n_sel && lane < w) {
-                        const size_t t = (size_t)(P.first_stream + sl) * P.n_frames + f;
-                        pcm[t * N + j0 + lane] = tout16[r * DE_OUT_STRIDE * 2 + lane];
-                    }
-                }
-            }
-            __syncwarp();
         }
+        __pipeline_commit();
+    };
+
+    for (int q = 0; q < DE_STAGES - 1; q++) prefetch(q);
+    bool my_skip = true;
+    for (int q = 0; q < T; q++) {
+        const int f = q / tpf, j0 = (q % tpf) * DE_TW;
+        const int w = min(DE_TW, N - j0);
+        if (j0 == 0) {
+            const size_t my_t = (size_t)my_s * P.n_frames + f;
+            my_skip = live ? (fe[my_t].skip != 0) : true;
+            if (live && my_c == 0) status[my_t] = hdr[my_t].status;
+        }
+        prefetch(q + DE_STAGES - 1);
+        __pipeline_wait_prior(DE_STAGES - 1);
+        __syncwarp();
+        const int32_t* src = tin[q % DE_STAGES];
+        // serial recurrence, one chain per lane
+        if (CC == 2) {
+            const int qs = lane >> 1;
+#pragma unroll 8
+            for (int j = 0; j < w; j++) {
+                s32 v = my_skip ? 0 : deemph_sample(src[lane * DE_IN_STRIDE + j], mem);
+                tout16[(qs * DE_OUT_STRIDE + j) * 2 + (lane & 1)] = (int16_t)v;
+            }
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < w; j++) {
+                s32 v = my_skip ? 0 : deemph_sample(src[lane * DE_IN_STRIDE + j], mem);
+                tout16[lane * DE_OUT_STRIDE * 2 + j] = (int16_t)v;
+            }
+        }
+        __syncwarp();
+        // store: interleaved PCM rows, int16x8 (16 B) per lane
+        if (CC == 2) {
+            for (int it = 0; it < 4; it++) {
+                const int qs = it * 4 + (lane >> 3), chunk = lane & 7;  // stream within the warp, 4 sample pairs per chunk
+                const int sl = chain0 / 2 + qs;                          // stream index relative to first_stream
+                if (sl < P.n_sel && chunk * 4 < w) {
+                    const size_t t = (size_t)(P.first_stream + sl) * P.n_frames + f;
+                    uint4 v = *reinterpret_cast<const uint4*>(&tout[qs * DE_OUT_STRIDE + chunk * 4]);
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(pcm) + (t * N + j0 + chunk * 4);
+                    if (chunk * 4 + 4 <= w) *reinterpret_cast<uint4*>(dst) = v;
+                    else { const uint32_t vv[4] = {v.x, v.y, v.z, v.w}; for (int k = 0; k < w - chunk * 4; k++) dst[k] = vv[k]; }
+                }
+            }
+        } else {
+            for (int r = 0; r < rows; r++) {
+                if (lane < w) {
+                    const size_t t = (size_t)(P.first_stream + chain0 + r) * P.n_frames + f;
+                    pcm[t * N + j0 + lane] = tout16[r * DE_OUT_STRIDE * 2 + lane];
+                }
+            }
+        }
+        __syncwarp();
     }
     if (live) st[my_s].preemph_mem[my_c] = mem;
 }

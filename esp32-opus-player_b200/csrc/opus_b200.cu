@@ -15,7 +15,7 @@
 using namespace opusb200;
 
 static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
-static_assert(sizeof(BandOp) == 12, "BandOp layout");
+static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
 enum { kStages = 6, kMaxChunks = 4 };
 static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph"};
@@ -100,7 +100,6 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     for (int i = 0; i < kMaxChunks; i++) CU_TRY(c, cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
     CU_TRY(c, cudaEventCreateWithFlags(&c->bytes_ready, cudaEventDisableTiming));
     for (int i = 0; i <= kStages; i++) CU_TRY(c, cudaEventCreate(&c->ev[i]));
-    CU_TRY(c, cudaFuncSetAttribute(k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxLeaf * K1_THREADS * 2));
     *out = c;
     return dm_reset(c, nullptr, 0);
 }
@@ -163,7 +162,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     const int nfr = n_sel * in->n_frames;
     const int wb = 32 * KW_WARPS;
     if (timed) cudaEventRecord(c->ev[0], s);
-    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, kMaxLeaf * K1_THREADS * 2, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_X);
+    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops);
     if (timed) cudaEventRecord(c->ev[1], s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[2], s);

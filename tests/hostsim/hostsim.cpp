@@ -11,12 +11,12 @@ extern "C" {
 
 int hs_celt_parse(const uint8_t* pkt, int len, int C, int LM, int start, int disable_inv, CeltFrameHdr* hdr, BandOp* ops,
                   int16_t* X) {
-    static int16_t leaf[kMaxLeaf];
+    (void)X;
     ParseCtx p;
     memset(&p, 0, sizeof(p));
     rd_init(p.rd, pkt, (u32)len);
     p.C = C; p.LM = LM; p.start = start; p.end = kNbEBands; p.disable_inv = disable_inv;
-    p.ops = ops; p.ops_cap = kMaxOps; p.Xg = X; p.leaf.p = leaf; p.leaf.stride = 1;
+    p.ops = ops; p.ops_cap = kMaxOps;
     return celt_parse_frame(p, *hdr);
 }
 int hs_sizeof_hdr() { return (int)sizeof(CeltFrameHdr); }
@@ -60,7 +60,7 @@ int hs_celt_decode(void* dv, const uint8_t* pkt, int len, int C, int frame_size,
     Lanes L;
     FrameEnergy fe;
     for (int i = 0; i < kNbEBands; i++) energy_step(st.band[i], i, hdr, fe);
-    memcpy(W + W_XY, Xg, sizeof(int16_t) * C * N);
+    leaf_stage(L, W, ops + kMaxOps - 1, hdr.n_leaves, hdr.spread);
     u32 seed = band_stage_ops(L, W, ops, hdr.n_ops, st.rng);
     if (hdr.flags & FF_ANTICOLLAPSE) band_stage_anti_collapse(L, W, hdr, fe, seed);
     const int transient = (hdr.flags & FF_TRANSIENT) != 0, silence = (hdr.flags & FF_SILENCE) != 0;

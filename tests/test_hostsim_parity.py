@@ -29,7 +29,7 @@ def test_parse_final_range_matches(hostsim, ref):
     rng = np.random.default_rng(11)
     ref.CeltLayer(2, 2)
     hdr = np.zeros(512, np.uint8)
-    ops = np.zeros(1360 * 12, np.uint8)
+    ops = np.zeros(1360 * 16, np.uint8)
     X = np.zeros(1920, np.int16)
     pcm = np.zeros(1920, np.int16)
     R = ref.lib()
