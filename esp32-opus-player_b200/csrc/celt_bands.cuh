@@ -226,8 +226,12 @@ OPUS_HD void leaf_stage(const Lanes& L, int16_t* W, const BandOp* last, int n_le
 // Replays the script of one frame.  `seed` = noise seed at frame start (= previous frame's final range).
 // Returns the seed after all fills (input of anti_collapse, ref src/celt.cpp:2371).
 OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_ops, u32 seed) {
+    // ops are fetched kLanes at a time (one 16-byte load per lane) and broadcast, so the replay loop
+    // never waits on a dependent global load per op
+    BandOp mine = BandOp();
     for (int k = 0; k < n_ops; k++) {
-        const BandOp o = ops[k];
+        if ((k % kLanes) == 0 && k + L.lane < n_ops) mine = ops[k + L.lane];
+        const BandOp o = L.bcast_op(mine, k % kLanes);
         int16_t* X = W + o.off;
         const int n = o.n;
         switch (o.code) {

@@ -227,74 +227,100 @@ OPUS_HD u32 band_n1(ParseCtx& p, int xoff, int yoff, int out) {
 }
 
 // ref quant_partition (src/celt.cpp:1382). Offsets index the W workspace; lowband < 0 means NULL.
-#if defined(__CUDACC__)
-__device__
-#endif
-inline u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, s16 gain, int fill) {
+// The reference recurses (a band splits into up to 16 leaves); here the tree is walked with an explicit
+// stack so that all lanes of a warp run the same loop whatever their depth -- recursion would leave
+// every lane in its own call frame and the warp would never reconverge.
+struct PartNode { int xoff, N, b, B, lowband, LM, fill; s16 gain; };
+struct PartFrame {
+    PartNode second;     // the child decoded second (its b is adjusted by the rebalance)
+    int first_bits, rebalance, itheta, shift;
+    u32 cm;
+    uint8_t first_is_mid, phase;
+};
+
+OPUS_HD u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, s16 gain, int fill) {
     const int i = p.band;
-    const uint8_t* cache = pulse_cache(i, LM);
-    u32 cm = 0;
-    const int B0 = B;
-    if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
-        ThetaOut t;
-        N >>= 1;
-        const int yoff = xoff + N;
-        LM -= 1;
-        if (B == 1) fill = (fill & 1) | (fill << 1);
-        B = (B + 1) >> 1;
-        decode_theta(p, t, N, &b, B, B0, LM, 0, &fill);
-        s16 mid = (s16)t.imid, side = (s16)t.iside;
-        int delta = t.delta;
-        const int itheta = t.itheta;
-        if (B0 > 1 && (itheta & 0x3fff)) {
-            if (itheta > 8192) delta -= delta >> (4 - LM);
-            else delta = imin(0, delta + (N << 3 >> (5 - LM)));
-        }
-        int mbits = imax(0, imin(b, (b - delta) / 2));
-        int sbits = b - mbits;
-        p.remaining_bits -= t.qalloc;
-        const int lowband2 = lowband >= 0 ? lowband + N : -1;
-        int rebalance = p.remaining_bits;
-        if (mbits >= sbits) {
-            cm = partition(p, xoff, N, mbits, B, lowband, LM, (s16)mul16_p15(gain, mid), fill);
-            rebalance = mbits - (rebalance - p.remaining_bits);
-            if (rebalance > 3 << 3 && itheta != 0) sbits += rebalance - (3 << 3);
-            cm |= partition(p, yoff, N, sbits, B, lowband2, LM, (s16)mul16_p15(gain, side), fill >> B) << (B0 >> 1);
-        } else {
-            cm = partition(p, yoff, N, sbits, B, lowband2, LM, (s16)mul16_p15(gain, side), fill >> B) << (B0 >> 1);
-            rebalance = sbits - (rebalance - p.remaining_bits);
-            if (rebalance > 3 << 3 && itheta != 16384) mbits += rebalance - (3 << 3);
-            cm |= partition(p, xoff, N, mbits, B, lowband, LM, (s16)mul16_p15(gain, mid), fill);
-        }
-    } else {
-        int q = bits2pulses(i, LM, b);
-        int curr_bits = pulses2bits(i, LM, q);
-        p.remaining_bits -= curr_bits;
-        while (p.remaining_bits < 0 && q > 0) {
-            p.remaining_bits += curr_bits;
-            q--;
-            curr_bits = pulses2bits(i, LM, q);
-            p.remaining_bits -= curr_bits;
-        }
-        if (q != 0) {
-            cm = leaf_unquant(p, xoff, N, get_pulses(q), B, gain);
-        } else {
-            u32 cm_mask = (u32)(1UL << B) - 1;
-            fill &= (int)cm_mask;
-            if (!fill) {
-                emit_op(p, OP_ZERO, 0, xoff, 0, N, 0, 0);
-            } else if (lowband < 0) {
-                emit_op(p, OP_NOISE, 0, xoff, 0, N, gain, 0);
-                p.lcg_steps += (u32)N;
-                cm = cm_mask;
+    PartFrame st[5];
+    int sp = 0;
+    PartNode cur;
+    cur.xoff = xoff; cur.N = N; cur.b = b; cur.B = B; cur.lowband = lowband; cur.LM = LM; cur.fill = fill; cur.gain = gain;
+    u32 ret = 0;
+    bool descend = true;
+    for (;;) {
+        if (descend) {
+            const uint8_t* cache = pulse_cache(i, cur.LM);
+            if (cur.LM != -1 && cur.b > cache[cache[0]] + 12 && cur.N > 2) {
+                ThetaOut t;
+                const int B0 = cur.B;
+                int Nh = cur.N >> 1, LMh = cur.LM - 1, bb = cur.b, fl = cur.fill;
+                if (cur.B == 1) fl = (fl & 1) | (fl << 1);
+                const int Bh = (cur.B + 1) >> 1;
+                decode_theta(p, t, Nh, &bb, Bh, B0, LMh, 0, &fl);
+                int delta = t.delta;
+                const int itheta = t.itheta;
+                if (B0 > 1 && (itheta & 0x3fff)) {
+                    if (itheta > 8192) delta -= delta >> (4 - LMh);
+                    else delta = imin(0, delta + (Nh << 3 >> (5 - LMh)));
+                }
+                const int mbits = imax(0, imin(bb, (bb - delta) / 2));
+                const int sbits = bb - mbits;
+                p.remaining_bits -= t.qalloc;
+                PartNode mid, side;
+                mid.xoff = cur.xoff; mid.N = Nh; mid.b = mbits; mid.B = Bh; mid.lowband = cur.lowband; mid.LM = LMh; mid.fill = fl;
+                mid.gain = (s16)mul16_p15(cur.gain, (s16)t.imid);
+                side.xoff = cur.xoff + Nh; side.N = Nh; side.b = sbits; side.B = Bh; side.lowband = cur.lowband >= 0 ? cur.lowband + Nh : -1;
+                side.LM = LMh; side.fill = fl >> Bh;
+                side.gain = (s16)mul16_p15(cur.gain, (s16)t.iside);
+                PartFrame& f = st[sp++];
+                f.rebalance = p.remaining_bits; f.itheta = itheta; f.shift = B0 >> 1; f.cm = 0; f.phase = 0;
+                if (mbits >= sbits) { f.first_is_mid = 1; f.first_bits = mbits; f.second = side; cur = mid; }
+                else { f.first_is_mid = 0; f.first_bits = sbits; f.second = mid; cur = side; }
             } else {
-                emit_op(p, OP_FOLD, 0, xoff, lowband, N, gain, 0);
-                p.lcg_steps += (u32)N;
-                cm = (u32)fill;
+                int q = bits2pulses(i, cur.LM, cur.b);
+                int curr_bits = pulses2bits(i, cur.LM, q);
+                p.remaining_bits -= curr_bits;
+                while (p.remaining_bits < 0 && q > 0) {
+                    p.remaining_bits += curr_bits;
+                    q--;
+                    curr_bits = pulses2bits(i, cur.LM, q);
+                    p.remaining_bits -= curr_bits;
+                }
+                ret = 0;
+                if (q != 0) {
+                    ret = leaf_unquant(p, cur.xoff, cur.N, get_pulses(q), cur.B, cur.gain);
+                } else {
+                    const u32 cm_mask = (u32)(1UL << cur.B) - 1;
+                    const int fl = cur.fill & (int)cm_mask;
+                    if (!fl) {
+                        emit_op(p, OP_ZERO, 0, cur.xoff, 0, cur.N, 0, 0);
+                    } else if (cur.lowband < 0) {
+                        emit_op(p, OP_NOISE, 0, cur.xoff, 0, cur.N, cur.gain, 0);
+                        p.lcg_steps += (u32)cur.N;
+                        ret = cm_mask;
+                    } else {
+                        emit_op(p, OP_FOLD, 0, cur.xoff, cur.lowband, cur.N, cur.gain, 0);
+                        p.lcg_steps += (u32)cur.N;
+                        ret = (u32)fl;
+                    }
+                }
+                descend = false;
+            }
+        } else {
+            if (sp == 0) return ret;
+            PartFrame& f = st[sp - 1];
+            if (f.phase == 0) {
+                f.cm = f.first_is_mid ? ret : ret << f.shift;
+                const int rebalance = f.first_bits - (f.rebalance - p.remaining_bits);
+                if (rebalance > 3 << 3 && f.itheta != (f.first_is_mid ? 0 : 16384)) f.second.b += rebalance - (3 << 3);
+                f.phase = 1;
+                cur = f.second;
+                descend = true;
+            } else {
+                ret = f.cm | (f.first_is_mid ? ret << f.shift : ret);
+                sp--;
             }
         }
     }
-    return cm;
 }
 
 // ref quant_band (src/celt.cpp:1526)
@@ -353,50 +379,12 @@ OPUS_HD u32 band_mono(ParseCtx& p, int xoff, int N, int b, int B, int lowband, i
     return cm;
 }
 
-// ref quant_band_stereo (src/celt.cpp:1628)
-OPUS_HD u32 band_stereo(ParseCtx& p, int xoff, int yoff, int N, int b, int B, int lowband, int LM, int lowband_out,
-                        int scratch, int fill) {
-    if (N == 1) return band_n1(p, xoff, yoff, lowband_out);
-    const int orig_fill = fill;
-    ThetaOut t;
-    decode_theta(p, t, N, &b, B, B, LM, 1, &fill);
-    const s16 mid = (s16)t.imid, side = (s16)t.iside;
-    const int itheta = t.itheta;
-    u32 cm;
-    if (N == 2) {
-        int mbits = b, sbits = 0;
-        if (itheta != 0 && itheta != 16384) sbits = 1 << 3;
-        mbits -= sbits;
-        const int c = itheta > 8192;
-        p.remaining_bits -= t.qalloc + sbits;
-        const int x2 = c ? yoff : xoff, y2 = c ? xoff : yoff;
-        int sign = 0;
-        if (sbits) sign = (int)rd_bits(p.rd, 1);
-        cm = band_mono(p, x2, N, mbits, B, lowband, LM, lowband_out, 32767, scratch, orig_fill);
-        emit_op(p, OP_N2, sign | (c << 1), x2, y2, 2, mid, side);
-    } else {
-        int mbits = imax(0, imin(b, (b - t.delta) / 2));
-        int sbits = b - mbits;
-        p.remaining_bits -= t.qalloc;
-        int rebalance = p.remaining_bits;
-        if (mbits >= sbits) {
-            cm = band_mono(p, xoff, N, mbits, B, lowband, LM, lowband_out, 32767, scratch, fill);
-            rebalance = mbits - (rebalance - p.remaining_bits);
-            if (rebalance > 3 << 3 && itheta != 0) sbits += rebalance - (3 << 3);
-            cm |= band_mono(p, yoff, N, sbits, B, -1, LM, -1, side, -1, fill >> B);
-        } else {
-            cm = band_mono(p, yoff, N, sbits, B, -1, LM, -1, side, -1, fill >> B);
-            rebalance = sbits - (rebalance - p.remaining_bits);
-            if (rebalance > 3 << 3 && itheta != 16384) mbits += rebalance - (3 << 3);
-            cm |= band_mono(p, xoff, N, mbits, B, lowband, LM, lowband_out, 32767, scratch, fill);
-        }
-        emit_op(p, OP_MERGE, 0, xoff, yoff, N, mid, 0);
-    }
-    if (t.inv) emit_op(p, OP_NEG, 0, yoff, 0, N, 0, 0);
-    return cm;
-}
+// ref quant_all_bands (src/celt.cpp:1754) with quant_band_stereo (:1628) folded in.
+// Every band is turned into at most two "mono jobs" (mid/side in either order, or the two channels of a
+// dual-stereo band) that go through ONE call site of band_mono: which job runs first is data, not
+// control flow, so the lanes of a warp keep executing the same code whatever their stereo decisions.
+struct BandJob { int xoff, b, lowband, out, scratch, fill; s16 gain; };
 
-// ref quant_all_bands (src/celt.cpp:1754)
 OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int shortBlocks, int dual_stereo, int intensity,
                        const int* tf_res, int total_bits, int balance, int codedBands) {
     const int LM = p.LM, C = p.C, start = p.start, end = p.end;
@@ -435,7 +423,7 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
         }
         const int tf_change = tf_res[i];
         p.tf_change = tf_change;
-        int scratch = last ? -1 : W_SCRATCH;
+        const int scratch = last ? -1 : W_SCRATCH;
         int effective_lowband = -1;
         u32 x_cm, y_cm;
         if (lowband_offset != 0 && (p.spread != 3 || B > 1 || tf_change < 0)) {
@@ -462,13 +450,77 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
         const int lb2 = effective_lowband != -1 ? W_NORM2 + effective_lowband : -1;
         const int out = last ? -1 : W_NORM + M * kEBands[i] - norm_offset;
         const int out2 = last ? -1 : W_NORM2 + M * kEBands[i] - norm_offset;
+
+        // ---- plan the jobs of this band
+        BandJob job[2];
+        int njobs = 0;
+        // mode: 0 = independent jobs (mono / dual stereo), 1 = mid/side with rebalance, 2 = N=2 stereo
+        int mode = 0, first_is_mid = 1, itheta = 0, inv = 0, first_bits = 0, rebalance0 = 0, n2_arg = 0, n2_x2 = 0, n2_y2 = 0;
+        s16 mid = 0, side = 0;
+        u32 cm_direct = 0;
         if (dual_stereo) {
-            x_cm = band_mono(p, xoff, Nb, b / 2, B, lb, LM, out, 32767, scratch, (int)x_cm);
-            y_cm = band_mono(p, yoff, Nb, b / 2, B, lb2, LM, out2, 32767, scratch, (int)y_cm);
+            job[0] = BandJob{xoff, b / 2, lb, out, scratch, (int)x_cm, 32767};
+            job[1] = BandJob{yoff, b / 2, lb2, out2, scratch, (int)y_cm, 32767};
+            njobs = 2;
+        } else if (yoff < 0) {
+            job[0] = BandJob{xoff, b, lb, out, scratch, (int)(x_cm | y_cm), 32767};
+            njobs = 1;
+        } else if (Nb == 1) {
+            cm_direct = band_n1(p, xoff, yoff, out);
+        } else {  // quant_band_stereo
+            int fill = (int)(x_cm | y_cm);
+            const int orig_fill = fill;
+            ThetaOut t;
+            int bb = b;
+            decode_theta(p, t, Nb, &bb, B, B, LM, 1, &fill);
+            mid = (s16)t.imid; side = (s16)t.iside; itheta = t.itheta; inv = t.inv;
+            if (Nb == 2) {
+                mode = 2;
+                int mbits = bb, sbits = 0;
+                if (itheta != 0 && itheta != 16384) sbits = 1 << 3;
+                mbits -= sbits;
+                const int c = itheta > 8192;
+                p.remaining_bits -= t.qalloc + sbits;
+                n2_x2 = c ? yoff : xoff;
+                n2_y2 = c ? xoff : yoff;
+                int sign = 0;
+                if (sbits) sign = (int)rd_bits(p.rd, 1);
+                n2_arg = sign | (c << 1);
+                job[0] = BandJob{n2_x2, mbits, lb, out, scratch, orig_fill, 32767};
+                njobs = 1;
+            } else {
+                mode = 1;
+                const int mbits = imax(0, imin(bb, (bb - t.delta) / 2));
+                const int sbits = bb - mbits;
+                p.remaining_bits -= t.qalloc;
+                rebalance0 = p.remaining_bits;
+                const BandJob jm = BandJob{xoff, mbits, lb, out, scratch, fill, 32767};
+                const BandJob js = BandJob{yoff, sbits, -1, -1, -1, fill >> B, side};
+                first_is_mid = mbits >= sbits;
+                first_bits = first_is_mid ? mbits : sbits;
+                job[0] = first_is_mid ? jm : js;
+                job[1] = first_is_mid ? js : jm;
+                njobs = 2;
+            }
+        }
+        // ---- run them through the single band_mono call site
+        u32 cm_job[2] = {0, 0};
+        for (int j = 0; j < njobs; j++) {
+            const BandJob& J = job[j];
+            cm_job[j] = band_mono(p, J.xoff, Nb, J.b, B, J.lowband, LM, J.out, J.gain, J.scratch, J.fill);
+            if (mode == 1 && j == 0) {
+                const int rebalance = first_bits - (rebalance0 - p.remaining_bits);
+                if (rebalance > 3 << 3 && itheta != (first_is_mid ? 0 : 16384)) job[1].b += rebalance - (3 << 3);
+            }
+        }
+        if (dual_stereo) {
+            x_cm = cm_job[0];
+            y_cm = cm_job[1];
         } else {
-            if (yoff >= 0) x_cm = band_stereo(p, xoff, yoff, Nb, b, B, lb, LM, out, scratch, (int)(x_cm | y_cm));
-            else x_cm = band_mono(p, xoff, Nb, b, B, lb, LM, out, 32767, scratch, (int)(x_cm | y_cm));
-            y_cm = x_cm;
+            if (mode == 2) emit_op(p, OP_N2, n2_arg, n2_x2, n2_y2, 2, mid, side);
+            if (mode == 1) emit_op(p, OP_MERGE, 0, xoff, yoff, Nb, mid, 0);
+            if (mode != 0 && inv) emit_op(p, OP_NEG, 0, yoff, 0, Nb, 0, 0);
+            x_cm = y_cm = cm_job[0] | cm_job[1] | cm_direct;
         }
         cmask[i * C + 0] = (uint8_t)x_cm;
         cmask[i * C + C - 1] = (uint8_t)y_cm;

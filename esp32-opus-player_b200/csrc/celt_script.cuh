@@ -50,7 +50,7 @@ enum BandOpCode : uint8_t {
     OP_LEAF,       // coded PVQ leaf: W[off..+n) = alg_unquant(index=aux, N=n, K=off2, B=a, gain=g) (ref :782)
 };
 
-struct BandOp {  // 16 bytes, one 128-bit access
+struct alignas(16) BandOp {  // 16 bytes, one 128-bit access
     uint8_t code;
     uint8_t a;
     uint16_t off;

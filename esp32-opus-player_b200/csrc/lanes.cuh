@@ -17,6 +17,16 @@ struct Lanes {
     __device__ __forceinline__ s32 sum(s32 v) const { return (s32)__reduce_add_sync(0xffffffffu, (unsigned)v); }
     __device__ __forceinline__ u32 any_or(u32 v) const { return __reduce_or_sync(0xffffffffu, v); }
     __device__ __forceinline__ s32 bcast(s32 v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    template <class T>
+    __device__ __forceinline__ T bcast_op(const T& v, int src) const {  // 16-byte POD broadcast
+        static_assert(sizeof(T) == 16, "bcast_op: 16-byte records");
+        uint4 u = *reinterpret_cast<const uint4*>(&v);
+        u.x = __shfl_sync(0xffffffffu, u.x, src); u.y = __shfl_sync(0xffffffffu, u.y, src);
+        u.z = __shfl_sync(0xffffffffu, u.z, src); u.w = __shfl_sync(0xffffffffu, u.w, src);
+        T r;
+        *reinterpret_cast<uint4*>(&r) = u;
+        return r;
+    }
 };
 #else
 enum { kLanes = 1 };
@@ -27,6 +37,8 @@ struct Lanes {
     s32 sum(s32 v) const { return v; }
     u32 any_or(u32 v) const { return v; }
     s32 bcast(s32 v, int) const { return v; }
+    template <class T>
+    T bcast_op(const T& v, int) const { return v; }
 };
 #endif
 
