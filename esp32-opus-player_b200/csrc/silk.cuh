@@ -1,0 +1,880 @@
+// silk.cuh -- SILK layer of the decode path, 20 ms frames, 8/12/16 kHz.
+//
+//   silk_parse_frame   entropy half, one thread per (stream, frame): VAD/LBRR flags, stereo predictor,
+//                      side-information indices, shell-coded pulses (ref src/silk.cpp:1565-1636, 708, 898)
+//   silk_synth_frame   synthesis half, serial per stream: gains, NLSF -> LPC, pitch, LTP + LPC synthesis,
+//                      mid/side -> left/right, 2x all-pass + 12-phase FIR resampling to 48 kHz
+//                      (ref src/silk.cpp:827, 1806, 4028, 3676)
+//
+// Parsing needs no decoder state because every packet carries one 20 ms frame, which the reference
+// always codes independently (FrameIndex <= 0, src/silk.cpp:1678-1681).
+// PLC/CNG bookkeeping (src/silk.cpp:1342, 2895) only feeds the loss-concealment code, which the reference
+// never reaches; it is not reproduced.
+#pragma once
+#include "celt_script.cuh"
+#include "rangedec.cuh"
+#include "silk_tables.cuh"
+
+namespace opusb200 {
+
+// ---- fixed-point helpers with the reference macro each one reproduces (src/silk.h:52-156, 446-486) ----
+OPUS_HD s32 smulbb(s32 a, s32 b) { return (s32)(s16)a * (s32)(s16)b; }                       // silk_SMULBB
+OPUS_HD s32 smlabb(s32 a, s32 b, s32 c) { return (s32)((u32)a + (u32)smulbb(b, c)); }          // silk_SMLABB (/_ovflw)
+OPUS_HD s32 smulwb(s32 a, s32 b) { return (s32)(((s64)a * (s64)(s16)b) >> 16); }              // silk_SMULWB
+OPUS_HD s32 smlawb(s32 a, s32 b, s32 c) { return (s32)((s64)a + (((s64)b * (s64)(s16)c) >> 16)); }  // silk_SMLAWB
+OPUS_HD s32 smulww(s32 a, s32 b) { return (s32)(((s64)a * (s64)b) >> 16); }                   // silk_SMULWW
+OPUS_HD s32 smlaww(s32 a, s32 b, s32 c) { return (s32)((s64)a + (((s64)b * (s64)c) >> 16)); } // silk_SMLAWW
+OPUS_HD s32 smmul(s32 a, s32 b) { return (s32)(((s64)a * (s64)b) >> 32); }                    // silk_SMMUL
+OPUS_HD s32 mul_w(s32 a, s32 b) { return (s32)((u32)a * (u32)b); }                            // silk_MUL (two's complement)
+OPUS_HD s32 rshift_round(s32 a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }  // silk_RSHIFT_ROUND
+OPUS_HD s64 rshift_round64(s64 a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
+OPUS_HD s32 limit32(s32 a, s32 lo, s32 hi) {                                                  // silk_LIMIT
+    return lo > hi ? (a > lo ? lo : (a < hi ? hi : a)) : (a > hi ? hi : (a < lo ? lo : a));
+}
+OPUS_HD s32 add_sat32(s32 a, s32 b) {                                                         // silk_ADD_SAT32
+    s64 r = (s64)a + (s64)b;
+    return r > 2147483647LL ? 2147483647 : (r < -2147483648LL ? (s32)(-2147483647 - 1) : (s32)r);
+}
+OPUS_HD s32 sub_sat32(s32 a, s32 b) {                                                         // silk_SUB_SAT32
+    s64 r = (s64)a - (s64)b;
+    return r > 2147483647LL ? 2147483647 : (r < -2147483648LL ? (s32)(-2147483647 - 1) : (s32)r);
+}
+OPUS_HD s32 lshift_sat32(s32 a, int s) {                                                      // silk_LSHIFT_SAT32
+    return shl32(limit32(a, (s32)(-2147483647 - 1) >> s, 2147483647 >> s), s);
+}
+OPUS_HD int clz32(s32 x) { return x ? 32 - ilog32((u32)x) : 32; }                            // silk_CLZ32
+OPUS_HD s32 iabs(s32 a) { return a > 0 ? a : (s32)(0u - (u32)a); }
+
+// ref silk_INVERSE32_varQ / silk_DIV32_varQ (src/silk.h:913-996)
+OPUS_HD s32 inverse32_varq(s32 b32, int Qres) {
+    int b_headrm = clz32(iabs(b32)) - 1;
+    s32 b32_nrm = shl32(b32, b_headrm);
+    s32 b32_inv = (2147483647 >> 2) / (b32_nrm >> 16);
+    s32 result = shl32(b32_inv, 16);
+    s32 err_Q32 = shl32(((s32)1 << 29) - smulwb(b32_nrm, b32_inv), 3);
+    result = smlaww(result, err_Q32, b32_inv);
+    int lshift = 61 - b_headrm - Qres;
+    if (lshift <= 0) return lshift_sat32(result, -lshift);
+    return lshift < 32 ? result >> lshift : 0;
+}
+OPUS_HD s32 div32_varq(s32 a32, s32 b32, int Qres) {
+    int a_headrm = clz32(iabs(a32)) - 1;
+    s32 a32_nrm = shl32(a32, a_headrm);
+    int b_headrm = clz32(iabs(b32)) - 1;
+    s32 b32_nrm = shl32(b32, b_headrm);
+    s32 b32_inv = (2147483647 >> 2) / (b32_nrm >> 16);
+    s32 result = smulwb(a32_nrm, b32_inv);
+    a32_nrm = sub_w(a32_nrm, shl32(smmul(b32_nrm, result), 3));
+    result = smlawb(result, a32_nrm, b32_inv);
+    int lshift = 29 + a_headrm - b_headrm - Qres;
+    if (lshift < 0) return lshift_sat32(result, -lshift);
+    return lshift < 32 ? result >> lshift : 0;
+}
+// ref silk_log2lin (src/silk.cpp:2248)
+OPUS_HD s32 log2lin(s32 inLog_Q7) {
+    if (inLog_Q7 < 0) return 0;
+    if (inLog_Q7 >= 3967) return 2147483647;
+    s32 out = shl32(1, inLog_Q7 >> 7);
+    s32 frac_Q7 = inLog_Q7 & 0x7F;
+    if (inLog_Q7 < 2048) out = out + (mul_w(out, smlawb(frac_Q7, smulbb(frac_Q7, 128 - frac_Q7), -174)) >> 7);
+    else out = out + mul_w(out >> 7, smlawb(frac_Q7, smulbb(frac_Q7, 128 - frac_Q7), -174));
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Script of one SILK frame (entropy -> synthesis hand-off)
+// ------------------------------------------------------------------------------------------------
+enum { kSilkMaxFrame = 320, kSilkMaxOrder = 16 };
+
+struct SilkIdx {  // ref SideInfoIndices_t (src/silk.h)
+    int8_t gains[4];
+    int8_t ltp[4];
+    int8_t nlsf[kSilkMaxOrder + 1];
+    int16_t lagIndex;
+    int8_t contour, signalType, quantOffsetType, interpQ2, perIndex, ltpScaleIndex, seed;
+};
+struct SilkFrame {
+    int32_t ms_pred_Q13[2];
+    uint8_t fs_kHz, nch, mid_only, present;
+    SilkIdx idx[2];
+    int16_t pulses[2][kSilkMaxFrame];
+};
+
+struct SilkCb {  // ref silk_NLSF_CB_struct
+    int order, quantStepSize_Q16;
+    const uint8_t *cb1_Q8, *cb1_icdf, *pred_Q8, *ec_sel, *ec_icdf;
+    const int16_t *cb1_wght_Q9, *deltaMin_Q15;
+};
+OPUS_HD SilkCb silk_cb(int fs_kHz) {
+    SilkCb c;
+    if (fs_kHz == 16) {
+        c.order = 16; c.quantStepSize_Q16 = 9830;
+        c.cb1_Q8 = kNlsfCb1WbQ8; c.cb1_icdf = kNlsfCb1WbIcdf; c.pred_Q8 = kNlsfPredWb; c.ec_sel = kNlsfSelWb; c.ec_icdf = kNlsfCb2WbIcdf;
+        c.cb1_wght_Q9 = kNlsfCb1WbWght; c.deltaMin_Q15 = kNlsfDeltaMinWb;
+    } else {
+        c.order = 10; c.quantStepSize_Q16 = 11796;
+        c.cb1_Q8 = kNlsfCb1NbQ8; c.cb1_icdf = kNlsfCb1NbIcdf; c.pred_Q8 = kNlsfPredNb; c.ec_sel = kNlsfSelNb; c.ec_icdf = kNlsfCb2NbIcdf;
+        c.cb1_wght_Q9 = kNlsfCb1NbWght; c.deltaMin_Q15 = kNlsfDeltaMinNb;
+    }
+    return c;
+}
+// ref silk_NLSF_unpack (src/silk.cpp:2762)
+OPUS_HD void nlsf_unpack(int16_t* ec_ix, uint8_t* pred_Q8, const SilkCb& cb, int CB1_index) {
+    const uint8_t* sel = cb.ec_sel + CB1_index * cb.order / 2;
+    for (int i = 0; i < cb.order; i += 2) {
+        uint8_t entry = *sel++;
+        ec_ix[i] = (int16_t)smulbb((entry >> 1) & 7, 9);
+        pred_Q8[i] = cb.pred_Q8[i + (entry & 1) * (cb.order - 1)];
+        ec_ix[i + 1] = (int16_t)smulbb((entry >> 5) & 7, 9);
+        pred_Q8[i + 1] = cb.pred_Q8[i + ((entry >> 4) & 1) * (cb.order - 1) + 1];
+    }
+}
+
+// ---- entropy half ----
+// ref silk_decode_indices (src/silk.cpp:708) with condCoding == CODE_INDEPENDENTLY
+OPUS_HD void silk_parse_indices(RangeDec& rd, SilkIdx& ix, int fs_kHz, int vad_or_lbrr) {
+    const uint8_t uni4[4] = {192, 128, 64, 0}, uni6[6] = {213, 171, 128, 85, 43, 0}, uni8[8] = {224, 192, 160, 128, 96, 64, 32, 0};
+    int Ix;
+    if (vad_or_lbrr) {
+        const uint8_t t[4] = {232, 158, 10, 0};
+        Ix = rd_icdf(rd, t, 8) + 2;
+    } else {
+        const uint8_t t[2] = {230, 0};
+        Ix = rd_icdf(rd, t, 8);
+    }
+    ix.signalType = (int8_t)(Ix >> 1);
+    ix.quantOffsetType = (int8_t)(Ix & 1);
+    ix.gains[0] = (int8_t)(rd_icdf(rd, kGainIcdf + ix.signalType * 8, 8) << 3);
+    ix.gains[0] += (int8_t)rd_icdf(rd, uni8, 8);
+    for (int i = 1; i < 4; i++) ix.gains[i] = (int8_t)rd_icdf(rd, kDeltaGainIcdf, 8);
+    const SilkCb cb = silk_cb(fs_kHz);
+    ix.nlsf[0] = (int8_t)rd_icdf(rd, cb.cb1_icdf + (ix.signalType >> 1) * 32, 8);
+    int16_t ec_ix[kSilkMaxOrder];
+    uint8_t pred_Q8[kSilkMaxOrder];
+    nlsf_unpack(ec_ix, pred_Q8, cb, ix.nlsf[0]);
+    const uint8_t ext[7] = {100, 40, 16, 7, 3, 1, 0};
+    for (int i = 0; i < cb.order; i++) {
+        Ix = rd_icdf(rd, cb.ec_icdf + ec_ix[i], 8);
+        if (Ix == 0) Ix -= rd_icdf(rd, ext, 8);
+        else if (Ix == 8) Ix += rd_icdf(rd, ext, 8);
+        ix.nlsf[i + 1] = (int8_t)(Ix - 4);
+    }
+    {
+        const uint8_t t[5] = {243, 221, 192, 181, 0};
+        ix.interpQ2 = (int8_t)rd_icdf(rd, t, 8);
+    }
+    ix.lagIndex = 0; ix.contour = 0; ix.perIndex = 0; ix.ltpScaleIndex = 0;
+    for (int k = 0; k < 4; k++) ix.ltp[k] = 0;
+    if (ix.signalType == 2) {
+        ix.lagIndex = (int16_t)((int16_t)rd_icdf(rd, kPitchLagIcdf, 8) * (fs_kHz >> 1));
+        ix.lagIndex += (int16_t)rd_icdf(rd, fs_kHz == 16 ? uni8 : fs_kHz == 12 ? uni6 : uni4, 8);
+        ix.contour = (int8_t)rd_icdf(rd, fs_kHz == 8 ? kPitchContourNbIcdf : kPitchContourIcdf, 8);
+        const uint8_t per[3] = {179, 99, 0};
+        ix.perIndex = (int8_t)rd_icdf(rd, per, 8);
+        const uint8_t* g = ix.perIndex == 0 ? kLtpGainIcdf0 : ix.perIndex == 1 ? kLtpGainIcdf1 : kLtpGainIcdf2;
+        for (int k = 0; k < 4; k++) ix.ltp[k] = (int8_t)rd_icdf(rd, g, 8);
+        const uint8_t sc[3] = {128, 64, 0};
+        ix.ltpScaleIndex = (int8_t)rd_icdf(rd, sc, 8);
+    }
+    ix.seed = (int8_t)rd_icdf(rd, uni4, 8);
+}
+
+// ref silk_shell_decoder / decode_split (src/silk.cpp:1146, 1162)
+OPUS_HD void shell_split(RangeDec& rd, int16_t* c1, int16_t* c2, int p, const uint8_t* table) {
+    if (p > 0) {
+        *c1 = (int16_t)rd_icdf(rd, table + kShellOffsets[p], 8);
+        *c2 = (int16_t)(p - *c1);
+    } else {
+        *c1 = 0;
+        *c2 = 0;
+    }
+}
+OPUS_HD void shell_decode(RangeDec& rd, int16_t* p0, int pulses4) {
+    int16_t p3[2], p2[4], p1[8];
+    shell_split(rd, &p3[0], &p3[1], pulses4, kShell3);
+    for (int a = 0; a < 2; a++) {
+        shell_split(rd, &p2[2 * a], &p2[2 * a + 1], p3[a], kShell2);
+        for (int b = 0; b < 2; b++) {
+            shell_split(rd, &p1[4 * a + 2 * b], &p1[4 * a + 2 * b + 1], p2[2 * a + b], kShell1);
+            for (int c = 0; c < 2; c++)
+                shell_split(rd, &p0[8 * a + 4 * b + 2 * c], &p0[8 * a + 4 * b + 2 * c + 1], p1[4 * a + 2 * b + c], kShell0);
+        }
+    }
+}
+
+// ref silk_decode_pulses + silk_decode_signs (src/silk.cpp:898, 1436)
+OPUS_HD void silk_parse_pulses(RangeDec& rd, int16_t* pulses, int signalType, int quantOffsetType, int frame_length) {
+    int sum_pulses[20], nLshifts[20];
+    const int rate = rd_icdf(rd, kRateLevelsIcdf + (signalType >> 1) * 9, 8);
+    int iter = frame_length >> 4;
+    if (iter * 16 < frame_length) iter++;
+    const uint8_t* cdf = kPulsesPerBlockIcdf + rate * 18;
+    for (int i = 0; i < iter; i++) {
+        nLshifts[i] = 0;
+        sum_pulses[i] = rd_icdf(rd, cdf, 8);
+        while (sum_pulses[i] == 17) {
+            nLshifts[i]++;
+            sum_pulses[i] = rd_icdf(rd, kPulsesPerBlockIcdf + 9 * 18 + (nLshifts[i] == 10), 8);
+        }
+    }
+    for (int i = 0; i < iter; i++) {
+        if (sum_pulses[i] > 0) shell_decode(rd, pulses + 16 * i, sum_pulses[i]);
+        else for (int k = 0; k < 16; k++) pulses[16 * i + k] = 0;
+    }
+    const uint8_t lsb[2] = {120, 0};
+    for (int i = 0; i < iter; i++) {
+        if (nLshifts[i] > 0) {
+            const int nLS = nLshifts[i];
+            int16_t* pp = pulses + 16 * i;
+            for (int k = 0; k < 16; k++) {
+                s32 abs_q = pp[k];
+                for (int j = 0; j < nLS; j++) {
+                    abs_q = shl32(abs_q, 1);
+                    abs_q += rd_icdf(rd, lsb, 8);
+                }
+                pp[k] = (int16_t)abs_q;
+            }
+            sum_pulses[i] |= nLS << 5;
+        }
+    }
+    uint8_t icdf[2];
+    icdf[1] = 0;
+    const uint8_t* icdf_ptr = kSignIcdf + smulbb(7, quantOffsetType + (signalType << 1));
+    const int nblk = (frame_length + 8) >> 4;
+    for (int i = 0; i < nblk; i++) {
+        const int p = sum_pulses[i];
+        if (p > 0) {
+            icdf[0] = icdf_ptr[imin(p & 0x1F, 6)];
+            for (int j = 0; j < 16; j++)
+                if (pulses[16 * i + j] > 0) pulses[16 * i + j] = (int16_t)(pulses[16 * i + j] * ((rd_icdf(rd, icdf, 8) << 1) - 1));
+        }
+    }
+}
+
+// ref silk_stereo_decode_pred (src/silk.cpp:592)
+OPUS_HD void silk_parse_stereo_pred(RangeDec& rd, int32_t* pred_Q13) {
+    const uint8_t uni3[3] = {171, 85, 0}, uni5[5] = {205, 154, 102, 51, 0};
+    int ix[2][3];
+    int n = rd_icdf(rd, kStereoJointIcdf, 8);
+    ix[0][2] = n / 5;
+    ix[1][2] = n - 5 * ix[0][2];
+    for (n = 0; n < 2; n++) {
+        ix[n][0] = rd_icdf(rd, uni3, 8);
+        ix[n][1] = rd_icdf(rd, uni5, 8);
+    }
+    for (n = 0; n < 2; n++) {
+        ix[n][0] += 3 * ix[n][2];
+        s32 low_Q13 = kStereoPredQ13[ix[n][0]];
+        s32 step_Q13 = smulwb(kStereoPredQ13[ix[n][0] + 1] - low_Q13, 6554);
+        pred_Q13[n] = smlabb(low_Q13, step_Q13, 2 * ix[n][1] + 1);
+    }
+    pred_Q13[0] -= pred_Q13[1];
+}
+
+// The SILK part of one Opus frame as silk_Decode reads it (ref src/silk.cpp:1565-1697, lostFlag = 0, one
+// 20 ms frame per packet).  `scratch` receives the discarded LBRR pulses.
+OPUS_HD void silk_parse_frame(RangeDec& rd, SilkFrame& f, int fs_kHz, int nch) {
+    const int frame_length = 20 * fs_kHz;
+    int vad[2] = {0, 0}, lbrr[2] = {0, 0};
+    f.fs_kHz = (uint8_t)fs_kHz; f.nch = (uint8_t)nch; f.mid_only = 0; f.present = 1;
+    f.ms_pred_Q13[0] = f.ms_pred_Q13[1] = 0;
+    for (int n = 0; n < nch; n++) {
+        vad[n] = rd_bit_logp(rd, 1);
+        lbrr[n] = rd_bit_logp(rd, 1);
+    }
+    // regular decoding skips the LBRR (FEC) copy of the previous frame by parsing it (ref :1590-1616)
+    for (int n = 0; n < nch; n++) {
+        if (lbrr[n]) {
+            if (nch == 2 && n == 0) {
+                int32_t tmp[2];
+                silk_parse_stereo_pred(rd, tmp);
+                if (lbrr[1] == 0) {
+                    const uint8_t t[2] = {64, 0};
+                    rd_icdf(rd, t, 8);
+                }
+            }
+            silk_parse_indices(rd, f.idx[n], fs_kHz, 1);
+            silk_parse_pulses(rd, f.pulses[n], f.idx[n].signalType, f.idx[n].quantOffsetType, frame_length);
+        }
+    }
+    int mid_only = 0;
+    if (nch == 2) {
+        silk_parse_stereo_pred(rd, f.ms_pred_Q13);
+        if (vad[1] == 0) {
+            const uint8_t t[2] = {64, 0};
+            mid_only = rd_icdf(rd, t, 8);
+        }
+    }
+    f.mid_only = (uint8_t)mid_only;
+    for (int n = 0; n < nch; n++) {
+        if (n == 0 || !mid_only) {
+            silk_parse_indices(rd, f.idx[n], fs_kHz, vad[n]);
+            silk_parse_pulses(rd, f.pulses[n], f.idx[n].signalType, f.idx[n].quantOffsetType, frame_length);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthesis half
+// ------------------------------------------------------------------------------------------------
+struct SilkResampler {  // ref silk_resampler_state_struct_t (src/silk.h:654-670), up-sampling to 48 kHz only
+    int32_t sIIR[6];
+    int16_t sFIR[8];
+    int16_t delayBuf[48];
+    int32_t inputDelay, invRatio_Q16, batchSize, Fs_in_kHz;
+};
+struct SilkChannel {    // ref silk_decoder_state_t (src/silk.h:705-741), live fields only
+    int32_t prev_gain_Q16;
+    int32_t sLPC_Q14_buf[kSilkMaxOrder];
+    int16_t outBuf[480];
+    int32_t lagPrev;
+    int32_t fs_kHz, fs_API_hz, frame_length, subfr_length, ltp_mem_length, LPC_order;
+    int16_t prevNLSF_Q15[kSilkMaxOrder];
+    int8_t LastGainIndex, prevSignalType, first_frame_after_reset, pad;
+    SilkResampler rs;
+};
+struct SilkStreamState {
+    SilkChannel ch[2];
+    int16_t pred_prev_Q13[2], sMid[2], sSide[2];  // ref stereo_dec_state (src/silk.h:672-676)
+    int32_t prev_decode_only_middle;
+    int32_t nChannelsInternal;                    // ref silk_decoder_t
+    int32_t prev_mode;                            // Opus layer: 0 none, 1000 SILK, 1001 hybrid, 1002 CELT
+};
+struct SilkScratch {  // per-stream working set of one frame
+    int16_t sLTP[kSilkMaxFrame];
+    int32_t sLTP_Q15[2 * kSilkMaxFrame];
+    int32_t exc_Q14[kSilkMaxFrame];
+    int32_t sLPC_Q14[80 + kSilkMaxOrder];
+    int32_t res_Q14[80];
+    int16_t tmp[2][kSilkMaxFrame + 2];  // samplesOut1_tmp
+    int16_t rbuf[2 * 160 + 8];          // resampler batch buffer
+};
+
+// ref silk_init_decoder (src/silk.cpp:2192)
+OPUS_HD void silk_channel_init(SilkChannel& c) {
+    c.prev_gain_Q16 = 65536;
+    for (int i = 0; i < kSilkMaxOrder; i++) { c.sLPC_Q14_buf[i] = 0; c.prevNLSF_Q15[i] = 0; }
+    for (int i = 0; i < 480; i++) c.outBuf[i] = 0;
+    c.lagPrev = 0; c.fs_kHz = 0; c.fs_API_hz = 0; c.frame_length = 0; c.subfr_length = 0; c.ltp_mem_length = 0; c.LPC_order = 0;
+    c.LastGainIndex = 0; c.prevSignalType = 0; c.first_frame_after_reset = 1; c.pad = 0;
+    for (int i = 0; i < 6; i++) c.rs.sIIR[i] = 0;
+    for (int i = 0; i < 8; i++) c.rs.sFIR[i] = 0;
+    for (int i = 0; i < 48; i++) c.rs.delayBuf[i] = 0;
+    c.rs.inputDelay = 0; c.rs.invRatio_Q16 = 0; c.rs.batchSize = 0; c.rs.Fs_in_kHz = 0;
+}
+// ref silk_InitDecoder (src/silk.cpp:1792); the resampler singletons are not touched by it
+OPUS_HD void silk_stream_reinit(SilkStreamState& s) {
+    for (int n = 0; n < 2; n++) {
+        SilkResampler keep = s.ch[n].rs;
+        silk_channel_init(s.ch[n]);
+        s.ch[n].rs = keep;
+    }
+    for (int i = 0; i < 2; i++) { s.pred_prev_Q13[i] = 0; s.sMid[i] = 0; s.sSide[i] = 0; }
+    s.prev_decode_only_middle = 0;
+}
+
+// ref silk_resampler_init (src/silk.cpp:3590), decoder side, output 48 kHz
+OPUS_HD void silk_resampler_setup(SilkResampler& r, int fs_kHz) {
+    for (int i = 0; i < 6; i++) r.sIIR[i] = 0;
+    for (int i = 0; i < 8; i++) r.sFIR[i] = 0;
+    for (int i = 0; i < 48; i++) r.delayBuf[i] = 0;
+    r.inputDelay = fs_kHz == 8 ? 0 : fs_kHz == 12 ? 4 : 7;
+    r.Fs_in_kHz = fs_kHz;
+    r.batchSize = fs_kHz * 10;
+    const s32 Fs_in = fs_kHz * 1000, Fs_out = 48000;
+    r.invRatio_Q16 = shl32(shl32(Fs_in, 14 + 1) / Fs_out, 2);
+    while (smulww(r.invRatio_Q16, Fs_out) < shl32(Fs_in, 1)) r.invRatio_Q16++;
+}
+// ref silk_decoder_set_fs (src/silk.cpp:978), nb_subfr = 4
+OPUS_HD void silk_set_fs(SilkChannel& c, int fs_kHz) {
+    c.subfr_length = 5 * fs_kHz;
+    const int frame_length = 4 * c.subfr_length;
+    if (c.fs_kHz != fs_kHz || c.fs_API_hz != 48000) {
+        silk_resampler_setup(c.rs, fs_kHz);
+        c.fs_API_hz = 48000;
+    }
+    if (c.fs_kHz != fs_kHz || frame_length != c.frame_length) {
+        if (c.fs_kHz != fs_kHz) {
+            c.ltp_mem_length = 20 * fs_kHz;
+            c.LPC_order = fs_kHz == 16 ? 16 : 10;
+            c.first_frame_after_reset = 1;
+            c.lagPrev = 100;
+            c.LastGainIndex = 10;
+            c.prevSignalType = 0;
+            for (int i = 0; i < 480; i++) c.outBuf[i] = 0;
+            for (int i = 0; i < kSilkMaxOrder; i++) c.sLPC_Q14_buf[i] = 0;
+        }
+        c.fs_kHz = fs_kHz;
+        c.frame_length = frame_length;
+    }
+}
+
+// ref silk_gains_dequant (src/silk.cpp:2148), conditional = 0
+OPUS_HD void silk_gains_dequant(s32* gain_Q16, const int8_t* ind, int8_t* prev_ind) {
+    for (int k = 0; k < 4; k++) {
+        if (k == 0) {
+            *prev_ind = (int8_t)imax(ind[k], *prev_ind - 16);
+        } else {
+            int ind_tmp = ind[k] + (-4);
+            int thr = 2 * 36 - 64 + *prev_ind;
+            if (ind_tmp > thr) *prev_ind = (int8_t)(*prev_ind + (shl32(ind_tmp, 1) - thr));
+            else *prev_ind = (int8_t)(*prev_ind + ind_tmp);
+        }
+        *prev_ind = (int8_t)limit32(*prev_ind, 0, 63);
+        gain_Q16[k] = log2lin(imin(smulwb(1907825, *prev_ind) + 2090, 3967));
+    }
+}
+
+// ref silk_NLSF_stabilize (src/silk.cpp:2676)
+OPUS_HD void silk_nlsf_stabilize(int16_t* NLSF_Q15, const int16_t* NDeltaMin_Q15, int L) {
+    int loops;
+    for (loops = 0; loops < 20; loops++) {
+        s32 min_diff = NLSF_Q15[0] - NDeltaMin_Q15[0];
+        int I = 0;
+        for (int i = 1; i <= L - 1; i++) {
+            s32 d = NLSF_Q15[i] - (NLSF_Q15[i - 1] + NDeltaMin_Q15[i]);
+            if (d < min_diff) { min_diff = d; I = i; }
+        }
+        s32 d = (1 << 15) - (NLSF_Q15[L - 1] + NDeltaMin_Q15[L]);
+        if (d < min_diff) { min_diff = d; I = L; }
+        if (min_diff >= 0) return;
+        if (I == 0) NLSF_Q15[0] = NDeltaMin_Q15[0];
+        else if (I == L) NLSF_Q15[L - 1] = (int16_t)((1 << 15) - NDeltaMin_Q15[L]);
+        else {
+            s32 min_center = 0;
+            for (int k = 0; k < I; k++) min_center += NDeltaMin_Q15[k];
+            min_center += NDeltaMin_Q15[I] >> 1;
+            s32 max_center = 1 << 15;
+            for (int k = L; k > I; k--) max_center -= NDeltaMin_Q15[k];
+            max_center -= NDeltaMin_Q15[I] >> 1;
+            int16_t center = (int16_t)limit32(rshift_round((s32)NLSF_Q15[I - 1] + (s32)NLSF_Q15[I], 1), min_center, max_center);
+            NLSF_Q15[I - 1] = (int16_t)(center - (NDeltaMin_Q15[I] >> 1));
+            NLSF_Q15[I] = (int16_t)(NLSF_Q15[I - 1] + NDeltaMin_Q15[I]);
+        }
+    }
+    // fall-back: sort, then enforce the minimum distances from both ends (ref :2741-2758)
+    for (int i = 1; i < L; i++) {
+        int16_t v = NLSF_Q15[i];
+        int j = i - 1;
+        for (; j >= 0 && v < NLSF_Q15[j]; j--) NLSF_Q15[j + 1] = NLSF_Q15[j];
+        NLSF_Q15[j + 1] = v;
+    }
+    NLSF_Q15[0] = (int16_t)imax(NLSF_Q15[0], NDeltaMin_Q15[0]);
+    for (int i = 1; i < L; i++) NLSF_Q15[i] = (int16_t)imax(NLSF_Q15[i], sat16((s32)NLSF_Q15[i - 1] + NDeltaMin_Q15[i]));
+    NLSF_Q15[L - 1] = (int16_t)imin(NLSF_Q15[L - 1], (1 << 15) - NDeltaMin_Q15[L]);
+    for (int i = L - 2; i >= 0; i--) NLSF_Q15[i] = (int16_t)imin(NLSF_Q15[i], NLSF_Q15[i + 1] - NDeltaMin_Q15[i + 1]);
+}
+
+// ref silk_NLSF_decode (src/silk.cpp:2466) with silk_NLSF_residual_dequant (:2445)
+OPUS_HD void silk_nlsf_decode(int16_t* pNLSF_Q15, const int8_t* NLSFIndices, const SilkCb& cb) {
+    uint8_t pred_Q8[kSilkMaxOrder];
+    int16_t ec_ix[kSilkMaxOrder], res_Q10[kSilkMaxOrder];
+    nlsf_unpack(ec_ix, pred_Q8, cb, NLSFIndices[0]);
+    s32 out_Q10 = 0;
+    for (int i = cb.order - 1; i >= 0; i--) {
+        s32 pred_Q10 = smulbb(out_Q10, (int16_t)pred_Q8[i]) >> 8;
+        out_Q10 = shl32(NLSFIndices[1 + i], 10);
+        if (out_Q10 > 0) out_Q10 = out_Q10 - 102;
+        else if (out_Q10 < 0) out_Q10 = out_Q10 + 102;
+        out_Q10 = smlawb(pred_Q10, out_Q10, cb.quantStepSize_Q16);
+        res_Q10[i] = (int16_t)out_Q10;
+    }
+    const uint8_t* el = cb.cb1_Q8 + NLSFIndices[0] * cb.order;
+    const int16_t* wg = cb.cb1_wght_Q9 + NLSFIndices[0] * cb.order;
+    for (int i = 0; i < cb.order; i++) {
+        s32 v = (shl32((s32)res_Q10[i], 14) / wg[i]) + shl32((s32)(int16_t)el[i], 7);
+        pNLSF_Q15[i] = (int16_t)limit32(v, 0, 32767);
+    }
+    silk_nlsf_stabilize(pNLSF_Q15, cb.deltaMin_Q15, cb.order);
+}
+
+// ref silk_bwexpander_32 (src/silk.cpp:561)
+OPUS_HD void silk_bwexpander_32(s32* ar, int d, s32 chirp_Q16) {
+    const s32 chirp_minus_one_Q16 = chirp_Q16 - 65536;
+    for (int i = 0; i < d - 1; i++) {
+        ar[i] = smulww(chirp_Q16, ar[i]);
+        chirp_Q16 += rshift_round(mul_w(chirp_Q16, chirp_minus_one_Q16), 16);
+    }
+    ar[d - 1] = smulww(chirp_Q16, ar[d - 1]);
+}
+// ref silk_LPC_fit (src/silk.cpp:2314) with QOUT = 12, QIN = 17
+OPUS_HD void silk_lpc_fit(int16_t* a_QOUT, s32* a_QIN, int d) {
+    int i, idx = 0;
+    for (i = 0; i < 10; i++) {
+        s32 maxabs = 0;
+        for (int k = 0; k < d; k++) {
+            s32 absval = iabs(a_QIN[k]);
+            if (absval > maxabs) { maxabs = absval; idx = k; }
+        }
+        maxabs = rshift_round(maxabs, 5);
+        if (maxabs > 32767) {
+            maxabs = imin(maxabs, 163838);
+            s32 chirp_Q16 = 65470 - shl32(maxabs - 32767, 14) / (mul_w(maxabs, idx + 1) >> 2);
+            silk_bwexpander_32(a_QIN, d, chirp_Q16);
+        } else {
+            break;
+        }
+    }
+    if (i == 10) {
+        for (int k = 0; k < d; k++) {
+            a_QOUT[k] = sat16(rshift_round(a_QIN[k], 5));
+            a_QIN[k] = shl32((s32)a_QOUT[k], 5);
+        }
+    } else {
+        for (int k = 0; k < d; k++) a_QOUT[k] = (int16_t)rshift_round(a_QIN[k], 5);
+    }
+}
+// ref silk_LPC_inverse_pred_gain_c + LPC_inverse_pred_gain_QA_c (src/silk.cpp:2359, 2425): 0 = unstable
+OPUS_HD s32 silk_lpc_inverse_pred_gain(const int16_t* A_Q12, int order) {
+    s32 A_QA[kSilkMaxOrder];
+    s32 DC_resp = 0;
+    for (int k = 0; k < order; k++) {
+        DC_resp += (s32)A_Q12[k];
+        A_QA[k] = shl32((s32)A_Q12[k], 12);
+    }
+    if (DC_resp >= 4096) return 0;
+    const s32 A_LIMIT = 16773022;
+    s32 invGain_Q30 = 1 << 30;
+    int k;
+    for (k = order - 1; k > 0; k--) {
+        if (A_QA[k] > A_LIMIT || A_QA[k] < -A_LIMIT) return 0;
+        s32 rc_Q31 = (s32)(0u - (u32)shl32(A_QA[k], 7));
+        s32 rc_mult1_Q30 = (1 << 30) - smmul(rc_Q31, rc_Q31);
+        invGain_Q30 = shl32(smmul(invGain_Q30, rc_mult1_Q30), 2);
+        if (invGain_Q30 < 107374) return 0;
+        int mult2Q = 32 - clz32(iabs(rc_mult1_Q30));
+        s32 rc_mult2 = inverse32_varq(rc_mult1_Q30, mult2Q + 30);
+        for (int n = 0; n < (k + 1) >> 1; n++) {
+            s32 tmp1 = A_QA[n], tmp2 = A_QA[k - n - 1];
+            s64 t64 = rshift_round64((s64)sub_sat32(tmp1, (s32)rshift_round64((s64)tmp2 * rc_Q31, 31)) * rc_mult2, mult2Q);
+            if (t64 > 2147483647LL || t64 < -2147483648LL) return 0;
+            A_QA[n] = (s32)t64;
+            t64 = rshift_round64((s64)sub_sat32(tmp2, (s32)rshift_round64((s64)tmp1 * rc_Q31, 31)) * rc_mult2, mult2Q);
+            if (t64 > 2147483647LL || t64 < -2147483648LL) return 0;
+            A_QA[k - n - 1] = (s32)t64;
+        }
+    }
+    if (A_QA[k] > A_LIMIT || A_QA[k] < -A_LIMIT) return 0;
+    s32 rc_Q31 = (s32)(0u - (u32)shl32(A_QA[0], 7));
+    s32 rc_mult1_Q30 = (1 << 30) - smmul(rc_Q31, rc_Q31);
+    invGain_Q30 = shl32(smmul(invGain_Q30, rc_mult1_Q30), 2);
+    if (invGain_Q30 < 107374) return 0;
+    return invGain_Q30;
+}
+// ref silk_NLSF2A_find_poly / silk_NLSF2A (src/silk.cpp:626, 642)
+OPUS_HD void silk_nlsf2a_find_poly(s32* out, const s32* cLSF, int dd) {
+    out[0] = 1 << 16;
+    out[1] = -cLSF[0];
+    for (int k = 1; k < dd; k++) {
+        s32 ftmp = cLSF[2 * k];
+        out[k + 1] = shl32(out[k - 1], 1) - (s32)rshift_round64((s64)ftmp * out[k], 16);
+        for (int n = k; n > 1; n--) out[n] += out[n - 2] - (s32)rshift_round64((s64)ftmp * out[n - 1], 16);
+        out[1] -= ftmp;
+    }
+}
+OPUS_HD void silk_nlsf2a(int16_t* a_Q12, const int16_t* NLSF, int d) {
+    const uint8_t ordering16[16] = {0, 15, 8, 7, 4, 11, 12, 3, 2, 13, 10, 5, 6, 9, 14, 1};
+    const uint8_t ordering10[10] = {0, 9, 6, 3, 4, 5, 8, 1, 2, 7};
+    const uint8_t* ordering = d == 16 ? ordering16 : ordering10;
+    s32 cos_LSF_QA[kSilkMaxOrder], P[kSilkMaxOrder / 2 + 1], Q[kSilkMaxOrder / 2 + 1], a32_QA1[kSilkMaxOrder];
+    for (int k = 0; k < d; k++) {
+        s32 f_int = NLSF[k] >> 8;
+        s32 f_frac = NLSF[k] - shl32(f_int, 8);
+        s32 cos_val = kLsfCos[f_int];
+        s32 delta = kLsfCos[f_int + 1] - cos_val;
+        cos_LSF_QA[ordering[k]] = rshift_round(shl32(cos_val, 8) + mul_w(delta, f_frac), 4);
+    }
+    const int dd = d >> 1;
+    silk_nlsf2a_find_poly(P, &cos_LSF_QA[0], dd);
+    silk_nlsf2a_find_poly(Q, &cos_LSF_QA[1], dd);
+    for (int k = 0; k < dd; k++) {
+        s32 Ptmp = P[k + 1] + P[k];
+        s32 Qtmp = Q[k + 1] - Q[k];
+        a32_QA1[k] = -Qtmp - Ptmp;
+        a32_QA1[d - k - 1] = Qtmp - Ptmp;
+    }
+    silk_lpc_fit(a_Q12, a32_QA1, d);
+    for (int i = 0; silk_lpc_inverse_pred_gain(a_Q12, d) == 0 && i < 16; i++) {
+        silk_bwexpander_32(a32_QA1, d, 65536 - shl32(2, i));
+        for (int k = 0; k < d; k++) a_Q12[k] = (int16_t)rshift_round(a32_QA1[k], 5);
+    }
+}
+
+struct SilkCtrl {  // ref silk_decoder_control_t
+    s32 pitchL[4];
+    s32 Gains_Q16[4];
+    int16_t PredCoef_Q12[2][kSilkMaxOrder];
+    int16_t LTPCoef_Q14[20];
+    s32 LTP_scale_Q14;
+};
+
+// ref silk_decode_parameters (src/silk.cpp:827) + silk_decode_pitch (:2055)
+OPUS_HD void silk_decode_parameters(SilkChannel& c, SilkIdx& ix, SilkCtrl& ctl) {
+    int16_t pNLSF_Q15[kSilkMaxOrder], pNLSF0_Q15[kSilkMaxOrder];
+    silk_gains_dequant(ctl.Gains_Q16, ix.gains, &c.LastGainIndex);
+    const SilkCb cb = silk_cb(c.fs_kHz);
+    silk_nlsf_decode(pNLSF_Q15, ix.nlsf, cb);
+    silk_nlsf2a(ctl.PredCoef_Q12[1], pNLSF_Q15, c.LPC_order);
+    if (c.first_frame_after_reset == 1) ix.interpQ2 = 4;
+    if (ix.interpQ2 < 4) {
+        for (int i = 0; i < c.LPC_order; i++)
+            pNLSF0_Q15[i] = (int16_t)(c.prevNLSF_Q15[i] + (mul_w(ix.interpQ2, pNLSF_Q15[i] - c.prevNLSF_Q15[i]) >> 2));
+        silk_nlsf2a(ctl.PredCoef_Q12[0], pNLSF0_Q15, c.LPC_order);
+    } else {
+        for (int i = 0; i < c.LPC_order; i++) ctl.PredCoef_Q12[0][i] = ctl.PredCoef_Q12[1][i];
+    }
+    for (int i = 0; i < c.LPC_order; i++) c.prevNLSF_Q15[i] = pNLSF_Q15[i];
+    if (ix.signalType == 2) {
+        const int8_t* cbk;
+        int cbk_size;
+        if (c.fs_kHz == 8) { cbk = kCbLagsStage2; cbk_size = 11; }
+        else { cbk = kCbLagsStage3; cbk_size = 34; }
+        const int min_lag = 2 * c.fs_kHz, max_lag = 18 * c.fs_kHz;
+        const int lag = min_lag + ix.lagIndex;
+        for (int k = 0; k < 4; k++) ctl.pitchL[k] = limit32(lag + cbk[k * cbk_size + ix.contour], min_lag, max_lag);
+        const int8_t* vq = ix.perIndex == 0 ? kLtpVq0 : ix.perIndex == 1 ? kLtpVq1 : kLtpVq2;
+        for (int k = 0; k < 4; k++)
+            for (int i = 0; i < 5; i++) ctl.LTPCoef_Q14[k * 5 + i] = (int16_t)shl32(vq[ix.ltp[k] * 5 + i], 7);
+        ctl.LTP_scale_Q14 = ix.ltpScaleIndex == 0 ? 15565 : ix.ltpScaleIndex == 1 ? 12288 : 8192;
+    } else {
+        for (int k = 0; k < 4; k++) ctl.pitchL[k] = 0;
+        for (int k = 0; k < 20; k++) ctl.LTPCoef_Q14[k] = 0;
+        ix.perIndex = 0;
+        ctl.LTP_scale_Q14 = 0;
+    }
+}
+
+// ref silk_LPC_analysis_filter (src/silk.cpp:2268)
+OPUS_HD void silk_lpc_analysis_filter(int16_t* out, const int16_t* in, const int16_t* B, int len, int d) {
+    for (int ix = d; ix < len; ix++) {
+        const int16_t* p = &in[ix - 1];
+        s32 acc = smulbb(p[0], B[0]);
+        for (int j = 1; j < d; j++) acc = smlabb(acc, p[-j], B[j]);
+        acc = sub_w(shl32((s32)p[1], 12), acc);
+        out[ix] = sat16(rshift_round(acc, 12));
+    }
+    for (int j = 0; j < d; j++) out[j] = 0;
+}
+
+// ref silk_decode_core (src/silk.cpp:1806)
+OPUS_HD void silk_decode_core(SilkChannel& c, const SilkIdx& ix, SilkCtrl& ctl, int16_t* xq, const int16_t* pulses, SilkScratch& w) {
+    const s32 offs[2][2] = {{100, 240}, {32, 100}};
+    const s32 offset_Q10 = offs[ix.signalType >> 1][ix.quantOffsetType];
+    const int NLSF_interpolation_flag = ix.interpQ2 < 4;
+    s32 rand_seed = ix.seed;
+    for (int i = 0; i < c.frame_length; i++) {
+        rand_seed = (s32)(907633515u + (u32)rand_seed * 196314165u);
+        s32 e = shl32((s32)pulses[i], 14);
+        if (e > 0) e -= 80 << 4;
+        else if (e < 0) e += 80 << 4;
+        e += offset_Q10 << 4;
+        if (rand_seed < 0) e = -e;
+        w.exc_Q14[i] = e;
+        rand_seed = add_w(rand_seed, pulses[i]);
+    }
+    for (int i = 0; i < kSilkMaxOrder; i++) w.sLPC_Q14[i] = c.sLPC_Q14_buf[i];
+    const s32* pexc_Q14 = w.exc_Q14;
+    int16_t* pxq = xq;
+    int sLTP_buf_idx = c.ltp_mem_length;
+    int lag = 0;
+    for (int k = 0; k < 4; k++) {
+        const s32* pres_Q14 = w.res_Q14;
+        const int16_t* A_Q12 = ctl.PredCoef_Q12[k >> 1];
+        const int16_t* B_Q14 = &ctl.LTPCoef_Q14[k * 5];
+        const int signalType = ix.signalType;
+        const s32 Gain_Q10 = ctl.Gains_Q16[k] >> 6;
+        s32 inv_gain_Q31 = inverse32_varq(ctl.Gains_Q16[k], 47);
+        s32 gain_adj_Q16;
+        if (ctl.Gains_Q16[k] != c.prev_gain_Q16) {
+            gain_adj_Q16 = div32_varq(c.prev_gain_Q16, ctl.Gains_Q16[k], 16);
+            for (int i = 0; i < kSilkMaxOrder; i++) w.sLPC_Q14[i] = smulww(gain_adj_Q16, w.sLPC_Q14[i]);
+        } else {
+            gain_adj_Q16 = 1 << 16;
+        }
+        c.prev_gain_Q16 = ctl.Gains_Q16[k];
+        if (signalType == 2) {
+            lag = ctl.pitchL[k];
+            if (k == 0 || (k == 2 && NLSF_interpolation_flag)) {
+                const int start_idx = c.ltp_mem_length - lag - c.LPC_order - 5 / 2;
+                if (k == 2) for (int i = 0; i < 2 * c.subfr_length; i++) c.outBuf[c.ltp_mem_length + i] = xq[i];
+                silk_lpc_analysis_filter(&w.sLTP[start_idx], &c.outBuf[start_idx + k * c.subfr_length], A_Q12, c.ltp_mem_length - start_idx, c.LPC_order);
+                if (k == 0) inv_gain_Q31 = shl32(smulwb(inv_gain_Q31, ctl.LTP_scale_Q14), 2);
+                for (int i = 0; i < lag + 5 / 2; i++) w.sLTP_Q15[sLTP_buf_idx - i - 1] = smulwb(inv_gain_Q31, w.sLTP[c.ltp_mem_length - i - 1]);
+            } else if (gain_adj_Q16 != 1 << 16) {
+                for (int i = 0; i < lag + 5 / 2; i++) w.sLTP_Q15[sLTP_buf_idx - i - 1] = smulww(gain_adj_Q16, w.sLTP_Q15[sLTP_buf_idx - i - 1]);
+            }
+            const s32* pred_lag_ptr = &w.sLTP_Q15[sLTP_buf_idx - lag + 5 / 2];
+            for (int i = 0; i < c.subfr_length; i++) {
+                s32 LTP_pred_Q13 = 2;
+                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[0], B_Q14[0]);
+                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-1], B_Q14[1]);
+                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-2], B_Q14[2]);
+                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-3], B_Q14[3]);
+                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-4], B_Q14[4]);
+                pred_lag_ptr++;
+                w.res_Q14[i] = pexc_Q14[i] + shl32(LTP_pred_Q13, 1);
+                w.sLTP_Q15[sLTP_buf_idx] = shl32(w.res_Q14[i], 1);
+                sLTP_buf_idx++;
+            }
+        } else {
+            pres_Q14 = pexc_Q14;
+        }
+        for (int i = 0; i < c.subfr_length; i++) {
+            s32 LPC_pred_Q10 = c.LPC_order >> 1;
+            for (int j = 0; j < c.LPC_order; j++) LPC_pred_Q10 = smlawb(LPC_pred_Q10, w.sLPC_Q14[kSilkMaxOrder + i - 1 - j], A_Q12[j]);
+            w.sLPC_Q14[kSilkMaxOrder + i] = add_sat32(pres_Q14[i], lshift_sat32(LPC_pred_Q10, 4));
+            pxq[i] = sat16(rshift_round(smulww(w.sLPC_Q14[kSilkMaxOrder + i], Gain_Q10), 8));
+        }
+        for (int i = 0; i < kSilkMaxOrder; i++) w.sLPC_Q14[i] = w.sLPC_Q14[c.subfr_length + i];
+        pexc_Q14 += c.subfr_length;
+        pxq += c.subfr_length;
+    }
+    for (int i = 0; i < kSilkMaxOrder; i++) c.sLPC_Q14_buf[i] = w.sLPC_Q14[i];
+}
+
+// ref silk_decode_frame (src/silk.cpp:1974), lostFlag = 0
+OPUS_HD void silk_decode_channel(SilkChannel& c, SilkIdx& ix, const int16_t* pulses, int16_t* pOut, SilkScratch& w) {
+    SilkCtrl ctl;
+    silk_decode_parameters(c, ix, ctl);
+    silk_decode_core(c, ix, ctl, pOut, pulses, w);
+    c.prevSignalType = ix.signalType;
+    c.first_frame_after_reset = 0;
+    const int mv_len = c.ltp_mem_length - c.frame_length;
+    for (int i = 0; i < mv_len; i++) c.outBuf[i] = c.outBuf[c.frame_length + i];
+    for (int i = 0; i < c.frame_length; i++) c.outBuf[mv_len + i] = pOut[i];
+    c.lagPrev = ctl.pitchL[3];
+}
+
+// ref silk_stereo_MS_to_LR (src/silk.cpp:4028)
+OPUS_HD void silk_ms_to_lr(SilkStreamState& s, int16_t* x1, int16_t* x2, const int32_t* pred_Q13, int fs_kHz, int frame_length) {
+    x1[0] = s.sMid[0]; x1[1] = s.sMid[1];
+    x2[0] = s.sSide[0]; x2[1] = s.sSide[1];
+    s.sMid[0] = x1[frame_length]; s.sMid[1] = x1[frame_length + 1];
+    s.sSide[0] = x2[frame_length]; s.sSide[1] = x2[frame_length + 1];
+    s32 pred0_Q13 = s.pred_prev_Q13[0], pred1_Q13 = s.pred_prev_Q13[1];
+    const s32 denom_Q16 = ((s32)1 << 16) / (8 * fs_kHz);
+    const s32 delta0_Q13 = rshift_round(smulbb(pred_Q13[0] - s.pred_prev_Q13[0], denom_Q16), 16);
+    const s32 delta1_Q13 = rshift_round(smulbb(pred_Q13[1] - s.pred_prev_Q13[1], denom_Q16), 16);
+    for (int n = 0; n < frame_length; n++) {
+        if (n < 8 * fs_kHz) { pred0_Q13 += delta0_Q13; pred1_Q13 += delta1_Q13; }
+        else { pred0_Q13 = pred_Q13[0]; pred1_Q13 = pred_Q13[1]; }
+        s32 sum = shl32(x1[n] + x1[n + 2] + shl32(x1[n + 1], 1), 9);
+        sum = smlawb(shl32((s32)x2[n + 1], 8), sum, pred0_Q13);
+        sum = smlawb(sum, shl32((s32)x1[n + 1], 11), pred1_Q13);
+        x2[n + 1] = sat16(rshift_round(sum, 8));
+    }
+    s.pred_prev_Q13[0] = (int16_t)pred_Q13[0];
+    s.pred_prev_Q13[1] = (int16_t)pred_Q13[1];
+    for (int n = 0; n < frame_length; n++) {
+        s32 sum = x1[n + 1] + (s32)x2[n + 1];
+        s32 diff = x1[n + 1] - (s32)x2[n + 1];
+        x1[n + 1] = sat16(sum);
+        x2[n + 1] = sat16(diff);
+    }
+}
+
+// ref silk_resampler_private_up2_HQ (src/silk.cpp:3515)
+OPUS_HD void silk_up2_hq(int32_t* S, int16_t* out, const int16_t* in, int len) {
+    for (int k = 0; k < len; k++) {
+        s32 in32 = shl32((s32)in[k], 10);
+        s32 Y = in32 - S[0];
+        s32 X = smulwb(Y, 1746);
+        s32 out32_1 = S[0] + X;
+        S[0] = in32 + X;
+        Y = out32_1 - S[1];
+        X = smulwb(Y, 14986);
+        s32 out32_2 = S[1] + X;
+        S[1] = out32_1 + X;
+        Y = out32_2 - S[2];
+        X = smlawb(Y, Y, -26453);
+        out32_1 = S[2] + X;
+        S[2] = out32_2 + X;
+        out[2 * k] = sat16(rshift_round(out32_1, 10));
+        Y = in32 - S[3];
+        X = smulwb(Y, 6854);
+        out32_1 = S[3] + X;
+        S[3] = in32 + X;
+        Y = out32_1 - S[4];
+        X = smulwb(Y, 25769);
+        out32_2 = S[4] + X;
+        S[4] = out32_1 + X;
+        Y = out32_2 - S[5];
+        X = smlawb(Y, Y, -9994);
+        out32_1 = S[5] + X;
+        S[5] = out32_2 + X;
+        out[2 * k + 1] = sat16(rshift_round(out32_1, 10));
+    }
+}
+// ref silk_resampler_private_IIR_FIR (+ _INTERPOL) (src/silk.cpp:3475, 3451); `out` has stride `ostride`
+OPUS_HD int16_t* silk_iir_fir(SilkResampler& r, int16_t* out, int ostride, const int16_t* in, int inLen, int16_t* buf) {
+    for (int i = 0; i < 8; i++) buf[i] = r.sFIR[i];
+    const s32 inc = r.invRatio_Q16;
+    int nSamplesIn;
+    for (;;) {
+        nSamplesIn = imin(inLen, r.batchSize);
+        silk_up2_hq(r.sIIR, &buf[8], in, nSamplesIn);
+        const s32 max_index_Q16 = shl32(nSamplesIn, 17);
+        for (s32 index_Q16 = 0; index_Q16 < max_index_Q16; index_Q16 += inc) {
+            const s32 ti = smulwb(index_Q16 & 0xFFFF, 12);
+            const int16_t* bp = &buf[index_Q16 >> 16];
+            s32 res = smulbb(bp[0], kResamplerFir12[ti * 4 + 0]);
+            res = smlabb(res, bp[1], kResamplerFir12[ti * 4 + 1]);
+            res = smlabb(res, bp[2], kResamplerFir12[ti * 4 + 2]);
+            res = smlabb(res, bp[3], kResamplerFir12[ti * 4 + 3]);
+            res = smlabb(res, bp[4], kResamplerFir12[(11 - ti) * 4 + 3]);
+            res = smlabb(res, bp[5], kResamplerFir12[(11 - ti) * 4 + 2]);
+            res = smlabb(res, bp[6], kResamplerFir12[(11 - ti) * 4 + 1]);
+            res = smlabb(res, bp[7], kResamplerFir12[(11 - ti) * 4 + 0]);
+            *out = sat16(rshift_round(res, 15));
+            out += ostride;
+        }
+        in += nSamplesIn;
+        inLen -= nSamplesIn;
+        if (inLen > 0) for (int i = 0; i < 8; i++) buf[i] = buf[(nSamplesIn << 1) + i];
+        else break;
+    }
+    for (int i = 0; i < 8; i++) r.sFIR[i] = buf[(nSamplesIn << 1) + i];
+    return out;
+}
+// ref silk_resampler (src/silk.cpp:3676)
+OPUS_HD void silk_resample(SilkResampler& r, int16_t* out, int ostride, const int16_t* in, int inLen, int16_t* buf) {
+    const int nSamples = r.Fs_in_kHz - r.inputDelay;
+    for (int i = 0; i < nSamples; i++) r.delayBuf[r.inputDelay + i] = in[i];
+    out = silk_iir_fir(r, out, ostride, r.delayBuf, r.Fs_in_kHz, buf);
+    silk_iir_fir(r, out, ostride, &in[nSamples], inLen - r.Fs_in_kHz, buf);
+    for (int i = 0; i < r.inputDelay; i++) r.delayBuf[i] = in[inLen - r.inputDelay + i];
+}
+
+// One frame of one stream (ref silk_Decode, src/silk.cpp:1481, with nChannelsAPI == nChannelsInternal as the
+// reference's opus_decode_frame always calls it, src/opus_decoder.cpp:167-168).  out: 960 * nch interleaved.
+OPUS_HD void silk_synth_frame(SilkStreamState& s, SilkFrame& f, int16_t* out, SilkScratch& w) {
+    const int nch = f.nch, fs_kHz = f.fs_kHz;
+    if (nch > s.nChannelsInternal && s.nChannelsInternal != 0) silk_channel_init(s.ch[1]);  // mono -> stereo (ref :1512)
+    for (int n = 0; n < nch; n++) silk_set_fs(s.ch[n], fs_kHz);
+    if (nch == 2 && s.nChannelsInternal == 1) {  // ref :1549-1555
+        s.pred_prev_Q13[0] = s.pred_prev_Q13[1] = 0;
+        s.sSide[0] = s.sSide[1] = 0;
+    }
+    s.nChannelsInternal = nch;
+    const int L = s.ch[0].frame_length;
+    if (nch == 2 && f.mid_only == 0 && s.prev_decode_only_middle == 1) {  // ref :1639-1646
+        SilkChannel& c = s.ch[1];
+        for (int i = 0; i < 480; i++) c.outBuf[i] = 0;
+        for (int i = 0; i < kSilkMaxOrder; i++) c.sLPC_Q14_buf[i] = 0;
+        c.lagPrev = 100; c.LastGainIndex = 10; c.prevSignalType = 0; c.first_frame_after_reset = 1;
+    }
+    for (int n = 0; n < nch; n++) {
+        if (n == 0 || !f.mid_only) silk_decode_channel(s.ch[n], f.idx[n], f.pulses[n], &w.tmp[n][2], w);
+        else for (int i = 0; i < L; i++) w.tmp[n][2 + i] = 0;
+    }
+    if (nch == 2) {
+        silk_ms_to_lr(s, w.tmp[0], w.tmp[1], f.ms_pred_Q13, fs_kHz, L);
+    } else {
+        w.tmp[0][0] = s.sMid[0]; w.tmp[0][1] = s.sMid[1];
+        s.sMid[0] = w.tmp[0][L]; s.sMid[1] = w.tmp[0][L + 1];
+    }
+    for (int n = 0; n < nch; n++) silk_resample(s.ch[n].rs, out + n, nch, &w.tmp[n][1], L, w.rbuf);
+    s.prev_decode_only_middle = f.mid_only;
+}
+
+}  // namespace opusb200

@@ -9,15 +9,20 @@ using namespace opusb200;
 
 extern "C" {
 
-int hs_celt_parse(const uint8_t* pkt, int len, int C, int LM, int start, int disable_inv, CeltFrameHdr* hdr, BandOp* ops,
-                  int16_t* X) {
-    (void)X;
+static int celt_parse_rd(const RangeDec& rd, int C, int LM, int start, int disable_inv, CeltFrameHdr* hdr, BandOp* ops) {
     ParseCtx p;
     memset(&p, 0, sizeof(p));
-    rd_init(p.rd, pkt, (u32)len);
+    p.rd = rd;
     p.C = C; p.LM = LM; p.start = start; p.end = kNbEBands; p.disable_inv = disable_inv;
     p.ops = ops; p.ops_cap = kMaxOps;
     return celt_parse_frame(p, *hdr);
+}
+int hs_celt_parse(const uint8_t* pkt, int len, int C, int LM, int start, int disable_inv, CeltFrameHdr* hdr, BandOp* ops,
+                  int16_t* X) {
+    (void)X;
+    RangeDec rd;
+    rd_init(rd, pkt, (u32)len);
+    return celt_parse_rd(rd, C, LM, start, disable_inv, hdr, ops);
 }
 int hs_sizeof_hdr() { return (int)sizeof(CeltFrameHdr); }
 int hs_sizeof_op() { return (int)sizeof(BandOp); }
@@ -43,9 +48,18 @@ void* hs_celt_new(int channels) {
 }
 void hs_celt_free(void* d) { free(d); }
 
+static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, int start, int16_t* pcm, int32_t* dbg_mem);
+
 // decode one CELT frame; C = coded channels, frame_size in {120,240,480,960}; pcm gets frame_size*CC
 int hs_celt_decode(void* dv, const uint8_t* pkt, int len, int C, int frame_size, int start, int16_t* pcm, int32_t* dbg_mem) {
-    HsCelt* d = (HsCelt*)dv;
+    RangeDec rd;
+    rd_init(rd, pkt, (u32)len);
+    return celt_decode_rd((HsCelt*)dv, rd, C, frame_size, start, pcm, dbg_mem);
+}
+
+}  // extern "C"
+
+static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, int start, int16_t* pcm, int32_t* dbg_mem) {
     CeltStreamState& st = d->st;
     const int CC = d->CC;
     int LM = frame_size == 120 ? 0 : frame_size == 240 ? 1 : frame_size == 480 ? 2 : frame_size == 960 ? 3 : -1;
@@ -54,7 +68,8 @@ int hs_celt_decode(void* dv, const uint8_t* pkt, int len, int C, int frame_size,
     static BandOp ops[kMaxOps];
     static int16_t Xg[2 * kMaxFrame];
     static int16_t W[W_SIZE];
-    int status = hs_celt_parse(pkt, len, C, LM, start, CC == 1, &hdr, ops, Xg);
+    (void)Xg;
+    int status = celt_parse_rd(rd, C, LM, start, CC == 1, &hdr, ops);
     if (status == OPUSB_CELT_BAD_ARG) return status;
     const int N = frame_size, M = 1 << LM;
     Lanes L;
@@ -95,6 +110,75 @@ int hs_celt_decode(void* dv, const uint8_t* pkt, int len, int C, int frame_size,
     if (LM != 0) { st.pf_period_old = st.pf_period; st.pf_gain_old = st.pf_gain; st.pf_tapset_old = st.pf_tapset; }
     st.rng = hdr.final_rng;
     return status;
+}
+
+// ---- Opus frame layer on top (ref opus_decode_frame, src/opus_decoder.cpp:154): SILK, hybrid, CELT ----
+#include "../../esp32-opus-player_b200/csrc/silk.cuh"
+
+struct HsOpus {
+    HsCelt celt;
+    SilkStreamState silk;
+    int channels, prev_mode;
+};
+
+extern "C" {
+
+void* hs_opus_new(int channels) {
+    HsOpus* d = (HsOpus*)calloc(1, sizeof(HsOpus));
+    d->channels = channels;
+    d->celt.CC = channels;
+    for (int i = 0; i < kNbEBands; i++)
+        for (int c = 0; c < 2; c++) d->celt.st.band[i].logE[c] = d->celt.st.band[i].logE2[c] = -(28 << 10);
+    silk_stream_reinit(d->silk);
+    return d;
+}
+void hs_opus_free(void* d) { free(d); }
+
+// one code-0 packet: toc + payload; returns samples per channel (960) or a negative error
+int hs_opus_decode(void* dv, int toc, const uint8_t* payload, int len, int16_t* pcm) {
+    HsOpus* d = (HsOpus*)dv;
+    const int CC = d->channels;
+    const int mode = (toc & 0x80) ? 1002 : ((toc & 0x60) == 0x60 ? 1001 : 1000);
+    const int C = (toc & 4) ? 2 : 1;
+    static int16_t pcm_silk[960 * 2];
+    static SilkFrame sf;
+    static SilkScratch sw;
+    RangeDec rd;
+    rd_init(rd, payload, (u32)len);
+    if (mode != 1002) {
+        if (C != CC) return OPUSB_UNIMPLEMENTED;
+        if (d->prev_mode == 1002) silk_stream_reinit(d->silk);
+        int fs_kHz = 16;
+        if (mode == 1000) {
+            const int bw = (toc >> 5) & 3;  // NB, MB, WB
+            fs_kHz = bw == 0 ? 8 : bw == 1 ? 12 : 16;
+        }
+        silk_parse_frame(rd, sf, fs_kHz, C);
+        silk_synth_frame(d->silk, sf, pcm_silk, sw);
+    }
+    int start = 0;
+    if (mode != 1002 && rd_tell(rd) + 17 + 20 * (mode == 1001) <= 8 * len) {
+        if (mode == 1001) rd_bit_logp(rd, 12);
+    }
+    if (mode != 1002) start = 17;
+    int ret = 960;
+    if (mode != 1000) {
+        if (mode != d->prev_mode && d->prev_mode > 0) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479)
+            CeltStreamState& st = d->celt.st;
+            st.rng = 0;
+            st.pf_period = st.pf_period_old = st.pf_gain = st.pf_gain_old = st.pf_tapset = st.pf_tapset_old = 0;
+            for (int i = 0; i < kNbEBands; i++)
+                for (int c = 0; c < 2; c++) st.band[i].logE[c] = st.band[i].logE2[c] = -(28 << 10);
+        }
+        int r = celt_decode_rd(&d->celt, rd, C, 960, start, pcm, nullptr);
+        if (r < 0) ret = r;
+    } else {
+        for (int i = 0; i < 960 * C; i++) pcm[i] = 0;
+    }
+    if (mode != 1002)
+        for (int i = 0; i < 960 * C; i++) pcm[i] = sat16((s32)pcm[i] + (s32)pcm_silk[i]);
+    d->prev_mode = mode;
+    return ret;
 }
 
 }
