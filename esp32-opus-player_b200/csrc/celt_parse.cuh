@@ -704,7 +704,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     const int C = p.C, LM = p.LM, start = p.start, end = p.end;
     const int M = 1 << LM;
     hdr.LM = (uint8_t)LM; hdr.C = (uint8_t)C; hdr.start = (uint8_t)start; hdr.end = (uint8_t)end;
-    hdr.n_ops = 0; hdr.n_leaves = 0; hdr.spread = 2; hdr.pad0 = 0; hdr.lcg_steps = 0; hdr.flags = 0; hdr.pf_pitch = 0; hdr.pf_gain = 0; hdr.pf_tapset = 0;
+    hdr.n_ops = 0; hdr.n_leaves = 0; hdr.spread = 2; hdr.lcg_steps = 0; hdr.flags = 0; hdr.pf_pitch = 0; hdr.pf_gain = 0; hdr.pf_tapset = 0;
     hdr.final_rng = 0;
     if (rd.storage > (u32)kMaxPacket || rd.storage <= 1) {  // ref :2216, :2225
         hdr.status = OPUSB_CELT_BAD_ARG;

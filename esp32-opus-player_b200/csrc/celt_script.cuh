@@ -98,7 +98,7 @@ struct CeltFrameHdr {
     uint8_t end;
     uint8_t pf_tapset;
     uint8_t spread;
-    uint8_t pad0;
+    uint8_t oflags;      // OpusFrameFlags (opus_frame.cuh)
     uint16_t n_ops;
     uint16_t n_leaves;
     int16_t pf_pitch;

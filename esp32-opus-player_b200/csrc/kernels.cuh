@@ -13,8 +13,8 @@
 #pragma once
 #include <cuda_pipeline.h>
 
-#include "celt_parse.cuh"
 #include "celt_synth.cuh"
+#include "opus_frame.cuh"
 
 namespace opusb200 {
 
@@ -44,37 +44,42 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1_THREADS)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
-          BandOp* __restrict__ ops) {
+          BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
     if (local >= P.n_sel * P.n_frames) return;
     const size_t t = (size_t)P.first_stream * P.n_frames + local;
     const FrameDesc d = fr[t];
     CeltFrameHdr& h = hdr[t];
-    int C, LM, start;
-    if (P.mode == 1) {
-        C = P.coded_channels;
-        LM = P.frame_size == 120 ? 0 : P.frame_size == 240 ? 1 : P.frame_size == 480 ? 2 : 3;
-        start = P.start_band;
-    } else {
-        if (!(d.toc & 0x80)) {  // SILK / hybrid frames are not handled by this kernel
-            h.status = OPUSB_UNIMPLEMENTED; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1; h.start = 0; h.end = kNbEBands;
-            return;
-        }
-        C = (d.toc & 0x4) ? 2 : 1;
-        LM = 3;  // the reference decodes every Opus frame as 960 samples (src/opus_decoder.cpp:161,259)
-        start = 0;
-    }
     ParseCtx p;
-    rd_init(p.rd, bytes + d.offset, d.len);
-    p.C = C; p.LM = LM; p.start = start; p.end = kNbEBands; p.disable_inv = (P.CC == 1);
+    p.end = kNbEBands; p.disable_inv = (P.CC == 1);
     p.band = 0; p.intensity = 0; p.spread = 0; p.tf_change = 0; p.remaining_bits = 0;
     p.ops = ops + t * kMaxOps; p.n_ops = 0; p.n_leaves = 0; p.ops_cap = kMaxOps; p.overflow = 0; p.lcg_steps = 0;
-    celt_parse_frame(p, h);
+    int oflags = 0;
+    bool celt = true, fade = false;
+    if (P.mode == 0) {
+        const int f = local % P.n_frames;
+        const int prev_mode = f > 0 ? opus_toc_mode(fr[t - 1].toc) : st[P.first_stream + local / P.n_frames].prev_mode;
+        oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade);
+    } else {
+        rd_init(p.rd, bytes + d.offset, d.len);
+        p.C = P.coded_channels;
+        p.LM = P.frame_size == 120 ? 0 : P.frame_size == 240 ? 1 : P.frame_size == 480 ? 2 : 3;
+        p.start = P.start_band;
+    }
+    if (celt) {
+        celt_parse_frame(p, h);  // the one call site: the parser is by far the largest body of code in this kernel
+        if (fade) {
+            if (h.status == OPUSB_CELT_BAD_ARG) oflags |= OF_NO_CELT;
+            h.status = 960;
+        }
+    }
+    h.oflags = (uint8_t)oflags;
 }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * KW_WARPS)
-k_sequence(const CeltFrameHdr* __restrict__ hdr, FrameEnergy* __restrict__ fe, CeltStreamState* __restrict__ st, DevParams P) {
+k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ fr, FrameEnergy* __restrict__ fe,
+           CeltStreamState* __restrict__ st, DevParams P) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= P.n_sel) return;
     const int s = P.first_stream + w;
@@ -87,9 +92,15 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, FrameEnergy* __restrict__ fe, C
         const size_t t = (size_t)s * P.n_frames + f;
         const CeltFrameHdr& h = hdr[t];
         FrameEnergy& o = fe[t];
-        const bool skip = frame_skipped(h.status);
+        const bool failed = frame_skipped(h.status);
+        const bool skip = failed || (h.oflags & OF_NO_CELT);
+        if (h.oflags & OF_RESET_CELT) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479-2498)
+            rng = 0; pfp = pfpo = pfg = pfgo = pft = pfto = 0;
+            if (lane < kNbEBands) for (int c = 0; c < 2; c++) b.logE[c] = b.logE2[c] = -(28 << 10);
+        }
         if (lane == 0) {
-            o.skip = skip;
+            o.skip = (uint8_t)((skip ? FS_NO_CELT : 0) | ((h.oflags & OF_HAS_SILK) ? FS_HAS_SILK : 0) | (failed ? FS_FAILED : 0));
+            o.celt_n = skip ? 0 : (uint16_t)(kShortMdct << h.LM);
             o.seed = rng;
             o.pf_period = (int16_t)pfp; o.pf_period_old = (int16_t)pfpo;
             o.pf_gain = (int16_t)pfg; o.pf_gain_old = (int16_t)pfgo;
@@ -105,6 +116,7 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, FrameEnergy* __restrict__ fe, C
     }
     if (lane < kNbEBands) S.band[lane] = b;
     if (lane == 0) {
+        if (P.mode == 0) S.prev_mode = opus_toc_mode(fr[(size_t)s * P.n_frames + P.n_frames - 1].toc);
         S.rng = rng;
         S.pf_period = pfp; S.pf_period_old = pfpo; S.pf_gain = pfg; S.pf_gain_old = pfgo; S.pf_tapset = pft; S.pf_tapset_old = pfto;
     }
@@ -120,7 +132,7 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
     const size_t t = (size_t)P.first_stream * P.n_frames + local;
     const CeltFrameHdr& h = hdr[t];
     const FrameEnergy& e = fe[t];
-    if (e.skip) return;
+    if (e.skip & FS_NO_CELT) return;
     Lanes L;
     int16_t* W = Wsm[threadIdx.x >> 5];
     const int words = (h.C * (kShortMdct << h.LM)) >> 1;
@@ -145,7 +157,7 @@ k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe
     const size_t t = (size_t)P.first_stream * P.n_frames + local / P.CC;
     const CeltFrameHdr& h = hdr[t];
     const FrameEnergy& e = fe[t];
-    if (e.skip) return;
+    if (e.skip & FS_NO_CELT) return;
     Lanes L;
     int32_t* freq = fsm[threadIdx.x >> 5][0];
     int32_t* work = fsm[threadIdx.x >> 5][1];
@@ -186,7 +198,7 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
     for (int f = 0; f < P.n_frames; f++) {
         const size_t t = (size_t)s * P.n_frames + f;
         const FrameEnergy& e = fe[t];
-        if (e.skip) continue;
+        if (e.skip & FS_NO_CELT) continue;
         const CeltFrameHdr& h = hdr[t];
         const int LM = h.LM, N = kShortMdct << LM;
         const int nblk = (h.flags & FF_TRANSIENT) ? (1 << LM) : 1;
@@ -257,13 +269,13 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     };
 
     for (int q = 0; q < DE_STAGES - 1; q++) prefetch(q);
-    bool my_skip = true;
+    int my_n = 0;  // samples of this frame that carry CELT output (0: none, 120 for a hybrid -> SILK fade-out frame)
     for (int q = 0; q < T; q++) {
         const int f = q / tpf, j0 = (q % tpf) * DE_TW;
         const int w = min(DE_TW, N - j0);
         if (j0 == 0) {
             const size_t my_t = (size_t)my_s * P.n_frames + f;
-            my_skip = live ? (fe[my_t].skip != 0) : true;
+            my_n = live ? fe[my_t].celt_n : 0;
             if (live && my_c == 0) status[my_t] = hdr[my_t].status;
         }
         prefetch(q + DE_STAGES - 1);
@@ -275,13 +287,13 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
             const int qs = lane >> 1;
 #pragma unroll 8
             for (int j = 0; j < w; j++) {
-                s32 v = my_skip ? 0 : deemph_sample(src[lane * DE_IN_STRIDE + j], mem);
+                s32 v = (j0 + j < my_n) ? deemph_sample(src[lane * DE_IN_STRIDE + j], mem) : 0;
                 tout16[(qs * DE_OUT_STRIDE + j) * 2 + (lane & 1)] = (int16_t)v;
             }
         } else {
 #pragma unroll 8
             for (int j = 0; j < w; j++) {
-                s32 v = my_skip ? 0 : deemph_sample(src[lane * DE_IN_STRIDE + j], mem);
+                s32 v = (j0 + j < my_n) ? deemph_sample(src[lane * DE_IN_STRIDE + j], mem) : 0;
                 tout16[lane * DE_OUT_STRIDE * 2 + j] = (int16_t)v;
             }
         }
@@ -310,6 +322,35 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
         __syncwarp();
     }
     if (live) st[my_s].preemph_mem[my_c] = mem;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SILK synthesis, frames of a stream in order (ref silk_Decode, src/silk.cpp:1481): parameters, LTP + LPC
+// synthesis, mid/side -> left/right, resampling to 48 kHz; the result is added to the CELT PCM with int16
+// saturation (ref src/opus_decoder.cpp:271-273).  Runs after k_deemph.
+struct SilkWork {
+    SilkScratch w;
+    int16_t out[2 * kMaxFrame];
+};
+
+__global__ void __launch_bounds__(32)
+k_silk(const CeltFrameHdr* __restrict__ hdr, SilkFrame* __restrict__ silk, SilkStreamState* __restrict__ sst,
+       SilkWork* __restrict__ work, int16_t* __restrict__ pcm, DevParams P) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= P.n_sel) return;
+    const int s = P.first_stream + w;
+    SilkStreamState& S = sst[s];
+    SilkWork& W = work[s];
+    for (int f = 0; f < P.n_frames; f++) {
+        const size_t t = (size_t)s * P.n_frames + f;
+        const int of = hdr[t].oflags;
+        if (!(of & OF_HAS_SILK)) continue;
+        if (of & OF_SILK_REINIT) silk_stream_reinit(S);
+        silk_synth_frame(S, silk[t], W.out, W.w);
+        int16_t* o = pcm + t * (size_t)(kMaxFrame * P.CC);
+        const int n = kMaxFrame * P.CC;
+        for (int i = 0; i < n; i++) o[i] = sat16((s32)o[i] + (s32)W.out[i]);
+    }
 }
 
 }  // namespace opusb200

@@ -17,16 +17,19 @@ using namespace opusb200;
 static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
 static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
-enum { kStages = 6, kMaxChunks = 4 };
-static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph"};
+enum { kStages = 7, kMaxChunks = 4 };
+static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph", "silk"};
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device;
     // per-stream state
     CeltStreamState* d_state;
+    SilkStreamState* d_sstate;
+    SilkWork* d_swork;
     // per-frame intermediates
     CeltFrameHdr* d_hdr;
     BandOp* d_ops;
+    SilkFrame* d_silk;
     int16_t* d_X;
     FrameEnergy* d_fe;
     int32_t* d_raw;
@@ -88,6 +91,9 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     const size_t nfr = (size_t)n_streams * max_frames;
     int r;
     if ((r = dev_alloc(c, &c->d_state, (size_t)n_streams))) return r;
+    if ((r = dev_alloc(c, &c->d_sstate, (size_t)n_streams))) return r;
+    if ((r = dev_alloc(c, &c->d_swork, (size_t)n_streams))) return r;
+    if ((r = dev_alloc(c, &c->d_silk, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
@@ -108,7 +114,7 @@ void dm_destroy(dm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_state); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
+    cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_swork); cudaFree(c->d_silk); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
     cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes); cudaFree(c->d_frames); cudaFree(c->d_pcm);
     cudaFree(c->d_status);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -135,6 +141,19 @@ int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
         }
     }
     free(init);
+    if (rc) return rc;
+    // SILK layer: silk_InitDecoder (ref src/silk.cpp:1792) + zeroed resamplers
+    SilkStreamState* si = (SilkStreamState*)calloc(1, sizeof(SilkStreamState));
+    if (!si) return DM_ERR_NOMEM;
+    for (int n = 0; n < 2; n++) { si->ch[n].prev_gain_Q16 = 65536; si->ch[n].first_frame_after_reset = 1; }  // ref silk_init_decoder :2192
+    if (!ids) {
+        std::vector<SilkStreamState> all((size_t)c->n_streams, *si);
+        if (cudaMemcpy(c->d_sstate, all.data(), all.size() * sizeof(SilkStreamState), cudaMemcpyHostToDevice) != cudaSuccess) rc = DM_ERR_CUDA;
+    } else {
+        for (int i = 0; i < n && !rc; i++)
+            if (cudaMemcpy(c->d_sstate + ids[i], si, sizeof(SilkStreamState), cudaMemcpyHostToDevice) != cudaSuccess) rc = DM_ERR_CUDA;
+    }
+    free(si);
     return rc;
 }
 
@@ -162,9 +181,9 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     const int nfr = n_sel * in->n_frames;
     const int wb = 32 * KW_WARPS;
     if (timed) cudaEventRecord(c->ev[0], s);
-    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops);
+    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state);
     if (timed) cudaEventRecord(c->ev[1], s);
-    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_state, P);
+    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[2], s);
     k_bands<<<(nfr + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, P);
     if (timed) cudaEventRecord(c->ev[3], s);
@@ -174,7 +193,12 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) cudaEventRecord(c->ev[5], s);
     k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[6], s);
-    c->launches += kStages;
+    if (in->mode == DM_MODE_OPUS) {  // exits per frame unless the TOC carries a SILK layer
+        k_silk<<<(n_sel + 31) / 32, 32, 0, s>>>(c->d_hdr, c->d_silk, c->d_sstate, c->d_swork, d_pcm, P);
+        c->launches++;
+    }
+    if (timed) cudaEventRecord(c->ev[7], s);
+    c->launches += kStages - 1;
     CU_TRY(c, cudaGetLastError());
     return 0;
 }

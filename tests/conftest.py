@@ -47,4 +47,8 @@ def hostsim():
     H.hs_celt_new.argtypes = [I]
     H.hs_celt_free.argtypes = [P]
     H.hs_celt_decode.argtypes = [P, P, I, I, I, I, P, P]
+    H.hs_opus_new.restype = P
+    H.hs_opus_new.argtypes = [I]
+    H.hs_opus_free.argtypes = [P]
+    H.hs_opus_decode.argtypes = [P, I, P, I, P]
     return H

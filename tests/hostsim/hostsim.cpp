@@ -113,7 +113,7 @@ static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, 
 }
 
 // ---- Opus frame layer on top (ref opus_decode_frame, src/opus_decoder.cpp:154): SILK, hybrid, CELT ----
-#include "../../esp32-opus-player_b200/csrc/silk.cuh"
+#include "../../esp32-opus-player_b200/csrc/opus_frame.cuh"
 
 struct HsOpus {
     HsCelt celt;
@@ -138,46 +138,34 @@ void hs_opus_free(void* d) { free(d); }
 int hs_opus_decode(void* dv, int toc, const uint8_t* payload, int len, int16_t* pcm) {
     HsOpus* d = (HsOpus*)dv;
     const int CC = d->channels;
-    const int mode = (toc & 0x80) ? 1002 : ((toc & 0x60) == 0x60 ? 1001 : 1000);
-    const int C = (toc & 4) ? 2 : 1;
     static int16_t pcm_silk[960 * 2];
     static SilkFrame sf;
     static SilkScratch sw;
-    RangeDec rd;
-    rd_init(rd, payload, (u32)len);
-    if (mode != 1002) {
-        if (C != CC) return OPUSB_UNIMPLEMENTED;
-        if (d->prev_mode == 1002) silk_stream_reinit(d->silk);
-        int fs_kHz = 16;
-        if (mode == 1000) {
-            const int bw = (toc >> 5) & 3;  // NB, MB, WB
-            fs_kHz = bw == 0 ? 8 : bw == 1 ? 12 : 16;
-        }
-        silk_parse_frame(rd, sf, fs_kHz, C);
-        silk_synth_frame(d->silk, sf, pcm_silk, sw);
+    static CeltFrameHdr hdr;
+    ParseCtx p;
+    memset(&p, 0, sizeof(p));
+    bool celt, fade;
+    const int oflags = opus_parse_prologue(p, payload, len, toc, d->prev_mode, CC, hdr, sf, &celt, &fade);
+    if (hdr.status == OPUSB_UNIMPLEMENTED && !celt && !(oflags & OF_HAS_SILK) && opus_toc_mode(toc) != MODE_CELT_ONLY && ((toc & 4) ? 2 : 1) != CC)
+        return OPUSB_UNIMPLEMENTED;
+    if (oflags & OF_SILK_REINIT) silk_stream_reinit(d->silk);
+    if (oflags & OF_HAS_SILK) silk_synth_frame(d->silk, sf, pcm_silk, sw);
+    if (oflags & OF_RESET_CELT) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479)
+        CeltStreamState& st = d->celt.st;
+        st.rng = 0;
+        st.pf_period = st.pf_period_old = st.pf_gain = st.pf_gain_old = st.pf_tapset = st.pf_tapset_old = 0;
+        for (int i = 0; i < kNbEBands; i++)
+            for (int c = 0; c < 2; c++) st.band[i].logE[c] = st.band[i].logE2[c] = -(28 << 10);
     }
-    int start = 0;
-    if (mode != 1002 && rd_tell(rd) + 17 + 20 * (mode == 1001) <= 8 * len) {
-        if (mode == 1001) rd_bit_logp(rd, 12);
-    }
-    if (mode != 1002) start = 17;
     int ret = 960;
-    if (mode != 1000) {
-        if (mode != d->prev_mode && d->prev_mode > 0) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479)
-            CeltStreamState& st = d->celt.st;
-            st.rng = 0;
-            st.pf_period = st.pf_period_old = st.pf_gain = st.pf_gain_old = st.pf_tapset = st.pf_tapset_old = 0;
-            for (int i = 0; i < kNbEBands; i++)
-                for (int c = 0; c < 2; c++) st.band[i].logE[c] = st.band[i].logE2[c] = -(28 << 10);
-        }
-        int r = celt_decode_rd(&d->celt, rd, C, 960, start, pcm, nullptr);
-        if (r < 0) ret = r;
-    } else {
-        for (int i = 0; i < 960 * C; i++) pcm[i] = 0;
+    for (int i = 0; i < 960 * CC; i++) pcm[i] = 0;
+    if (celt) {
+        const int r = celt_decode_rd(&d->celt, p.rd, p.C, kShortMdct << p.LM, p.start, pcm, nullptr);
+        if (r < 0 && !fade) ret = r;
     }
-    if (mode != 1002)
-        for (int i = 0; i < 960 * C; i++) pcm[i] = sat16((s32)pcm[i] + (s32)pcm_silk[i]);
-    d->prev_mode = mode;
+    if (oflags & OF_HAS_SILK)
+        for (int i = 0; i < 960 * CC; i++) pcm[i] = sat16((s32)pcm[i] + (s32)pcm_silk[i]);
+    d->prev_mode = opus_toc_mode(toc);
     return ret;
 }
 

@@ -39,3 +39,43 @@ def test_parse_final_range_matches(hostsim, ref):
         R.ref_celt_decode(frame.ctypes.data, L, pcm.ctypes.data, 960)
         hostsim.hs_celt_parse(frame.ctypes.data, L, 2, 3, 0, 0, hdr.ctypes.data, ops.ctypes.data, X.ctypes.data)
         assert int(hdr[:4].view(np.uint32)[0]) == R.ref_ec_rng()
+
+
+# ---- Opus frame layer: SILK-only, hybrid, CELT-only and the transitions between them ----
+def _opus_run(hostsim, ref, ch, plan, seed):
+    """plan: list of (toc, payload_len, n_frames). Decodes the same packets with the oracle and the host simulation."""
+    rng = np.random.default_rng(seed)
+    dec = ref.PacketDecoder(ch)
+    d = hostsim.hs_opus_new(ch)
+    got = np.zeros(960 * 2, np.int16)
+    k = 0
+    try:
+        for toc, ln, n in plan:
+            for _ in range(n):
+                L = ln if ln > 0 else int(rng.integers(3, 400))
+                payload = rng.integers(0, 256, L, dtype=np.uint8)
+                pkt = np.concatenate([np.array([toc], np.uint8), payload])
+                r, want = dec.decode(pkt)
+                s = hostsim.hs_opus_decode(d, toc, payload.ctypes.data, L, got.ctypes.data)
+                assert r == s, "frame %d: status %d vs %d" % (k, r, s)
+                if r > 0:
+                    assert np.array_equal(got[: 960 * ch].reshape(960, ch), want), "frame %d toc %#x" % (k, toc)
+                k += 1
+    finally:
+        dec.close()
+        hostsim.hs_opus_free(d)
+
+
+@pytest.mark.parametrize("toc,ch,ln", [(0x08, 1, 40), (0x28, 1, 50), (0x48, 1, 60), (0x4C, 2, 80), (0x0C, 2, 60), (0x2C, 2, 70),
+                                       (0x68, 1, 100), (0x6C, 2, 120), (0x78, 1, 110), (0x7C, 2, 160), (0x48, 1, 0), (0x7C, 2, 0)])
+def test_opus_single_mode_bit_exact(hostsim, ref, toc, ch, ln):
+    _opus_run(hostsim, ref, ch, [(toc, ln, 60)], toc * 131 + ln)
+
+
+@pytest.mark.parametrize("ch", [1, 2])
+def test_opus_mode_switching_bit_exact(hostsim, ref, ch):
+    s = 4 if ch == 2 else 0
+    plan = [(0xF8 | s, 100, 6), (0x48 | s, 60, 6), (0x78 | s, 120, 6), (0x48 | s, 60, 5), (0x08 | s, 40, 5), (0x28 | s, 50, 5),
+            (0x68 | s, 100, 5), (0xF8 | s, 100, 4), (0x78 | s, 120, 4), (0xD8 | s, 90, 4), (0x48 | s, 0, 8), (0x78 | s, 0, 8),
+            (0x08 | s, 0, 6), (0xF8 | s, 0, 6)]
+    _opus_run(hostsim, ref, ch, plan, 77 + ch)
