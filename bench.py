@@ -31,9 +31,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "decoded audio-sec/sec (x realtime), 4096 CELT FB streams, 1/2/4/8 B200"
 UNIT = "audio-s/s"
-TOC, PAYLOAD = 0xFC, 159          # 160-byte packets
-BYTES_PER_FRAME_ALGO = 160 + 3840  # packet in + int16 stereo PCM out
-OPS_PER_FRAME = 5.35e5            # reference x86-64 instructions per frame
+OPS_PER_FRAME = 5.35e5            # reference x86-64 instructions per CELT FB stereo frame
+# name -> (TOC, payload bytes, channels, default streams per GPU, ops per frame relative to CELT FB stereo, description)
+WORKLOADS = {
+    "celt": (0xFC, 159, 2, 4096, 1.0, "configs[1]: %d concurrent CELT-only FB stereo 20 ms streams per GPU, 160 B packets"),
+    "silk": (0x48, 59, 1, 16384, 0.4, "configs[2]: %d concurrent SILK-only WB mono 20 ms streams per GPU, 60 B packets"),
+    "hybrid": (0x7C, 159, 2, 4096, 1.1, "configs[3]: %d concurrent hybrid FB stereo 20 ms streams per GPU, 160 B packets"),
+    "hybrid_swb": (0x68, 99, 1, 8192, 0.6, "configs[3]: %d concurrent hybrid SWB mono 20 ms streams per GPU, 100 B packets"),
+}
+TOC, PAYLOAD, CHANNELS = 0xFC, 159, 2
 
 
 def peaks():
@@ -96,11 +102,11 @@ def cpu_reference(n_frames, target_s, jobs=None):
 
     cores = jobs or os.cpu_count() or 1
     t0 = time.perf_counter()
-    ref.decode_synth_stream(TOC, PAYLOAD + 1, 2, 250, want_pcm=False)
+    ref.decode_synth_stream(TOC, PAYLOAD + 1, CHANNELS, 250, want_pcm=False)
     rate1 = 250 * 0.02 / max(time.perf_counter() - t0, 1e-6)  # x realtime on one core
     per_core = max(1, int(round(target_s * rate1 / (n_frames * 0.02))))
     n_streams = cores * per_core
-    wall, hashes = ref.bench_fork(TOC, PAYLOAD + 1, 2, n_streams, n_frames, jobs=cores)
+    wall, hashes = ref.bench_fork(TOC, PAYLOAD + 1, CHANNELS, n_streams, n_frames, jobs=cores)
     audio = n_streams * n_frames * 0.02
     return {"value": audio / wall, "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": "%d streams x %d frames (%.0f audio-s) of the same corpus, one forked reference decoder per core, %.1f s wall"
@@ -122,7 +128,7 @@ def run_reference(args, rank, world):
     v = a_total / t_total
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed-point",
-            "data": "synthetic", "config": {"workload": "CELT FB stereo 20 ms, 160 B packets, reference CPU decoder (oracle/_ref) forked per core",
+            "data": "synthetic", "config": {"workload": (WORKLOADS[args.workload][5] % 0).replace("0 concurrent ", "") + ", reference CPU decoder (oracle/_ref) forked per core",
                                             "frames_per_stream_per_step": args.frames * 10},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "reference", "sample": last["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -134,12 +140,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--workload", default="celt", choices=sorted(WORKLOADS), help="celt = BASELINE.json's metric config (default)")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
     ap.add_argument("--frames", type=int, default=50, help="frames per stream per step (50 = 1 s of audio)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    global TOC, PAYLOAD, CHANNELS, METRIC
+    TOC, PAYLOAD, CHANNELS, def_streams, ops_rel, wl_desc = WORKLOADS[args.workload]
+    args.streams = args.streams or def_streams
+    if args.workload != "celt":
+        METRIC = "decoded audio-sec/sec (x realtime), %s workload (not the BASELINE.json headline)" % args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +174,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     S, F, K, W = args.streams, args.frames, args.steps, args.warmup
     n_steps = W + K
-    CC = 2
+    CC = CHANNELS
+    bytes_per_frame_algo = (PAYLOAD + 1) + 960 * CC * 2  # packet in + int16 PCM out
+    ops_per_frame = OPS_PER_FRAME * ops_rel
 
     # ---- synthetic corpus: global stream g = rank + world * s (round-robin shard), n_steps*F frames each
     lib = pkg.lib()
@@ -259,7 +273,7 @@ def main():
         hbm_peak, peak_src, sm_max = peaks()
         top = max(stage_acc, key=lambda n: stage_acc[n]) if stage_acc else None
         top_ms = stage_acc.get(top, 0.0) if top else 0.0
-        algo_bytes = S * F * BYTES_PER_FRAME_ALGO
+        algo_bytes = S * F * bytes_per_frame_algo
         achieved = algo_bytes / (top_ms * 1e-3) / 1e9 if top_ms > 0 else None
         sm_clock = (clocks.get("sm_mhz") or sm_max) * 1e6
         n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
@@ -269,12 +283,11 @@ def main():
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": top_ms, "stage_ms": stage_acc,
                 "issue": {"note": "the path is issue bound (SURVEY 8d): algorithmic integer ops vs SM issue peak over the whole step",
-                          "achieved_lane_ops_per_s": S * F * OPS_PER_FRAME / step_s, "peak_lane_ops_per_s": issue_peak,
-                          "frac": S * F * OPS_PER_FRAME / step_s / issue_peak, "sm_clock_hz_under_load": sm_clock}}
+                          "achieved_lane_ops_per_s": S * F * ops_per_frame / step_s, "peak_lane_ops_per_s": issue_peak,
+                          "frac": S * F * ops_per_frame / step_s / issue_peak, "sm_clock_hz_under_load": sm_clock}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed-point", "data": "synthetic",
-                "config": {"workload": "configs[1]: %d concurrent CELT-only FB stereo 20 ms streams per GPU, 160 B packets, %d frames (%.1f s) per stream per step"
-                                       % (S, F, F * 0.02), "streams_per_gpu": S, "frames_per_step": F, "sharding": "stream i -> GPU i mod N, no collective",
+                "config": {"workload": (wl_desc % S) + ", %d frames (%.1f s) per stream per step" % (F, F * 0.02), "streams_per_gpu": S, "frames_per_step": F, "sharding": "stream i -> GPU i mod N, no collective",
                            "l2": "inputs and intermediates per step (%.1f GB) exceed L2; every step decodes new packets" % (dec.device_bytes / 1e9)},
                 "clocks": clocks, "roofline": roof, "gpu_launches": int(launches)}
         if e2e:

@@ -268,3 +268,153 @@ class OpusDecoder:
             self.close()
         except Exception:
             pass
+
+
+# ---- player layer (include/opusfile_b200.h; ref src/opusfile.h:141-156) ----
+OPFB_PENDING = -2100
+OP_HOLE, OP_EREAD, OP_EBADPACKET, OP_ENOTFORMAT, OP_EBADHEADER, OP_EBADTIMESTAMP = -3, -128, -136, -132, -133, -139
+READ_FUNC = ctypes.CFUNCTYPE(_I, _P, _P, _I)
+_player_bound = False
+
+
+def _plib():
+    global _player_bound
+    L = lib()
+    if not _player_bound:
+        L.opusb_head_parse.argtypes = [_P, _P, ctypes.c_size_t]
+        L.opusb_init_decoder.restype = _P
+        L.opusb_init_decoder.argtypes = [READ_FUNC, _P, _I, ctypes.POINTER(_I)]
+        L.opusb_read_stereo.argtypes = [_P, _P, _I]
+        L.opusb_free_decoder.argtypes = [_P]
+        L.opfb_set_create.argtypes = [ctypes.POINTER(_P), _I, _I, _I, _I]
+        L.opfb_set_destroy.argtypes = [_P]
+        L.opfb_set_open_memory.argtypes = [_P, _I, _P, ctypes.c_size_t, _I]
+        L.opfb_set_prepare.argtypes = [_P]
+        L.opfb_set_open_result.argtypes = [_P, _I]
+        L.opfb_set_decode_round.argtypes = [_P]
+        L.opfb_set_decode.argtypes = [_P]
+        L.opfb_set_read_stereo.argtypes = [_P, _I, _P, _I]
+        L.opfb_set_pcm_total.restype = ctypes.c_int64
+        L.opfb_set_pcm_total.argtypes = [_P, _I]
+        L.opfb_set_stats.argtypes = [_P, _P, _I]
+        L.opfb_debug_events.argtypes = [_P, ctypes.c_size_t, _I, _P, _I, ctypes.POINTER(_I)]
+        _player_bound = True
+    return L
+
+
+class OpusHead(ctypes.Structure):
+    _fields_ = [("version", _I), ("channel_count", _I), ("pre_skip", ctypes.c_uint), ("input_sample_rate", ctypes.c_uint32),
+                ("output_gain", _I), ("mapping_family", _I), ("stream_count", _I), ("coupled_count", _I), ("mapping", ctypes.c_uint8 * 2)]
+
+
+def opus_head_parse(data):
+    """ref opus_head_parse (src/opusfile.cpp:1333) -> (rc, OpusHead)."""
+    p = _pkt(data)
+    h = OpusHead()
+    rc = _plib().opusb_head_parse(ctypes.cast(ctypes.byref(h), _P), p.ctypes.data, p.size)
+    return rc, h
+
+
+def demux_events(data, clean_eof=False, cap=1 << 16):
+    """Host demux stage alone (no GPU): (open_result, int32[n][6] rows of kind, code, bytes, duration, od_pos, od_size)."""
+    p = _pkt(data)
+    out = np.zeros((cap, 6), np.int32)
+    res = _I(0)
+    n = _plib().opfb_debug_events(p.ctypes.data, p.size, int(clean_eof), out.ctypes.data, cap, ctypes.byref(res))
+    return res.value, out[: min(n, cap)]
+
+
+class OggOpusFile:
+    """Single-stream player with the reference's call sequence: opus_init_decoder() + op_read_stereo()
+    (src/opusfile.cpp:784, 1293). `read` is SD_read: read(nbytes) -> bytes (b"" at the end)."""
+
+    def __init__(self, source, device=0, eof_is_error=True):
+        if isinstance(source, (bytes, bytearray, np.ndarray)):
+            blob = bytes(source)
+            pos = [0]
+
+            def read(n):
+                b = blob[pos[0]: pos[0] + n]
+                pos[0] += len(b)
+                return b
+        else:
+            read = source
+
+        def cb(user, buf, n):
+            if n == 0:
+                return 0
+            b = read(n)
+            if not b:
+                return -1 if eof_is_error else 0
+            ctypes.memmove(buf, b, len(b))
+            return len(b)
+
+        self._cb = READ_FUNC(cb)
+        err = _I(0)
+        self._of = _plib().opusb_init_decoder(self._cb, None, device, ctypes.byref(err))
+        self.error = err.value
+        if not self._of:
+            raise RuntimeError("opus_init_decoder failed: %d" % err.value)
+
+    def read_stereo(self, buf_size=2048):
+        """-> (ret, pcm int16[ret][2]) exactly like op_read_stereo(pcm, buf_size)."""
+        pcm = np.zeros(buf_size, np.int16)
+        n = _plib().opusb_read_stereo(self._of, pcm.ctypes.data, buf_size)
+        return n, pcm[: 2 * max(n, 0)].reshape(-1, 2)
+
+    def close(self):
+        if self._of:
+            _plib().opusb_free_decoder(self._of)
+            self._of = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OggOpusFileSet:
+    """Many Ogg Opus files at once: host-thread demux + batched GPU decode + op_read_stereo per file."""
+
+    def __init__(self, blobs, device=0, frames_per_round=50, n_threads=0, clean_eof=False):
+        self._set = _P()
+        self._blobs = [np.frombuffer(bytes(b), np.uint8) if not isinstance(b, np.ndarray) else np.ascontiguousarray(b, np.uint8) for b in blobs]
+        L = _plib()
+        rc = L.opfb_set_create(ctypes.byref(self._set), len(self._blobs), device, frames_per_round, n_threads)
+        if rc:
+            raise RuntimeError("opfb_set_create: %d" % rc)
+        for i, b in enumerate(self._blobs):
+            rc = L.opfb_set_open_memory(self._set, i, b.ctypes.data, b.size, int(clean_eof))
+            if rc:
+                raise RuntimeError("opfb_set_open_memory: %d" % rc)
+        rc = L.opfb_set_prepare(self._set)
+        if rc:
+            raise RuntimeError("opfb_set_prepare: %d (no CUDA device => no decode path)" % rc)
+
+    def open_result(self, i):
+        return _plib().opfb_set_open_result(self._set, i)
+
+    def decode_round(self):
+        return _plib().opfb_set_decode_round(self._set)
+
+    def read_stereo(self, i, buf_size=2048):
+        pcm = np.zeros(buf_size, np.int16)
+        n = _plib().opfb_set_read_stereo(self._set, i, pcm.ctypes.data, buf_size)
+        return n, pcm[: 2 * max(n, 0)].reshape(-1, 2)
+
+    def stats(self):
+        v = (ctypes.c_double * 6)()
+        _plib().opfb_set_stats(self._set, ctypes.cast(v, _P), 6)
+        return dict(zip(("demux_s", "decode_s", "packets", "frames", "ogg_bytes", "launches"), [float(x) for x in v]))
+
+    def close(self):
+        if self._set:
+            _plib().opfb_set_destroy(self._set)
+            self._set = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

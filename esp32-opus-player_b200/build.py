@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "lib", "libopusb200.so")
-SRCS = [os.path.join(HERE, "csrc", "opus_b200.cu"), os.path.join(HERE, "csrc", "host_api.cpp")]
+SRCS = [os.path.join(HERE, "csrc", f) for f in ("opus_b200.cu", "host_api.cpp", "opus_player.cpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 

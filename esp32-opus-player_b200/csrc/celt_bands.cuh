@@ -19,12 +19,12 @@ struct FrameEnergy {
     int16_t pf_period, pf_period_old;  // post-filter state entering the frame (ref :2381-2402)
     int16_t pf_gain, pf_gain_old;
     uint8_t pf_tapset, pf_tapset_old;
-    uint8_t skip;                // bit0: no CELT layer this frame; bit1: SILK layer present; bit2: frame failed, no output
+    uint8_t skip;                // bit0: no CELT layer this frame; bit1: SILK layer present; bit2: frame failed, no output; bit3: frame not decoded at all
     uint8_t pad;
     uint16_t celt_n;             // samples the CELT layer produces in this frame (120 << LM), 0 when inactive
     uint16_t pad2;
 };
-enum { FS_NO_CELT = 1, FS_HAS_SILK = 2, FS_FAILED = 4 };
+enum { FS_NO_CELT = 1, FS_HAS_SILK = 2, FS_FAILED = 4, FS_DROPPED = 8 };
 
 // advance the LCG by cnt (1..kLanes) draws
 OPUS_HD u32 lcg_jump(u32 seed, int cnt) { return kLcgMul[cnt - 1] * seed + kLcgAdd[cnt - 1]; }

@@ -85,6 +85,7 @@ enum {
     OPUSB_INVALID_PACKET = -4,
     OPUSB_UNIMPLEMENTED = -5,
     OPUSB_CELT_BAD_ARG = -18,       // ERR_OPUS_CELT_BAD_ARG
+    OPUSB_FRAME_SKIPPED = -2004,       // ours: filler frame, or a frame behind a failed frame of the same packet
     OPUSB_SCRIPT_OVERFLOW = -1000,  // ours: script capacity exceeded (cannot happen for valid sizes)
 };
 

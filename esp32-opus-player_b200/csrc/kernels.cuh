@@ -36,6 +36,7 @@ struct DevParams {
 };
 
 enum { K1_THREADS = 128, KW_WARPS = 4 };
+enum { FD_CONT = 1, FD_NULL = 2 };  // dm_frame.flags (include/opus_b200.h)
 
 __device__ __forceinline__ bool frame_skipped(int status) {
     return status == OPUSB_CELT_BAD_ARG || status == OPUSB_UNIMPLEMENTED || status == OPUSB_BAD_ARG;
@@ -50,6 +51,11 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     const size_t t = (size_t)P.first_stream * P.n_frames + local;
     const FrameDesc d = fr[t];
     CeltFrameHdr& h = hdr[t];
+    if (d.flags & FD_NULL) {  // filler behind the last frame of a stream: no output, no state change
+        h.status = OPUSB_FRAME_SKIPPED; h.oflags = OF_NO_CELT; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1;
+        h.start = 0; h.end = kNbEBands;
+        return;
+    }
     ParseCtx p;
     p.end = kNbEBands; p.disable_inv = (P.CC == 1);
     p.band = 0; p.intensity = 0; p.spread = 0; p.tf_change = 0; p.remaining_bits = 0;
@@ -88,18 +94,30 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ f
     if (lane < kNbEBands) b = S.band[lane];
     u32 rng = S.rng;
     int pfp = S.pf_period, pfpo = S.pf_period_old, pfg = S.pf_gain, pfgo = S.pf_gain_old, pft = S.pf_tapset, pfto = S.pf_tapset_old;
+    bool pkt_failed = false;
+    int last_toc = -1;
     for (int f = 0; f < P.n_frames; f++) {
         const size_t t = (size_t)s * P.n_frames + f;
         const CeltFrameHdr& h = hdr[t];
         FrameEnergy& o = fe[t];
-        const bool failed = frame_skipped(h.status);
+        // a frame that fails ends its packet: the reference returns from opus_decode_native without touching the
+        // remaining frames (ref src/opus_decoder.cpp:334-338)
+        const int fl = fr[t].flags;
+        if (!(fl & FD_CONT)) pkt_failed = false;
+        const bool dropped = (fl & FD_NULL) || pkt_failed;
+        if (!dropped) {
+            last_toc = fr[t].toc;
+            if (h.status < 0) pkt_failed = true;
+        }
+        const bool failed = dropped || frame_skipped(h.status);
         const bool skip = failed || (h.oflags & OF_NO_CELT);
-        if (h.oflags & OF_RESET_CELT) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479-2498)
+        if (!dropped && (h.oflags & OF_RESET_CELT)) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479-2498)
             rng = 0; pfp = pfpo = pfg = pfgo = pft = pfto = 0;
             if (lane < kNbEBands) for (int c = 0; c < 2; c++) b.logE[c] = b.logE2[c] = -(28 << 10);
         }
         if (lane == 0) {
-            o.skip = (uint8_t)((skip ? FS_NO_CELT : 0) | ((h.oflags & OF_HAS_SILK) ? FS_HAS_SILK : 0) | (failed ? FS_FAILED : 0));
+            o.skip = (uint8_t)((skip ? FS_NO_CELT : 0) | ((h.oflags & OF_HAS_SILK) ? FS_HAS_SILK : 0) | (failed ? FS_FAILED : 0) |
+                               (dropped ? FS_DROPPED : 0));
             o.celt_n = skip ? 0 : (uint16_t)(kShortMdct << h.LM);
             o.seed = rng;
             o.pf_period = (int16_t)pfp; o.pf_period_old = (int16_t)pfpo;
@@ -116,7 +134,7 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ f
     }
     if (lane < kNbEBands) S.band[lane] = b;
     if (lane == 0) {
-        if (P.mode == 0) S.prev_mode = opus_toc_mode(fr[(size_t)s * P.n_frames + P.n_frames - 1].toc);
+        if (P.mode == 0 && last_toc >= 0) S.prev_mode = opus_toc_mode(last_toc);
         S.rng = rng;
         S.pf_period = pfp; S.pf_period_old = pfpo; S.pf_gain = pfg; S.pf_gain_old = pfgo; S.pf_tapset = pft; S.pf_tapset_old = pfto;
     }
@@ -276,7 +294,7 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
         if (j0 == 0) {
             const size_t my_t = (size_t)my_s * P.n_frames + f;
             my_n = live ? fe[my_t].celt_n : 0;
-            if (live && my_c == 0) status[my_t] = hdr[my_t].status;
+            if (live && my_c == 0) status[my_t] = (fe[my_t].skip & FS_DROPPED) ? OPUSB_FRAME_SKIPPED : hdr[my_t].status;
         }
         prefetch(q + DE_STAGES - 1);
         __pipeline_wait_prior(DE_STAGES - 1);
@@ -334,7 +352,7 @@ struct SilkWork {
 };
 
 __global__ void __launch_bounds__(32)
-k_silk(const CeltFrameHdr* __restrict__ hdr, SilkFrame* __restrict__ silk, SilkStreamState* __restrict__ sst,
+k_silk(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkFrame* __restrict__ silk, SilkStreamState* __restrict__ sst,
        SilkWork* __restrict__ work, int16_t* __restrict__ pcm, DevParams P) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= P.n_sel) return;
@@ -344,13 +362,29 @@ k_silk(const CeltFrameHdr* __restrict__ hdr, SilkFrame* __restrict__ silk, SilkS
     for (int f = 0; f < P.n_frames; f++) {
         const size_t t = (size_t)s * P.n_frames + f;
         const int of = hdr[t].oflags;
-        if (!(of & OF_HAS_SILK)) continue;
+        if (!(of & OF_HAS_SILK) || (fe[t].skip & FS_DROPPED)) continue;
         if (of & OF_SILK_REINIT) silk_stream_reinit(S);
         silk_synth_frame(S, silk[t], W.out, W.w);
         int16_t* o = pcm + t * (size_t)(kMaxFrame * P.CC);
         const int n = kMaxFrame * P.CC;
         for (int i = 0; i < n; i++) o[i] = sat16((s32)o[i] + (s32)W.out[i]);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// OPUS_RESET_STATE for a list of streams (ref opus_decoder_ctl, src/opus_decoder.cpp:380-388): CELT soft reset
+// (src/celt.cpp:2479-2498: range seed, post-filter, oldLogE/oldLogE2 -- not the history, oldBandE or de-emphasis
+// memory), silk_InitDecoder, prev_mode = 0.
+__global__ void k_reset_state(const int32_t* __restrict__ ids, int n, CeltStreamState* __restrict__ st, SilkStreamState* __restrict__ sst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    CeltStreamState& S = st[ids[i]];
+    S.rng = 0;
+    S.pf_period = S.pf_period_old = S.pf_gain = S.pf_gain_old = S.pf_tapset = S.pf_tapset_old = 0;
+    S.prev_mode = 0;
+    for (int b = 0; b < kNbEBands; b++)
+        for (int c = 0; c < 2; c++) S.band[b].logE[c] = S.band[b].logE2[c] = -(28 << 10);
+    silk_stream_reinit(sst[ids[i]]);
 }
 
 }  // namespace opusb200

@@ -157,6 +157,32 @@ int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
     return rc;
 }
 
+int dm_reset_state(dm_ctx* c, const int32_t* ids, int n) {
+    if (!c) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    std::vector<int32_t> all;
+    if (!ids) {
+        all.resize((size_t)c->n_streams);
+        for (int i = 0; i < c->n_streams; i++) all[(size_t)i] = i;
+        ids = all.data();
+        n = c->n_streams;
+    }
+    if (n <= 0) return 0;
+    for (int i = 0; i < n; i++)
+        if (ids[i] < 0 || ids[i] >= c->n_streams) return OPUSB_BAD_ARG;
+    int32_t* d_ids = nullptr;
+    CU_TRY(c, cudaMalloc((void**)&d_ids, sizeof(int32_t) * (size_t)n));
+    cudaError_t e = cudaMemcpy(d_ids, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_reset_state<<<(n + 127) / 128, 128>>>(d_ids, n, c->d_state, c->d_sstate);
+        c->launches++;
+        e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_ids);
+    CU_TRY(c, e);
+    return 0;
+}
+
 static int check_batch(const dm_ctx* c, const dm_batch* in) {
     if (!c || !in || !in->frames || (!in->bytes && in->n_bytes)) return OPUSB_BAD_ARG;
     if (in->n_frames < 1 || in->n_frames > c->max_frames) return DM_ERR_CAPACITY;
@@ -194,7 +220,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[6], s);
     if (in->mode == DM_MODE_OPUS) {  // exits per frame unless the TOC carries a SILK layer
-        k_silk<<<(n_sel + 31) / 32, 32, 0, s>>>(c->d_hdr, c->d_silk, c->d_sstate, c->d_swork, d_pcm, P);
+        k_silk<<<(n_sel + 31) / 32, 32, 0, s>>>(c->d_hdr, c->d_fe, c->d_silk, c->d_sstate, c->d_swork, d_pcm, P);
         c->launches++;
     }
     if (timed) cudaEventRecord(c->ev[7], s);

@@ -25,6 +25,7 @@ extern "C" {
 #define DM_ERR_CUDA (-2001)
 #define DM_ERR_NOMEM (-2002)
 #define DM_ERR_CAPACITY (-2003)
+#define DM_FRAME_SKIPPED (-2004) /* per-frame status: filler frame, or a frame behind a failed frame of its packet */
 
 /* ------------------------------------------------------------------------------------------------
  * Batched decoder.  One context owns the decoder state of n_streams independent streams on one GPU
@@ -43,6 +44,9 @@ void dm_destroy(dm_ctx* ctx);
 /* opus_decoder_init / OPUS_RESET_STATE for a subset of streams (src/opus_decoder.cpp:82, 361):
  * stream_ids == NULL resets all. */
 int dm_reset(dm_ctx* ctx, const int32_t* stream_ids, int n);
+/* opus_decoder_ctl(OPUS_RESET_STATE) (src/opus_decoder.cpp:380-388) for a subset of streams (NULL = all): CELT soft
+ * reset (src/celt.cpp:2479-2498 keeps the signal history, oldBandE and de-emphasis memory), silk_InitDecoder. */
+int dm_reset_state(dm_ctx* ctx, const int32_t* stream_ids, int n);
 
 /* How frames are interpreted. */
 #define DM_MODE_OPUS 0     /* frames are Opus frames; toc[] gives mode/bandwidth/channels (player-level
@@ -50,11 +54,17 @@ int dm_reset(dm_ctx* ctx, const int32_t* stream_ids, int n);
 #define DM_MODE_CELT_RAW 1 /* frames are raw CELT frames for celt_decode_with_ec (src/celt.cpp:2162):
                               frame_size 120/240/480/960, coded_channels, start_band given explicitly */
 
+/* dm_frame.flags */
+#define DMF_CONT 1 /* 2nd..nth frame of a multi-frame packet: not decoded if an earlier frame of the packet failed
+                      (opus_decode_native returns at the first failing frame, src/opus_decoder.cpp:334-338) */
+#define DMF_NULL 2 /* filler behind the last real frame of a stream in this call: no output, no state change;
+                      must trail the stream's row and repeat the last real frame's toc */
+
 typedef struct dm_frame {  /* one coded frame of one stream */
     uint32_t offset;       /* byte offset of the frame payload inside `bytes` (TOC already stripped) */
     uint16_t len;          /* payload bytes (<= 1275) */
     uint8_t toc;           /* the packet's TOC byte (DM_MODE_OPUS) */
-    uint8_t flags;         /* reserved, 0 */
+    uint8_t flags;         /* DMF_* */
 } dm_frame;
 
 typedef struct dm_batch {
