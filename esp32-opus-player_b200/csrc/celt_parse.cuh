@@ -24,6 +24,7 @@ struct ParseCtx {
     BandOp* ops;      // transform ops from the front, leaf records from the back
     int n_ops, n_leaves, ops_cap, overflow;
     uint32_t lcg_steps;
+    unsigned wmask;   // lanes of this warp that parse a CELT frame together (warp_converge / warp_any)
 };
 
 OPUS_HD void emit_op(ParseCtx& p, uint8_t code, int a, int off, int off2, int n, int g, int g2) {
@@ -238,15 +239,19 @@ struct PartFrame {
     uint8_t first_is_mid, phase;
 };
 
-OPUS_HD u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, s16 gain, int fill) {
+// Every lane of p.wmask calls this once per band job (`active` false: nothing to decode) and all of them step
+// through the loop together: one tree node per step, so the lanes that split run decode_theta side by side
+// and the lanes at a leaf read their PVQ index side by side.
+OPUS_HD u32 partition(ParseCtx& p, bool active, int xoff, int N, int b, int B, int lowband, int LM, s16 gain, int fill) {
     const int i = p.band;
     PartFrame st[5];
     int sp = 0;
     PartNode cur;
     cur.xoff = xoff; cur.N = N; cur.b = b; cur.B = B; cur.lowband = lowband; cur.LM = LM; cur.fill = fill; cur.gain = gain;
     u32 ret = 0;
-    bool descend = true;
-    for (;;) {
+    bool descend = true, done = !active;
+    while (warp_any(p.wmask, !done)) {
+        if (done) continue;
         if (descend) {
             const uint8_t* cache = pulse_cache(i, cur.LM);
             if (cur.LM != -1 && cur.b > cache[cache[0]] + 12 && cur.N > 2) {
@@ -305,8 +310,9 @@ OPUS_HD u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, i
                 }
                 descend = false;
             }
+        } else if (sp == 0) {
+            done = true;
         } else {
-            if (sp == 0) return ret;
             PartFrame& f = st[sp - 1];
             if (f.phase == 0) {
                 f.cm = f.first_is_mid ? ret : ret << f.shift;
@@ -321,17 +327,24 @@ OPUS_HD u32 partition(ParseCtx& p, int xoff, int N, int b, int B, int lowband, i
             }
         }
     }
+    return ret;
 }
 
-// ref quant_band (src/celt.cpp:1526)
-OPUS_HD u32 band_mono(ParseCtx& p, int xoff, int N, int b, int B, int lowband, int LM, int lowband_out, s16 gain,
-                      int scratch, int fill) {
-    const int N0 = N;
+// ref quant_band (src/celt.cpp:1526), split around the partition walk so that the walk has one call site that
+// every lane reaches: band_mono_pre emits the transforms of the folding source and says whether there is a tree
+// to walk, band_mono_post undoes the time/frequency reshaping on the decoded band.
+struct MonoCtx { int xoff, N0, B, B0, N_B, N_B0, recombine, time_divide, longBlocks, lowband, lowband_out, fill; };
+
+OPUS_HD bool band_mono_pre(ParseCtx& p, MonoCtx& m, int xoff, int N, int B, int lowband, int lowband_out, int scratch, int fill) {
+    m.xoff = xoff; m.N0 = N; m.lowband_out = lowband_out;
     int N_B = (int)((u32)N / (u32)B);
     int B0 = B, time_divide = 0, recombine = 0;
     int tf_change = p.tf_change;
-    const int longBlocks = B0 == 1;
-    if (N == 1) return band_n1(p, xoff, -1, lowband_out);
+    m.longBlocks = B0 == 1;
+    if (N == 1) {
+        band_n1(p, xoff, -1, lowband_out);
+        return false;
+    }
     if (tf_change > 0) recombine = tf_change;
     if (scratch >= 0 && lowband >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
         emit_op(p, OP_COPY, 0, scratch, lowband, N, 0, 0);
@@ -353,15 +366,18 @@ OPUS_HD u32 band_mono(ParseCtx& p, int xoff, int N, int b, int B, int lowband, i
         tf_change++;
     }
     B0 = B;
-    const int N_B0 = N_B;
-    if (B0 > 1 && lowband >= 0) emit_op(p, OP_DEINT, B0 << recombine, lowband, 0, N_B >> recombine, longBlocks, 0);
+    if (B0 > 1 && lowband >= 0) emit_op(p, OP_DEINT, B0 << recombine, lowband, 0, N_B >> recombine, m.longBlocks, 0);
+    m.B = B; m.B0 = B0; m.N_B = N_B; m.N_B0 = N_B; m.recombine = recombine; m.time_divide = time_divide; m.lowband = lowband; m.fill = fill;
+    return true;
+}
 
-    u32 cm = partition(p, xoff, N, b, B, lowband, LM, gain, fill);
-
-    if (B0 > 1) emit_op(p, OP_INT, B0 << recombine, xoff, 0, N_B >> recombine, longBlocks, 0);
-    N_B = N_B0;
+OPUS_HD u32 band_mono_post(ParseCtx& p, const MonoCtx& m, u32 cm) {
+    const int xoff = m.xoff, recombine = m.recombine, B0 = m.B0;
+    int N_B = m.N_B, B = m.B;
+    if (B0 > 1) emit_op(p, OP_INT, B0 << recombine, xoff, 0, N_B >> recombine, m.longBlocks, 0);
+    N_B = m.N_B0;
     B = B0;
-    for (int k = 0; k < time_divide; k++) {
+    for (int k = 0; k < m.time_divide; k++) {
         B >>= 1;
         N_B <<= 1;
         cm |= cm >> B;
@@ -371,10 +387,10 @@ OPUS_HD u32 band_mono(ParseCtx& p, int xoff, int N, int b, int B, int lowband, i
         const uint8_t bit_deinterleave[16] = {0x00, 0x03, 0x0C, 0x0F, 0x30, 0x33, 0x3C, 0x3F,
                                               0xC0, 0xC3, 0xCC, 0xCF, 0xF0, 0xF3, 0xFC, 0xFF};
         cm = bit_deinterleave[cm];
-        emit_op(p, OP_HAAR, 1 << k, xoff, 0, N0 >> k, 0, 0);
+        emit_op(p, OP_HAAR, 1 << k, xoff, 0, m.N0 >> k, 0, 0);
     }
     B <<= recombine;
-    if (lowband_out >= 0) emit_op(p, OP_SCALE_OUT, 0, xoff, lowband_out, N0, sqrt_q(shl32(N0, 22)), 0);
+    if (m.lowband_out >= 0) emit_op(p, OP_SCALE_OUT, 0, xoff, m.lowband_out, m.N0, sqrt_q(shl32(m.N0, 22)), 0);
     cm &= (u32)((1 << B) - 1);
     return cm;
 }
@@ -394,7 +410,14 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
     const int norm_offset = M * kEBands[start];
     int lowband_offset = 0, update_lowband = 1;
     p.intensity = intensity;
-    for (int i = start; i < end; i++) {
+    const int start0 = warp_min(p.wmask, start);  // lanes may start at band 0 or 17 (hybrid): one loop for all of them
+    for (int i = start0; i < end; i++) {
+        warp_converge(p.wmask);
+        if (i < start) {
+            // keep in step with the lanes that do have this band: two empty job slots
+            for (int j = 0; j < 2; j++) partition(p, false, 0, 0, 0, 0, 0, 0, 0, 0);
+            continue;
+        }
         p.band = i;
         const int last = (i == end - 1);
         const int xoff = M * kEBands[i];
@@ -452,7 +475,7 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
         const int out2 = last ? -1 : W_NORM2 + M * kEBands[i] - norm_offset;
 
         // ---- plan the jobs of this band
-        BandJob job[2];
+        BandJob job[2] = {};
         int njobs = 0;
         // mode: 0 = independent jobs (mono / dual stereo), 1 = mid/side with rebalance, 2 = N=2 stereo
         int mode = 0, first_is_mid = 1, itheta = 0, inv = 0, first_bits = 0, rebalance0 = 0, n2_arg = 0, n2_x2 = 0, n2_y2 = 0;
@@ -505,9 +528,13 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
         }
         // ---- run them through the single band_mono call site
         u32 cm_job[2] = {0, 0};
-        for (int j = 0; j < njobs; j++) {
-            const BandJob& J = job[j];
-            cm_job[j] = band_mono(p, J.xoff, Nb, J.b, B, J.lowband, LM, J.out, J.gain, J.scratch, J.fill);
+        for (int j = 0; j < 2; j++) {
+            const BandJob& J = job[j < njobs ? j : 0];
+            MonoCtx m = {};
+            const bool act = j < njobs;
+            const bool walk = act && band_mono_pre(p, m, J.xoff, Nb, B, J.lowband, J.out, J.scratch, J.fill);
+            const u32 cm = partition(p, walk, J.xoff, Nb, J.b, m.B, m.lowband, LM, J.gain, m.fill);
+            if (act) cm_job[j] = walk ? band_mono_post(p, m, cm) : 1u;
             if (mode == 1 && j == 0) {
                 const int rebalance = first_bits - (rebalance0 - p.remaining_bits);
                 if (rebalance > 3 << 3 && itheta != (first_is_mid ? 0 : 16384)) job[1].b += rebalance - (3 << 3);
@@ -711,6 +738,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         return hdr.status;
     }
     p.n_ops = 0; p.n_leaves = 0; p.overflow = 0; p.lcg_steps = 0;
+    const int start0 = warp_min(p.wmask, start);  // common first band of the lanes that parse together
 
     int total_bits = (int)rd.storage * 8;
     int tell = rd_tell(rd);
@@ -752,7 +780,9 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         const s16 beta = intra ? (s16)4915 : (LM == 0 ? (s16)30147 : LM == 1 ? (s16)22282 : LM == 2 ? (s16)12124 : (s16)6554);
         s32 prev[2] = {0, 0};
         const int budget = (int)rd.storage * 8;
-        for (int i = start; i < end; i++) {
+        for (int i = start0; i < end; i++) {
+            warp_converge(p.wmask);
+            if (i < start) continue;
             for (int c = 0; c < C; c++) {
                 int qi;
                 int t = rd_tell(rd);
@@ -814,7 +844,9 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     int dynalloc_logp = 6;
     total_bits <<= 3;
     tell = (int)rd_tell_frac(rd);
-    for (int i = start; i < end; i++) {
+    for (int i = start0; i < end; i++) {
+        warp_converge(p.wmask);
+        if (i < start) continue;
         int width = C * (kEBands[i + 1] - kEBands[i]) << LM;
         int quanta = imin(width << 3, imax(6 << 3, width));
         int loop_logp = dynalloc_logp;
@@ -845,8 +877,9 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     // ---- fine energy (ref unquant_fine_energy :3664)
     s32 fine_acc[2][kNbEBands];
     for (int c = 0; c < 2; c++) for (int i = 0; i < kNbEBands; i++) fine_acc[c][i] = 0;
-    for (int i = start; i < end; i++) {
-        if (fine_quant[i] <= 0) continue;
+    for (int i = start0; i < end; i++) {
+        warp_converge(p.wmask);
+        if (i < start || fine_quant[i] <= 0) continue;
         for (int c = 0; c < C; c++) {
             s32 q2 = (s32)rd_bits(rd, (u32)fine_quant[i]);
             s32 offset = sub16((shl32(q2, 10) + 512) >> fine_quant[i], 512);

@@ -47,22 +47,25 @@ __global__ void __launch_bounds__(K1_THREADS)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
           BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
-    if (local >= P.n_sel * P.n_frames) return;
+    const bool in_range = local < P.n_sel * P.n_frames;
+    const unsigned warp = __ballot_sync(0xffffffffu, in_range);  // the lanes of this warp that own a frame
+    if (!in_range) return;
     const size_t t = (size_t)P.first_stream * P.n_frames + local;
     const FrameDesc d = fr[t];
     CeltFrameHdr& h = hdr[t];
-    if (d.flags & FD_NULL) {  // filler behind the last frame of a stream: no output, no state change
-        h.status = OPUSB_FRAME_SKIPPED; h.oflags = OF_NO_CELT; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1;
-        h.start = 0; h.end = kNbEBands;
-        return;
-    }
     ParseCtx p;
     p.end = kNbEBands; p.disable_inv = (P.CC == 1);
     p.band = 0; p.intensity = 0; p.spread = 0; p.tf_change = 0; p.remaining_bits = 0;
     p.ops = ops + t * kMaxOps; p.n_ops = 0; p.n_leaves = 0; p.ops_cap = kMaxOps; p.overflow = 0; p.lcg_steps = 0;
+    p.C = 1; p.LM = 3; p.start = 0;
     int oflags = 0;
     bool celt = true, fade = false;
-    if (P.mode == 0) {
+    if (d.flags & FD_NULL) {  // filler behind the last frame of a stream: no output, no state change
+        h.status = OPUSB_FRAME_SKIPPED; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1;
+        h.start = 0; h.end = kNbEBands;
+        oflags = OF_NO_CELT;
+        celt = false;
+    } else if (P.mode == 0) {
         const int f = local % P.n_frames;
         const int prev_mode = f > 0 ? opus_toc_mode(fr[t - 1].toc) : st[P.first_stream + local / P.n_frames].prev_mode;
         oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade);
@@ -72,6 +75,10 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
         p.LM = P.frame_size == 120 ? 0 : P.frame_size == 240 ? 1 : P.frame_size == 480 ? 2 : 3;
         p.start = P.start_band;
     }
+    // the lanes that go through the CELT parser step through its band loops together; a frame the parser refuses
+    // (ref src/celt.cpp:2216, 2225) leaves it before the first meeting point
+    const bool refused = celt && (p.rd.storage > (u32)kMaxPacket || p.rd.storage <= 1);
+    p.wmask = __ballot_sync(warp, celt && !refused);
     if (celt) {
         celt_parse_frame(p, h);  // the one call site: the parser is by far the largest body of code in this kernel
         if (fade) {
