@@ -44,6 +44,8 @@ def lib():
     L.dm_destroy.argtypes = [_P]
     L.dm_reset.argtypes = [_P, _P, _I]
     L.decode_many.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out)]
+    L.decode_many_async.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), ctypes.POINTER(ctypes.c_longlong)]
+    L.dm_wait.argtypes = [_P, ctypes.c_longlong]
     L.dm_decode_device.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), _P]
     L.dm_host_alloc.restype = _P
     L.dm_host_alloc.argtypes = [ctypes.c_size_t]
@@ -162,6 +164,19 @@ class BatchDecoder:
         o = _Out(_ptr(pcm), _ptr(status))
         rc = lib().decode_many(self._ctx, ctypes.byref(b), ctypes.byref(o))
         return rc, pcm, status
+
+    def decode_many_async(self, data, frames, pcm, status, mode=DM_MODE_OPUS, frame_size=960, coded_channels=2, start_band=0):
+        """Enqueue one call and return (rc, ticket) at once; `wait(ticket)` blocks until pcm/status (pinned host arrays
+        owned by the caller, one set per call in flight) are filled.  data/frames must stay alive until then."""
+        assert frames.dtype == FRAME_DTYPE and frames.shape[0] == self.n_streams and frames.flags["C_CONTIGUOUS"]
+        b = self._batch(_ptr(data), data.size, _ptr(frames), frames.shape[1], mode, frame_size, coded_channels, start_band)
+        o = _Out(_ptr(pcm), _ptr(status))
+        t = ctypes.c_longlong(0)
+        rc = lib().decode_many_async(self._ctx, ctypes.byref(b), ctypes.byref(o), ctypes.byref(t))
+        return rc, t.value
+
+    def wait(self, ticket):
+        return lib().dm_wait(self._ctx, ticket)
 
     def decode_device(self, d_bytes, n_bytes, d_frames, n_frames, d_pcm, d_status, cuda_stream=0, mode=DM_MODE_OPUS, frame_size=960,
                       coded_channels=2, start_band=0):

@@ -17,7 +17,7 @@ using namespace opusb200;
 static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
 static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
-enum { kStages = 7, kMaxChunks = 4 };
+enum { kStages = 7, kMaxChunks = 4, kRing = 4 };
 static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph", "silk"};
 
 struct dm_ctx {
@@ -35,13 +35,19 @@ struct dm_ctx {
     int32_t* d_raw;
     int32_t* d_syn;
     // staging for the host-buffer path
-    uint8_t* d_bytes;
-    size_t d_bytes_cap;
+    uint8_t* d_bytes[2];     // packet bytes, double buffered so that call n+1 can upload while call n still parses
+    size_t d_bytes_cap[2];
     FrameDesc* d_frames;
     int16_t* d_pcm;
     int32_t* d_status;
+    int16_t* d_pcm2;         // second output buffer, allocated on the first decode_many_async
+    int32_t* d_status2;
     cudaStream_t streams[kMaxChunks];
     cudaEvent_t bytes_ready;
+    // calls in flight (decode_many_async): per chunk stream, "packets parsed" and "results in host memory"
+    cudaEvent_t parsed[kRing][kMaxChunks], done[kRing][kMaxChunks];
+    cudaEvent_t uploaded[kRing], kernels_done[kRing];
+    long long next_ticket;
     cudaEvent_t ev[kStages + 1];
     long long launches;
     size_t dev_bytes;
@@ -105,6 +111,15 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_status, nfr))) return r;
     for (int i = 0; i < kMaxChunks; i++) CU_TRY(c, cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
     CU_TRY(c, cudaEventCreateWithFlags(&c->bytes_ready, cudaEventDisableTiming));
+    for (int r = 0; r < kRing; r++)
+        for (int k = 0; k < kMaxChunks; k++) {
+            CU_TRY(c, cudaEventCreateWithFlags(&c->parsed[r][k], cudaEventDisableTiming));
+            CU_TRY(c, cudaEventCreateWithFlags(&c->done[r][k], cudaEventDisableTiming));
+        }
+    for (int r = 0; r < kRing; r++) {
+        CU_TRY(c, cudaEventCreateWithFlags(&c->uploaded[r], cudaEventDisableTiming));
+        CU_TRY(c, cudaEventCreateWithFlags(&c->kernels_done[r], cudaEventDisableTiming));
+    }
     for (int i = 0; i <= kStages; i++) CU_TRY(c, cudaEventCreate(&c->ev[i]));
     *out = c;
     return dm_reset(c, nullptr, 0);
@@ -115,10 +130,19 @@ void dm_destroy(dm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_swork); cudaFree(c->d_silk); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
-    cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes); cudaFree(c->d_frames); cudaFree(c->d_pcm);
+    cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames); cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status2);
     cudaFree(c->d_status);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->bytes_ready) cudaEventDestroy(c->bytes_ready);
+    for (int r = 0; r < kRing; r++)
+        for (int k = 0; k < kMaxChunks; k++) {
+            if (c->parsed[r][k]) cudaEventDestroy(c->parsed[r][k]);
+            if (c->done[r][k]) cudaEventDestroy(c->done[r][k]);
+        }
+    for (int r = 0; r < kRing; r++) {
+        if (c->uploaded[r]) cudaEventDestroy(c->uploaded[r]);
+        if (c->kernels_done[r]) cudaEventDestroy(c->kernels_done[r]);
+    }
     for (int i = 0; i <= kStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
@@ -126,6 +150,7 @@ void dm_destroy(dm_ctx* c) {
 int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
     if (!c) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());  // calls in flight (decode_many_async) finish first
     CeltStreamState* init = (CeltStreamState*)malloc(sizeof(CeltStreamState));
     if (!init) return DM_ERR_NOMEM;
     init_state_host(*init);
@@ -160,6 +185,7 @@ int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
 int dm_reset_state(dm_ctx* c, const int32_t* ids, int n) {
     if (!c) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());  // calls in flight (decode_many_async) finish first
     std::vector<int32_t> all;
     if (!ids) {
         all.resize((size_t)c->n_streams);
@@ -196,9 +222,19 @@ static int check_batch(const dm_ctx* c, const dm_batch* in) {
     return 0;
 }
 
+static int reserve_bytes(dm_ctx* c, int bi, size_t n) {
+    if (n <= c->d_bytes_cap[bi]) return 0;
+    if (c->d_bytes[bi]) { cudaFree(c->d_bytes[bi]); c->dev_bytes -= c->d_bytes_cap[bi]; }
+    c->d_bytes[bi] = nullptr; c->d_bytes_cap[bi] = 0;
+    const size_t cap = n + n / 4 + 4096;
+    CU_TRY(c, cudaMalloc((void**)&c->d_bytes[bi], cap));
+    c->d_bytes_cap[bi] = cap; c->dev_bytes += cap;
+    return 0;
+}
+
 // Enqueue the six kernels for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
 static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
-                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed) {
+                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr) {
     DevParams P;
     P.n_streams = c->n_streams; P.n_frames = in->n_frames; P.mode = in->mode;
     P.frame_size = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
@@ -209,6 +245,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) cudaEventRecord(c->ev[0], s);
     k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state);
     if (timed) cudaEventRecord(c->ev[1], s);
+    if (parsed) cudaEventRecord(parsed, s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[2], s);
     k_bands<<<(nfr + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, P);
@@ -238,39 +275,92 @@ int dm_decode_device(dm_ctx* c, const dm_batch* in, dm_out* out, void* cuda_stre
                            (cudaStream_t)cuda_stream, true);
 }
 
+// Blocking call: per stream range (chunk) frames H2D -> kernels -> PCM/status D2H, each chunk on its own CUDA stream so
+// that the read-back of one range overlaps the kernels of the next.
 int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
     int r = check_batch(c, in);
     if (r) return r;
     if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    if (in->n_bytes > c->d_bytes_cap) {
-        if (c->d_bytes) { cudaFree(c->d_bytes); c->dev_bytes -= c->d_bytes_cap; }
-        c->d_bytes = nullptr; c->d_bytes_cap = 0;
-        size_t cap = in->n_bytes + in->n_bytes / 4 + 4096;
-        CU_TRY(c, cudaMalloc((void**)&c->d_bytes, cap));
-        c->d_bytes_cap = cap; c->dev_bytes += cap;
-    }
+    if (c->next_ticket) CU_TRY(c, cudaDeviceSynchronize());  // asynchronous calls in flight finish first
+    r = reserve_bytes(c, 0, in->n_bytes);
+    if (r) return r;
     const int nf = in->n_frames, CC = c->channels;
     const int fs = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
     // packets are small: one copy on stream 0, the other chunk streams wait for it
-    CU_TRY(c, cudaMemcpyAsync(c->d_bytes, in->bytes, in->n_bytes, cudaMemcpyHostToDevice, c->streams[0]));
+    CU_TRY(c, cudaMemcpyAsync(c->d_bytes[0], in->bytes, in->n_bytes, cudaMemcpyHostToDevice, c->streams[0]));
     CU_TRY(c, cudaEventRecord(c->bytes_ready, c->streams[0]));
-    // stream ranges are pipelined so that the PCM read-back of one range overlaps the kernels of the next
-    int n_chunks = c->n_streams >= 64 * kMaxChunks ? kMaxChunks : 1;
+    const int n_chunks = c->n_streams >= 64 * kMaxChunks ? kMaxChunks : 1;
     for (int k = 0; k < n_chunks; k++) {
         const int first = (int)((long long)c->n_streams * k / n_chunks), last = (int)((long long)c->n_streams * (k + 1) / n_chunks);
         const int n_sel = last - first;
-        if (n_sel <= 0) continue;
         cudaStream_t s = c->streams[k];
         const size_t f0 = (size_t)first * nf, fn = (size_t)n_sel * nf;
         if (k) CU_TRY(c, cudaStreamWaitEvent(s, c->bytes_ready, 0));
         CU_TRY(c, cudaMemcpyAsync(c->d_frames + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
-        r = launch_pipeline(c, in, c->d_bytes, c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false);
+        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false);
         if (r) return r;
         CU_TRY(c, cudaMemcpyAsync(out->pcm + f0 * fs * CC, c->d_pcm + f0 * fs * CC, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(out->status + f0, c->d_status + f0, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     for (int k = 0; k < n_chunks; k++) CU_TRY(c, cudaStreamSynchronize(c->streams[k]));
+    return 0;
+}
+
+// Pipelined call: upload, kernels and read-back each have their own CUDA stream and every buffer that crosses a
+// stage is double buffered, so with two calls in flight the GPU decodes call n+1 while call n's PCM crosses PCIe and
+// call n+2's packets arrive.  The kernels run over ALL streams at once: the stages that walk a stream's frames in
+// order (sequence, post-filter, de-emphasis, SILK) take as long for 1024 streams as for 4096.
+int decode_many_async(dm_ctx* c, const dm_batch* in, dm_out* out, long long* ticket_out) {
+    int r = check_batch(c, in);
+    if (r) return r;
+    if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t nfr_cap = (size_t)c->n_streams * c->max_frames;
+    if (!c->d_pcm2) {
+        if ((r = dev_alloc(c, &c->d_pcm2, nfr_cap * c->channels * kMaxFrame))) return r;
+        if ((r = dev_alloc(c, &c->d_status2, nfr_cap))) return r;
+    }
+    const long long ticket = c->next_ticket;
+    const int slot = (int)(ticket % kRing), bi = (int)(ticket & 1);
+    if (ticket >= kRing) CU_TRY(c, cudaEventSynchronize(c->done[slot][0]));  // the slot's previous call is over
+    if (in->n_bytes > c->d_bytes_cap[bi]) CU_TRY(c, cudaDeviceSynchronize());
+    r = reserve_bytes(c, bi, in->n_bytes);
+    if (r) return r;
+    const int nf = in->n_frames, CC = c->channels;
+    const int fs = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
+    const size_t fn = (size_t)c->n_streams * nf;
+    cudaStream_t up = c->streams[2], run = c->streams[0], down = c->streams[1];
+    int16_t* d_pcm = bi ? c->d_pcm2 : c->d_pcm;
+    int32_t* d_status = bi ? c->d_status2 : c->d_status;
+    FrameDesc* d_frames = c->d_frames;
+    // upload: this byte buffer was last parsed two calls ago; the frame descriptors by the previous call
+    if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(up, c->parsed[(ticket - 2) % kRing][0], 0));
+    CU_TRY(c, cudaMemcpyAsync(c->d_bytes[bi], in->bytes, in->n_bytes, cudaMemcpyHostToDevice, up));
+    if (ticket >= 1) CU_TRY(c, cudaStreamWaitEvent(up, c->kernels_done[(ticket - 1) % kRing], 0));
+    CU_TRY(c, cudaMemcpyAsync(d_frames, in->frames, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, up));
+    CU_TRY(c, cudaEventRecord(c->uploaded[slot], up));
+    // kernels: the output buffer of this parity was last read back two calls ago
+    CU_TRY(c, cudaStreamWaitEvent(run, c->uploaded[slot], 0));
+    if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(run, c->done[(ticket - 2) % kRing][0], 0));
+    r = launch_pipeline(c, in, c->d_bytes[bi], d_frames, d_pcm, d_status, 0, c->n_streams, run, false, c->parsed[slot][0]);
+    if (r) return r;
+    CU_TRY(c, cudaEventRecord(c->kernels_done[slot], run));
+    // read-back
+    CU_TRY(c, cudaStreamWaitEvent(down, c->kernels_done[slot], 0));
+    CU_TRY(c, cudaMemcpyAsync(out->pcm, d_pcm, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, down));
+    CU_TRY(c, cudaMemcpyAsync(out->status, d_status, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, down));
+    CU_TRY(c, cudaEventRecord(c->done[slot][0], down));
+    c->next_ticket = ticket + 1;
+    if (ticket_out) *ticket_out = ticket;
+    return 0;
+}
+
+int dm_wait(dm_ctx* c, long long ticket) {
+    if (!c) return OPUSB_BAD_ARG;
+    if (ticket < 0 || ticket >= c->next_ticket) return OPUSB_BAD_ARG;
+    if (ticket + kRing <= c->next_ticket - 1) return 0;  // long finished: its ring slot was recycled after a synchronise
+    CU_TRY(c, cudaEventSynchronize(c->done[(int)(ticket % kRing)][0]));
     return 0;
 }
 

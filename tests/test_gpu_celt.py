@@ -211,3 +211,37 @@ def test_device_resident_path(pkg, ref):
     times = dec.stage_times()
     assert set(times) >= {"entropy", "bands", "imdct", "postfilter", "deemph"} and all(v >= 0 for v in times.values())
     dec.close()
+
+
+def test_async_calls_in_flight_match_blocking_calls(pkg):
+    """decode_many_async/dm_wait with two calls in flight == the same steps through blocking decode_many."""
+    S, F, steps = 256, 10, 6
+    data, frames = pkg.synth_corpus(S, F * steps, 159, 0xFC)
+    a = pkg.BatchDecoder(S, F, channels=2)
+    want = []
+    for k in range(steps):
+        rc, pcm, st = a.decode_many(data, np.ascontiguousarray(frames[:, k * F:(k + 1) * F]))
+        assert rc == 0 and (st == 960).all()
+        want.append(pcm.copy())
+    a.close()
+    b = pkg.BatchDecoder(S, F, channels=2)
+    hb = pkg.api.PinnedArray(data.size, np.uint8)
+    hb.array[:] = data
+    hf = [pkg.api.PinnedArray((S, F), pkg.FRAME_DTYPE) for _ in range(steps)]
+    outs = [(pkg.api.PinnedArray((S, F, 960, 2), np.int16), pkg.api.PinnedArray((S, F), np.int32)) for _ in range(2)]
+    pending = None
+    got = []
+    for k in range(steps):
+        hf[k].array[:] = frames[:, k * F:(k + 1) * F]
+        o = outs[k & 1]
+        rc, ticket = b.decode_many_async(hb.array, hf[k].array, o[0].array, o[1].array)
+        assert rc == 0
+        if pending is not None:
+            assert b.wait(pending[0]) == 0
+            got.append(pending[1][0].array.copy())
+        pending = (ticket, o)
+    assert b.wait(pending[0]) == 0
+    got.append(pending[1][0].array.copy())
+    for k in range(steps):
+        assert np.array_equal(got[k], want[k]), k
+    b.close()
