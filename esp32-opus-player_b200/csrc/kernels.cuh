@@ -252,99 +252,119 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // De-emphasis is a strictly serial 1-pole IIR with per-step truncation (ref src/celt.cpp:1977-1982):
-// one lane owns one (stream, channel) chain.  A warp owns 32 chains and moves 32x32 tiles through
-// shared memory so that every global access is a full 128 B line (loads) or int16x8 vectors (stores).
-// The next tiles are prefetched with cp.async (LDGSTS) into a 4-deep shared-memory ring while the
-// lanes run the recurrence on the current one: with only one warp of work per 32 chains there is no
-// other way to hide HBM latency.
-enum { DE_TW = 32, DE_IN_STRIDE = 33, DE_OUT_STRIDE = 36, DE_STAGES = 4 };
+// one lane owns one (stream, channel) chain, a warp owns 32 chains -- there is no more parallelism to be had
+// (S x CC chains per GPU), so the kernel is built around the LATENCY of one warp: each lane streams its own row
+// 32 samples at a time through a private shared-memory ring (8 x 16-byte cp.async per tile, 4 tiles ahead, no
+// address arithmetic on the critical path), pulls a tile into registers with 8 LDS.128, runs the recurrence
+// (add -> 64-bit multiply -> shift per sample), and the stereo pair of lanes swaps halves with 8 shuffles so that
+// every lane ends up with 16 consecutive interleaved frames = 64 contiguous bytes, written as 4 x int16x8 stores.
+enum { DE_TW = 32, DE_ROW = 36, DE_STAGES = 4 };
 
 __global__ void __launch_bounds__(32)
 k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hdr, const int32_t* __restrict__ syn,
          int16_t* __restrict__ pcm, int32_t* __restrict__ status, CeltStreamState* __restrict__ st, DevParams P) {
-    __shared__ int32_t tin[DE_STAGES][32 * DE_IN_STRIDE];
-    __shared__ __align__(16) uint32_t tout[32 * DE_OUT_STRIDE];
+    __shared__ __align__(16) int32_t ring[DE_STAGES][32 * DE_ROW];
     const int lane = threadIdx.x;
     const int CC = P.CC;
-    const int chain0 = blockIdx.x * 32;              // chains are (stream - first_stream) * CC + c
-    const int n_chains = P.n_sel * CC;
-    const int my = chain0 + lane;
+    const int n_chains = P.n_sel * CC;          // chains are (stream - first_stream) * CC + c
+    const int my = blockIdx.x * 32 + lane;
     const bool live = my < n_chains;
     const int my_s = P.first_stream + (live ? my / CC : 0), my_c = live ? my % CC : 0;
     s32 mem = live ? st[my_s].preemph_mem[my_c] : 0;
     const int N = P.frame_size;
     const int tpf = (N + DE_TW - 1) / DE_TW, T = tpf * P.n_frames;
-    const int rows = min(32, n_chains - chain0);
-    int16_t* tout16 = reinterpret_cast<int16_t*>(tout);
+    const int32_t* row0 = syn + ((size_t)my_s * P.n_frames * CC + my_c) * kMaxFrame;  // frame f of this chain: + f * CC * kMaxFrame
+    int16_t* out0 = pcm + (size_t)my_s * P.n_frames * N * CC;                            // frame f of this stream: + f * N * CC
 
-    auto prefetch = [&](int q) {
-        if (q < T) {
-            const int f = q / tpf, j0 = (q % tpf) * DE_TW;
-            int32_t* dst = tin[q % DE_STAGES];
-            if (j0 + lane < N) {
-#pragma unroll 4
-                for (int r = 0; r < rows; r++) {
-                    const int qc = chain0 + r;
-                    const size_t t = (size_t)(P.first_stream + qc / CC) * P.n_frames + f;
-                    __pipeline_memcpy_async(&dst[r * DE_IN_STRIDE + lane], &syn[(t * CC + (qc % CC)) * kMaxFrame + j0 + lane], 4);
-                }
-            }
+    // prefetch cursor (tile index -> frame, offset) kept incrementally
+    int pf_q = 0, pf_f = 0, pf_j = 0;
+    auto prefetch = [&]() {
+        if (pf_q < T && live) {
+            const int w = min(DE_TW, N - pf_j);
+            const int32_t* src = row0 + (size_t)pf_f * CC * kMaxFrame + pf_j;
+            int32_t* dst = &ring[pf_q % DE_STAGES][lane * DE_ROW];
+#pragma unroll
+            for (int k = 0; k < DE_TW / 4; k++)
+                if (4 * k < w) __pipeline_memcpy_async(dst + 4 * k, src + 4 * k, 16);
         }
         __pipeline_commit();
+        pf_q++;
+        pf_j += DE_TW;
+        if (pf_j >= N) { pf_j = 0; pf_f++; }
     };
+    for (int q = 0; q < DE_STAGES - 1; q++) prefetch();
 
-    for (int q = 0; q < DE_STAGES - 1; q++) prefetch(q);
-    int my_n = 0;  // samples of this frame that carry CELT output (0: none, 120 for a hybrid -> SILK fade-out frame)
+    int f = 0, j0 = 0, my_n = 0;
     for (int q = 0; q < T; q++) {
-        const int f = q / tpf, j0 = (q % tpf) * DE_TW;
         const int w = min(DE_TW, N - j0);
         if (j0 == 0) {
             const size_t my_t = (size_t)my_s * P.n_frames + f;
-            my_n = live ? fe[my_t].celt_n : 0;
+            my_n = live ? fe[my_t].celt_n : 0;  // samples of this frame that carry CELT output (0, or 120 for a fade-out frame)
             if (live && my_c == 0) status[my_t] = (fe[my_t].skip & FS_DROPPED) ? OPUSB_FRAME_SKIPPED : hdr[my_t].status;
         }
-        prefetch(q + DE_STAGES - 1);
+        prefetch();
         __pipeline_wait_prior(DE_STAGES - 1);
-        __syncwarp();
-        const int32_t* src = tin[q % DE_STAGES];
-        // serial recurrence, one chain per lane
-        if (CC == 2) {
-            const int qs = lane >> 1;
-#pragma unroll 8
-            for (int j = 0; j < w; j++) {
-                s32 v = (j0 + j < my_n) ? deemph_sample(src[lane * DE_IN_STRIDE + j], mem) : 0;
-                tout16[(qs * DE_OUT_STRIDE + j) * 2 + (lane & 1)] = (int16_t)v;
-            }
-        } else {
-#pragma unroll 8
-            for (int j = 0; j < w; j++) {
-                s32 v = (j0 + j < my_n) ? deemph_sample(src[lane * DE_IN_STRIDE + j], mem) : 0;
-                tout16[lane * DE_OUT_STRIDE * 2 + j] = (int16_t)v;
-            }
+        // tile -> registers (a lane only ever reads what it copied itself: no warp synchronisation needed)
+        const int4* src = reinterpret_cast<const int4*>(&ring[q % DE_STAGES][lane * DE_ROW]);
+        s32 xv[DE_TW];
+#pragma unroll
+        for (int k = 0; k < DE_TW / 4; k++) {
+            const int4 v = src[k];
+            xv[4 * k] = v.x; xv[4 * k + 1] = v.y; xv[4 * k + 2] = v.z; xv[4 * k + 3] = v.w;
         }
-        __syncwarp();
-        // store: interleaved PCM rows, int16x8 (16 B) per lane
+        // the recurrence; two samples per 32-bit word
+        const int live_n = my_n - j0;
+        uint32_t pk[DE_TW / 2];
+#pragma unroll
+        for (int j = 0; j < DE_TW; j += 2) {
+            s32 a = 0, b = 0;
+            if (j < live_n) a = deemph_sample(xv[j], mem);
+            if (j + 1 < live_n) b = deemph_sample(xv[j + 1], mem);
+            pk[j >> 1] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+        }
         if (CC == 2) {
-            for (int it = 0; it < 4; it++) {
-                const int qs = it * 4 + (lane >> 3), chunk = lane & 7;  // stream within the warp, 4 sample pairs per chunk
-                const int sl = chain0 / 2 + qs;                          // stream index relative to first_stream
-                if (sl < P.n_sel && chunk * 4 < w) {
-                    const size_t t = (size_t)(P.first_stream + sl) * P.n_frames + f;
-                    uint4 v = *reinterpret_cast<const uint4*>(&tout[qs * DE_OUT_STRIDE + chunk * 4]);
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(pcm) + (t * N + j0 + chunk * 4);
-                    if (chunk * 4 + 4 <= w) *reinterpret_cast<uint4*>(dst) = v;
-                    else { const uint32_t vv[4] = {v.x, v.y, v.z, v.w}; for (int k = 0; k < w - chunk * 4; k++) dst[k] = vv[k]; }
+            // lanes 2k (left) and 2k+1 (right): the left lane keeps frames 0..15 of the tile, the right lane 16..31
+            uint32_t other[DE_TW / 4];
+            const bool right = lane & 1;
+#pragma unroll
+            for (int k = 0; k < DE_TW / 4; k++) {
+                const uint32_t give = right ? pk[k] : pk[k + DE_TW / 4];
+                other[k] = __shfl_xor_sync(0xffffffffu, give, 1);
+            }
+            uint32_t ow[DE_TW / 2];  // 16 interleaved frames: (R << 16) | L
+#pragma unroll
+            for (int k = 0; k < DE_TW / 4; k++) {
+                const uint32_t l = right ? other[k] : pk[k], r = right ? pk[k + DE_TW / 4] : other[k];
+                ow[2 * k] = __byte_perm(l, r, 0x5410);
+                ow[2 * k + 1] = __byte_perm(l, r, 0x7632);
+            }
+            if (live) {
+                const int h0 = right ? DE_TW / 2 : 0;  // first frame of this lane's half inside the tile
+                uint32_t* dst = reinterpret_cast<uint32_t*>(out0 + (size_t)f * N * 2) + j0 + h0;
+                if (w == DE_TW) {
+#pragma unroll
+                    for (int k = 0; k < DE_TW / 8; k++)
+                        *reinterpret_cast<uint4*>(dst + 4 * k) = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DE_TW / 2; k++)
+                        if (h0 + k < w) dst[k] = ow[k];
                 }
             }
-        } else {
-            for (int r = 0; r < rows; r++) {
-                if (lane < w) {
-                    const size_t t = (size_t)(P.first_stream + chain0 + r) * P.n_frames + f;
-                    pcm[t * N + j0 + lane] = tout16[r * DE_OUT_STRIDE * 2 + lane];
-                }
+        } else if (live) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out0 + (size_t)f * N + j0);  // N and j0 are even: 4-byte aligned
+            if (w == DE_TW && (((size_t)f * N + j0) & 7) == 0) {
+#pragma unroll
+                for (int k = 0; k < DE_TW / 8; k++)
+                    *reinterpret_cast<uint4*>(dst + 4 * k) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < DE_TW / 2; k++)
+                    if (2 * k < w) dst[k] = pk[k];
             }
         }
-        __syncwarp();
+        j0 += DE_TW;
+        if (j0 >= N) { j0 = 0; f++; }
     }
     if (live) st[my_s].preemph_mem[my_c] = mem;
 }
