@@ -41,12 +41,27 @@ OPUS_HD void w_renormalise(const Lanes& L, int16_t* X, int N, s16 gain) {
     L.sync();
 }
 
-// ref haar1 (src/celt.cpp:1202)
+// d / n and d % n for small operands without the 20-instruction integer divide: rcp = ceil(2^32 / n) is exact
+// for d * n < 2^32 (here d < 2048, n <= 176).  n == 1 has no 32-bit reciprocal.
+struct SmallDiv {
+    u32 n, rcp;
+    OPUS_HD explicit SmallDiv(int n_) : n((u32)n_), rcp(n_ > 1 ? 0xFFFFFFFFu / (u32)n_ + 1u : 0u) {}
+    OPUS_HD int div(int d) const {
+#if defined(__CUDA_ARCH__)
+        return n > 1 ? (int)__umulhi((u32)d, rcp) : d;
+#else
+        return (int)((u32)d / n);
+#endif
+    }
+};
+
+// ref haar1 (src/celt.cpp:1202); stride is a power of two (1 << k or the block count B)
 OPUS_HD void w_haar(const Lanes& L, int16_t* X, int N0, int stride) {
     const int pairs = (N0 >> 1) * stride;
+    const int sh = ilog2p(stride);
     for (int t = L.lane; t < pairs; t += kLanes) {
-        int i = t % stride, j = t / stride;
-        int ia = stride * 2 * j + i, ib = stride * (2 * j + 1) + i;
+        const int i = t & (stride - 1), j = t >> sh;
+        const int ia = ((2 * j) << sh) + i, ib = ia + stride;
         s32 t1 = mul16(23170, X[ia]), t2 = mul16(23170, X[ib]);
         X[ia] = (s16)pshr32(t1 + t2, 15);
         X[ib] = (s16)pshr32(t1 - t2, 15);
@@ -54,10 +69,19 @@ OPUS_HD void w_haar(const Lanes& L, int16_t* X, int N0, int stride) {
     L.sync();
 }
 
-// ref deinterleave_hadamard / interleave_hadamard (src/celt.cpp:1162, 1183): a permutation of N0*stride values
+// inverse of the ordery permutation (ref ordery_table, src/celt.cpp:1160), same packing as kOrdery
+OPUS_TABLE uint8_t kOrderyInv[30] = {
+    1, 0, 1, 3, 2, 0, 1, 5, 7, 3, 2, 6, 4, 0, 1, 9, 13, 5, 7, 15, 11, 3, 2, 10, 14, 6, 4, 12, 8, 0,
+};
+
+// ref deinterleave_hadamard / interleave_hadamard (src/celt.cpp:1162, 1183): a permutation of N0*stride values;
+// stride is a power of two
 OPUS_HD void w_hadamard_perm(const Lanes& L, int16_t* X, int N0, int stride, int hadamard, int inverse) {
     const int N = N0 * stride;
     const uint8_t* ordery = kOrdery + stride - 2;
+    const uint8_t* orderyinv = kOrderyInv + stride - 2;
+    const int sh = ilog2p(stride);
+    const SmallDiv byN0(N0);
     enum { kPer = (kMaxLeaf + kLanes - 1) / kLanes };
     s16 tmp[kPer];
     // destination index d -> source index
@@ -65,12 +89,11 @@ OPUS_HD void w_hadamard_perm(const Lanes& L, int16_t* X, int N0, int stride, int
     for (int d = L.lane; d < N; d += kLanes, q++) {
         int src;
         if (!inverse) {  // tmp[ord(i)*N0 + j] = X[j*stride + i]
-            int oi = d / N0, j = d % N0;
-            int i = oi;
-            if (hadamard) { for (i = 0; i < stride; i++) if (ordery[i] == oi) break; }
-            src = j * stride + i;
+            const int oi = byN0.div(d), j = d - oi * N0;
+            const int i = hadamard ? orderyinv[oi] : oi;
+            src = (j << sh) + i;
         } else {         // tmp[j*stride + i] = X[ord(i)*N0 + j]
-            int j = d / stride, i = d % stride;
+            const int j = d >> sh, i = d & (stride - 1);
             src = (hadamard ? ordery[i] : i) * N0 + j;
         }
         tmp[q] = X[src];

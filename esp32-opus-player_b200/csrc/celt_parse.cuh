@@ -24,6 +24,8 @@ struct ParseCtx {
     BandOp* ops;      // transform ops from the front, leaf records from the back
     int n_ops, n_leaves, ops_cap, overflow;
     uint32_t lcg_steps;
+    // transforms of the folding source of the current band job, emitted only if a leaf really folds (see lowband_prep)
+    int prep_on, prep_scratch, prep_src, prep_N, prep_recombine, prep_tf, prep_NB, prep_B, prep_long;
     unsigned wmask;   // lanes of this warp that parse a CELT frame together (warp_converge / warp_any)
 };
 
@@ -40,6 +42,34 @@ OPUS_HD void emit_leaf(ParseCtx& p, int B, int off, int K, int n, int gain, u32 
     o.code = OP_LEAF; o.a = (uint8_t)B; o.off = (uint16_t)off; o.off2 = (uint16_t)K; o.n = (uint16_t)n;
     o.g = (int16_t)gain; o.g2 = 0; o.aux = index;
     p.ops[p.ops_cap - 1 - p.n_leaves++] = o;
+}
+
+// The reference reshapes the folding source of every band (copy to scratch, haar1 per tf step, deinterleave;
+// src/celt.cpp:1553-1584) whether or not any leaf of the band ends up folding.  Here the reshaping is emitted on
+// demand, in front of the first OP_FOLD of the band job; when every leaf is coded (the common case at 64 kb/s)
+// none of it is emitted and the band kernel replays a quarter fewer ops.  The result is the same: nothing else
+// reads the scratch copy, and the in-place variant (last band) only touches folding history nobody reads again.
+OPUS_HD void lowband_prep(ParseCtx& p) {
+    if (!p.prep_on) return;
+    p.prep_on = 0;
+    int lowband = p.prep_src;
+    const int N = p.prep_N, recombine = p.prep_recombine;
+    int tf_change = p.prep_tf, N_B = p.prep_NB, B = p.prep_B;
+    const int B00 = B;
+    if (p.prep_scratch >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B00 > 1)) {
+        emit_op(p, OP_COPY, 0, p.prep_scratch, lowband, N, 0, 0);
+        lowband = p.prep_scratch;
+    }
+    for (int k = 0; k < recombine; k++) emit_op(p, OP_HAAR, 1 << k, lowband, 0, N >> k, 0, 0);
+    B >>= recombine;
+    N_B <<= recombine;
+    while ((N_B & 1) == 0 && tf_change < 0) {
+        emit_op(p, OP_HAAR, B, lowband, 0, N_B, 0, 0);
+        B <<= 1;
+        N_B >>= 1;
+        tf_change++;
+    }
+    if (B > 1) emit_op(p, OP_DEINT, B << recombine, lowband, 0, N_B >> recombine, p.prep_long, 0);
 }
 
 // ---- pulse cache helpers (ref src/celt.h:533-569) ----
@@ -303,6 +333,7 @@ OPUS_HD u32 partition(ParseCtx& p, bool active, int xoff, int N, int b, int B, i
                         p.lcg_steps += (u32)cur.N;
                         ret = cm_mask;
                     } else {
+                        lowband_prep(p);
                         emit_op(p, OP_FOLD, 0, cur.xoff, cur.lowband, cur.N, cur.gain, 0);
                         p.lcg_steps += (u32)cur.N;
                         ret = (u32)fl;
@@ -346,19 +377,17 @@ OPUS_HD bool band_mono_pre(ParseCtx& p, MonoCtx& m, int xoff, int N, int B, int 
         return false;
     }
     if (tf_change > 0) recombine = tf_change;
-    if (scratch >= 0 && lowband >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
-        emit_op(p, OP_COPY, 0, scratch, lowband, N, 0, 0);
-        lowband = scratch;
-    }
+    p.prep_on = lowband >= 0;
+    p.prep_scratch = scratch; p.prep_src = lowband; p.prep_N = N; p.prep_recombine = recombine; p.prep_tf = tf_change;
+    p.prep_NB = N_B; p.prep_B = B; p.prep_long = m.longBlocks;
+    if (scratch >= 0 && lowband >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) lowband = scratch;
     for (int k = 0; k < recombine; k++) {
         const uint8_t bit_interleave[16] = {0, 1, 1, 1, 2, 3, 3, 3, 2, 3, 3, 3, 2, 3, 3, 3};
-        if (lowband >= 0) emit_op(p, OP_HAAR, 1 << k, lowband, 0, N >> k, 0, 0);
         fill = bit_interleave[fill & 0xF] | bit_interleave[fill >> 4] << 2;
     }
     B >>= recombine;
     N_B <<= recombine;
     while ((N_B & 1) == 0 && tf_change < 0) {
-        if (lowband >= 0) emit_op(p, OP_HAAR, B, lowband, 0, N_B, 0, 0);
         fill |= fill << B;
         B <<= 1;
         N_B >>= 1;
@@ -366,7 +395,6 @@ OPUS_HD bool band_mono_pre(ParseCtx& p, MonoCtx& m, int xoff, int N, int B, int 
         tf_change++;
     }
     B0 = B;
-    if (B0 > 1 && lowband >= 0) emit_op(p, OP_DEINT, B0 << recombine, lowband, 0, N_B >> recombine, m.longBlocks, 0);
     m.B = B; m.B0 = B0; m.N_B = N_B; m.N_B0 = N_B; m.recombine = recombine; m.time_divide = time_divide; m.lowband = lowband; m.fill = fill;
     return true;
 }
@@ -534,6 +562,7 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
             const bool act = j < njobs;
             const bool walk = act && band_mono_pre(p, m, J.xoff, Nb, B, J.lowband, J.out, J.scratch, J.fill);
             const u32 cm = partition(p, walk, J.xoff, Nb, J.b, m.B, m.lowband, LM, J.gain, m.fill);
+            p.prep_on = 0;
             if (act) cm_job[j] = walk ? band_mono_post(p, m, cm) : 1u;
             if (mode == 1 && j == 0) {
                 const int rebalance = first_bits - (rebalance0 - p.remaining_bits);

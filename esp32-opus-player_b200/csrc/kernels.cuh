@@ -57,7 +57,7 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     p.end = kNbEBands; p.disable_inv = (P.CC == 1);
     p.band = 0; p.intensity = 0; p.spread = 0; p.tf_change = 0; p.remaining_bits = 0;
     p.ops = ops + t * kMaxOps; p.n_ops = 0; p.n_leaves = 0; p.ops_cap = kMaxOps; p.overflow = 0; p.lcg_steps = 0;
-    p.C = 1; p.LM = 3; p.start = 0;
+    p.C = 1; p.LM = 3; p.start = 0; p.prep_on = 0;
     int oflags = 0;
     bool celt = true, fade = false;
     if (d.flags & FD_NULL) {  // filler behind the last frame of a stream: no output, no state change
