@@ -32,11 +32,13 @@ OPUS_HD u32 lcg_jump(u32 seed, int cnt) { return kLcgMul[cnt - 1] * seed + kLcgA
 // ref renormalise_vector (src/celt.cpp:797)
 OPUS_HD void w_renormalise(const Lanes& L, int16_t* X, int N, s16 gain) {
     s32 acc = 0;
+#pragma unroll 1
     for (int j = L.lane; j < N; j += kLanes) acc = add_w(acc, mul16(X[j], X[j]));
     s32 E = add_w(1, L.sum(acc));
     int k = ilog2p(E) >> 1;
     s32 t = vshr32(E, 2 * (k - 7));
     s16 g = (s16)mul16_p15(rsqrt_norm(t), gain);
+#pragma unroll 1
     for (int j = L.lane; j < N; j += kLanes) X[j] = (s16)pshr32(mul16(g, X[j]), k + 1);
     L.sync();
 }
@@ -59,6 +61,7 @@ struct SmallDiv {
 OPUS_HD void w_haar(const Lanes& L, int16_t* X, int N0, int stride) {
     const int pairs = (N0 >> 1) * stride;
     const int sh = ilog2p(stride);
+#pragma unroll 1
     for (int t = L.lane; t < pairs; t += kLanes) {
         const int i = t & (stride - 1), j = t >> sh;
         const int ia = ((2 * j) << sh) + i, ib = ia + stride;
@@ -86,6 +89,7 @@ OPUS_HD void w_hadamard_perm(const Lanes& L, int16_t* X, int N0, int stride, int
     s16 tmp[kPer];
     // destination index d -> source index
     int q = 0;
+#pragma unroll 1
     for (int d = L.lane; d < N; d += kLanes, q++) {
         int src;
         if (!inverse) {  // tmp[ord(i)*N0 + j] = X[j*stride + i]
@@ -100,6 +104,7 @@ OPUS_HD void w_hadamard_perm(const Lanes& L, int16_t* X, int N0, int stride, int
     }
     L.sync();
     q = 0;
+#pragma unroll 1
     for (int d = L.lane; d < N; d += kLanes, q++) X[d] = tmp[q];
     L.sync();
 }
@@ -107,6 +112,7 @@ OPUS_HD void w_hadamard_perm(const Lanes& L, int16_t* X, int N0, int stride, int
 // ref stereo_merge (src/celt.cpp:1113)
 OPUS_HD void w_stereo_merge(const Lanes& L, int16_t* X, int16_t* Y, s16 mid, int N) {
     s32 a = 0, b = 0;
+#pragma unroll 1
     for (int j = L.lane; j < N; j += kLanes) {
         a = add_w(a, mul16(Y[j], X[j]));
         b = add_w(b, mul16(Y[j], Y[j]));
@@ -117,6 +123,7 @@ OPUS_HD void w_stereo_merge(const Lanes& L, int16_t* X, int16_t* Y, s16 mid, int
     s32 El = mul16(mid2, mid2) + side - 2 * xp;
     s32 Er = mul16(mid2, mid2) + side + 2 * xp;
     if (Er < 161061 || El < 161061) {  // QCONST32(6e-4f, 28)
+#pragma unroll 1
         for (int j = L.lane; j < N; j += kLanes) Y[j] = X[j];
         L.sync();
         return;
@@ -126,6 +133,7 @@ OPUS_HD void w_stereo_merge(const Lanes& L, int16_t* X, int16_t* Y, s16 mid, int
     s32 rgain = rsqrt_norm(vshr32(Er, (kr - 7) << 1));
     if (kl < 7) kl = 7;
     if (kr < 7) kr = 7;
+#pragma unroll 1
     for (int j = L.lane; j < N; j += kLanes) {
         s16 l = (s16)mul16_p15(mid, X[j]);
         s16 r = Y[j];
@@ -198,11 +206,13 @@ OPUS_HD s32 pvq_expand(int n, int k, u32 i, int16_t* y) {
 // recurrence with per-step rounding: serial along the vector, so a lane keeps the carried value in a register.
 OPUS_HD void leaf_rotate1(int16_t* X, int len, int stride, s16 c, s16 s) {
     const s16 ms = (s16)(-(s32)s);
+#pragma unroll 1
     for (int i = 0; i < len - stride; i++) {
         s16 x1 = X[i], x2 = X[i + stride];
         X[i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
         X[i] = (s16)pshr32(mul16(c, x1) + mul16(ms, x2), 15);
     }
+#pragma unroll 1
     for (int i = len - 2 * stride - 1; i >= 0; i--) {
         s16 x1 = X[i], x2 = X[i + stride];
         X[i + stride] = (s16)pshr32(mul16(c, x2) + mul16(s, x1), 15);
@@ -222,6 +232,7 @@ OPUS_HD void leaf_rotate(int16_t* X, int len, int stride, int K, int spread) {
         while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
     }
     len = (int)((u32)len / (u32)stride);
+#pragma unroll 1
     for (int i = 0; i < stride; i++) {
         if (stride2) leaf_rotate1(X + i * len, len, stride2, s, c);
         leaf_rotate1(X + i * len, len, 1, c, s);
@@ -231,6 +242,7 @@ OPUS_HD void leaf_rotate(int16_t* X, int len, int stride, int K, int spread) {
 // ref alg_unquant (src/celt.cpp:782) for every coded leaf of the frame.  `last` points at the first leaf
 // record (leaves are stored downwards from the end of the frame's op buffer).
 OPUS_HD void leaf_stage(const Lanes& L, int16_t* W, const BandOp* last, int n_leaves, int spread) {
+#pragma unroll 1
     for (int l0 = 0; l0 < n_leaves; l0 += kLanes) {
         const int l = l0 + L.lane;
         if (l < n_leaves) {
@@ -242,6 +254,7 @@ OPUS_HD void leaf_stage(const Lanes& L, int16_t* W, const BandOp* last, int n_le
             const int k = ilog2p(Ryy) >> 1;
             const s32 t = vshr32(Ryy, 2 * (k - 7));
             const s16 g = (s16)mul16_p15(rsqrt_norm(t), o.g);
+#pragma unroll 1
             for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
             leaf_rotate(y, N, B, K, spread);
         }
@@ -255,6 +268,7 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
     // ops are fetched kLanes at a time (one 16-byte load per lane) and broadcast, so the replay loop
     // never waits on a dependent global load per op
     BandOp mine = BandOp();
+#pragma unroll 1
     for (int k = 0; k < n_ops; k++) {
         if ((k % kLanes) == 0 && k + L.lane < n_ops) mine = ops[k + L.lane];
         const BandOp o = L.bcast_op(mine, k % kLanes);
@@ -262,6 +276,7 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
         const int n = o.n;
         switch (o.code) {
             case OP_NOISE:
+#pragma unroll 1
                 for (int j0 = 0; j0 < n; j0 += kLanes) {
                     int cnt = imin(kLanes, n - j0);
                     if (L.lane < cnt) {
@@ -275,6 +290,7 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
                 break;
             case OP_FOLD: {
                 const int16_t* lb = W + o.off2;
+#pragma unroll 1
                 for (int j0 = 0; j0 < n; j0 += kLanes) {
                     int cnt = imin(kLanes, n - j0);
                     if (L.lane < cnt) {
@@ -289,6 +305,7 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
             } break;
             case OP_COPY: {
                 const int16_t* src = W + o.off2;
+#pragma unroll 1
                 for (int j = L.lane; j < n; j += kLanes) X[j] = src[j];
                 L.sync();
             } break;
@@ -297,6 +314,7 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
             case OP_INT: w_hadamard_perm(L, X, n, o.a, o.g, 1); break;
             case OP_SCALE_OUT: {
                 int16_t* dst = W + o.off2;
+#pragma unroll 1
                 for (int j = L.lane; j < n; j += kLanes) dst[j] = (s16)mul16_q15(o.g, X[j]);
                 L.sync();
             } break;
@@ -306,6 +324,7 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
                 break;
             case OP_MERGE: w_stereo_merge(L, X, W + o.off2, o.g, n); break;
             case OP_NEG:
+#pragma unroll 1
                 for (int j = L.lane; j < n; j += kLanes) X[j] = (s16)(-(s32)X[j]);
                 L.sync();
                 break;
@@ -332,11 +351,13 @@ OPUS_HD u32 band_stage_ops(const Lanes& L, int16_t* W, const BandOp* ops, int n_
                 L.sync();
             } break;
             case OP_ZERO:
+#pragma unroll 1
                 for (int j = L.lane; j < n; j += kLanes) X[j] = 0;
                 L.sync();
                 break;
             case OP_AVG: {
                 const int16_t* src = W + o.off2;
+#pragma unroll 1
                 for (int j = L.lane; j < n; j += kLanes) X[j] = (s16)(((s32)X[j] + (s32)src[j]) >> 1);
                 L.sync();
             } break;
@@ -358,6 +379,7 @@ OPUS_HD void band_stage_anti_collapse(const Lanes& L, int16_t* W, const CeltFram
         const int shift = ilog2p(t) >> 1;
         t = shl32(t, (7 - shift) << 1);
         const s16 sqrt_1 = rsqrt_norm(t);
+#pragma unroll 1
         for (int c = 0; c < C; c++) {
             s32 Ediff = (s32)fe.E[c][i] - (s32)fe.pmin[c][i];
             Ediff = imax(0, Ediff);
@@ -373,8 +395,10 @@ OPUS_HD void band_stage_anti_collapse(const Lanes& L, int16_t* W, const CeltFram
             r = (s16)(mul16_q15(sqrt_1, r) >> shift);
             int16_t* X = W + W_XY + c * size + (kEBands[i] << LM);
             int renorm = 0;
+#pragma unroll 1
             for (int k = 0; k < (1 << LM); k++) {
                 if (!(h.cmask[i * C + c] & (1 << k))) {
+#pragma unroll 1
                     for (int j0 = 0; j0 < N0; j0 += kLanes) {
                         int cnt = imin(kLanes, N0 - j0);
                         if (L.lane < cnt) {
