@@ -60,9 +60,11 @@ OPUS_HD void lowband_prep(ParseCtx& p) {
         emit_op(p, OP_COPY, 0, p.prep_scratch, lowband, N, 0, 0);
         lowband = p.prep_scratch;
     }
+#pragma unroll 1
     for (int k = 0; k < recombine; k++) emit_op(p, OP_HAAR, 1 << k, lowband, 0, N >> k, 0, 0);
     B >>= recombine;
     N_B <<= recombine;
+#pragma unroll 1
     while ((N_B & 1) == 0 && tf_change < 0) {
         emit_op(p, OP_HAAR, B, lowband, 0, N_B, 0, 0);
         B <<= 1;
@@ -79,6 +81,7 @@ OPUS_HD int bits2pulses(int band, int LM, int bits) {
     const uint8_t* cache = pulse_cache(band, LM);
     int lo = 0, hi = cache[0];
     bits--;
+#pragma unroll 1
     for (int i = 0; i < 6; i++) {
         int mid = (lo + hi + 1) >> 1;
         if ((int)cache[mid] >= bits) hi = mid; else lo = mid;
@@ -101,6 +104,7 @@ OPUS_HD u32 pvq_index_mask(int n, int k, u32 i, int B) {
     const int N0 = (int)((u32)n / (u32)B);
     u32 p, cm = 0;
     int s, k0, pos = 0;
+#pragma unroll 1
     while (n > 2) {
         u32 q;
         int val;
@@ -113,8 +117,10 @@ OPUS_HD u32 pvq_index_mask(int n, int k, u32 i, int B) {
             q = row[n];
             if (q > i) {
                 k = n;
+#pragma unroll 1
                 do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
             } else {
+#pragma unroll 1
                 for (p = row[k]; p > i; p = row[k]) k--;
             }
             i -= p;
@@ -129,6 +135,7 @@ OPUS_HD u32 pvq_index_mask(int n, int k, u32 i, int B) {
                 s = -(int)(i >= q);
                 i -= q & (u32)s;
                 k0 = k;
+#pragma unroll 1
                 do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
                 i -= p;
                 val = k0 - k;
@@ -243,6 +250,7 @@ OPUS_HD void decode_theta(ParseCtx& p, ThetaOut& o, int N, int* b, int B, int B0
 // ref quant_band_n1 (src/celt.cpp:1357). xoff/yoff index X (yoff < 0: mono), out = lowband_out offset or -1.
 OPUS_HD u32 band_n1(ParseCtx& p, int xoff, int yoff, int out) {
     int x0 = 0;
+#pragma unroll 1
     for (int c = 0; c < 1 + (yoff >= 0); c++) {
         int sign = 0;
         if (p.remaining_bits >= 1 << 3) {
@@ -280,6 +288,7 @@ OPUS_HD u32 partition(ParseCtx& p, bool active, int xoff, int N, int b, int B, i
     cur.xoff = xoff; cur.N = N; cur.b = b; cur.B = B; cur.lowband = lowband; cur.LM = LM; cur.fill = fill; cur.gain = gain;
     u32 ret = 0;
     bool descend = true, done = !active;
+#pragma unroll 1
     while (warp_any(p.wmask, !done)) {
         if (done) continue;
         if (descend) {
@@ -314,6 +323,7 @@ OPUS_HD u32 partition(ParseCtx& p, bool active, int xoff, int N, int b, int B, i
                 int q = bits2pulses(i, cur.LM, cur.b);
                 int curr_bits = pulses2bits(i, cur.LM, q);
                 p.remaining_bits -= curr_bits;
+#pragma unroll 1
                 while (p.remaining_bits < 0 && q > 0) {
                     p.remaining_bits += curr_bits;
                     q--;
@@ -381,12 +391,14 @@ OPUS_HD bool band_mono_pre(ParseCtx& p, MonoCtx& m, int xoff, int N, int B, int 
     p.prep_scratch = scratch; p.prep_src = lowband; p.prep_N = N; p.prep_recombine = recombine; p.prep_tf = tf_change;
     p.prep_NB = N_B; p.prep_B = B; p.prep_long = m.longBlocks;
     if (scratch >= 0 && lowband >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) lowband = scratch;
+#pragma unroll 1
     for (int k = 0; k < recombine; k++) {
         const uint8_t bit_interleave[16] = {0, 1, 1, 1, 2, 3, 3, 3, 2, 3, 3, 3, 2, 3, 3, 3};
         fill = bit_interleave[fill & 0xF] | bit_interleave[fill >> 4] << 2;
     }
     B >>= recombine;
     N_B <<= recombine;
+#pragma unroll 1
     while ((N_B & 1) == 0 && tf_change < 0) {
         fill |= fill << B;
         B <<= 1;
@@ -405,12 +417,14 @@ OPUS_HD u32 band_mono_post(ParseCtx& p, const MonoCtx& m, u32 cm) {
     if (B0 > 1) emit_op(p, OP_INT, B0 << recombine, xoff, 0, N_B >> recombine, m.longBlocks, 0);
     N_B = m.N_B0;
     B = B0;
+#pragma unroll 1
     for (int k = 0; k < m.time_divide; k++) {
         B >>= 1;
         N_B <<= 1;
         cm |= cm >> B;
         emit_op(p, OP_HAAR, B, xoff, 0, N_B, 0, 0);
     }
+#pragma unroll 1
     for (int k = 0; k < recombine; k++) {
         const uint8_t bit_deinterleave[16] = {0x00, 0x03, 0x0C, 0x0F, 0x30, 0x33, 0x3C, 0x3F,
                                               0xC0, 0xC3, 0xCC, 0xCF, 0xF0, 0xF3, 0xFC, 0xFF};
@@ -439,10 +453,12 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
     int lowband_offset = 0, update_lowband = 1;
     p.intensity = intensity;
     const int start0 = warp_min(p.wmask, start);  // lanes may start at band 0 or 17 (hybrid): one loop for all of them
+#pragma unroll 1
     for (int i = start0; i < end; i++) {
         warp_converge(p.wmask);
         if (i < start) {
             // keep in step with the lanes that do have this band: two empty job slots
+#pragma unroll 1
             for (int j = 0; j < 2; j++) partition(p, false, 0, 0, 0, 0, 0, 0, 0, 0);
             continue;
         }
@@ -480,11 +496,14 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
         if (lowband_offset != 0 && (p.spread != 3 || B > 1 || tf_change < 0)) {
             effective_lowband = imax(0, M * kEBands[lowband_offset] - norm_offset - Nb);
             int fold_start = lowband_offset;
+#pragma unroll 1
             while (M * kEBands[--fold_start] > effective_lowband + norm_offset) {}
             int fold_end = lowband_offset - 1;
+#pragma unroll 1
             while (++fold_end < i && M * kEBands[fold_end] < effective_lowband + norm_offset + Nb) {}
             x_cm = y_cm = 0;
             int fold_i = fold_start;
+#pragma unroll 1
             do {
                 x_cm |= cmask[fold_i * C + 0];
                 y_cm |= cmask[fold_i * C + C - 1];
@@ -556,6 +575,7 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
         }
         // ---- run them through the single band_mono call site
         u32 cm_job[2] = {0, 0};
+#pragma unroll 1
         for (int j = 0; j < 2; j++) {
             const BandJob& J = job[j < njobs ? j : 0];
             MonoCtx m = {};
@@ -594,9 +614,11 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
     const int stereo = C > 1;
     const int logM = LM << 3;
     int lo = 0, hi = 1 << 6, psum, done, j;
+#pragma unroll 1
     for (int it = 0; it < 6; it++) {
         int mid = (lo + hi) >> 1;
         psum = 0; done = 0;
+#pragma unroll 1
         for (j = end; j-- > start;) {
             int tmp = bits1[j] + (mid * bits2[j] >> 6);
             if (tmp >= thresh[j] || done) { done = 1; psum += imin(tmp, cap[j]); }
@@ -605,6 +627,7 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
         if (psum > total) hi = mid; else lo = mid;
     }
     psum = 0; done = 0;
+#pragma unroll 1
     for (j = end; j-- > start;) {
         int tmp = bits1[j] + (lo * bits2[j] >> 6);
         if (tmp < thresh[j] && !done) tmp = tmp >= alloc_floor ? alloc_floor : 0;
@@ -614,6 +637,7 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
         psum += tmp;
     }
     int codedBands, left, percoeff;
+#pragma unroll 1
     for (codedBands = end;; codedBands--) {
         j = codedBands - 1;
         if (j <= skip_start) { total += skip_rsv; break; }
@@ -643,13 +667,16 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
     left = total - psum;
     percoeff = (int)((u32)left / (u32)(kEBands[codedBands] - kEBands[start]));
     left -= (kEBands[codedBands] - kEBands[start]) * percoeff;
+#pragma unroll 1
     for (j = start; j < codedBands; j++) bits[j] += percoeff * (kEBands[j + 1] - kEBands[j]);
+#pragma unroll 1
     for (j = start; j < codedBands; j++) {
         int tmp = imin(left, kEBands[j + 1] - kEBands[j]);
         bits[j] += tmp;
         left -= tmp;
     }
     int balance = 0;
+#pragma unroll 1
     for (j = start; j < codedBands; j++) {
         int N0 = kEBands[j + 1] - kEBands[j];
         int N = N0 << LM;
@@ -686,6 +713,7 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
         balance = excess;
     }
     *balance_out = balance;
+#pragma unroll 1
     for (; j < end; j++) {
         ebits[j] = bits[j] >> stereo >> 3;
         bits[j] = 0;
@@ -714,6 +742,7 @@ OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offs
         }
     }
     int bits1[kNbEBands], bits2[kNbEBands], thresh[kNbEBands], trim_offset[kNbEBands];
+#pragma unroll 1
     for (int j = start; j < end; j++) {
         int w = kEBands[j + 1] - kEBands[j];
         thresh[j] = imax(C << 3, (3 * w << LM << 3) >> 4);
@@ -721,9 +750,11 @@ OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offs
         if (w << LM == 1) trim_offset[j] -= C << 3;
     }
     int lo = 1, hi = 11 - 1;
+#pragma unroll 1
     do {
         int done = 0, psum = 0;
         int mid = (lo + hi) >> 1;
+#pragma unroll 1
         for (int j = end; j-- > start;) {
             int w = kEBands[j + 1] - kEBands[j];
             int bitsj = C * w * kBandAlloc[mid * len + j] << LM >> 2;
@@ -735,6 +766,7 @@ OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offs
         if (psum > total) hi = mid - 1; else lo = mid + 1;
     } while (lo <= hi);
     hi = lo--;
+#pragma unroll 1
     for (int j = start; j < end; j++) {
         int w = kEBands[j + 1] - kEBands[j];
         int bits1j = C * w * kBandAlloc[lo * len + j] << LM >> 2;
@@ -809,9 +841,11 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         const s16 beta = intra ? (s16)4915 : (LM == 0 ? (s16)30147 : LM == 1 ? (s16)22282 : LM == 2 ? (s16)12124 : (s16)6554);
         s32 prev[2] = {0, 0};
         const int budget = (int)rd.storage * 8;
+#pragma unroll 1
         for (int i = start0; i < end; i++) {
             warp_converge(p.wmask);
             if (i < start) continue;
+#pragma unroll 1
             for (int c = 0; c < C; c++) {
                 int qi;
                 int t = rd_tell(rd);
@@ -843,6 +877,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         int tf_select_rsv = LM > 0 && t + (u32)logp + 1 <= budget;
         budget -= (u32)tf_select_rsv;
         int tf_changed = 0, curr = 0;
+#pragma unroll 1
         for (int i = start; i < end; i++) {
             if (t + (u32)logp <= budget) {
                 curr ^= rd_bit_logp(rd, (u32)logp);
@@ -855,6 +890,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         int tf_select = 0;
         if (tf_select_rsv && kTfSelect[LM * 8 + 4 * isTransient + 0 + tf_changed] != kTfSelect[LM * 8 + 4 * isTransient + 2 + tf_changed])
             tf_select = rd_bit_logp(rd, 1);
+#pragma unroll 1
         for (int i = start; i < end; i++) tf_res[i] = kTfSelect[LM * 8 + 4 * isTransient + 2 * tf_select + tf_res[i]];
     }
 
@@ -865,6 +901,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
 
     // ---- caps + dynalloc (ref :911, :2301-2328)
     int cap[kNbEBands], offsets[kNbEBands];
+#pragma unroll 1
     for (int i = 0; i < kNbEBands; i++) {
         int N = (kEBands[i + 1] - kEBands[i]) << LM;
         cap[i] = (kCacheCaps[kNbEBands * (2 * LM + C - 1) + i] + 64) * C * N >> 2;
@@ -873,6 +910,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     int dynalloc_logp = 6;
     total_bits <<= 3;
     tell = (int)rd_tell_frac(rd);
+#pragma unroll 1
     for (int i = start0; i < end; i++) {
         warp_converge(p.wmask);
         if (i < start) continue;
@@ -880,6 +918,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         int quanta = imin(width << 3, imax(6 << 3, width));
         int loop_logp = dynalloc_logp;
         int boost = 0;
+#pragma unroll 1
         while (tell + (loop_logp << 3) < total_bits && boost < cap[i]) {
             int flag = rd_bit_logp(rd, (u32)loop_logp);
             tell = (int)rd_tell_frac(rd);
@@ -898,6 +937,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     bits -= anti_collapse_rsv;
 
     int pulses[kNbEBands], fine_quant[kNbEBands], fine_priority[kNbEBands];
+#pragma unroll 1
     for (int i = 0; i < kNbEBands; i++) { pulses[i] = 0; fine_quant[i] = 0; fine_priority[i] = 0; }
     int intensity = 0, dual_stereo = 0, balance = 0;
     const int codedBands = compute_allocation(rd, start, end, offsets, cap, alloc_trim, &intensity, &dual_stereo, bits, &balance,
@@ -905,10 +945,13 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
 
     // ---- fine energy (ref unquant_fine_energy :3664)
     s32 fine_acc[2][kNbEBands];
+#pragma unroll 1
     for (int c = 0; c < 2; c++) for (int i = 0; i < kNbEBands; i++) fine_acc[c][i] = 0;
+#pragma unroll 1
     for (int i = start0; i < end; i++) {
         warp_converge(p.wmask);
         if (i < start || fine_quant[i] <= 0) continue;
+#pragma unroll 1
         for (int c = 0; c < C; c++) {
             s32 q2 = (s32)rd_bits(rd, (u32)fine_quant[i]);
             s32 offset = sub16((shl32(q2, 10) + 512) >> fine_quant[i], 512);
@@ -918,6 +961,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
 
     // ---- PVQ / band structure (ref quant_all_bands :1754)
     uint8_t cmask[2 * kNbEBands];
+#pragma unroll 1
     for (int i = 0; i < 2 * kNbEBands; i++) cmask[i] = 0;
     all_bands(p, cmask, pulses, shortBlocks, dual_stereo, intensity, tf_res,
               (int)rd.storage * (8 << 3) - anti_collapse_rsv, balance, codedBands);
@@ -928,9 +972,12 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     // ---- final energy bits (ref unquant_energy_finalise :3681)
     {
         int bits_left = (int)rd.storage * 8 - rd_tell(rd);
+#pragma unroll 1
         for (int prio = 0; prio < 2; prio++) {
+#pragma unroll 1
             for (int i = start; i < end && bits_left >= C; i++) {
                 if (fine_quant[i] >= 8 || fine_priority[i] != prio) continue;
+#pragma unroll 1
                 for (int c = 0; c < C; c++) {
                     s32 q2 = (s32)rd_bits(rd, 1);
                     s32 offset = ((s32)shl16(q2, 10) - 512) >> (fine_quant[i] + 1);
@@ -941,12 +988,16 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         }
     }
 
+#pragma unroll 1
     for (int c = 0; c < 2; c++)
+#pragma unroll 1
         for (int i = 0; i < kNbEBands; i++) {
             hdr.fine[c][i] = (int16_t)fine_acc[c][i];
             if (c >= C || i < start || i >= end) hdr.pq[c][i] = 0;
         }
+#pragma unroll 1
     for (int i = 0; i < kNbEBands; i++) hdr.pulses[i] = (int16_t)pulses[i];
+#pragma unroll 1
     for (int i = 0; i < 2 * kNbEBands; i++) hdr.cmask[i] = cmask[i];
     if (silence) flags |= FF_SILENCE;
     if (isTransient) flags |= FF_TRANSIENT;

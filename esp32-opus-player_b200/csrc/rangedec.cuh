@@ -27,6 +27,7 @@ OPUS_HD int rd_read_byte_end(RangeDec& d) { return d.end_offs < d.storage ? d.bu
 
 // ref ec_dec_normalize (src/celt.cpp:2649)
 OPUS_HD void rd_normalize(RangeDec& d) {
+#pragma unroll 1
     while (d.rng <= 0x800000u) {
         d.nbits_total += 8;
         d.rng <<= 8;
@@ -98,6 +99,7 @@ OPUS_HD int rd_bit_logp(RangeDec& d, u32 logp) {
 OPUS_HD int rd_icdf(RangeDec& d, const uint8_t* icdf, u32 ftb) {
     u32 s = d.rng, v = d.val, r = s >> ftb, t;
     int ret = -1;
+#pragma unroll 1
     do {
         t = s;
         s = r * icdf[++ret];
@@ -113,6 +115,7 @@ OPUS_HD u32 rd_bits(RangeDec& d, u32 bits) {
     u32 window = d.end_window;
     int available = d.nend_bits;
     if ((u32)available < bits) {
+#pragma unroll 1
         do {
             window |= (u32)rd_read_byte_end(d) << available;
             available += 8;
@@ -156,6 +159,7 @@ OPUS_HD int rd_laplace(RangeDec& d, u32 fs, int decay) {
         val++;
         fl = fs;
         fs = (((32768u - 32u - fs) * (u32)(16384 - decay)) >> 15) + 1;  // ec_laplace_get_freq1 :3041
+#pragma unroll 1
         while (fs > 1 && fm >= fl + 2 * fs) {
             fs *= 2;
             fl += fs;
