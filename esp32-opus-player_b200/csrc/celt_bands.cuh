@@ -43,20 +43,6 @@ OPUS_HD void w_renormalise(const Lanes& L, int16_t* X, int N, s16 gain) {
     L.sync();
 }
 
-// d / n and d % n for small operands without the 20-instruction integer divide: rcp = ceil(2^32 / n) is exact
-// for d * n < 2^32 (here d < 2048, n <= 176).  n == 1 has no 32-bit reciprocal.
-struct SmallDiv {
-    u32 n, rcp;
-    OPUS_HD explicit SmallDiv(int n_) : n((u32)n_), rcp(n_ > 1 ? 0xFFFFFFFFu / (u32)n_ + 1u : 0u) {}
-    OPUS_HD int div(int d) const {
-#if defined(__CUDA_ARCH__)
-        return n > 1 ? (int)__umulhi((u32)d, rcp) : d;
-#else
-        return (int)((u32)d / n);
-#endif
-    }
-};
-
 // ref haar1 (src/celt.cpp:1202); stride is a power of two (1 << k or the block count B)
 OPUS_HD void w_haar(const Lanes& L, int16_t* X, int N0, int stride) {
     const int pairs = (N0 >> 1) * stride;

@@ -62,27 +62,39 @@ OPUS_HD void energy_step(CeltBandState& s, int i, const CeltFrameHdr& h, FrameEn
 }
 
 // ---- denormalise_bands (ref src/celt.cpp:948): freq[j] = X[j] * 2^(E+eMeans) ----
+// band of every short-block bin (eBands5ms, ref src/celt.cpp:200); 21 = above the last band
+OPUS_TABLE uint8_t kBinBand[120] = {
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 12, 12, 13, 13, 13, 13, 14, 14, 14, 14, 15, 15, 15, 15, 15, 15, 16, 16, 16, 16, 16, 16, 17, 17, 17, 17, 17, 17, 17, 17, 18, 18, 18, 18, 18, 18, 18, 18, 18, 18, 18, 18, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21, 21,
+};
+// Two phases: lane b works out the gain mantissa and shift of band b once (`gs`, kNbEBands + 1 words of warp-private
+// scratch), then all lanes sweep the N bins in one flat loop -- the bands are 8 to 176 bins wide at LM = 3, a
+// per-band loop leaves most lanes idle in two thirds of them.
 OPUS_HD void denormalise(const Lanes& L, const int16_t* X, int32_t* freq, const int16_t* bandLogE, int start, int end, int M,
-                         int silence) {
+                         int silence, int32_t* gs) {
     const int N = M * kShortMdct;
-    int bound = M * kEBands[end];
-    if (silence) { bound = 0; start = end = 0; }
-    for (int j = L.lane; j < M * kEBands[start]; j += kLanes) freq[j] = 0;
-    for (int i = start; i < end; i++) {
-        const int j0 = M * kEBands[i], j1 = M * kEBands[i + 1];
-        s16 lg = sat16((s32)bandLogE[i] + shl32((s32)kEMeans[i], 6));
-        int shift = 16 - (lg >> 10);
-        s16 g;
-        if (shift > 31) { shift = 0; g = 0; }
-        else g = (s16)exp2_frac((s16)(lg & 1023));
-        if (shift < 0) {
+    const int LM = ilog2p(M);
+    if (silence) start = end = 0;
+    for (int i = L.lane; i <= kNbEBands; i += kLanes) {
+        int32_t packed = 0;  // g = 0: bins outside [start, end) come out as zero
+        if (i >= start && i < end) {
+            s16 lg = sat16((s32)bandLogE[i] + shl32((s32)kEMeans[i], 6));
+            int shift = 16 - (lg >> 10);
+            s16 g;
+            if (shift > 31) { shift = 0; g = 0; }
+            else g = (s16)exp2_frac((s16)(lg & 1023));
             if (shift <= -2) { g = 16384; shift = -2; }
-            for (int j = j0 + L.lane; j < j1; j += kLanes) freq[j] = shl32(mul16(X[j], g), -shift);
-        } else {
-            for (int j = j0 + L.lane; j < j1; j += kLanes) freq[j] = mul16(X[j], g) >> shift;
+            packed = (int32_t)(((u32)(uint16_t)g << 16) | (u32)(shift & 0xff));
         }
+        gs[i] = packed;
     }
-    for (int j = bound + L.lane; j < N; j += kLanes) freq[j] = 0;
+    L.sync();
+    for (int j = L.lane; j < N; j += kLanes) {
+        const int32_t pk = gs[kBinBand[j >> LM]];
+        const s16 g = (s16)(pk >> 16);
+        const int shift = (int)(int8_t)(pk & 0xff);
+        const s32 v = mul16(X[j], g);
+        freq[j] = shift < 0 ? shl32(v, -shift) : v >> shift;
+    }
     L.sync();
 }
 
@@ -101,11 +113,11 @@ OPUS_HD Cpx csub(Cpx a, Cpx b) { Cpx c; c.r = sub_w(a.r, b.r); c.i = sub_w(a.i, 
 
 struct FftStage { uint8_t radix, m, N, fstride, mm; };
 
-// radix-4, unit t in [0, N*m)
-OPUS_HD void bfly4(Cpx* f, int t, const FftStage& s) {
+// radix-4, unit (i, j) = (t / m, t % m), t in [0, N*m)
+OPUS_HD void bfly4(Cpx* f, int i, int j, const FftStage& s) {
     const int m = s.m;
     if (m == 1) {
-        Cpx* F = f + 4 * t;
+        Cpx* F = f + 4 * i;
         Cpx a0 = F[0], a1 = F[1], a2 = F[2], a3 = F[3];
         Cpx s0 = csub(a0, a2);
         a0 = cadd(a0, a2);
@@ -116,7 +128,6 @@ OPUS_HD void bfly4(Cpx* f, int t, const FftStage& s) {
         F[1].r = add_w(s0.r, s1.i); F[1].i = sub_w(s0.i, s1.r);
         F[3].r = sub_w(s0.r, s1.i); F[3].i = add_w(s0.i, s1.r);
     } else {
-        const int i = t / m, j = t % m;
         Cpx* F = f + i * s.mm + j;
         Cpx c0 = cmul(F[m], j * s.fstride);
         Cpx c1 = cmul(F[2 * m], 2 * j * s.fstride);
@@ -145,9 +156,9 @@ OPUS_HD void bfly2(Cpx* f, int t) {
     F[4] = csub(a, tt);
     F[0] = cadd(a, tt);
 }
-// radix-3, unit t in [0, N*m)
-OPUS_HD void bfly3(Cpx* f, int t, const FftStage& s) {
-    const int m = s.m, i = t / m, j = t % m;
+// radix-3, unit (i, j) = (t / m, t % m)
+OPUS_HD void bfly3(Cpx* f, int i, int j, const FftStage& s) {
+    const int m = s.m;
     Cpx* F = f + i * s.mm + j;
     Cpx c1 = cmul(F[m], j * s.fstride);
     Cpx c2 = cmul(F[2 * m], 2 * j * s.fstride);
@@ -162,9 +173,9 @@ OPUS_HD void bfly3(Cpx* f, int t, const FftStage& s) {
     F[2 * m].r = add_w(fm.r, c0.i); F[2 * m].i = sub_w(fm.i, c0.r);
     F[m].r = sub_w(fm.r, c0.i);     F[m].i = add_w(fm.i, c0.r);
 }
-// radix-5, unit t in [0, N*m)
-OPUS_HD void bfly5(Cpx* f, int t, const FftStage& s) {
-    const int m = s.m, i = t / m, u = t % m;
+// radix-5, unit (i, u) = (t / m, t % m)
+OPUS_HD void bfly5(Cpx* f, int i, int u, const FftStage& s) {
+    const int m = s.m;
     Cpx* F = f + i * s.mm + u;
     const s16 yar = 10126, yai = -31164, ybr = -26510, ybi = -19261;
     Cpx s0 = F[0];
@@ -225,9 +236,10 @@ OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int s
     const int Nm = 1920 >> shift, N2 = Nm >> 1, N4 = Nm >> 2;
     const int16_t* trig = kMdctTrig + (shift == 0 ? 0 : shift == 1 ? 960 : shift == 2 ? 1440 : 1680);
     const int16_t* bitrev = shift == 0 ? kBitrev480 : shift == 1 ? kBitrev240 : shift == 2 ? kBitrev120 : kBitrev60;
+    const SmallDiv byN4(N4);
     // pre-rotation into bit-reversed order (ref :3219-3239)
     for (int t = L.lane; t < nblk * N4; t += kLanes) {
-        const int b = t / N4, i = t % N4;
+        const int b = nblk > 1 ? byN4.div(t) : 0, i = t - b * N4;
         const int32_t* in = freq + b;
         s32 x1 = in[2 * i * nblk], x2 = in[nblk * (N2 - 1 - 2 * i)];
         s16 t0 = trig[i], t1 = trig[N4 + i];
@@ -243,20 +255,24 @@ OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int s
     for (int s = 0; s < ns; s++) {
         const FftStage g = st[s];
         const int units = (g.radix == 2 ? g.N * 4 : g.N * g.m);
+        const SmallDiv byUnits(units), byM(g.m);
         for (int t = L.lane; t < nblk * units; t += kLanes) {
-            Cpx* f = (Cpx*)(work + (t / units) * N2);
-            const int u = t % units;
-            if (g.radix == 4) bfly4(f, u, g);
+            const int blk = nblk > 1 ? byUnits.div(t) : 0;
+            Cpx* f = (Cpx*)(work + blk * N2);
+            const int u = t - blk * units;
+            const int i = byM.div(u), j = u - i * g.m;
+            if (g.radix == 4) bfly4(f, i, j, g);
             else if (g.radix == 2) bfly2(f, u);
-            else if (g.radix == 3) bfly3(f, u, g);
-            else bfly5(f, u, g);
+            else if (g.radix == 3) bfly3(f, i, j, g);
+            else bfly5(f, i, j, g);
         }
         L.sync();
     }
     // post-rotation, in place from both ends (ref :3244-3277)
     const int half = (N4 + 1) >> 1;
+    const SmallDiv byHalf(half);
     for (int t = L.lane; t < nblk * half; t += kLanes) {
-        const int b = t / half, i = t % half;
+        const int b = nblk > 1 ? byHalf.div(t) : 0, i = t - b * half;
         int32_t* yp0 = work + b * N2 + 2 * i;
         int32_t* yp1 = work + b * N2 + N2 - 2 - 2 * i;
         s32 re = yp0[1], im = yp0[0];

@@ -168,4 +168,18 @@ OPUS_HD u32 isqrt32(u32 v) {
 // ref celt_lcg_rand (src/celt.cpp:921)
 OPUS_HD u32 lcg_next(u32 seed) { return 1664525u * seed + 1013904223u; }
 
+// d / n and d % n for small operands without the 20-instruction integer divide: rcp = ceil(2^32 / n) is exact
+// for d * n < 2^32 (here d < 2048, n <= 176).  n == 1 has no 32-bit reciprocal.
+struct SmallDiv {
+    u32 n, rcp;
+    OPUS_HD explicit SmallDiv(int n_) : n((u32)n_), rcp(n_ > 1 ? 0xFFFFFFFFu / (u32)n_ + 1u : 0u) {}
+    OPUS_HD int div(int d) const {
+#if defined(__CUDA_ARCH__)
+        return n > 1 ? (int)__umulhi((u32)d, rcp) : d;
+#else
+        return (int)((u32)d / n);
+#endif
+    }
+};
+
 }  // namespace opusb200

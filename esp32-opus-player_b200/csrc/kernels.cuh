@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(32 * KW_WARPS)
 k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int16_t* __restrict__ X,
         int32_t* __restrict__ raw, DevParams P) {
     __shared__ int32_t fsm[KW_WARPS][2][kMaxFrame];
+    __shared__ int32_t gsm[KW_WARPS][kNbEBands + 1];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.n_frames * P.CC) return;
     const int c = local % P.CC;
@@ -186,18 +187,19 @@ k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe
     Lanes L;
     int32_t* freq = fsm[threadIdx.x >> 5][0];
     int32_t* work = fsm[threadIdx.x >> 5][1];
+    int32_t* gs = gsm[threadIdx.x >> 5];
     const int LM = h.LM, M = 1 << LM, N = kShortMdct << LM, C = h.C, CC = P.CC;
     const int transient = (h.flags & FF_TRANSIENT) != 0, silence = (h.flags & FF_SILENCE) != 0;
     const int16_t* Xf = X + t * (2 * kMaxFrame);
     if (CC == 2 && C == 1) {
-        denormalise(L, Xf, freq, e.E[0], h.start, h.end, M, silence);
+        denormalise(L, Xf, freq, e.E[0], h.start, h.end, M, silence, gs);
     } else if (CC == 1 && C == 2) {
-        denormalise(L, Xf, freq, e.E[0], h.start, h.end, M, silence);
-        denormalise(L, Xf + N, work, e.E[1], h.start, h.end, M, silence);
+        denormalise(L, Xf, freq, e.E[0], h.start, h.end, M, silence, gs);
+        denormalise(L, Xf + N, work, e.E[1], h.start, h.end, M, silence, gs);
         for (int i = L.lane; i < N; i += 32) freq[i] = (freq[i] >> 1) + (work[i] >> 1);
         L.sync();
     } else {
-        denormalise(L, Xf + c * N, freq, e.E[c], h.start, h.end, M, silence);
+        denormalise(L, Xf + c * N, freq, e.E[c], h.start, h.end, M, silence, gs);
     }
     imdct_raw(L, freq, work, transient ? 3 : 3 - LM, transient ? M : 1);
     int32_t* out = raw + (t * CC + c) * kMaxFrame;
