@@ -293,13 +293,31 @@ OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int s
     L.sync();
 }
 
+// Signal buffers of the TDAC / post-filter stage are addressed through a view: a plain pointer, or a power-of-two ring
+// (the post-filter kernel keeps each stream's last 1028 samples plus the current frame in a 2048-entry ring, so the
+// history never has to be moved).
+struct LinView {
+    int32_t* p;
+    OPUS_HD int32_t& operator[](int i) const { return p[i]; }
+    OPUS_HD LinView operator+(int k) const { return LinView{p + k}; }
+};
+enum { kRingSize = 2048 };
+struct RingView {
+    int32_t* base;
+    int pos;  // ring index of element 0
+    OPUS_HD int32_t& operator[](int i) const { return base[(pos + i) & (kRingSize - 1)]; }
+    OPUS_HD RingView operator+(int k) const { return RingView{base, pos + k}; }
+};
+
 // TDAC mirror + window for one frame (ref :3279-3295 applied block by block, then SATURATE :2121-2125).
 // raw: this frame's nblk * N2 raw values; tail: previous block's last overlap/2 raw values (in/out).
 // out[0..N) receives the frame's time-domain signal (before the post-filter).
-OPUS_HD void tdac_frame(const Lanes& L, const int32_t* raw, int32_t* tail, int32_t* out, int N2, int nblk) {
+template <class View>
+OPUS_HD void tdac_frame(const Lanes& L, const int32_t* raw, int32_t* tail, View out, int N2, int nblk) {
     const int N = N2 * nblk;
+    const SmallDiv byN2(N2);
     for (int n = L.lane; n < N; n += kLanes) {
-        const int b = n / N2, k = n % N2;
+        const int b = nblk > 1 ? byN2.div(n) : 0, k = n - b * N2;
         s32 v;
         if (k < kOverlap) {
             const int i = k < kOverlap / 2 ? k : kOverlap - 1 - k;
@@ -322,7 +340,8 @@ OPUS_HD void tdac_frame(const Lanes& L, const int32_t* raw, int32_t* tail, int32
 // x points at the first sample to filter inside a buffer that holds >= T+2 valid earlier samples.
 // In-place IIR: y[i] depends on y[i-T+2 .. i-T-2], T >= 15, so `chunk` = min(T0,T1)-2 >= 13 samples
 // are independent and are computed by the lanes in parallel.
-OPUS_HD void comb_filter_inplace(const Lanes& L, int32_t* x, int T0, int T1, int N, s16 g0, s16 g1, int tapset0, int tapset1) {
+template <class View>
+OPUS_HD void comb_filter_inplace(const Lanes& L, View x, int T0, int T1, int N, s16 g0, s16 g1, int tapset0, int tapset1) {
     if (g0 == 0 && g1 == 0) return;
     const s16 gains[3][3] = {{10048, 7112, 4248}, {15200, 8784, 0}, {26208, 3280, 0}};
     T0 = imax(T0, 15);

@@ -207,30 +207,59 @@ k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * KW_WARPS)
+// One warp walks the frames of one (stream, channel) in order.  The signal history the comb filter reaches back
+// into (<= 1026 samples) and the frame being filtered live in a 2048-entry ring in shared memory, so nothing is
+// moved between frames; the next frame's raw IMDCT output is fetched with cp.async into a staging row while the
+// current frame is being filtered (the warp has nothing else to overlap a global-memory round trip with).
+enum { PF_WARPS = 4 };
+
+__global__ void __launch_bounds__(32 * PF_WARPS)
 k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ raw,
              int32_t* __restrict__ syn, CeltStreamState* __restrict__ st, DevParams P) {
-    __shared__ int32_t bsm[KW_WARPS][kCombHist + kMaxFrame];
-    __shared__ int32_t tsm[KW_WARPS][kOverlap / 2];
+    __shared__ __align__(16) int32_t rsm[PF_WARPS][kRingSize];
+    __shared__ __align__(16) int32_t ssm[PF_WARPS][kMaxFrame];
+    __shared__ int32_t tsm[PF_WARPS][kOverlap / 2];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.CC) return;
     const int c = local % P.CC, s = P.first_stream + local / P.CC;
     Lanes L;
-    int32_t* buf = bsm[threadIdx.x >> 5];
+    int32_t* ring = rsm[threadIdx.x >> 5];
+    int32_t* stage = ssm[threadIdx.x >> 5];
     int32_t* tail = tsm[threadIdx.x >> 5];
     CeltStreamState& S = st[s];
-    for (int i = L.lane; i < kCombHist; i += 32) buf[i] = S.hist[c][i];
+    for (int i = L.lane; i < kCombHist; i += 32) ring[i] = S.hist[c][i];
     for (int i = L.lane; i < kOverlap / 2; i += 32) tail[i] = S.tail[c][i];
-    L.sync();
+    int pos = kCombHist;  // ring index of the first sample of the next frame
+    const size_t t0 = (size_t)s * P.n_frames;
+
+    // stage <- raw output of frame f (16 bytes per lane and copy), if that frame has a CELT layer
+    auto fetch = [&](int f) {
+        if (f < P.n_frames) {
+            const FrameEnergy& e = fe[t0 + f];
+            if (!(e.skip & FS_NO_CELT)) {
+                const int n = e.celt_n;
+                const int32_t* src = raw + ((t0 + f) * P.CC + c) * kMaxFrame;
+                for (int i = 4 * L.lane; i < n; i += 128) __pipeline_memcpy_async(stage + i, src + i, 16);
+            }
+        }
+        __pipeline_commit();
+    };
+    fetch(0);
     for (int f = 0; f < P.n_frames; f++) {
-        const size_t t = (size_t)s * P.n_frames + f;
+        const size_t t = t0 + f;
         const FrameEnergy& e = fe[t];
-        if (e.skip & FS_NO_CELT) continue;
+        __pipeline_wait_prior(0);
+        L.sync();
+        if (e.skip & FS_NO_CELT) {
+            fetch(f + 1);
+            continue;
+        }
         const CeltFrameHdr& h = hdr[t];
         const int LM = h.LM, N = kShortMdct << LM;
         const int nblk = (h.flags & FF_TRANSIENT) ? (1 << LM) : 1;
-        int32_t* x = buf + kCombHist;
-        tdac_frame(L, raw + (t * P.CC + c) * kMaxFrame, tail, x, N / nblk, nblk);
+        const RingView x{ring, pos};
+        tdac_frame(L, stage, tail, x, N / nblk, nblk);  // ends with a warp barrier: the staging row is free again
+        fetch(f + 1);
         comb_filter_inplace(L, x, e.pf_period_old, e.pf_period, kShortMdct, e.pf_gain_old, e.pf_gain, e.pf_tapset_old, e.pf_tapset);
         if (LM != 0)
             comb_filter_inplace(L, x + kShortMdct, e.pf_period, h.pf_pitch, N - kShortMdct, e.pf_gain, h.pf_gain, e.pf_tapset,
@@ -238,17 +267,12 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
         L.sync();
         int32_t* out = syn + (t * P.CC + c) * kMaxFrame;
         for (int i = L.lane; i < N; i += 32) out[i] = x[i];
-        // slide the history window: buf[k] = buf[N + k]; ascending order is hazard free because N > 32
-        for (int k0 = 0; k0 < kCombHist; k0 += 32) {
-            const int k = k0 + L.lane;
-            int32_t v = 0;
-            if (k < kCombHist) v = buf[N + k];
-            L.sync();
-            if (k < kCombHist) buf[k] = v;
-        }
-        L.sync();
+        pos = (pos + N) & (kRingSize - 1);
     }
-    for (int i = L.lane; i < kCombHist; i += 32) S.hist[c][i] = buf[i];
+    __pipeline_wait_prior(0);
+    L.sync();
+    const RingView endv{ring, pos};
+    for (int i = L.lane; i < kCombHist; i += 32) S.hist[c][i] = endv[i - kCombHist];
     for (int i = L.lane; i < kOverlap / 2; i += 32) S.tail[c][i] = tail[i];
 }
 

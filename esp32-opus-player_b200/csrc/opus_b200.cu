@@ -252,7 +252,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) cudaEventRecord(c->ev[3], s);
     k_imdct<<<(nfr * P.CC + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
     if (timed) cudaEventRecord(c->ev[4], s);
-    k_postfilter<<<(n_sel * P.CC + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
+    k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[5], s);
     k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[6], s);

@@ -92,14 +92,21 @@ static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, 
             denormalise(L, W + W_XY + c * N, freq, fe.E[c], hdr.start, hdr.end, M, silence, gs);
         }
         imdct_raw(L, freq, work, shift, nblk);
-        memcpy(buf, st.hist[c], sizeof(int32_t) * kCombHist);
-        tdac_frame(L, work, st.tail[c], buf + kCombHist, N2, nblk);
-        comb_filter_inplace(L, buf + kCombHist, st.pf_period_old, st.pf_period, kShortMdct, (s16)st.pf_gain_old, (s16)st.pf_gain,
+        // the signal history lives in a ring like in the post-filter kernel; the ring origin moves from call to call so
+        // that frames wrap around its end
+        static int32_t ring[kRingSize];
+        static int origin = 0;
+        origin = (origin + 777) & (kRingSize - 1);
+        RingView x{ring, origin + kCombHist};
+        for (int i = 0; i < kCombHist; i++) x[i - kCombHist] = st.hist[c][i];
+        tdac_frame(L, work, st.tail[c], x, N2, nblk);
+        comb_filter_inplace(L, x, st.pf_period_old, st.pf_period, kShortMdct, (s16)st.pf_gain_old, (s16)st.pf_gain,
                             st.pf_tapset_old, st.pf_tapset);
         if (LM != 0)
-            comb_filter_inplace(L, buf + kCombHist + kShortMdct, st.pf_period, hdr.pf_pitch, N - kShortMdct, (s16)st.pf_gain,
+            comb_filter_inplace(L, x + kShortMdct, st.pf_period, hdr.pf_pitch, N - kShortMdct, (s16)st.pf_gain,
                                 hdr.pf_gain, st.pf_tapset, hdr.pf_tapset);
-        memcpy(st.hist[c], buf + N, sizeof(int32_t) * kCombHist);
+        for (int i = 0; i < kCombHist; i++) st.hist[c][i] = x[N - kCombHist + i];
+        for (int i = 0; i < N; i++) buf[kCombHist + i] = x[i];
         if (dbg_mem) memcpy(dbg_mem + c * kMaxFrame, buf + kCombHist, sizeof(int32_t) * N);
         s32 mem = st.preemph_mem[c];
         for (int j = 0; j < N; j++) pcm[j * CC + c] = (int16_t)deemph_sample(buf[kCombHist + j], mem);
