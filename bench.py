@@ -40,6 +40,10 @@ WORKLOADS = {
     "hybrid_swb": (0x68, 99, 1, 8192, 0.6, "configs[3]: %d concurrent hybrid SWB mono 20 ms streams per GPU, 100 B packets"),
 }
 TOC, PAYLOAD, CHANNELS = 0xFC, 159, 2
+# dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full captures of the
+# 20 480-frame run (profiles/r01_v2_ncu_summary_entropy_bands.txt, profiles/r01_v3_ncu_summary_bands_imdct_postfilter.txt);
+# one launch of the bench step moves this times its frame count
+NCU_DRAM_BYTES_PER_FRAME = {"entropy": 57.81e6 / 20480, "bands": 93.56e6 / 20480, "imdct": 178.24e6 / 20480, "postfilter": 293.44e6 / 20480}
 
 
 def peaks():
@@ -183,11 +187,8 @@ def main():
     nb_step = S * F * PAYLOAD
     h_bytes = [pkg.api.PinnedArray(nb_step, np.uint8) for _ in range(n_steps)]
     h_frames = [pkg.api.PinnedArray((S, F), pkg.FRAME_DTYPE) for _ in range(n_steps)]
-    full = np.empty(S * n_steps * F * PAYLOAD, np.uint8)
-    fr_full = pkg.make_frames(S, n_steps * F)
-    for s in range(S):  # stream ids are interleaved across ranks, so fill one stream at a time
-        pkg.synth_corpus(1, n_steps * F, PAYLOAD, TOC, first_stream=rank + world * s,
-                         bytes_out=full[s * n_steps * F * PAYLOAD:(s + 1) * n_steps * F * PAYLOAD], frames_out=fr_full[s:s + 1])
+    # stream ids are interleaved across ranks (shard.rank_corpus seeds every stream by its GLOBAL id)
+    full, fr_full = pkg.shard.rank_corpus(pkg.api, rank, world, S, n_steps * F, PAYLOAD, TOC)
     full = full.reshape(S, n_steps, F * PAYLOAD)
     for k in range(n_steps):
         h_bytes[k].array[:] = full[:, k, :].reshape(-1)
@@ -238,12 +239,9 @@ def main():
     assert (st_status == 960).all(), "decode errors in the timed region"
     # per-stage times of the last step (events recorded inside the library on the same stream)
     stage_acc = dec.stage_times()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = pkg.shard.max_over_ranks(ms, dist if world > 1 else None, "cuda")
     audio_per_step = S * F * 0.02
-    value = world * K * audio_per_step / (ms_max * 1e-3)
+    value = pkg.shard.aggregate_rate(K * audio_per_step, world, ms_max * 1e-3)
 
     # ---- e2e: C ABI with pinned host buffers (fresh decoder so that the same packets are legal input)
     e2e = None
@@ -296,7 +294,9 @@ def main():
         issue_peak = n_sm * 4 * sm_max * 1e6 * 32  # lane-ops/s at max clock
         step_s = ms_max * 1e-3 / K
         roof = {"bound": "hbm", "kernel": "k_" + str(top), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / hbm_peak) if achieved else None,
+                "traffic": (NCU_DRAM_BYTES_PER_FRAME[top] * S * F) if (args.workload == "celt" and top in NCU_DRAM_BYTES_PER_FRAME) else None,
+                "traffic_source": "ncu dram bytes per frame at 20 480 frames (profiles/) x frames per launch", "peak_source": peak_src,
                 "kernel_ms": top_ms, "stage_ms": stage_acc,
                 "issue": {"note": "the path is issue bound (SURVEY 8d): algorithmic integer ops vs SM issue peak over the whole step",
                           "achieved_lane_ops_per_s": S * F * ops_per_frame / step_s, "peak_lane_ops_per_s": issue_peak,

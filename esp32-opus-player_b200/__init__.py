@@ -27,3 +27,4 @@ from .api import (  # noqa: F401
     synth_corpus,
 )
 from .build import build  # noqa: F401
+from . import api, shard  # noqa: F401,E402
