@@ -5,7 +5,8 @@
 //   k_bands     warp   per (stream, frame)   folding, Haar/Hadamard, stereo merge, anti-collapse   [a4-a7]
 //   k_imdct     warp   per (stream, frame, ch) denormalise + inverse MDCT (radix 2/3/4/5 FFT)      [a8,a9]
 //   k_postfilter warp  per (stream, ch)      TDAC overlap-add + comb filter, frames in order       [a9,a10]
-//   k_deemph    thread per (stream, ch)      1-pole IIR + int16 PCM, coalesced through smem tiles   [a11]
+//   k_deemph    lane   per (stream, ch)      1-pole IIR + int16 PCM                                 [a11]
+//   k_silk_*    see silk_kernels.cuh         SILK parameters, LTP/LPC synthesis, unmix, resampler   [a14-a20]
 //
 // Frames are indexed t = stream * n_frames + frame.  All intermediates live in HBM between kernels
 // (<= 36 KB per frame; the traffic is three orders of magnitude under the HBM roofline -- the path is
@@ -45,7 +46,7 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1_THREADS)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
-          BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st) {
+          BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
     const bool in_range = local < P.n_sel * P.n_frames;
     const unsigned warp = __ballot_sync(0xffffffffu, in_range);  // the lanes of this warp that own a frame
@@ -87,6 +88,7 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
         }
     }
     h.oflags = (uint8_t)oflags;
+    if (oflags & OF_HAS_SILK) *any_silk = 1;  // the SILK kernels of this call have work
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,35 +398,6 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
 }
 
 // ------------------------------------------------------------------------------------------------
-// SILK synthesis, frames of a stream in order (ref silk_Decode, src/silk.cpp:1481): parameters, LTP + LPC
-// synthesis, mid/side -> left/right, resampling to 48 kHz; the result is added to the CELT PCM with int16
-// saturation (ref src/opus_decoder.cpp:271-273).  Runs after k_deemph.
-struct SilkWork {
-    SilkScratch w;
-    int16_t out[2 * kMaxFrame];
-};
-
-__global__ void __launch_bounds__(32)
-k_silk(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkFrame* __restrict__ silk, SilkStreamState* __restrict__ sst,
-       SilkWork* __restrict__ work, int16_t* __restrict__ pcm, DevParams P) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= P.n_sel) return;
-    const int s = P.first_stream + w;
-    SilkStreamState& S = sst[s];
-    SilkWork& W = work[s];
-    for (int f = 0; f < P.n_frames; f++) {
-        const size_t t = (size_t)s * P.n_frames + f;
-        const int of = hdr[t].oflags;
-        if (!(of & OF_HAS_SILK) || (fe[t].skip & FS_DROPPED)) continue;
-        if (of & OF_SILK_REINIT) silk_stream_reinit(S);
-        silk_synth_frame(S, silk[t], W.out, W.w);
-        int16_t* o = pcm + t * (size_t)(kMaxFrame * P.CC);
-        const int n = kMaxFrame * P.CC;
-        for (int i = 0; i < n; i++) o[i] = sat16((s32)o[i] + (s32)W.out[i]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // OPUS_RESET_STATE for a list of streams (ref opus_decoder_ctl, src/opus_decoder.cpp:380-388): CELT soft reset
 // (src/celt.cpp:2479-2498: range seed, post-filter, oldLogE/oldLogE2 -- not the history, oldBandE or de-emphasis
 // memory), silk_InitDecoder, prev_mode = 0.
@@ -441,3 +414,5 @@ __global__ void k_reset_state(const int32_t* __restrict__ ids, int n, CeltStream
 }
 
 }  // namespace opusb200
+
+#include "silk_kernels.cuh"

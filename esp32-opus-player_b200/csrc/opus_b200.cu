@@ -21,15 +21,20 @@ enum { kStages = 7, kMaxChunks = 4, kRing = 4 };
 static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph", "silk"};
 
 struct dm_ctx {
-    int n_streams, max_frames, channels, device;
+    int n_streams, max_frames, channels, device, n_sm;
     // per-stream state
     CeltStreamState* d_state;
     SilkStreamState* d_sstate;
-    SilkWork* d_swork;
     // per-frame intermediates
     CeltFrameHdr* d_hdr;
     BandOp* d_ops;
     SilkFrame* d_silk;
+    SilkCtl* d_sctl;         // SILK stage hand-offs (silk_kernels.cuh)
+    SilkPost* d_spost;
+    int16_t* d_sxq;
+    int16_t* d_slr;
+    int16_t* d_sup;
+    int* d_any_silk;
     int16_t* d_X;
     FrameEnergy* d_fe;
     int32_t* d_raw;
@@ -92,14 +97,21 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     memset(c, 0, sizeof(*c));
     c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
     CU_TRY(c, cudaSetDevice(device));
+    CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     // quant_partition recursion (<= 5 levels) + per-thread allocation arrays live on the local stack
     CU_TRY(c, cudaDeviceSetLimit(cudaLimitStackSize, 6 * 1024));
     const size_t nfr = (size_t)n_streams * max_frames;
     int r;
     if ((r = dev_alloc(c, &c->d_state, (size_t)n_streams))) return r;
     if ((r = dev_alloc(c, &c->d_sstate, (size_t)n_streams))) return r;
-    if ((r = dev_alloc(c, &c->d_swork, (size_t)n_streams))) return r;
     if ((r = dev_alloc(c, &c->d_silk, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_sctl, nfr * 2))) return r;
+    if ((r = dev_alloc(c, &c->d_spost, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_sxq, nfr * 2 * kXqRow))) return r;
+    if ((r = dev_alloc(c, &c->d_slr, nfr * 2 * kXqRow))) return r;
+    if ((r = dev_alloc(c, &c->d_sup, nfr * 2 * kUpRow))) return r;
+    if ((r = dev_alloc(c, &c->d_any_silk, 1))) return r;
+    CU_TRY(c, cudaFuncSetAttribute(k_silk_core, cudaFuncAttributeMaxDynamicSharedMemorySize, kSilkCoreSmem));
     if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
@@ -129,7 +141,8 @@ void dm_destroy(dm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_swork); cudaFree(c->d_silk); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
+    cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_silk); cudaFree(c->d_sctl); cudaFree(c->d_spost); cudaFree(c->d_sxq); cudaFree(c->d_slr);
+    cudaFree(c->d_sup); cudaFree(c->d_any_silk); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
     cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames); cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status2);
     cudaFree(c->d_status);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -234,7 +247,7 @@ static int reserve_bytes(dm_ctx* c, int bi, size_t n) {
 
 // Enqueue the six kernels for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
 static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
-                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr) {
+                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, bool clear_flag = true) {
     DevParams P;
     P.n_streams = c->n_streams; P.n_frames = in->n_frames; P.mode = in->mode;
     P.frame_size = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
@@ -243,7 +256,8 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     const int nfr = n_sel * in->n_frames;
     const int wb = 32 * KW_WARPS;
     if (timed) cudaEventRecord(c->ev[0], s);
-    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state);
+    if (clear_flag) cudaMemsetAsync(c->d_any_silk, 0, sizeof(int), s);
+    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, c->d_any_silk);
     if (timed) cudaEventRecord(c->ev[1], s);
     if (parsed) cudaEventRecord(parsed, s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
@@ -256,9 +270,16 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) cudaEventRecord(c->ev[5], s);
     k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[6], s);
-    if (in->mode == DM_MODE_OPUS) {  // exits per frame unless the TOC carries a SILK layer
-        k_silk<<<(n_sel + 31) / 32, 32, 0, s>>>(c->d_hdr, c->d_fe, c->d_silk, c->d_sstate, c->d_swork, d_pcm, P);
-        c->launches++;
+    if (in->mode == DM_MODE_OPUS) {  // every one of these returns at once unless k_entropy saw a frame with a SILK layer
+        SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
+        const int chains = n_sel * P.CC;
+        const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs five empty launches
+        k_silk_params<<<wide, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P);
+        k_silk_core<<<(chains + 31) / 32, 32, kSilkCoreSmem, s>>>(c->d_hdr, c->d_fe, B, P);
+        k_silk_unmix<<<wide, 256, 0, s>>>(B, P);
+        k_silk_up2<<<(chains + 31) / 32, 32, 0, s>>>(B, P);
+        k_silk_fir<<<wide, 256, 0, s>>>(B, d_pcm, P);
+        c->launches += 5;
     }
     if (timed) cudaEventRecord(c->ev[7], s);
     c->launches += kStages - 1;
@@ -289,6 +310,7 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
     const int fs = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
     // packets are small: one copy on stream 0, the other chunk streams wait for it
     CU_TRY(c, cudaMemcpyAsync(c->d_bytes[0], in->bytes, in->n_bytes, cudaMemcpyHostToDevice, c->streams[0]));
+    CU_TRY(c, cudaMemsetAsync(c->d_any_silk, 0, sizeof(int), c->streams[0]));  // one flag for all chunks of the call
     CU_TRY(c, cudaEventRecord(c->bytes_ready, c->streams[0]));
     const int n_chunks = c->n_streams >= 64 * kMaxChunks ? kMaxChunks : 1;
     for (int k = 0; k < n_chunks; k++) {
@@ -298,7 +320,7 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
         const size_t f0 = (size_t)first * nf, fn = (size_t)n_sel * nf;
         if (k) CU_TRY(c, cudaStreamWaitEvent(s, c->bytes_ready, 0));
         CU_TRY(c, cudaMemcpyAsync(c->d_frames + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
-        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false);
+        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false, nullptr, false);
         if (r) return r;
         CU_TRY(c, cudaMemcpyAsync(out->pcm + f0 * fs * CC, c->d_pcm + f0 * fs * CC, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(out->status + f0, c->d_status + f0, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

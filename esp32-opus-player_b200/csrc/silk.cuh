@@ -93,11 +93,11 @@ struct SilkIdx {  // ref SideInfoIndices_t (src/silk.h)
     int16_t lagIndex;
     int8_t contour, signalType, quantOffsetType, interpQ2, perIndex, ltpScaleIndex, seed;
 };
-struct SilkFrame {
+struct alignas(16) SilkFrame {
+    int16_t pulses[2][kSilkMaxFrame];  // first: every channel's row starts on a 16-byte boundary
     int32_t ms_pred_Q13[2];
     uint8_t fs_kHz, nch, mid_only, present;
     SilkIdx idx[2];
-    int16_t pulses[2][kSilkMaxFrame];
 };
 
 struct SilkCb {  // ref silk_NLSF_CB_struct

@@ -1,0 +1,295 @@
+// silk_kernels.cuh -- the five SILK synthesis kernels (stage bodies in silk_stages.cuh).
+//
+//   k_silk_params  thread per (stream, frame, channel)   NLSF -> LPC, pitch, LTP filter                [a16]
+//   k_silk_core    lane   per (stream, channel) chain    gains, excitation, LTP + LPC synthesis          [a16, a17]
+//   k_silk_unmix   thread per internal-rate sample       mid/side -> left/right + 1-sample delay         [a19]
+//   k_silk_up2     lane   per (stream, channel) chain    input delay + 2x all-pass up-sampler            [a20]
+//   k_silk_fir     thread per 48 kHz output sample       12-phase FIR interpolation, + CELT PCM          [a20, a13]
+//
+// All of them return at once when the call holds no frame with a SILK layer (*any_silk == 0, set by k_entropy).
+#pragma once
+#include "silk_stages.cuh"
+
+namespace opusb200 {
+
+enum { kXqRow = kSilkMaxFrame, kUpRow = 2 * kSilkMaxFrame + 8 };
+
+struct SilkBufs {
+    SilkFrame* frames;        // [frame]                 entropy -> params, core
+    SilkCtl* ctl;             // [frame][2]              params -> core
+    SilkPost* post;           // [frame]                 core -> unmix, up2, fir
+    int16_t* xq;              // [frame][2][kXqRow]      core -> unmix (mid/side or mono at the internal rate)
+    int16_t* lr;              // [frame][2][kXqRow]      unmix -> up2 (what the resampler is fed)
+    int16_t* up;              // [frame][2][kUpRow]      up2 -> fir (8 samples of history + 2x up-sampled frame)
+    SilkStreamState* state;   // [stream]
+    const int* any_silk;
+};
+
+__device__ __forceinline__ bool silk_frame_live(const CeltFrameHdr* hdr, const FrameEnergy* fe, size_t t) {
+    return (hdr[t].oflags & OF_HAS_SILK) && !(fe[t].skip & FS_DROPPED);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkBufs B, DevParams P) {
+    if (*B.any_silk == 0) return;
+    const int total = P.n_sel * P.n_frames * 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int local = idx >> 1, n = idx & 1;
+        if (n >= P.CC) continue;
+        const int f = local % P.n_frames, s = P.first_stream + local / P.n_frames;
+        const size_t t = (size_t)s * P.n_frames + f;
+        if (!silk_frame_live(hdr, fe, t)) continue;
+        const SilkFrame& F = B.frames[t];
+        if (n == 1 && F.mid_only) continue;
+        const int fs = F.fs_kHz;
+        // the NLSF vector this frame interpolates from: the previous frame this chain decoded, unless a reset lies between
+        int16_t prev[kSilkMaxOrder];
+        bool have_prev = false;
+        if (!(hdr[t].oflags & OF_SILK_REINIT)) {
+            int u = f - 1;
+            while (u >= 0 && !silk_frame_live(hdr, fe, t - (size_t)(f - u))) u--;
+            if (u >= 0) {
+                const SilkFrame& Q = B.frames[t - (size_t)(f - u)];
+                if (Q.fs_kHz == fs && !(n == 1 && Q.mid_only)) {
+                    silk_nlsf_decode(prev, Q.idx[n].nlsf, silk_cb(fs));
+                    have_prev = true;
+                }
+            } else {
+                const SilkStreamState& S = B.state[s];
+                const SilkChannel& C = S.ch[n];
+                if (!C.first_frame_after_reset && C.fs_kHz == fs && !(n == 1 && S.prev_decode_only_middle)) {
+                    for (int i = 0; i < kSilkMaxOrder; i++) prev[i] = C.prevNLSF_Q15[i];
+                    have_prev = true;
+                }
+            }
+        }
+        silk_params_item(F.idx[n], fs, have_prev ? prev : nullptr, B.ctl[t * 2 + n]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp = 32 chains.  Dynamic shared memory: the output-history ring (int16) and the LTP-state ring (int32) of
+// every lane, lane-interleaved: 32 KB + 64 KB.
+enum { kSilkCoreSmem = kSilkRing * 32 * (int)(sizeof(int16_t) + sizeof(int32_t)) };
+
+__global__ void __launch_bounds__(32)
+k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkBufs B, DevParams P) {
+    if (*B.any_silk == 0) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* ltp_base = reinterpret_cast<int32_t*>(smem_raw);
+    int16_t* out_base = reinterpret_cast<int16_t*>(smem_raw + kSilkRing * 32 * sizeof(int32_t));
+    const int lane = threadIdx.x;
+    const int chain = blockIdx.x * 32 + lane;
+    if (chain >= P.n_sel * P.CC) return;
+    const int n = chain % P.CC, s = P.first_stream + chain / P.CC;
+    const ChainRing<int16_t, 32> out{out_base + lane};
+    const ChainRing<int32_t, 32> ltp{ltp_base + lane};
+    SilkStreamState& S = B.state[s];
+    SilkChannel& C = S.ch[n];
+    SilkChainRegs R;
+    SilkChainCtl K;
+    for (int j = 0; j < kSilkMaxOrder; j++) R.h[j] = C.sLPC_Q14_buf[kSilkMaxOrder - 1 - j];
+    R.prev_gain_Q16 = C.prev_gain_Q16;
+    for (int i = 0; i < kSilkMaxFrame; i++) out[i] = C.outBuf[i];  // the newest 320 output samples, oldest first
+    R.out_pos = kSilkMaxFrame;
+    R.ltp_pos = 0;
+    K.fs_kHz = C.fs_kHz; K.LastGainIndex = C.LastGainIndex; K.first = C.first_frame_after_reset;
+    int prev_mid_only = S.prev_decode_only_middle;
+    int last_out_f = -1, last_dec_f = -1;
+    bool hist_zero = false;  // a re-init happened in this call and no frame has produced output since
+    const size_t t0 = (size_t)s * P.n_frames;
+    for (int f = 0; f < P.n_frames; f++) {
+        const size_t t = t0 + f;
+        SilkPost& post = B.post[t];
+        if (!silk_frame_live(hdr, fe, t)) {
+            if (n == 0) post.has_out = 0;
+            continue;
+        }
+        const SilkFrame& F = B.frames[t];
+        const int fs = F.fs_kHz;
+        const bool reinit = (hdr[t].oflags & OF_SILK_REINIT) != 0;
+        if (reinit) { prev_mid_only = 0; hist_zero = true; }
+        bool rs_reset;
+        const bool decode = silk_chain_begin_frame(K, R, out, n, reinit, fs, F.mid_only, prev_mid_only, &rs_reset);
+        if (decode) {
+            s32 gains[4];
+            int8_t lgi = (int8_t)K.LastGainIndex;
+            silk_gains_dequant(gains, F.idx[n].gains, &lgi);
+            K.LastGainIndex = lgi;
+            silk_core_frame(R, out, ltp, F.pulses[n], B.ctl[t * 2 + n], gains, F.idx[n].signalType, F.idx[n].quantOffsetType,
+                            F.idx[n].seed, fs, B.xq + (t * 2 + n) * kXqRow);
+            K.first = 0;
+            last_dec_f = f;
+        }
+        post.rs_reset[n] = rs_reset;
+        if (n == 0) {
+            post.prev = hist_zero ? (int16_t)0 : last_out_f >= 0 ? (int16_t)(last_out_f - f) : (int16_t)1;
+            post.has_out = 1;
+            post.fs_kHz = (uint8_t)fs;
+            post.dec_mask = (uint8_t)(1 | ((P.CC == 2 && !F.mid_only) ? 2 : 0));
+            post.reinit = reinit;
+        }
+        prev_mid_only = F.mid_only;
+        last_out_f = f;
+        hist_zero = false;
+    }
+    for (int j = 0; j < kSilkMaxOrder; j++) C.sLPC_Q14_buf[kSilkMaxOrder - 1 - j] = R.h[j];
+    C.prev_gain_Q16 = R.prev_gain_Q16;
+    for (int i = 0; i < kSilkMaxFrame; i++) C.outBuf[i] = out[R.out_pos - kSilkMaxFrame + i];
+    C.fs_kHz = K.fs_kHz; C.LastGainIndex = (int8_t)K.LastGainIndex; C.first_frame_after_reset = (int8_t)K.first;
+    if (last_dec_f >= 0) {
+        const SilkCtl& L = B.ctl[(t0 + last_dec_f) * 2 + n];
+        for (int i = 0; i < kSilkMaxOrder; i++) C.prevNLSF_Q15[i] = L.nlsf_Q15[i];
+    }
+    if (n == 0) S.prev_decode_only_middle = prev_mid_only;
+}
+
+// ------------------------------------------------------------------------------------------------
+// history of the mid / side signals in front of frame t (ref stereo_dec_state sMid, sSide, pred_prev_Q13)
+struct SilkHist { s32 m2, m1, s1, p0, p1; };
+__device__ __forceinline__ SilkHist silk_hist(const SilkBufs& B, size_t t, int s, int CC) {
+    SilkHist h = {0, 0, 0, 0, 0};
+    const SilkPost& post = B.post[t];
+    if (post.prev < 0) {
+        const size_t u = t + post.prev;
+        const SilkPost& pp = B.post[u];
+        const int Lp = 20 * pp.fs_kHz;
+        const int16_t* m = B.xq + (u * 2) * kXqRow;
+        h.m2 = m[Lp - 2]; h.m1 = m[Lp - 1];
+        if (CC == 2) {
+            if (pp.dec_mask & 2) h.s1 = B.xq[(u * 2 + 1) * kXqRow + Lp - 1];
+            h.p0 = (int16_t)B.frames[u].ms_pred_Q13[0];
+            h.p1 = (int16_t)B.frames[u].ms_pred_Q13[1];
+        }
+    } else if (post.prev == 1) {
+        const SilkStreamState& S = B.state[s];
+        h.m2 = S.sMid[0]; h.m1 = S.sMid[1]; h.s1 = S.sSide[1];
+        h.p0 = S.pred_prev_Q13[0]; h.p1 = S.pred_prev_Q13[1];
+    }
+    return h;
+}
+
+__global__ void __launch_bounds__(256)
+k_silk_unmix(SilkBufs B, DevParams P) {
+    if (*B.any_silk == 0) return;
+    const int nfr = P.n_sel * P.n_frames;
+    for (int local = blockIdx.x; local < nfr; local += gridDim.x) {
+        const int s = P.first_stream + local / P.n_frames;
+        const size_t t = (size_t)P.first_stream * P.n_frames + local;
+        const SilkPost& post = B.post[t];
+        if (!post.has_out) continue;
+        const int fs = post.fs_kHz, L = 20 * fs;
+        const SilkHist h = silk_hist(B, t, s, P.CC);
+        const int16_t* mid = B.xq + (t * 2) * kXqRow;
+        if (P.CC == 1) {
+            int16_t* o = B.lr + (t * 2) * kXqRow;
+            for (int i = threadIdx.x; i < L; i += blockDim.x) o[i] = i == 0 ? (int16_t)h.m1 : mid[i - 1];
+        } else {
+            const int16_t* side = B.xq + (t * 2 + 1) * kXqRow;
+            const bool has_side = post.dec_mask & 2;
+            SilkUnmix U;
+            U.setup(B.frames[t].ms_pred_Q13, h.p0, h.p1, fs);
+            int16_t* ol = B.lr + (t * 2) * kXqRow;
+            int16_t* orr = B.lr + (t * 2 + 1) * kXqRow;
+            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+                const s32 x1a = i >= 2 ? mid[i - 2] : (i == 1 ? h.m1 : h.m2);
+                const s32 x1b = i >= 1 ? mid[i - 1] : h.m1;
+                const s32 x1c = mid[i];
+                const s32 x2b = i >= 1 ? (has_side ? side[i - 1] : 0) : h.s1;
+                U.sample(i, x1a, x1b, x1c, x2b, &ol[i], &orr[i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_silk_up2(SilkBufs B, DevParams P) {
+    if (*B.any_silk == 0) return;
+    const int chain = blockIdx.x * 32 + threadIdx.x;
+    if (chain >= P.n_sel * P.CC) return;
+    const int n = chain % P.CC, s = P.first_stream + chain / P.CC;
+    SilkStreamState& S = B.state[s];
+    SilkResampler& Rs = S.ch[n].rs;
+    SilkUp2Regs R;
+    uint32_t fh[4];  // the newest 8 up-sampled samples, two per word
+    for (int i = 0; i < 6; i++) R.S[i] = Rs.sIIR[i];
+    int fs = Rs.Fs_in_kHz, D = silk_input_delay(fs);
+    for (int j = 0; j < 8; j++) R.d[j] = 0;
+    for (int i = 0; i < D; i++) R.d[D - 1 - i] = Rs.delayBuf[i];
+    for (int i = 0; i < 4; i++) fh[i] = (uint32_t)(uint16_t)Rs.sFIR[2 * i] | (uint32_t)(uint16_t)Rs.sFIR[2 * i + 1] << 16;
+    const size_t t0 = (size_t)s * P.n_frames;
+    int last_out_f = -1;
+    for (int f = 0; f < P.n_frames; f++) {
+        const size_t t = t0 + f;
+        const SilkPost& post = B.post[t];
+        if (!post.has_out) continue;
+        if (post.rs_reset[n]) {  // ref silk_resampler_init :3590
+            for (int i = 0; i < 6; i++) R.S[i] = 0;
+            for (int j = 0; j < 8; j++) R.d[j] = 0;
+            for (int j = 0; j < 4; j++) fh[j] = 0;
+        }
+        fs = post.fs_kHz;
+        D = silk_input_delay(fs);
+        const int L = 20 * fs;
+        const int16_t* in = B.lr + (t * 2 + n) * kXqRow;
+        int16_t* u = B.up + (t * 2 + n) * kUpRow;
+        *reinterpret_cast<uint4*>(u) = make_uint4(fh[0], fh[1], fh[2], fh[3]);
+#pragma unroll 1
+        for (int i = 0; i < L; i += 4) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(in + i);
+            const int16_t x[4] = {(int16_t)(raw.x & 0xffff), (int16_t)(raw.x >> 16), (int16_t)(raw.y & 0xffff), (int16_t)(raw.y >> 16)};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int16_t a, b;
+                silk_up2_sample(R, x[k], D, &a, &b);
+                fh[k] = (uint32_t)(uint16_t)a | (uint32_t)(uint16_t)b << 16;
+            }
+            *reinterpret_cast<uint4*>(u + 8 + 2 * i) = make_uint4(fh[0], fh[1], fh[2], fh[3]);
+        }
+        last_out_f = f;
+    }
+    for (int i = 0; i < 6; i++) Rs.sIIR[i] = R.S[i];
+    for (int i = 0; i < 4; i++) { Rs.sFIR[2 * i] = (int16_t)(fh[i] & 0xffff); Rs.sFIR[2 * i + 1] = (int16_t)(fh[i] >> 16); }
+    for (int i = 0; i < D; i++) Rs.delayBuf[i] = (int16_t)R.d[D - 1 - i];
+    Rs.Fs_in_kHz = fs;
+    if (n == 0 && last_out_f >= 0) {  // stereo history for the next call (ref silk_stereo_MS_to_LR :4040-4043, :4066-4067)
+        const size_t tl = t0 + last_out_f;
+        const SilkPost& pl = B.post[tl];
+        const int L = 20 * pl.fs_kHz;
+        const int16_t* m = B.xq + (tl * 2) * kXqRow;
+        S.sMid[0] = m[L - 2]; S.sMid[1] = m[L - 1];
+        if (P.CC == 2) {
+            const int16_t* sd = B.xq + (tl * 2 + 1) * kXqRow;
+            const bool has_side = pl.dec_mask & 2;
+            S.sSide[0] = has_side ? sd[L - 2] : (int16_t)0;
+            S.sSide[1] = has_side ? sd[L - 1] : (int16_t)0;
+            S.pred_prev_Q13[0] = (int16_t)B.frames[tl].ms_pred_Q13[0];
+            S.pred_prev_Q13[1] = (int16_t)B.frames[tl].ms_pred_Q13[1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_silk_fir(SilkBufs B, int16_t* __restrict__ pcm, DevParams P) {
+    if (*B.any_silk == 0) return;
+    const int nfr = P.n_sel * P.n_frames;
+    const int CC = P.CC;
+    for (int local = blockIdx.x; local < nfr; local += gridDim.x) {
+        const size_t t = (size_t)P.first_stream * P.n_frames + local;
+        const SilkPost& post = B.post[t];
+        if (!post.has_out) continue;
+        const int fs = post.fs_kHz;
+        const s32 inv = silk_inv_ratio_Q16(fs);
+        int16_t* o = pcm + t * (size_t)(kMaxFrame * CC);
+        for (int i = threadIdx.x; i < kMaxFrame * CC; i += blockDim.x) {
+            const int n = CC == 2 ? (i & 1) : 0, k = CC == 2 ? (i >> 1) : i;
+            const s32 v = silk_fir_sample(B.up + (t * 2 + n) * kUpRow, k, fs, inv);
+            o[i] = sat16((s32)o[i] + v);  // ref src/opus_decoder.cpp:271-273
+        }
+    }
+}
+
+}  // namespace opusb200

@@ -121,10 +121,79 @@ static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, 
 
 // ---- Opus frame layer on top (ref opus_decode_frame, src/opus_decoder.cpp:154): SILK, hybrid, CELT ----
 #include "../../esp32-opus-player_b200/csrc/opus_frame.cuh"
+#include "../../esp32-opus-player_b200/csrc/silk_stages.cuh"
+
+// The SILK stages of silk_stages.cuh run back to back for one stream (rings with stride 1).
+struct HsSilk {
+    SilkChainRegs R[2];
+    SilkChainCtl K[2];
+    int16_t out_ring[2][kSilkRing];
+    int32_t ltp_ring[2][kSilkRing];
+    int16_t prevNLSF[2][kSilkMaxOrder];
+    int prev_mid_only;
+    s32 m2, m1, s2, s1, p0, p1;  // stereo history (ref stereo_dec_state)
+    SilkUp2Regs U[2];
+    int16_t fh[2][8];
+};
+static void hs_silk_init(HsSilk& h) {
+    memset(&h, 0, sizeof(h));
+    for (int n = 0; n < 2; n++) { h.R[n].prev_gain_Q16 = 65536; h.K[n].first = 1; h.R[n].out_pos = kSilkMaxFrame; }
+}
+// one frame -> 960 * nch samples at 48 kHz, interleaved
+static void hs_silk_frame(HsSilk& h, SilkFrame& F, bool reinit, int16_t* pcm48) {
+    const int nch = F.nch, fs = F.fs_kHz, L = 20 * fs;
+    static int16_t xq[2][kSilkMaxFrame], lr[2][kSilkMaxFrame], up[2][2 * kSilkMaxFrame + 8];
+    if (reinit) { h.prev_mid_only = 0; h.m2 = h.m1 = h.s2 = h.s1 = h.p0 = h.p1 = 0; }
+    bool rs_reset[2] = {false, false}, dec[2] = {false, false};
+    for (int n = 0; n < nch; n++) {
+        ChainRing<int16_t, 1> out{h.out_ring[n]};
+        ChainRing<int32_t, 1> ltp{h.ltp_ring[n]};
+        dec[n] = silk_chain_begin_frame(h.K[n], h.R[n], out, n, reinit, fs, F.mid_only, h.prev_mid_only, &rs_reset[n]);
+        if (dec[n]) {
+            SilkCtl ctl;
+            silk_params_item(F.idx[n], fs, h.K[n].first ? nullptr : h.prevNLSF[n], ctl);
+            s32 gains[4];
+            int8_t lgi = (int8_t)h.K[n].LastGainIndex;
+            silk_gains_dequant(gains, F.idx[n].gains, &lgi);
+            h.K[n].LastGainIndex = lgi;
+            silk_core_frame(h.R[n], out, ltp, F.pulses[n], ctl, gains, F.idx[n].signalType, F.idx[n].quantOffsetType, F.idx[n].seed, fs,
+                            xq[n]);
+            h.K[n].first = 0;
+            memcpy(h.prevNLSF[n], ctl.nlsf_Q15, sizeof(ctl.nlsf_Q15));
+        } else {
+            for (int i = 0; i < L; i++) xq[n][i] = 0;
+        }
+    }
+    if (nch == 1) {
+        for (int i = 0; i < L; i++) lr[0][i] = i == 0 ? (int16_t)h.m1 : xq[0][i - 1];
+    } else {
+        SilkUnmix U;
+        U.setup(F.ms_pred_Q13, h.p0, h.p1, fs);
+        for (int i = 0; i < L; i++) {
+            const s32 x1a = i >= 2 ? xq[0][i - 2] : (i == 1 ? h.m1 : h.m2);
+            const s32 x1b = i >= 1 ? xq[0][i - 1] : h.m1;
+            const s32 x2b = i >= 1 ? xq[1][i - 1] : h.s1;
+            U.sample(i, x1a, x1b, xq[0][i], x2b, &lr[0][i], &lr[1][i]);
+        }
+        h.p0 = (int16_t)F.ms_pred_Q13[0]; h.p1 = (int16_t)F.ms_pred_Q13[1];
+        h.s2 = xq[1][L - 2]; h.s1 = xq[1][L - 1];
+    }
+    h.m2 = xq[0][L - 2]; h.m1 = xq[0][L - 1];
+    const s32 inv = silk_inv_ratio_Q16(fs);
+    for (int n = 0; n < nch; n++) {
+        if (rs_reset[n]) { memset(&h.U[n], 0, sizeof(h.U[n])); memset(h.fh[n], 0, sizeof(h.fh[n])); }
+        const int D = silk_input_delay(fs);
+        memcpy(up[n], h.fh[n], sizeof(h.fh[n]));
+        for (int i = 0; i < L; i++) silk_up2_sample(h.U[n], lr[n][i], D, &up[n][8 + 2 * i], &up[n][8 + 2 * i + 1]);
+        memcpy(h.fh[n], &up[n][2 * L], sizeof(h.fh[n]));
+        for (int o = 0; o < 960; o++) pcm48[o * nch + n] = silk_fir_sample(up[n], o, fs, inv);
+    }
+    h.prev_mid_only = F.mid_only;
+}
 
 struct HsOpus {
     HsCelt celt;
-    SilkStreamState silk;
+    HsSilk silk;
     int channels, prev_mode;
 };
 
@@ -136,7 +205,7 @@ void* hs_opus_new(int channels) {
     d->celt.CC = channels;
     for (int i = 0; i < kNbEBands; i++)
         for (int c = 0; c < 2; c++) d->celt.st.band[i].logE[c] = d->celt.st.band[i].logE2[c] = -(28 << 10);
-    silk_stream_reinit(d->silk);
+    hs_silk_init(d->silk);
     return d;
 }
 void hs_opus_free(void* d) { free(d); }
@@ -147,16 +216,13 @@ int hs_opus_decode(void* dv, int toc, const uint8_t* payload, int len, int16_t* 
     const int CC = d->channels;
     static int16_t pcm_silk[960 * 2];
     static SilkFrame sf;
-    static SilkScratch sw;
     static CeltFrameHdr hdr;
     ParseCtx p;
     memset(&p, 0, sizeof(p));
     bool celt, fade;
     const int oflags = opus_parse_prologue(p, payload, len, toc, d->prev_mode, CC, hdr, sf, &celt, &fade);
-    if (hdr.status == OPUSB_UNIMPLEMENTED && !celt && !(oflags & OF_HAS_SILK) && opus_toc_mode(toc) != MODE_CELT_ONLY && ((toc & 4) ? 2 : 1) != CC)
-        return OPUSB_UNIMPLEMENTED;
-    if (oflags & OF_SILK_REINIT) silk_stream_reinit(d->silk);
-    if (oflags & OF_HAS_SILK) silk_synth_frame(d->silk, sf, pcm_silk, sw);
+    if (!celt && !(oflags & OF_HAS_SILK) && opus_toc_mode(toc) != MODE_CELT_ONLY && ((toc & 4) ? 2 : 1) != CC) return OPUSB_UNIMPLEMENTED;
+    if (oflags & OF_HAS_SILK) hs_silk_frame(d->silk, sf, (oflags & OF_SILK_REINIT) != 0, pcm_silk);
     if (oflags & OF_RESET_CELT) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479)
         CeltStreamState& st = d->celt.st;
         st.rng = 0;
