@@ -24,6 +24,11 @@
 
 namespace opusb200 {
 
+#if !defined(__CUDACC__)
+struct uint2 { uint32_t x, y; };
+#endif
+OPUS_HD uint2 make_uint2_(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
+
 enum { kSilkRing = 512 };  // >= max pitch lag (288) + LPC order + 2 + one sub-frame; power of two
 
 // element i of a chain-private ring; stride = 32 (lane-interleaved shared memory) or 1 (host)
@@ -31,6 +36,9 @@ template <class T, int kStride>
 struct ChainRing {
     T* base;
     OPUS_HD T& operator[](int i) const { return base[(i & (kSilkRing - 1)) * kStride]; }
+    // elements i .. i+3 for i a multiple of 4 (a block never wraps): p[0], p[kStride], p[2 * kStride], p[3 * kStride]
+    OPUS_HD T* block4(int i) const { return base + (i & (kSilkRing - 1)) * kStride; }
+    enum { stride = kStride };
 };
 
 // per (frame, channel) output of the params stage
@@ -114,6 +122,10 @@ struct SilkChainRegs {       // what a chain carries from frame to frame in regi
 
 // One frame of one chain (ref silk_decode_core, src/silk.cpp:1806).  `out` holds the chain's output history (ref
 // outBuf), `ltp` the LTP state (ref sLTP_Q15); xq receives frame_length samples at the internal rate.
+// A chain runs alone on its lane and a warp has few neighbours on its SM (the rings take 96 KB per warp), so the
+// code is written for the latency of one instruction stream: the 16-tap sums are split over four accumulators (the
+// reference's 32-bit wrapping adds are associative), the next block's pulses are loaded before the current block is
+// computed, ring addresses are formed once per block of four samples.
 template <class OutRing, class LtpRing>
 OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const int16_t* pulses, const SilkCtl& ctl, const s32* Gains_Q16,
                              int signalType, int quantOffsetType, int seed, int fs_kHz, int16_t* xq) {
@@ -123,9 +135,12 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
     const s32 offset_Q14 = offs[signalType >> 1][quantOffsetType] << 4;
     u32 rand_seed = (u32)(s32)seed;
     int lag = 0;
+    const uint2* p4 = reinterpret_cast<const uint2*>(pulses);  // four pulses per load (rows are 16-byte aligned)
+    uint2* x4 = reinterpret_cast<uint2*>(xq);
+    uint2 pnext = p4[0];
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-        s32 A[kSilkMaxOrder];  // A_Q12 << 16
+        s32 A[kSilkMaxOrder];  // A_Q12 << 16 (multiply-high form)
 #pragma unroll
         for (int j = 0; j < kSilkMaxOrder; j++) A[j] = (s32)((u32)(uint16_t)ctl.A_Q12[k >> 1][j] << 16);
         const s32 gain_Q16 = Gains_Q16[k];
@@ -149,6 +164,9 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
                 // ltp_mem) (+ the first two sub-frames when k == 2) is simply the newest lag + order + 2 samples of the
                 // output ring.
                 if (k == 0) inv_gain_Q31 = shl32(smulwb(inv_gain_Q31, ctl.LTP_scale_Q14), 2);
+                s32 a16[kSilkMaxOrder];
+#pragma unroll
+                for (int j = 0; j < kSilkMaxOrder; j++) a16[j] = ctl.A_Q12[k >> 1][j];
                 const int n_out = lag + 2;
                 const int in0 = R.out_pos - n_out;  // ring index of the first sample that gets whitened
                 s32 w[kSilkMaxOrder];               // w[j] = in[ix - 1 - j]
@@ -158,15 +176,17 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
                 for (int o0 = 0; o0 < n_out; o0 += 4) {
                     s32 c[4];
 #pragma unroll
+                    for (int u = 0; u < 4; u++) c[u] = out[in0 + o0 + u];
+#pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        c[u] = out[in0 + o0 + u];
-                        s32 acc = 0;
+                        s32 acc[4] = {0, 0, 0, 0};  // silk_SMLABB_ovflw: int16 x int16 products, wrapping sum
 #pragma unroll
                         for (int j = 0; j < kSilkMaxOrder; j++) {
                             const s32 v = (u - 1 - j >= 0) ? c[(u - 1 - j) & 3] : w[(j - u) & (kSilkMaxOrder - 1)];
-                            acc = (s32)((u32)acc + (u32)(v * (A[j] >> 16)));  // silk_SMLABB_ovflw: int16 x int16, wrapping sum
+                            acc[j & 3] = (s32)((u32)acc[j & 3] + (u32)(v * a16[j]));
                         }
-                        const s32 r = sub_w(shl32(c[u], 12), acc);
+                        const s32 sum = (s32)(((u32)acc[0] + (u32)acc[1]) + ((u32)acc[2] + (u32)acc[3]));
+                        const s32 r = sub_w(shl32(c[u], 12), sum);
                         const s32 white = sat16(rshift_round(r, 12));
                         if (o0 + u < n_out) ltp[R.ltp_pos - n_out + o0 + u] = smulwb(inv_gain_Q31, white);
                     }
@@ -176,19 +196,32 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
                     for (int j = 0; j < 4; j++) w[j] = c[3 - j];
                 }
             } else if (gain_adj_Q16 != 1 << 16) {
-#pragma unroll 1
-                for (int i = 0; i < lag + 2; i++) ltp[R.ltp_pos - i - 1] = smulww(gain_adj_Q16, ltp[R.ltp_pos - i - 1]);
+#pragma unroll 2
+                for (int i = 0; i < lag + 2; i++) {
+                    s32& e = ltp[R.ltp_pos - i - 1];
+                    e = smulww(gain_adj_Q16, e);
+                }
             }
         }
-        const int16_t* p = pulses + k * subfr;
-        int16_t* x = xq + k * subfr;
 #pragma unroll 1
         for (int i = 0; i < subfr; i += 4) {
+            const uint2 pw = pnext;
+            const int blk = (k * subfr + i) >> 2;
+            if (blk + 1 < 20 * fs_kHz / 4) pnext = p4[blk + 1];
+            const s32 pl4[4] = {(s32)(int16_t)(pw.x & 0xffff), (s32)(int16_t)(pw.x >> 16), (s32)(int16_t)(pw.y & 0xffff), (s32)(int16_t)(pw.y >> 16)};
             s32 nw[4];
+            s32 yq[4];
+            // LTP taps of the whole block first: they lie at least lag - 2 >= 14 samples back, never inside the block
+            s32 lt[8];
+            if (signalType == 2) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) lt[t] = ltp[R.ltp_pos - lag - 2 + t];  // state samples q-4 .. q+3 of u = 0
+            }
+            int32_t* lw = ltp.block4(R.ltp_pos);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 // excitation (ref :1827-1842)
-                const s32 pl = p[i + u];
+                const s32 pl = pl4[u];
                 rand_seed = 907633515u + rand_seed * 196314165u;
                 s32 e = shl32(pl, 14);
                 if (e > 0) e -= 80 << 4;
@@ -196,33 +229,31 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
                 e += offset_Q14;
                 if ((s32)rand_seed < 0) e = -e;
                 rand_seed += (u32)pl;
-                // long-term prediction (ref :1907-1920)
+                // long-term prediction (ref :1907-1920): taps q, q-1, .., q-4 with q = pos - lag + 2 (+ u)
                 s32 res = e;
                 if (signalType == 2) {
-                    const int q = R.ltp_pos - lag + 2;
-                    s32 pred = 2;
-                    pred = smlawt(pred, ltp[q], B[0]);
-                    pred = smlawt(pred, ltp[q - 1], B[1]);
-                    pred = smlawt(pred, ltp[q - 2], B[2]);
-                    pred = smlawt(pred, ltp[q - 3], B[3]);
-                    pred = smlawt(pred, ltp[q - 4], B[4]);
-                    res = e + shl32(pred, 1);
-                    ltp[R.ltp_pos] = shl32(res, 1);
-                    R.ltp_pos++;
+                    const s32 pa = smlawt(smlawt(smlawt(2, lt[u + 4], B[0]), lt[u + 3], B[1]), lt[u + 2], B[2]);
+                    const s32 pb = smlawt(smlawt(0, lt[u + 1], B[3]), lt[u], B[4]);
+                    res = e + shl32(pa + pb, 1);
+                    lw[u * LtpRing::stride] = shl32(res, 1);
                 }
                 // short-term prediction (ref :1925-1960): taps beyond the order are zero
-                s32 acc = order >> 1;
+                s32 acc[4] = {order >> 1, 0, 0, 0};
 #pragma unroll
                 for (int j = 0; j < kSilkMaxOrder; j++) {
                     const s32 v = (u - 1 - j >= 0) ? nw[(u - 1 - j) & 3] : R.h[(j - u) & (kSilkMaxOrder - 1)];
-                    acc = smlawt(acc, v, A[j]);
+                    acc[j & 3] = smlawt(acc[j & 3], v, A[j]);
                 }
-                const s32 s = add_sat32(res, lshift_sat32(acc, 4));
+                const s32 pred = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                const s32 s = add_sat32(res, lshift_sat32(pred, 4));
                 nw[u] = s;
-                const int16_t y = sat16(rshift_round(smulww(s, Gain_Q10), 8));
-                x[i + u] = y;
-                out[R.out_pos + u] = y;
+                yq[u] = sat16(rshift_round(smulww(s, Gain_Q10), 8));
             }
+            if (signalType == 2) R.ltp_pos += 4;
+            int16_t* ow = out.block4(R.out_pos);
+#pragma unroll
+            for (int u = 0; u < 4; u++) ow[u * OutRing::stride] = (int16_t)yq[u];
+            x4[blk] = make_uint2_((u32)(yq[0] & 0xffff) | (u32)yq[1] << 16, (u32)(yq[2] & 0xffff) | (u32)yq[3] << 16);
             R.out_pos += 4;
 #pragma unroll
             for (int j = kSilkMaxOrder - 1; j >= 4; j--) R.h[j] = R.h[j - 4];
