@@ -69,21 +69,20 @@ k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp = 32 chains.  Dynamic shared memory: the output-history ring (int16) and the LTP-state ring (int32) of
-// every lane, lane-interleaved: 32 KB + 64 KB.
-enum { kSilkCoreSmem = kSilkRing * 32 * (int)(sizeof(int16_t) + sizeof(int32_t)) };
+// One warp = 32 chains.  Dynamic shared memory: the LTP-state ring (int32) of every lane, lane-interleaved: 48 KB,
+// so four warps share an SM and 16384 chains are resident at once on 148 SMs.  The chain's output history, which the
+// LTP re-whitening reads, is the xq rows this lane wrote earlier (global memory, L1/L2).
+enum { kSilkCoreSmem = kSilkRing * 32 * (int)sizeof(int32_t) };
 
 __global__ void __launch_bounds__(32)
 k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkBufs B, DevParams P) {
     if (*B.any_silk == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* ltp_base = reinterpret_cast<int32_t*>(smem_raw);
-    int16_t* out_base = reinterpret_cast<int16_t*>(smem_raw + kSilkRing * 32 * sizeof(int32_t));
     const int lane = threadIdx.x;
     const int chain = blockIdx.x * 32 + lane;
     if (chain >= P.n_sel * P.CC) return;
     const int n = chain % P.CC, s = P.first_stream + chain / P.CC;
-    const ChainRing<int16_t, 32> out{out_base + lane};
     const ChainRing<int32_t, 32> ltp{ltp_base + lane};
     SilkStreamState& S = B.state[s];
     SilkChannel& C = S.ch[n];
@@ -91,10 +90,9 @@ k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict_
     SilkChainCtl K;
     for (int j = 0; j < kSilkMaxOrder; j++) R.h[j] = C.sLPC_Q14_buf[kSilkMaxOrder - 1 - j];
     R.prev_gain_Q16 = C.prev_gain_Q16;
-    for (int i = 0; i < kSilkMaxFrame; i++) out[i] = C.outBuf[i];  // the newest 320 output samples, oldest first
-    R.out_pos = kSilkMaxFrame;
     R.ltp_pos = 0;
     K.fs_kHz = C.fs_kHz; K.LastGainIndex = C.LastGainIndex; K.first = C.first_frame_after_reset;
+    const int16_t* hist_end = C.outBuf + kSilkMaxFrame;  // carried history: the newest 320 output samples, oldest first
     int prev_mid_only = S.prev_decode_only_middle;
     int last_out_f = -1, last_dec_f = -1;
     bool hist_zero = false;  // a re-init happened in this call and no frame has produced output since
@@ -110,15 +108,18 @@ k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict_
         const int fs = F.fs_kHz;
         const bool reinit = (hdr[t].oflags & OF_SILK_REINIT) != 0;
         if (reinit) { prev_mid_only = 0; hist_zero = true; }
-        bool rs_reset;
-        const bool decode = silk_chain_begin_frame(K, R, out, n, reinit, fs, F.mid_only, prev_mid_only, &rs_reset);
+        bool rs_reset, cleared;
+        const bool decode = silk_chain_begin_frame(K, R, n, reinit, fs, F.mid_only, prev_mid_only, &rs_reset, &cleared);
+        if (cleared) hist_end = nullptr;
         if (decode) {
             s32 gains[4];
             int8_t lgi = (int8_t)K.LastGainIndex;
             silk_gains_dequant(gains, F.idx[n].gains, &lgi);
             K.LastGainIndex = lgi;
-            silk_core_frame(R, out, ltp, F.pulses[n], B.ctl[t * 2 + n], gains, F.idx[n].signalType, F.idx[n].quantOffsetType,
-                            F.idx[n].seed, fs, B.xq + (t * 2 + n) * kXqRow);
+            int16_t* row = B.xq + (t * 2 + n) * kXqRow;
+            silk_core_frame(R, ChainHistory{hist_end, row}, ltp, F.pulses[n], B.ctl[t * 2 + n], gains, F.idx[n].signalType,
+                            F.idx[n].quantOffsetType, F.idx[n].seed, fs, row);
+            hist_end = row + 20 * fs;
             K.first = 0;
             last_dec_f = f;
         }
@@ -136,11 +137,14 @@ k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict_
     }
     for (int j = 0; j < kSilkMaxOrder; j++) C.sLPC_Q14_buf[kSilkMaxOrder - 1 - j] = R.h[j];
     C.prev_gain_Q16 = R.prev_gain_Q16;
-    for (int i = 0; i < kSilkMaxFrame; i++) C.outBuf[i] = out[R.out_pos - kSilkMaxFrame + i];
+    if (hist_end != C.outBuf + kSilkMaxFrame) {  // the history moved on: keep its newest frame (zeros after a clear)
+        const int L = 20 * K.fs_kHz;
+        for (int i = 0; i < L; i++) C.outBuf[kSilkMaxFrame - L + i] = hist_end ? hist_end[i - L] : (int16_t)0;
+    }
     C.fs_kHz = K.fs_kHz; C.LastGainIndex = (int8_t)K.LastGainIndex; C.first_frame_after_reset = (int8_t)K.first;
     if (last_dec_f >= 0) {
-        const SilkCtl& L = B.ctl[(t0 + last_dec_f) * 2 + n];
-        for (int i = 0; i < kSilkMaxOrder; i++) C.prevNLSF_Q15[i] = L.nlsf_Q15[i];
+        const SilkCtl& Lc = B.ctl[(t0 + last_dec_f) * 2 + n];
+        for (int i = 0; i < kSilkMaxOrder; i++) C.prevNLSF_Q15[i] = Lc.nlsf_Q15[i];
     }
     if (n == 0) S.prev_decode_only_middle = prev_mid_only;
 }
@@ -275,6 +279,8 @@ k_silk_up2(SilkBufs B, DevParams P) {
 __global__ void __launch_bounds__(256)
 k_silk_fir(SilkBufs B, int16_t* __restrict__ pcm, DevParams P) {
     if (*B.any_silk == 0) return;
+    // the up-sampled rows of the frame are staged in shared memory: every output reads 8 neighbouring taps of them
+    __shared__ __align__(16) int16_t rows[2][kUpRow];
     const int nfr = P.n_sel * P.n_frames;
     const int CC = P.CC;
     for (int local = blockIdx.x; local < nfr; local += gridDim.x) {
@@ -282,12 +288,23 @@ k_silk_fir(SilkBufs B, int16_t* __restrict__ pcm, DevParams P) {
         const SilkPost& post = B.post[t];
         if (!post.has_out) continue;
         const int fs = post.fs_kHz;
+        const int words = (2 * 20 * fs + 8) / 8;  // 16-byte words per row
+        __syncthreads();
+        for (int i = threadIdx.x; i < words * CC; i += blockDim.x) {
+            const int n = i / words, w = i - n * words;
+            reinterpret_cast<uint4*>(rows[n])[w] = reinterpret_cast<const uint4*>(B.up + (t * 2 + n) * kUpRow)[w];
+        }
+        __syncthreads();
         const s32 inv = silk_inv_ratio_Q16(fs);
-        int16_t* o = pcm + t * (size_t)(kMaxFrame * CC);
-        for (int i = threadIdx.x; i < kMaxFrame * CC; i += blockDim.x) {
-            const int n = CC == 2 ? (i & 1) : 0, k = CC == 2 ? (i >> 1) : i;
-            const s32 v = silk_fir_sample(B.up + (t * 2 + n) * kUpRow, k, fs, inv);
-            o[i] = sat16((s32)o[i] + v);  // ref src/opus_decoder.cpp:271-273
+        // two interleaved int16 samples (one stereo frame, or two mono samples) per thread and store
+        uint32_t* o = reinterpret_cast<uint32_t*>(pcm + t * (size_t)(kMaxFrame * CC));
+        for (int i = threadIdx.x; i < kMaxFrame * CC / 2; i += blockDim.x) {
+            const uint32_t old = o[i];
+            s32 a, b;
+            if (CC == 2) { a = silk_fir_sample(rows[0], i, fs, inv); b = silk_fir_sample(rows[1], i, fs, inv); }
+            else { a = silk_fir_sample(rows[0], 2 * i, fs, inv); b = silk_fir_sample(rows[0], 2 * i + 1, fs, inv); }
+            const s32 lo = sat16((s32)(int16_t)(old & 0xffff) + a), hi = sat16((s32)(int16_t)(old >> 16) + b);  // ref src/opus_decoder.cpp:271-273
+            o[i] = (uint32_t)(lo & 0xffff) | (uint32_t)hi << 16;
         }
     }
 }

@@ -29,16 +29,29 @@ struct uint2 { uint32_t x, y; };
 #endif
 OPUS_HD uint2 make_uint2_(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
 
-enum { kSilkRing = 512 };  // >= max pitch lag (288) + LPC order + 2 + one sub-frame; power of two
+enum { kSilkRing = 384 };  // >= max pitch lag (288) + 2 + one sub-frame (80), a multiple of 4
 
-// element i of a chain-private ring; stride = 32 (lane-interleaved shared memory) or 1 (host)
+// element i of a chain-private ring, i within one ring length of [0, kSilkRing); stride = 32 (lane-interleaved shared
+// memory) or 1 (host)
 template <class T, int kStride>
 struct ChainRing {
     T* base;
-    OPUS_HD T& operator[](int i) const { return base[(i & (kSilkRing - 1)) * kStride]; }
+    OPUS_HD static int wrap(int i) { return i < 0 ? i + kSilkRing : (i >= kSilkRing ? i - kSilkRing : i); }
+    OPUS_HD T& operator[](int i) const { return base[wrap(i) * kStride]; }
     // elements i .. i+3 for i a multiple of 4 (a block never wraps): p[0], p[kStride], p[2 * kStride], p[3 * kStride]
-    OPUS_HD T* block4(int i) const { return base + (i & (kSilkRing - 1)) * kStride; }
+    OPUS_HD T* block4(int i) const { return base + wrap(i) * kStride; }
     enum { stride = kStride };
+};
+
+// The chain's own output history, newest last, as two spans of global memory: what the previous decoded frame left
+// (its xq row, or the history carried from the previous call) and this frame's row so far.  The LTP re-whitening reads
+// at most lag + order + 2 <= frame length samples back (ref ltp_mem_length = one frame), so two spans always suffice.
+struct ChainHistory {
+    const int16_t* prev_end;  // one past the newest sample before this frame; nullptr: the history is all zero
+    const int16_t* cur;       // this frame's xq row
+    OPUS_HD s32 back(int n_cur, int d) const {  // the sample d >= 1 positions before sample n_cur of this frame
+        return d <= n_cur ? (s32)cur[n_cur - d] : (prev_end ? (s32)prev_end[n_cur - d] : 0);
+    }
 };
 
 // per (frame, channel) output of the params stage
@@ -116,18 +129,17 @@ OPUS_HD s32 smlawt(s32 a, s32 b, s32 c_hi) {
 struct SilkChainRegs {       // what a chain carries from frame to frame in registers
     s32 h[kSilkMaxOrder];    // h[j] = sLPC_Q14 of sample (now - 1 - j)  (ref sLPC_Q14_buf, newest first)
     s32 prev_gain_Q16;
-    int out_pos;             // ring index one past the newest output sample
-    int ltp_pos;             // ring index one past the newest LTP state sample
+    int ltp_pos;             // ring index one past the newest LTP state sample, in [0, kSilkRing)
 };
 
-// One frame of one chain (ref silk_decode_core, src/silk.cpp:1806).  `out` holds the chain's output history (ref
-// outBuf), `ltp` the LTP state (ref sLTP_Q15); xq receives frame_length samples at the internal rate.
+// One frame of one chain (ref silk_decode_core, src/silk.cpp:1806).  `hist` is the chain's output history (ref outBuf),
+// `ltp` the LTP state (ref sLTP_Q15); xq receives frame_length samples at the internal rate.
 // A chain runs alone on its lane and a warp has few neighbours on its SM (the rings take 96 KB per warp), so the
 // code is written for the latency of one instruction stream: the 16-tap sums are split over four accumulators (the
 // reference's 32-bit wrapping adds are associative), the next block's pulses are loaded before the current block is
 // computed, ring addresses are formed once per block of four samples.
-template <class OutRing, class LtpRing>
-OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const int16_t* pulses, const SilkCtl& ctl, const s32* Gains_Q16,
+template <class LtpRing>
+OPUS_HD void silk_core_frame(SilkChainRegs& R, ChainHistory hist, LtpRing ltp, const int16_t* pulses, const SilkCtl& ctl, const s32* Gains_Q16,
                              int signalType, int quantOffsetType, int seed, int fs_kHz, int16_t* xq) {
     const int order = fs_kHz == 16 ? 16 : 10;
     const int subfr = 5 * fs_kHz;
@@ -168,15 +180,15 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
 #pragma unroll
                 for (int j = 0; j < kSilkMaxOrder; j++) a16[j] = ctl.A_Q12[k >> 1][j];
                 const int n_out = lag + 2;
-                const int in0 = R.out_pos - n_out;  // ring index of the first sample that gets whitened
-                s32 w[kSilkMaxOrder];               // w[j] = in[ix - 1 - j]
+                const int n_cur = k * subfr;        // samples of this frame that already exist
+                s32 w[kSilkMaxOrder];               // w[j] = in[ix - 1 - j]; the sample whitened first lies n_out back
 #pragma unroll
-                for (int j = 0; j < kSilkMaxOrder; j++) w[j] = out[in0 - 1 - j];
+                for (int j = 0; j < kSilkMaxOrder; j++) w[j] = hist.back(n_cur, n_out + 1 + j);
 #pragma unroll 1
                 for (int o0 = 0; o0 < n_out; o0 += 4) {
                     s32 c[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) c[u] = out[in0 + o0 + u];
+                    for (int u = 0; u < 4; u++) c[u] = o0 + u < n_out ? hist.back(n_cur, n_out - o0 - u) : 0;
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         s32 acc[4] = {0, 0, 0, 0};  // silk_SMLABB_ovflw: int16 x int16 products, wrapping sum
@@ -249,12 +261,8 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, OutRing out, LtpRing ltp, const i
                 nw[u] = s;
                 yq[u] = sat16(rshift_round(smulww(s, Gain_Q10), 8));
             }
-            if (signalType == 2) R.ltp_pos += 4;
-            int16_t* ow = out.block4(R.out_pos);
-#pragma unroll
-            for (int u = 0; u < 4; u++) ow[u * OutRing::stride] = (int16_t)yq[u];
+            if (signalType == 2) R.ltp_pos = LtpRing::wrap(R.ltp_pos + 4);
             x4[blk] = make_uint2_((u32)(yq[0] & 0xffff) | (u32)yq[1] << 16, (u32)(yq[2] & 0xffff) | (u32)yq[3] << 16);
-            R.out_pos += 4;
 #pragma unroll
             for (int j = kSilkMaxOrder - 1; j >= 4; j--) R.h[j] = R.h[j - 4];
 #pragma unroll
@@ -269,33 +277,32 @@ struct SilkChainCtl {
     int fs_kHz, LastGainIndex;
     int first;  // no frame decoded since the last clear (ref first_frame_after_reset)
 };
-template <class OutRing>
-OPUS_HD void silk_chain_clear(SilkChainRegs& R, OutRing out) {
+OPUS_HD void silk_chain_clear(SilkChainRegs& R) {
 #pragma unroll
     for (int j = 0; j < kSilkMaxOrder; j++) R.h[j] = 0;
-#pragma unroll 1
-    for (int i = 0; i < kSilkRing; i++) out[i] = 0;
 }
-template <class OutRing>
-OPUS_HD bool silk_chain_begin_frame(SilkChainCtl& c, SilkChainRegs& R, OutRing out, int n, bool reinit, int fs_kHz, int mid_only,
-                                    int prev_mid_only, bool* rs_reset) {
+// *cleared: the output history (ref outBuf) and the LPC state were zeroed before this frame
+OPUS_HD bool silk_chain_begin_frame(SilkChainCtl& c, SilkChainRegs& R, int n, bool reinit, int fs_kHz, int mid_only, int prev_mid_only,
+                                    bool* rs_reset, bool* cleared) {
+    *cleared = false;
     if (reinit) {  // silk_InitDecoder: both channels as new; the resampler follows through the rate check below
-        silk_chain_clear(R, out);
+        *cleared = true;
         R.prev_gain_Q16 = 65536;
         c.LastGainIndex = 0;
         c.fs_kHz = 0;
-        c.first = 1;
     }
     *rs_reset = c.fs_kHz != fs_kHz;
     if (c.fs_kHz != fs_kHz) {  // silk_decoder_set_fs
-        silk_chain_clear(R, out);
+        *cleared = true;
         c.LastGainIndex = 10;
         c.fs_kHz = fs_kHz;
-        c.first = 1;
     }
     if (n == 1 && !mid_only && prev_mid_only == 1) {  // the side channel comes back after mid-only frames
-        silk_chain_clear(R, out);
+        *cleared = true;
         c.LastGainIndex = 10;
+    }
+    if (*cleared) {
+        silk_chain_clear(R);
         c.first = 1;
     }
     return n == 0 || !mid_only;

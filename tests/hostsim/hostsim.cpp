@@ -127,7 +127,8 @@ static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, 
 struct HsSilk {
     SilkChainRegs R[2];
     SilkChainCtl K[2];
-    int16_t out_ring[2][kSilkRing];
+    int16_t prev_row[2][kSilkMaxFrame];  // the previous decoded frame of the chain (its output history)
+    int prev_len[2];                      // 0: history is all zero
     int32_t ltp_ring[2][kSilkRing];
     int16_t prevNLSF[2][kSilkMaxOrder];
     int prev_mid_only;
@@ -137,7 +138,7 @@ struct HsSilk {
 };
 static void hs_silk_init(HsSilk& h) {
     memset(&h, 0, sizeof(h));
-    for (int n = 0; n < 2; n++) { h.R[n].prev_gain_Q16 = 65536; h.K[n].first = 1; h.R[n].out_pos = kSilkMaxFrame; }
+    for (int n = 0; n < 2; n++) { h.R[n].prev_gain_Q16 = 65536; h.K[n].first = 1; }
 }
 // one frame -> 960 * nch samples at 48 kHz, interleaved
 static void hs_silk_frame(HsSilk& h, SilkFrame& F, bool reinit, int16_t* pcm48) {
@@ -146,9 +147,10 @@ static void hs_silk_frame(HsSilk& h, SilkFrame& F, bool reinit, int16_t* pcm48) 
     if (reinit) { h.prev_mid_only = 0; h.m2 = h.m1 = h.s2 = h.s1 = h.p0 = h.p1 = 0; }
     bool rs_reset[2] = {false, false}, dec[2] = {false, false};
     for (int n = 0; n < nch; n++) {
-        ChainRing<int16_t, 1> out{h.out_ring[n]};
         ChainRing<int32_t, 1> ltp{h.ltp_ring[n]};
-        dec[n] = silk_chain_begin_frame(h.K[n], h.R[n], out, n, reinit, fs, F.mid_only, h.prev_mid_only, &rs_reset[n]);
+        bool cleared;
+        dec[n] = silk_chain_begin_frame(h.K[n], h.R[n], n, reinit, fs, F.mid_only, h.prev_mid_only, &rs_reset[n], &cleared);
+        if (cleared) h.prev_len[n] = 0;
         if (dec[n]) {
             SilkCtl ctl;
             silk_params_item(F.idx[n], fs, h.K[n].first ? nullptr : h.prevNLSF[n], ctl);
@@ -156,8 +158,11 @@ static void hs_silk_frame(HsSilk& h, SilkFrame& F, bool reinit, int16_t* pcm48) 
             int8_t lgi = (int8_t)h.K[n].LastGainIndex;
             silk_gains_dequant(gains, F.idx[n].gains, &lgi);
             h.K[n].LastGainIndex = lgi;
-            silk_core_frame(h.R[n], out, ltp, F.pulses[n], ctl, gains, F.idx[n].signalType, F.idx[n].quantOffsetType, F.idx[n].seed, fs,
+            const ChainHistory hist{h.prev_len[n] ? h.prev_row[n] + h.prev_len[n] : nullptr, xq[n]};
+            silk_core_frame(h.R[n], hist, ltp, F.pulses[n], ctl, gains, F.idx[n].signalType, F.idx[n].quantOffsetType, F.idx[n].seed, fs,
                             xq[n]);
+            memcpy(h.prev_row[n], xq[n], sizeof(int16_t) * (size_t)L);
+            h.prev_len[n] = L;
             h.K[n].first = 0;
             memcpy(h.prevNLSF[n], ctl.nlsf_Q15, sizeof(ctl.nlsf_Q15));
         } else {
