@@ -305,10 +305,11 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     int16_t* out0 = pcm + (size_t)my_s * P.n_frames * N * CC;                            // frame f of this stream: + f * N * CC
 
     // prefetch cursor (tile index -> frame, offset) kept incrementally
-    int pf_q = 0, pf_f = 0, pf_j = 0;
+    int pf_q = 0, pf_f = 0, pf_j = 0, pf_n = 0;
     auto prefetch = [&]() {
         if (pf_q < T && live) {
-            const int w = min(DE_TW, N - pf_j);
+            if (pf_j == 0) pf_n = fe[(size_t)my_s * P.n_frames + pf_f].celt_n;  // nothing to fetch for frames without a CELT layer
+            const int w = min(DE_TW, pf_n - pf_j);
             const int32_t* src = row0 + (size_t)pf_f * CC * kMaxFrame + pf_j;
             int32_t* dst = &ring[pf_q % DE_STAGES][lane * DE_ROW];
 #pragma unroll

@@ -276,33 +276,37 @@ k_silk_up2(SilkBufs B, DevParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+enum { FIR_WARPS = 8 };
+__global__ void __launch_bounds__(32 * FIR_WARPS)
 k_silk_fir(SilkBufs B, int16_t* __restrict__ pcm, DevParams P) {
     if (*B.any_silk == 0) return;
-    // the up-sampled rows of the frame are staged in shared memory: every output reads 8 neighbouring taps of them
-    __shared__ __align__(16) int16_t rows[2][kUpRow];
+    // one warp per frame; the up-sampled rows of the frame are staged in shared memory (every output reads 8
+    // neighbouring taps of them), warps run independently of each other
+    __shared__ __align__(16) int16_t rows[FIR_WARPS][2][kUpRow];
     const int nfr = P.n_sel * P.n_frames;
     const int CC = P.CC;
-    for (int local = blockIdx.x; local < nfr; local += gridDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int16_t(*my)[kUpRow] = rows[warp];
+    for (int local = blockIdx.x * FIR_WARPS + warp; local < nfr; local += gridDim.x * FIR_WARPS) {
         const size_t t = (size_t)P.first_stream * P.n_frames + local;
         const SilkPost& post = B.post[t];
         if (!post.has_out) continue;
         const int fs = post.fs_kHz;
         const int words = (2 * 20 * fs + 8) / 8;  // 16-byte words per row
-        __syncthreads();
-        for (int i = threadIdx.x; i < words * CC; i += blockDim.x) {
-            const int n = i / words, w = i - n * words;
-            reinterpret_cast<uint4*>(rows[n])[w] = reinterpret_cast<const uint4*>(B.up + (t * 2 + n) * kUpRow)[w];
-        }
-        __syncthreads();
+        __syncwarp();
+        for (int n = 0; n < CC; n++)
+            for (int w = lane; w < words; w += 32)
+                reinterpret_cast<uint4*>(my[n])[w] = reinterpret_cast<const uint4*>(B.up + (t * 2 + n) * kUpRow)[w];
+        __syncwarp();
         const s32 inv = silk_inv_ratio_Q16(fs);
-        // two interleaved int16 samples (one stereo frame, or two mono samples) per thread and store
+        // two interleaved int16 samples (one stereo frame, or two mono samples) per lane and store
         uint32_t* o = reinterpret_cast<uint32_t*>(pcm + t * (size_t)(kMaxFrame * CC));
-        for (int i = threadIdx.x; i < kMaxFrame * CC / 2; i += blockDim.x) {
+#pragma unroll 2
+        for (int i = lane; i < kMaxFrame * CC / 2; i += 32) {
             const uint32_t old = o[i];
             s32 a, b;
-            if (CC == 2) { a = silk_fir_sample(rows[0], i, fs, inv); b = silk_fir_sample(rows[1], i, fs, inv); }
-            else { a = silk_fir_sample(rows[0], 2 * i, fs, inv); b = silk_fir_sample(rows[0], 2 * i + 1, fs, inv); }
+            if (CC == 2) { a = silk_fir_sample(my[0], i, fs, inv); b = silk_fir_sample(my[1], i, fs, inv); }
+            else { a = silk_fir_sample(my[0], 2 * i, fs, inv); b = silk_fir_sample(my[0], 2 * i + 1, fs, inv); }
             const s32 lo = sat16((s32)(int16_t)(old & 0xffff) + a), hi = sat16((s32)(int16_t)(old >> 16) + b);  // ref src/opus_decoder.cpp:271-273
             o[i] = (uint32_t)(lo & 0xffff) | (uint32_t)hi << 16;
         }
