@@ -1,10 +1,10 @@
-// silk.cuh -- SILK layer of the decode path, 20 ms frames, 8/12/16 kHz.
+// silk.cuh -- SILK layer of the decode path, 20 ms frames, 8/12/16 kHz: the entropy
+// half, the per-stream state, and the parameter arithmetic.
 //
 //   silk_parse_frame   entropy half, one thread per (stream, frame): VAD/LBRR flags, stereo predictor,
 //                      side-information indices, shell-coded pulses (ref src/silk.cpp:1565-1636, 708, 898)
-//   silk_synth_frame   synthesis half, serial per stream: gains, NLSF -> LPC, pitch, LTP + LPC synthesis,
-//                      mid/side -> left/right, 2x all-pass + 12-phase FIR resampling to 48 kHz
-//                      (ref src/silk.cpp:827, 1806, 4028, 3676)
+//   silk_gains_dequant, silk_nlsf_decode, silk_nlsf2a ...   building blocks of the synthesis stages, which live in
+//                      silk_stages.cuh (stage bodies) and silk_kernels.cuh (kernels)
 //
 // Parsing needs no decoder state because every packet carries one 20 ms frame, which the reference
 // always codes independently (FrameIndex <= 0, src/silk.cpp:1678-1681).
@@ -340,16 +340,6 @@ struct SilkStreamState {
     int32_t nChannelsInternal;                    // ref silk_decoder_t
     int32_t prev_mode;                            // Opus layer: 0 none, 1000 SILK, 1001 hybrid, 1002 CELT
 };
-struct SilkScratch {  // per-stream working set of one frame
-    int16_t sLTP[kSilkMaxFrame];
-    int32_t sLTP_Q15[2 * kSilkMaxFrame];
-    int32_t exc_Q14[kSilkMaxFrame];
-    int32_t sLPC_Q14[80 + kSilkMaxOrder];
-    int32_t res_Q14[80];
-    int16_t tmp[2][kSilkMaxFrame + 2];  // samplesOut1_tmp
-    int16_t rbuf[2 * 160 + 8];          // resampler batch buffer
-};
-
 // ref silk_init_decoder (src/silk.cpp:2192)
 OPUS_HD void silk_channel_init(SilkChannel& c) {
     c.prev_gain_Q16 = 65536;
@@ -371,42 +361,6 @@ OPUS_HD void silk_stream_reinit(SilkStreamState& s) {
     }
     for (int i = 0; i < 2; i++) { s.pred_prev_Q13[i] = 0; s.sMid[i] = 0; s.sSide[i] = 0; }
     s.prev_decode_only_middle = 0;
-}
-
-// ref silk_resampler_init (src/silk.cpp:3590), decoder side, output 48 kHz
-OPUS_HD void silk_resampler_setup(SilkResampler& r, int fs_kHz) {
-    for (int i = 0; i < 6; i++) r.sIIR[i] = 0;
-    for (int i = 0; i < 8; i++) r.sFIR[i] = 0;
-    for (int i = 0; i < 48; i++) r.delayBuf[i] = 0;
-    r.inputDelay = fs_kHz == 8 ? 0 : fs_kHz == 12 ? 4 : 7;
-    r.Fs_in_kHz = fs_kHz;
-    r.batchSize = fs_kHz * 10;
-    const s32 Fs_in = fs_kHz * 1000, Fs_out = 48000;
-    r.invRatio_Q16 = shl32(shl32(Fs_in, 14 + 1) / Fs_out, 2);
-    while (smulww(r.invRatio_Q16, Fs_out) < shl32(Fs_in, 1)) r.invRatio_Q16++;
-}
-// ref silk_decoder_set_fs (src/silk.cpp:978), nb_subfr = 4
-OPUS_HD void silk_set_fs(SilkChannel& c, int fs_kHz) {
-    c.subfr_length = 5 * fs_kHz;
-    const int frame_length = 4 * c.subfr_length;
-    if (c.fs_kHz != fs_kHz || c.fs_API_hz != 48000) {
-        silk_resampler_setup(c.rs, fs_kHz);
-        c.fs_API_hz = 48000;
-    }
-    if (c.fs_kHz != fs_kHz || frame_length != c.frame_length) {
-        if (c.fs_kHz != fs_kHz) {
-            c.ltp_mem_length = 20 * fs_kHz;
-            c.LPC_order = fs_kHz == 16 ? 16 : 10;
-            c.first_frame_after_reset = 1;
-            c.lagPrev = 100;
-            c.LastGainIndex = 10;
-            c.prevSignalType = 0;
-            for (int i = 0; i < 480; i++) c.outBuf[i] = 0;
-            for (int i = 0; i < kSilkMaxOrder; i++) c.sLPC_Q14_buf[i] = 0;
-        }
-        c.fs_kHz = fs_kHz;
-        c.frame_length = frame_length;
-    }
 }
 
 // ref silk_gains_dequant (src/silk.cpp:2148), conditional = 0
@@ -598,283 +552,6 @@ OPUS_HD void silk_nlsf2a(int16_t* a_Q12, const int16_t* NLSF, int d) {
         silk_bwexpander_32(a32_QA1, d, 65536 - shl32(2, i));
         for (int k = 0; k < d; k++) a_Q12[k] = (int16_t)rshift_round(a32_QA1[k], 5);
     }
-}
-
-struct SilkCtrl {  // ref silk_decoder_control_t
-    s32 pitchL[4];
-    s32 Gains_Q16[4];
-    int16_t PredCoef_Q12[2][kSilkMaxOrder];
-    int16_t LTPCoef_Q14[20];
-    s32 LTP_scale_Q14;
-};
-
-// ref silk_decode_parameters (src/silk.cpp:827) + silk_decode_pitch (:2055)
-OPUS_HD void silk_decode_parameters(SilkChannel& c, SilkIdx& ix, SilkCtrl& ctl) {
-    int16_t pNLSF_Q15[kSilkMaxOrder], pNLSF0_Q15[kSilkMaxOrder];
-    silk_gains_dequant(ctl.Gains_Q16, ix.gains, &c.LastGainIndex);
-    const SilkCb cb = silk_cb(c.fs_kHz);
-    silk_nlsf_decode(pNLSF_Q15, ix.nlsf, cb);
-    silk_nlsf2a(ctl.PredCoef_Q12[1], pNLSF_Q15, c.LPC_order);
-    if (c.first_frame_after_reset == 1) ix.interpQ2 = 4;
-    if (ix.interpQ2 < 4) {
-        for (int i = 0; i < c.LPC_order; i++)
-            pNLSF0_Q15[i] = (int16_t)(c.prevNLSF_Q15[i] + (mul_w(ix.interpQ2, pNLSF_Q15[i] - c.prevNLSF_Q15[i]) >> 2));
-        silk_nlsf2a(ctl.PredCoef_Q12[0], pNLSF0_Q15, c.LPC_order);
-    } else {
-        for (int i = 0; i < c.LPC_order; i++) ctl.PredCoef_Q12[0][i] = ctl.PredCoef_Q12[1][i];
-    }
-    for (int i = 0; i < c.LPC_order; i++) c.prevNLSF_Q15[i] = pNLSF_Q15[i];
-    if (ix.signalType == 2) {
-        const int8_t* cbk;
-        int cbk_size;
-        if (c.fs_kHz == 8) { cbk = kCbLagsStage2; cbk_size = 11; }
-        else { cbk = kCbLagsStage3; cbk_size = 34; }
-        const int min_lag = 2 * c.fs_kHz, max_lag = 18 * c.fs_kHz;
-        const int lag = min_lag + ix.lagIndex;
-        for (int k = 0; k < 4; k++) ctl.pitchL[k] = limit32(lag + cbk[k * cbk_size + ix.contour], min_lag, max_lag);
-        const int8_t* vq = ix.perIndex == 0 ? kLtpVq0 : ix.perIndex == 1 ? kLtpVq1 : kLtpVq2;
-        for (int k = 0; k < 4; k++)
-            for (int i = 0; i < 5; i++) ctl.LTPCoef_Q14[k * 5 + i] = (int16_t)shl32(vq[ix.ltp[k] * 5 + i], 7);
-        ctl.LTP_scale_Q14 = ix.ltpScaleIndex == 0 ? 15565 : ix.ltpScaleIndex == 1 ? 12288 : 8192;
-    } else {
-        for (int k = 0; k < 4; k++) ctl.pitchL[k] = 0;
-        for (int k = 0; k < 20; k++) ctl.LTPCoef_Q14[k] = 0;
-        ix.perIndex = 0;
-        ctl.LTP_scale_Q14 = 0;
-    }
-}
-
-// ref silk_LPC_analysis_filter (src/silk.cpp:2268)
-OPUS_HD void silk_lpc_analysis_filter(int16_t* out, const int16_t* in, const int16_t* B, int len, int d) {
-    for (int ix = d; ix < len; ix++) {
-        const int16_t* p = &in[ix - 1];
-        s32 acc = smulbb(p[0], B[0]);
-        for (int j = 1; j < d; j++) acc = smlabb(acc, p[-j], B[j]);
-        acc = sub_w(shl32((s32)p[1], 12), acc);
-        out[ix] = sat16(rshift_round(acc, 12));
-    }
-    for (int j = 0; j < d; j++) out[j] = 0;
-}
-
-// ref silk_decode_core (src/silk.cpp:1806)
-OPUS_HD void silk_decode_core(SilkChannel& c, const SilkIdx& ix, SilkCtrl& ctl, int16_t* xq, const int16_t* pulses, SilkScratch& w) {
-    const s32 offs[2][2] = {{100, 240}, {32, 100}};
-    const s32 offset_Q10 = offs[ix.signalType >> 1][ix.quantOffsetType];
-    const int NLSF_interpolation_flag = ix.interpQ2 < 4;
-    s32 rand_seed = ix.seed;
-    for (int i = 0; i < c.frame_length; i++) {
-        rand_seed = (s32)(907633515u + (u32)rand_seed * 196314165u);
-        s32 e = shl32((s32)pulses[i], 14);
-        if (e > 0) e -= 80 << 4;
-        else if (e < 0) e += 80 << 4;
-        e += offset_Q10 << 4;
-        if (rand_seed < 0) e = -e;
-        w.exc_Q14[i] = e;
-        rand_seed = add_w(rand_seed, pulses[i]);
-    }
-    for (int i = 0; i < kSilkMaxOrder; i++) w.sLPC_Q14[i] = c.sLPC_Q14_buf[i];
-    const s32* pexc_Q14 = w.exc_Q14;
-    int16_t* pxq = xq;
-    int sLTP_buf_idx = c.ltp_mem_length;
-    int lag = 0;
-    for (int k = 0; k < 4; k++) {
-        const s32* pres_Q14 = w.res_Q14;
-        const int16_t* A_Q12 = ctl.PredCoef_Q12[k >> 1];
-        const int16_t* B_Q14 = &ctl.LTPCoef_Q14[k * 5];
-        const int signalType = ix.signalType;
-        const s32 Gain_Q10 = ctl.Gains_Q16[k] >> 6;
-        s32 inv_gain_Q31 = inverse32_varq(ctl.Gains_Q16[k], 47);
-        s32 gain_adj_Q16;
-        if (ctl.Gains_Q16[k] != c.prev_gain_Q16) {
-            gain_adj_Q16 = div32_varq(c.prev_gain_Q16, ctl.Gains_Q16[k], 16);
-            for (int i = 0; i < kSilkMaxOrder; i++) w.sLPC_Q14[i] = smulww(gain_adj_Q16, w.sLPC_Q14[i]);
-        } else {
-            gain_adj_Q16 = 1 << 16;
-        }
-        c.prev_gain_Q16 = ctl.Gains_Q16[k];
-        if (signalType == 2) {
-            lag = ctl.pitchL[k];
-            if (k == 0 || (k == 2 && NLSF_interpolation_flag)) {
-                const int start_idx = c.ltp_mem_length - lag - c.LPC_order - 5 / 2;
-                if (k == 2) for (int i = 0; i < 2 * c.subfr_length; i++) c.outBuf[c.ltp_mem_length + i] = xq[i];
-                silk_lpc_analysis_filter(&w.sLTP[start_idx], &c.outBuf[start_idx + k * c.subfr_length], A_Q12, c.ltp_mem_length - start_idx, c.LPC_order);
-                if (k == 0) inv_gain_Q31 = shl32(smulwb(inv_gain_Q31, ctl.LTP_scale_Q14), 2);
-                for (int i = 0; i < lag + 5 / 2; i++) w.sLTP_Q15[sLTP_buf_idx - i - 1] = smulwb(inv_gain_Q31, w.sLTP[c.ltp_mem_length - i - 1]);
-            } else if (gain_adj_Q16 != 1 << 16) {
-                for (int i = 0; i < lag + 5 / 2; i++) w.sLTP_Q15[sLTP_buf_idx - i - 1] = smulww(gain_adj_Q16, w.sLTP_Q15[sLTP_buf_idx - i - 1]);
-            }
-            const s32* pred_lag_ptr = &w.sLTP_Q15[sLTP_buf_idx - lag + 5 / 2];
-            for (int i = 0; i < c.subfr_length; i++) {
-                s32 LTP_pred_Q13 = 2;
-                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[0], B_Q14[0]);
-                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-1], B_Q14[1]);
-                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-2], B_Q14[2]);
-                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-3], B_Q14[3]);
-                LTP_pred_Q13 = smlawb(LTP_pred_Q13, pred_lag_ptr[-4], B_Q14[4]);
-                pred_lag_ptr++;
-                w.res_Q14[i] = pexc_Q14[i] + shl32(LTP_pred_Q13, 1);
-                w.sLTP_Q15[sLTP_buf_idx] = shl32(w.res_Q14[i], 1);
-                sLTP_buf_idx++;
-            }
-        } else {
-            pres_Q14 = pexc_Q14;
-        }
-        for (int i = 0; i < c.subfr_length; i++) {
-            s32 LPC_pred_Q10 = c.LPC_order >> 1;
-            for (int j = 0; j < c.LPC_order; j++) LPC_pred_Q10 = smlawb(LPC_pred_Q10, w.sLPC_Q14[kSilkMaxOrder + i - 1 - j], A_Q12[j]);
-            w.sLPC_Q14[kSilkMaxOrder + i] = add_sat32(pres_Q14[i], lshift_sat32(LPC_pred_Q10, 4));
-            pxq[i] = sat16(rshift_round(smulww(w.sLPC_Q14[kSilkMaxOrder + i], Gain_Q10), 8));
-        }
-        for (int i = 0; i < kSilkMaxOrder; i++) w.sLPC_Q14[i] = w.sLPC_Q14[c.subfr_length + i];
-        pexc_Q14 += c.subfr_length;
-        pxq += c.subfr_length;
-    }
-    for (int i = 0; i < kSilkMaxOrder; i++) c.sLPC_Q14_buf[i] = w.sLPC_Q14[i];
-}
-
-// ref silk_decode_frame (src/silk.cpp:1974), lostFlag = 0
-OPUS_HD void silk_decode_channel(SilkChannel& c, SilkIdx& ix, const int16_t* pulses, int16_t* pOut, SilkScratch& w) {
-    SilkCtrl ctl;
-    silk_decode_parameters(c, ix, ctl);
-    silk_decode_core(c, ix, ctl, pOut, pulses, w);
-    c.prevSignalType = ix.signalType;
-    c.first_frame_after_reset = 0;
-    const int mv_len = c.ltp_mem_length - c.frame_length;
-    for (int i = 0; i < mv_len; i++) c.outBuf[i] = c.outBuf[c.frame_length + i];
-    for (int i = 0; i < c.frame_length; i++) c.outBuf[mv_len + i] = pOut[i];
-    c.lagPrev = ctl.pitchL[3];
-}
-
-// ref silk_stereo_MS_to_LR (src/silk.cpp:4028)
-OPUS_HD void silk_ms_to_lr(SilkStreamState& s, int16_t* x1, int16_t* x2, const int32_t* pred_Q13, int fs_kHz, int frame_length) {
-    x1[0] = s.sMid[0]; x1[1] = s.sMid[1];
-    x2[0] = s.sSide[0]; x2[1] = s.sSide[1];
-    s.sMid[0] = x1[frame_length]; s.sMid[1] = x1[frame_length + 1];
-    s.sSide[0] = x2[frame_length]; s.sSide[1] = x2[frame_length + 1];
-    s32 pred0_Q13 = s.pred_prev_Q13[0], pred1_Q13 = s.pred_prev_Q13[1];
-    const s32 denom_Q16 = ((s32)1 << 16) / (8 * fs_kHz);
-    const s32 delta0_Q13 = rshift_round(smulbb(pred_Q13[0] - s.pred_prev_Q13[0], denom_Q16), 16);
-    const s32 delta1_Q13 = rshift_round(smulbb(pred_Q13[1] - s.pred_prev_Q13[1], denom_Q16), 16);
-    for (int n = 0; n < frame_length; n++) {
-        if (n < 8 * fs_kHz) { pred0_Q13 += delta0_Q13; pred1_Q13 += delta1_Q13; }
-        else { pred0_Q13 = pred_Q13[0]; pred1_Q13 = pred_Q13[1]; }
-        s32 sum = shl32(x1[n] + x1[n + 2] + shl32(x1[n + 1], 1), 9);
-        sum = smlawb(shl32((s32)x2[n + 1], 8), sum, pred0_Q13);
-        sum = smlawb(sum, shl32((s32)x1[n + 1], 11), pred1_Q13);
-        x2[n + 1] = sat16(rshift_round(sum, 8));
-    }
-    s.pred_prev_Q13[0] = (int16_t)pred_Q13[0];
-    s.pred_prev_Q13[1] = (int16_t)pred_Q13[1];
-    for (int n = 0; n < frame_length; n++) {
-        s32 sum = x1[n + 1] + (s32)x2[n + 1];
-        s32 diff = x1[n + 1] - (s32)x2[n + 1];
-        x1[n + 1] = sat16(sum);
-        x2[n + 1] = sat16(diff);
-    }
-}
-
-// ref silk_resampler_private_up2_HQ (src/silk.cpp:3515)
-OPUS_HD void silk_up2_hq(int32_t* S, int16_t* out, const int16_t* in, int len) {
-    for (int k = 0; k < len; k++) {
-        s32 in32 = shl32((s32)in[k], 10);
-        s32 Y = in32 - S[0];
-        s32 X = smulwb(Y, 1746);
-        s32 out32_1 = S[0] + X;
-        S[0] = in32 + X;
-        Y = out32_1 - S[1];
-        X = smulwb(Y, 14986);
-        s32 out32_2 = S[1] + X;
-        S[1] = out32_1 + X;
-        Y = out32_2 - S[2];
-        X = smlawb(Y, Y, -26453);
-        out32_1 = S[2] + X;
-        S[2] = out32_2 + X;
-        out[2 * k] = sat16(rshift_round(out32_1, 10));
-        Y = in32 - S[3];
-        X = smulwb(Y, 6854);
-        out32_1 = S[3] + X;
-        S[3] = in32 + X;
-        Y = out32_1 - S[4];
-        X = smulwb(Y, 25769);
-        out32_2 = S[4] + X;
-        S[4] = out32_1 + X;
-        Y = out32_2 - S[5];
-        X = smlawb(Y, Y, -9994);
-        out32_1 = S[5] + X;
-        S[5] = out32_2 + X;
-        out[2 * k + 1] = sat16(rshift_round(out32_1, 10));
-    }
-}
-// ref silk_resampler_private_IIR_FIR (+ _INTERPOL) (src/silk.cpp:3475, 3451); `out` has stride `ostride`
-OPUS_HD int16_t* silk_iir_fir(SilkResampler& r, int16_t* out, int ostride, const int16_t* in, int inLen, int16_t* buf) {
-    for (int i = 0; i < 8; i++) buf[i] = r.sFIR[i];
-    const s32 inc = r.invRatio_Q16;
-    int nSamplesIn;
-    for (;;) {
-        nSamplesIn = imin(inLen, r.batchSize);
-        silk_up2_hq(r.sIIR, &buf[8], in, nSamplesIn);
-        const s32 max_index_Q16 = shl32(nSamplesIn, 17);
-        for (s32 index_Q16 = 0; index_Q16 < max_index_Q16; index_Q16 += inc) {
-            const s32 ti = smulwb(index_Q16 & 0xFFFF, 12);
-            const int16_t* bp = &buf[index_Q16 >> 16];
-            s32 res = smulbb(bp[0], kResamplerFir12[ti * 4 + 0]);
-            res = smlabb(res, bp[1], kResamplerFir12[ti * 4 + 1]);
-            res = smlabb(res, bp[2], kResamplerFir12[ti * 4 + 2]);
-            res = smlabb(res, bp[3], kResamplerFir12[ti * 4 + 3]);
-            res = smlabb(res, bp[4], kResamplerFir12[(11 - ti) * 4 + 3]);
-            res = smlabb(res, bp[5], kResamplerFir12[(11 - ti) * 4 + 2]);
-            res = smlabb(res, bp[6], kResamplerFir12[(11 - ti) * 4 + 1]);
-            res = smlabb(res, bp[7], kResamplerFir12[(11 - ti) * 4 + 0]);
-            *out = sat16(rshift_round(res, 15));
-            out += ostride;
-        }
-        in += nSamplesIn;
-        inLen -= nSamplesIn;
-        if (inLen > 0) for (int i = 0; i < 8; i++) buf[i] = buf[(nSamplesIn << 1) + i];
-        else break;
-    }
-    for (int i = 0; i < 8; i++) r.sFIR[i] = buf[(nSamplesIn << 1) + i];
-    return out;
-}
-// ref silk_resampler (src/silk.cpp:3676)
-OPUS_HD void silk_resample(SilkResampler& r, int16_t* out, int ostride, const int16_t* in, int inLen, int16_t* buf) {
-    const int nSamples = r.Fs_in_kHz - r.inputDelay;
-    for (int i = 0; i < nSamples; i++) r.delayBuf[r.inputDelay + i] = in[i];
-    out = silk_iir_fir(r, out, ostride, r.delayBuf, r.Fs_in_kHz, buf);
-    silk_iir_fir(r, out, ostride, &in[nSamples], inLen - r.Fs_in_kHz, buf);
-    for (int i = 0; i < r.inputDelay; i++) r.delayBuf[i] = in[inLen - r.inputDelay + i];
-}
-
-// One frame of one stream (ref silk_Decode, src/silk.cpp:1481, with nChannelsAPI == nChannelsInternal as the
-// reference's opus_decode_frame always calls it, src/opus_decoder.cpp:167-168).  out: 960 * nch interleaved.
-OPUS_HD void silk_synth_frame(SilkStreamState& s, SilkFrame& f, int16_t* out, SilkScratch& w) {
-    const int nch = f.nch, fs_kHz = f.fs_kHz;
-    if (nch > s.nChannelsInternal && s.nChannelsInternal != 0) silk_channel_init(s.ch[1]);  // mono -> stereo (ref :1512)
-    for (int n = 0; n < nch; n++) silk_set_fs(s.ch[n], fs_kHz);
-    if (nch == 2 && s.nChannelsInternal == 1) {  // ref :1549-1555
-        s.pred_prev_Q13[0] = s.pred_prev_Q13[1] = 0;
-        s.sSide[0] = s.sSide[1] = 0;
-    }
-    s.nChannelsInternal = nch;
-    const int L = s.ch[0].frame_length;
-    if (nch == 2 && f.mid_only == 0 && s.prev_decode_only_middle == 1) {  // ref :1639-1646
-        SilkChannel& c = s.ch[1];
-        for (int i = 0; i < 480; i++) c.outBuf[i] = 0;
-        for (int i = 0; i < kSilkMaxOrder; i++) c.sLPC_Q14_buf[i] = 0;
-        c.lagPrev = 100; c.LastGainIndex = 10; c.prevSignalType = 0; c.first_frame_after_reset = 1;
-    }
-    for (int n = 0; n < nch; n++) {
-        if (n == 0 || !f.mid_only) silk_decode_channel(s.ch[n], f.idx[n], f.pulses[n], &w.tmp[n][2], w);
-        else for (int i = 0; i < L; i++) w.tmp[n][2 + i] = 0;
-    }
-    if (nch == 2) {
-        silk_ms_to_lr(s, w.tmp[0], w.tmp[1], f.ms_pred_Q13, fs_kHz, L);
-    } else {
-        w.tmp[0][0] = s.sMid[0]; w.tmp[0][1] = s.sMid[1];
-        s.sMid[0] = w.tmp[0][L]; s.sMid[1] = w.tmp[0][L + 1];
-    }
-    for (int n = 0; n < nch; n++) silk_resample(s.ch[n].rs, out + n, nch, &w.tmp[n][1], L, w.rbuf);
-    s.prev_decode_only_middle = f.mid_only;
 }
 
 }  // namespace opusb200
