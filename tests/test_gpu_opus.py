@@ -119,3 +119,92 @@ def test_single_stream_dropin_silk_and_hybrid(pkg, ref):
         assert np.array_equal(got, want)
     o.close()
     d.close()
+
+
+@pytest.mark.parametrize("ch", [1, 2])
+def test_tiny_and_maximal_frames_every_mode(pkg, ref, ch):
+    """Payloads of 0, 1, 2, 3 bytes (the reference fails or decodes silence-like frames), ordinary ones and the 1275-byte
+    maximum, for SILK, hybrid and CELT TOCs, interleaved so that failures sit between good frames."""
+    s = 4 if ch == 2 else 0
+    rng = np.random.default_rng(40 + ch)
+    lens = [0, 1, 2, 3, 5, 8, 60, 1275, 2, 100, 1, 0, 40, 1275, 3, 200]
+    plans = []
+    for toc in (0x08, 0x48, 0x68, 0x78, 0xF8, 0xD8):
+        plan = []
+        for k, L in enumerate(lens):
+            plan.append((toc | s, -L if L == 0 else L))
+        plans.append(plan)
+    # _pack treats ln <= 0 as "random length": build by hand instead
+    n_streams, n_frames = len(plans), len(lens)
+    frames = pkg.make_frames(n_streams, n_frames)
+    chunks, pos, pk = [], 0, []
+    for i, plan in enumerate(plans):
+        row = []
+        for f, (toc, _) in enumerate(plan):
+            L = lens[f]
+            payload = rng.integers(0, 256, L, dtype=np.uint8)
+            frames[i, f] = (pos, L, toc, 0)
+            chunks.append(payload)
+            pos += L
+            row.append(np.concatenate([np.array([toc], np.uint8), payload]))
+        pk.append(row)
+    data = np.concatenate(chunks)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=ch)
+    rc, pcm, status = dec.decode_many(data, frames)
+    assert rc == 0
+    dec.close()
+    for i in range(n_streams):
+        o = ref.PacketDecoder(ch)
+        try:
+            for f in range(n_frames):
+                r, want = o.decode(pk[i][f])
+                assert status[i, f] == r, (i, f, status[i, f], r)
+                if r > 0:
+                    assert np.array_equal(pcm[i, f], want), (i, f, hex(pk[i][f][0]), lens[f])
+        finally:
+            o.close()
+
+
+def test_filler_and_continuation_frames(pkg, ref):
+    """DMF_NULL fillers behind a stream's last frame change nothing (the next call carries on as if they were not there);
+    a DMF_CONT frame behind a failed frame of its packet is not decoded (opus_decode_native returns at the first failing
+    frame, src/opus_decoder.cpp:334-338)."""
+    rng = np.random.default_rng(77)
+    toc = 0xFC
+    pay = [rng.integers(0, 256, 120, dtype=np.uint8) for _ in range(8)]
+    data = np.concatenate(pay + [np.zeros(1, np.uint8)])
+    off = np.cumsum([0] + [len(p) for p in pay])
+    DMF_CONT, DMF_NULL = 1, 2
+    # call 1: frames 0,1,2 real, 3 = a 1-byte frame that CELT refuses, 4 = continuation of that packet (must be skipped), 5 = filler
+    fr1 = pkg.make_frames(1, 6)
+    for f in range(3):
+        fr1[0, f] = (off[f], 120, toc, 0)
+    fr1[0, 3] = (off[8], 1, toc, 0)
+    fr1[0, 4] = (off[3], 120, toc, DMF_CONT)
+    fr1[0, 5] = (0, 0, toc, DMF_NULL)
+    # call 2: frames 4..7 real
+    fr2 = pkg.make_frames(1, 6)
+    for k, f in enumerate(range(4, 8)):
+        fr2[0, k] = (off[f], 120, toc, 0)
+    fr2[0, 4] = (0, 0, toc, DMF_NULL)
+    fr2[0, 5] = (0, 0, toc, DMF_NULL)
+    dec = pkg.BatchDecoder(1, 6, channels=2)
+    rc, p1, s1 = dec.decode_many(data, fr1)
+    rc2, p2, s2 = dec.decode_many(data, fr2)
+    dec.close()
+    assert rc == 0 and rc2 == 0
+    assert list(s1[0]) == [960, 960, 960, -18, -2004, -2004]
+    assert list(s2[0]) == [960, 960, 960, 960, -2004, -2004]
+    assert not p1[0, 4].any() and not p1[0, 5].any()
+    o = ref.PacketDecoder(2)
+    want = []
+    for f in (0, 1, 2):
+        want.append(o.decode(np.concatenate([[toc], pay[f]]).astype(np.uint8))[1])
+    r, _ = o.decode(np.array([toc | 1, 0, 0], np.uint8))  # code 1, two 1-byte frames: the first fails, the second is never decoded
+    assert r == -18
+    for f in (4, 5, 6, 7):
+        want.append(o.decode(np.concatenate([[toc], pay[f]]).astype(np.uint8))[1])
+    o.close()
+    got = [p1[0, 0], p1[0, 1], p1[0, 2], p2[0, 0], p2[0, 1], p2[0, 2], p2[0, 3]]
+    for k in range(7):
+        assert np.array_equal(got[k], want[k]), k
