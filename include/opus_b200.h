@@ -90,9 +90,9 @@ typedef struct dm_out {
 int decode_many(dm_ctx* ctx, const dm_batch* in, dm_out* out);
 
 /* The same call split in two so that consecutive calls pipeline: decode_many_async() enqueues the copies and kernels
- * and returns at once with a ticket; dm_wait() blocks until that call's PCM and status are in host memory.  Up to 2
+ * and returns at once with a ticket; dm_wait() blocks until that call's PCM and status are in host memory.  Up to 3
  * calls may be in flight; the input buffers of a call (pinned) must stay valid until dm_wait() returned for it, and
- * each call in flight needs its own output buffers.  With two calls in flight the kernels of call n+1 overlap the
+ * each call in flight needs its own output buffers.  With calls in flight the kernels of call n+1 overlap the
  * PCM read-back of call n, which is what bounds a single call (PCIe D2H of 3840 B per decoded frame). */
 int decode_many_async(dm_ctx* ctx, const dm_batch* in, dm_out* out, long long* ticket);
 int dm_wait(dm_ctx* ctx, long long ticket);
