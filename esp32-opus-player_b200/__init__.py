@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     OggOpusFile,
     OggOpusFileSet,
     OpusDecoder,
+    OpusMSDecoder,
     demux_events,
     lib,
     make_frames,

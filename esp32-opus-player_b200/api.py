@@ -73,6 +73,12 @@ def lib():
     L.opusb_decoder_destroy.argtypes = [_P]
     L.opusb_decoder_init.argtypes = [_P, ctypes.c_int32, _I]
     L.opusb_decode.argtypes = [_P, _P, ctypes.c_int32, _P, _I]
+    L.opusb_decoder_ctl.argtypes = [_P, _I, ctypes.POINTER(ctypes.c_int32)]
+    L.opusb_multistream_decoder_create.restype = _P
+    L.opusb_multistream_decoder_create.argtypes = [ctypes.c_int32, _I, _I, _I, _P, ctypes.POINTER(_I)]
+    L.opusb_multistream_decode.argtypes = [_P, _P, ctypes.c_int32, _P, _I]
+    L.opusb_multistream_decoder_ctl.argtypes = [_P, _I, ctypes.POINTER(ctypes.c_int32)]
+    L.opusb_multistream_decoder_destroy.argtypes = [_P]
     _lib = L
     return L
 
@@ -273,9 +279,49 @@ class OpusDecoder:
         n = lib().opusb_decode(self._st, p.ctypes.data, p.size, pcm.ctypes.data, frame_size)
         return n, pcm[: max(n, 0)]
 
+    def ctl(self, request, value=None):
+        """opus_decoder_ctl (src/opus_decoder.cpp:361): returns (rc, value) -- value is read for SET requests."""
+        v = ctypes.c_int32(0 if value is None else int(value))
+        rc = lib().opusb_decoder_ctl(self._st, request, ctypes.byref(v))
+        return rc, v.value
+
     def close(self):
         if self._st:
             lib().opusb_decoder_destroy(self._st)
+            self._st = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OpusMSDecoder:
+    """opus_multistream_decoder_create / _decode / _ctl (src/opus_decoder.h:205-218), one Opus stream."""
+
+    def __init__(self, Fs, channels, streams, coupled_streams, mapping):
+        err = _I(0)
+        m = np.ascontiguousarray(mapping, np.uint8)
+        self._st = lib().opusb_multistream_decoder_create(Fs, channels, streams, coupled_streams, m.ctypes.data, ctypes.byref(err))
+        self.channels, self.error = channels, err.value
+        if not self._st:
+            raise RuntimeError("opus_multistream_decoder_create failed: %d" % err.value)
+
+    def decode(self, data, frame_size=5760):
+        p = _pkt(data)
+        pcm = np.zeros((frame_size, self.channels), np.int16)
+        n = lib().opusb_multistream_decode(self._st, p.ctypes.data, p.size, pcm.ctypes.data, frame_size)
+        return n, pcm[: max(n, 0)]
+
+    def ctl(self, request, value=None):
+        v = ctypes.c_int32(0 if value is None else int(value))
+        rc = lib().opusb_multistream_decoder_ctl(self._st, request, ctypes.byref(v))
+        return rc, v.value
+
+    def close(self):
+        if self._st:
+            lib().opusb_multistream_decoder_destroy(self._st)
             self._st = None
 
     def __del__(self):

@@ -29,6 +29,9 @@ struct XorShift64 {  // SURVEY 8c generator
 struct OpusB200Decoder {
     dm_ctx* ctx;
     int channels;
+    int32_t Fs;
+    // what opus_decoder_ctl reports (ref struct OpusDecoder, src/opus_decoder.cpp:40-59)
+    int bandwidth, last_packet_duration, decode_gain;
     uint8_t* h_bytes;   // pinned
     int16_t* h_pcm;     // pinned
     int32_t* h_status;  // pinned
@@ -193,6 +196,7 @@ OpusB200Decoder* opusb_decoder_create(int32_t Fs, int channels, int* error) {
         err = st ? dm_create(&st->ctx, 1, 48, channels, 0) : -7;
         if (!err) {
             st->channels = channels;
+            st->Fs = Fs;
             st->h_bytes = (uint8_t*)dm_host_alloc(48 * 1275 + 64);
             st->h_pcm = (int16_t*)dm_host_alloc(sizeof(int16_t) * 48 * 960 * 2);
             st->h_status = (int32_t*)dm_host_alloc(sizeof(int32_t) * 48);
@@ -212,6 +216,7 @@ void opusb_decoder_destroy(OpusB200Decoder* st) {
 }
 int opusb_decoder_init(OpusB200Decoder* st, int32_t Fs, int channels) {
     if (!st || (Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || channels != st->channels) return kOpusBadArg;
+    st->Fs = Fs; st->bandwidth = 0; st->last_packet_duration = 0; st->decode_gain = 0;
     return dm_reset(st->ctx, nullptr, 0);
 }
 // ref opus_decode -> opus_decode_native (src/opus_decoder.cpp:280): parse the packet, decode each frame as
@@ -232,13 +237,14 @@ int opusb_decode(OpusB200Decoder* st, const uint8_t* data, int32_t len, int16_t*
         st->h_frames[i].offset = (uint32_t)pos;
         st->h_frames[i].len = (uint16_t)size[i];
         st->h_frames[i].toc = toc;
-        st->h_frames[i].flags = 0;
+        st->h_frames[i].flags = i ? DMF_CONT : 0;  // a failing frame ends the packet (ref src/opus_decoder.cpp:334-338)
         pos += (size_t)size[i];
     }
     dm_batch in;
     memset(&in, 0, sizeof(in));
     in.n_frames = count; in.mode = DM_MODE_OPUS; in.bytes = st->h_bytes; in.n_bytes = pos; in.frames = st->h_frames;
     dm_out out = {st->h_pcm, st->h_status};
+    st->bandwidth = opusb_packet_get_bandwidth(data);  // set once the packet parsed, before its frames run (ref :325-329)
     int r = decode_many(st->ctx, &in, &out);
     if (r) return r;
     int n = 0;
@@ -247,7 +253,109 @@ int opusb_decode(OpusB200Decoder* st, const uint8_t* data, int32_t len, int16_t*
         memcpy(pcm + (size_t)n * st->channels, st->h_pcm + (size_t)i * 960 * st->channels, sizeof(int16_t) * 960 * st->channels);
         n += st->h_status[i];
     }
+    st->last_packet_duration = n;
     return n;
+}
+
+// ref opus_decoder_ctl (src/opus_decoder.cpp:361-454).  One int32 argument: written by GET requests, read by SET requests.
+int opusb_decoder_ctl(OpusB200Decoder* st, int request, int32_t* value) {
+    if (!st) return kOpusBadArg;
+    switch (request) {
+        case 4009:  // OPUS_GET_BANDWIDTH_REQUEST
+            if (!value) return kOpusBadArg;
+            *value = st->bandwidth;
+            return 0;
+        case 4031:  // OPUS_GET_FINAL_RANGE_REQUEST: the reference never stores it
+            if (!value) return kOpusBadArg;
+            *value = 0;
+            return 0;
+        case 4028:  // OPUS_RESET_STATE
+            st->bandwidth = 0; st->last_packet_duration = 0;
+            return dm_reset_state(st->ctx, nullptr, 0);
+        case 4029:  // OPUS_GET_SAMPLE_RATE_REQUEST
+            if (!value) return kOpusBadArg;
+            *value = st->Fs;
+            return 0;
+        case 4045:  // OPUS_GET_GAIN_REQUEST (stored, never applied: SURVEY F4)
+            if (!value) return kOpusBadArg;
+            *value = st->decode_gain;
+            return 0;
+        case 4034:  // OPUS_SET_GAIN_REQUEST
+            if (!value || *value < -32768 || *value > 32767) return kOpusBadArg;
+            st->decode_gain = *value;
+            return 0;
+        case 4039:  // OPUS_GET_LAST_PACKET_DURATION_REQUEST
+            if (!value) return kOpusBadArg;
+            *value = st->last_packet_duration;
+            return 0;
+        case 4046:  // OPUS_SET_PHASE_INVERSION_DISABLED_REQUEST: the reference forwards the VALUE as the CELT request code
+        case 4047:  // (src/opus_decoder.cpp:428, 435), which CELT answers with OPUS_UNIMPLEMENTED; phase inversion stays as
+            if (request == 4046 && value && (*value < 0 || *value > 1)) return kOpusBadArg;  // celt_decoder_init set it
+            if (request == 4047 && !value) return kOpusBadArg;
+            return -5;
+        default:    // incl. OPUS_GET_PITCH_REQUEST (the decoder state it reads is loss-concealment bookkeeping, not kept here)
+            return -5;  // OPUS_UNIMPLEMENTED
+    }
+}
+
+// ---- multistream wrapper (ref opus_multistream_decoder_create / _decode / _ctl / _destroy, src/opus_decoder.cpp:781-1046)
+// for the layouts the player uses: ONE Opus stream (mono or coupled) mapped onto 1..255 output channels.
+struct OpusB200MSDecoder {
+    OpusB200Decoder* dec;
+    int nb_channels, coupled;
+    uint8_t mapping[256];
+    int16_t* tmp;
+};
+OpusB200MSDecoder* opusb_multistream_decoder_create(int32_t Fs, int channels, int streams, int coupled_streams, const uint8_t* mapping,
+                                                    int* error) {
+    int err = 0;
+    OpusB200MSDecoder* st = nullptr;
+    if (channels > 255 || channels < 1 || coupled_streams > streams || streams < 1 || coupled_streams < 0 || streams > 255 - coupled_streams ||
+        !mapping) {
+        err = kOpusBadArg;
+    } else if (streams != 1) {
+        err = -5;  // several multiplexed streams: not needed by the player (mapping family 0, or 1 with one stream)
+    } else {
+        for (int c = 0; c < channels && !err; c++)
+            if (mapping[c] != 255 && mapping[c] >= streams + coupled_streams) err = kOpusBadArg;  // ref validate_layout
+    }
+    if (!err) {
+        st = (OpusB200MSDecoder*)calloc(1, sizeof(*st));
+        if (!st) err = -7;
+    }
+    if (!err) {
+        st->nb_channels = channels; st->coupled = coupled_streams;
+        memcpy(st->mapping, mapping, (size_t)channels);
+        st->tmp = (int16_t*)malloc(sizeof(int16_t) * 5760 * 2);
+        st->dec = opusb_decoder_create(Fs, coupled_streams ? 2 : 1, &err);
+        if (!st->tmp && !err) err = -7;
+        if (err) { opusb_multistream_decoder_destroy(st); st = nullptr; }
+    }
+    if (error) *error = err;
+    return st;
+}
+void opusb_multistream_decoder_destroy(OpusB200MSDecoder* st) {
+    if (!st) return;
+    opusb_decoder_destroy(st->dec);
+    free(st->tmp);
+    free(st);
+}
+int opusb_multistream_decode(OpusB200MSDecoder* st, const uint8_t* data, int32_t len, int16_t* pcm, int frame_size) {
+    if (!st || frame_size <= 0 || len < 0) return kOpusBadArg;
+    if (len < 1) return kOpusBadArg;  // len == 0 is packet-loss concealment, which the reference cannot do either
+    if (frame_size > 5760) frame_size = 5760;
+    const int n = opusb_decode(st->dec, data, len, st->tmp, frame_size);
+    if (n <= 0) return n;
+    const int dc = st->coupled ? 2 : 1;
+    for (int c = 0; c < st->nb_channels; c++) {
+        const int src = st->mapping[c];
+        for (int i = 0; i < n; i++) pcm[(size_t)i * st->nb_channels + c] = src == 255 ? (int16_t)0 : st->tmp[(size_t)i * dc + src];
+    }
+    return n;
+}
+int opusb_multistream_decoder_ctl(OpusB200MSDecoder* st, int request, int32_t* value) {
+    if (!st) return kOpusBadArg;
+    return opusb_decoder_ctl(st->dec, request, value);  // one stream: every request goes to it (ref :944-1031)
 }
 
 }  // extern "C"

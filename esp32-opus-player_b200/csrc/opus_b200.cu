@@ -365,7 +365,7 @@ int decode_many_async(dm_ctx* c, const dm_batch* in, dm_out* out, long long* tic
     // kernels: the output buffer of this parity was last read back two calls ago
     CU_TRY(c, cudaStreamWaitEvent(run, c->uploaded[slot], 0));
     if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(run, c->done[(ticket - 2) % kRing][0], 0));
-    r = launch_pipeline(c, in, c->d_bytes[bi], d_frames, d_pcm, d_status, 0, c->n_streams, run, false, c->parsed[slot][0]);
+    r = launch_pipeline(c, in, c->d_bytes[bi], d_frames, d_pcm, d_status, 0, c->n_streams, run, true, c->parsed[slot][0]);
     if (r) return r;
     CU_TRY(c, cudaEventRecord(c->kernels_done[slot], run));
     // read-back

@@ -147,6 +147,20 @@ OpusB200Decoder* opusb_decoder_create(int32_t Fs, int channels, int* error);
 void opusb_decoder_destroy(OpusB200Decoder* st);
 int opusb_decoder_init(OpusB200Decoder* st, int32_t Fs, int channels);
 int opusb_decode(OpusB200Decoder* st, const uint8_t* data, int32_t len, int16_t* pcm, int frame_size);
+/* opus_decoder_ctl (src/opus_decoder.cpp:361-454) without varargs: `value` is written by GET requests and read by SET
+ * requests; request codes are the reference's (src/opus_decoder.h:84-123).  GET_BANDWIDTH, GET_FINAL_RANGE (always 0,
+ * as in the reference), RESET_STATE, GET_SAMPLE_RATE, GET/SET_GAIN (stored, never applied), GET_LAST_PACKET_DURATION;
+ * the phase-inversion requests return OPUS_UNIMPLEMENTED exactly as the reference's do; anything else too. */
+int opusb_decoder_ctl(OpusB200Decoder* st, int request, int32_t* value);
+
+/* Multistream wrapper (src/opus_decoder.h:205-218) for what the player creates: one Opus stream, mono or coupled,
+ * mapped onto `channels` output channels (mapping[c] = 0/1 or 255 for silence).  streams != 1: OPUS_UNIMPLEMENTED. */
+typedef struct OpusB200MSDecoder OpusB200MSDecoder;
+OpusB200MSDecoder* opusb_multistream_decoder_create(int32_t Fs, int channels, int streams, int coupled_streams, const uint8_t* mapping,
+                                                    int* error);
+int opusb_multistream_decode(OpusB200MSDecoder* st, const uint8_t* data, int32_t len, int16_t* pcm, int frame_size);
+int opusb_multistream_decoder_ctl(OpusB200MSDecoder* st, int request, int32_t* value);
+void opusb_multistream_decoder_destroy(OpusB200MSDecoder* st);
 
 #ifdef __cplusplus
 }

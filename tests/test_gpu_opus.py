@@ -208,3 +208,63 @@ def test_filler_and_continuation_frames(pkg, ref):
     got = [p1[0, 0], p1[0, 1], p1[0, 2], p2[0, 0], p2[0, 1], p2[0, 2], p2[0, 3]]
     for k in range(7):
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_decoder_ctl_and_multistream_match_reference(pkg, ref):
+    """opus_decoder_ctl requests and the one-stream multistream wrapper the player creates (src/opusfile.cpp:693),
+    against the reference's own functions (variadic C++ symbols called through ctypes)."""
+    import ctypes
+
+    R = ref.lib()
+    rctl = getattr(R, "_Z16opus_decoder_ctlP11OpusDecoderiz")
+    ms_create = getattr(R, "_Z31opus_multistream_decoder_createiiiiPKhPi")
+    ms_decode = getattr(R, "_Z23opus_multistream_decodeP13OpusMSDecoderPhiPsi")
+    ms_create.restype = ctypes.c_void_p
+    ms_create.argtypes = [ctypes.c_int32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    ms_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(91)
+    GET_BW, GET_RANGE, RESET, GET_FS, SET_GAIN, GET_GAIN, GET_DUR = 4009, 4031, 4028, 4029, 4034, 4045, 4039
+
+    def ref_get(st, req):
+        v = ctypes.c_int32(-77)
+        rc = rctl(ctypes.c_void_p(st), ctypes.c_int(req), ctypes.byref(v))
+        return rc, v.value
+
+    o = ref.PacketDecoder(2)
+    d = pkg.OpusDecoder(48000, 2)
+    for toc in (0xFC, 0xDC, 0x4C, 0x7C | 1, 0x9C):
+        body = rng.integers(0, 256, 2 * int(rng.integers(20, 90)), dtype=np.uint8)
+        pkt = np.concatenate([np.array([toc], np.uint8), body])
+        r, want = o.decode(pkt)
+        n, got = d.decode(pkt)
+        assert n == r and np.array_equal(got, want)
+        for req in (GET_BW, GET_RANGE, GET_FS, GET_GAIN, GET_DUR):
+            assert d.ctl(req) == ref_get(o.st, req), req
+    assert d.ctl(SET_GAIN, 1234)[0] == rctl(ctypes.c_void_p(o.st), ctypes.c_int(SET_GAIN), ctypes.c_int32(1234)) == 0
+    assert d.ctl(GET_GAIN) == ref_get(o.st, GET_GAIN) == (0, 1234)
+    assert d.ctl(SET_GAIN, 40000)[0] == -1
+    # OPUS_RESET_STATE, then the same packets again: same PCM as the reference after its own reset
+    assert d.ctl(RESET)[0] == rctl(ctypes.c_void_p(o.st), ctypes.c_int(RESET)) == 0
+    for toc in (0x4C, 0xFC, 0x7C):
+        pkt = np.concatenate([np.array([toc], np.uint8), rng.integers(0, 256, 100, dtype=np.uint8)])
+        r, want = o.decode(pkt)
+        n, got = d.decode(pkt)
+        assert n == r and np.array_equal(got, want)
+    o.close()
+    d.close()
+    # multistream: a coupled stream played swapped, a mono stream fanned out to two channels with a muted third
+    for channels, coupled, mapping, toc in ((2, 1, [1, 0], 0xFC), (3, 0, [0, 255, 0], 0x48), (1, 0, [0], 0xF8)):
+        m = np.array(mapping, np.uint8)
+        err = ctypes.c_int(0)
+        rst = ms_create(48000, channels, 1, coupled, m.ctypes.data, ctypes.addressof(err))
+        assert rst and err.value == 0
+        ours = pkg.OpusMSDecoder(48000, channels, 1, coupled, mapping)
+        for _ in range(4):
+            pkt = np.concatenate([np.array([toc], np.uint8), rng.integers(0, 256, 80, dtype=np.uint8)])
+            want = np.zeros((960, channels), np.int16)
+            r = ms_decode(rst, pkt.ctypes.data, pkt.size, want.ctypes.data, 960)
+            n, got = ours.decode(pkt, 960)
+            assert n == r == 960
+            assert np.array_equal(got, want)
+        ours.close()
+        ctypes.CDLL(None).free(ctypes.c_void_p(rst))
