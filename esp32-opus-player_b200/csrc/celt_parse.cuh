@@ -102,8 +102,11 @@ OPUS_HD u32 pvq_v(int n, int k) { return pvq_u(n, k) + pvq_u(n, k + 1); }
 // folding decisions, so the entropy thread needs it; the pulses themselves are expanded by the band kernel.
 OPUS_HD u32 pvq_index_mask(int n, int k, u32 i, int B) {
     const int N0 = (int)((u32)n / (u32)B);
+    const u32 full = (1u << B) - 1u;
     u32 p, cm = 0;
-    int s, k0, pos = 0;
+    int s, k0;
+    u32 bit = 1;      // mask bit of the block the current coefficient lies in
+    int left = N0;    // coefficients left in that block
 #pragma unroll 1
     while (n > 2) {
         u32 q;
@@ -141,19 +144,20 @@ OPUS_HD u32 pvq_index_mask(int n, int k, u32 i, int B) {
                 val = k0 - k;
             }
         }
-        if (val) cm |= 1u << (pos / N0);
-        pos++;
+        if (val) cm |= bit;
+        if (--left == 0) { left = N0; bit <<= 1; }
         n--;
-        if (k == 0) return cm;  // no pulses left: the remaining coefficients are zero
+        // no pulses left: the remaining coefficients are zero; every block hit: nothing more to learn
+        if (k == 0 || cm == full) return cm;
     }
     p = 2 * (u32)k + 1;
     s = -(int)(i >= p);
     i -= p & (u32)s;
     k0 = k;
     k = (int)((i + 1) >> 1);
-    if (k0 - k) cm |= 1u << (pos / N0);
-    pos++;
-    if (k) cm |= 1u << (pos / N0);
+    if (k0 - k) cm |= bit;
+    if (--left == 0) bit <<= 1;
+    if (k) cm |= bit;
     return cm;
 }
 
