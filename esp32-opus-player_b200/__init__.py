@@ -26,6 +26,7 @@ from .api import (  # noqa: F401
     opus_packet_get_samples_per_frame,
     opus_packet_parse,
     synth_corpus,
+    synth_ogg,
 )
 from .build import build  # noqa: F401
 from . import api, shard  # noqa: F401,E402

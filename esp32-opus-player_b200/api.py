@@ -358,7 +358,11 @@ def _plib():
         L.opfb_set_pcm_total.restype = ctypes.c_int64
         L.opfb_set_pcm_total.argtypes = [_P, _I]
         L.opfb_set_stats.argtypes = [_P, _P, _I]
+        L.opfb_set_drain.restype = ctypes.c_int64
+        L.opfb_set_drain.argtypes = [_P, _I]
         L.opfb_debug_events.argtypes = [_P, ctypes.c_size_t, _I, _P, _I, ctypes.POINTER(_I)]
+        L.opfb_synth_ogg.restype = ctypes.c_size_t
+        L.opfb_synth_ogg.argtypes = [_P, ctypes.c_size_t, _I, _I, _I, _I, _I, _I, ctypes.c_uint64, ctypes.c_uint32]
         _player_bound = True
     return L
 
@@ -383,6 +387,15 @@ def demux_events(data, clean_eof=False, cap=1 << 16):
     res = _I(0)
     n = _plib().opfb_debug_events(p.ctypes.data, p.size, int(clean_eof), out.ctypes.data, cap, ctypes.byref(res))
     return res.value, out[: min(n, cap)]
+
+
+def synth_ogg(channels, toc, packet_len, n_packets, per_page=4, pre_skip=0, seed=0x9E3779B97F4A7C15, serial=1):
+    """Synthetic Ogg Opus file as uint8 array (opfb_synth_ogg)."""
+    L = _plib()
+    n = L.opfb_synth_ogg(None, 0, channels, pre_skip, toc, packet_len, n_packets, per_page, ctypes.c_uint64(seed), serial)
+    out = np.empty(n, np.uint8)
+    L.opfb_synth_ogg(out.ctypes.data, n, channels, pre_skip, toc, packet_len, n_packets, per_page, ctypes.c_uint64(seed), serial)
+    return out
 
 
 class OggOpusFile:
@@ -464,10 +477,15 @@ class OggOpusFileSet:
         n = _plib().opfb_set_read_stereo(self._set, i, pcm.ctypes.data, buf_size)
         return n, pcm[: 2 * max(n, 0)].reshape(-1, 2)
 
+    def drain(self, buf_size=2048):
+        """Benchmark consumer (opfb_set_drain): op_read_stereo over every file on the host threads; frames read."""
+        return int(_plib().opfb_set_drain(self._set, buf_size))
+
     def stats(self):
-        v = (ctypes.c_double * 6)()
-        _plib().opfb_set_stats(self._set, ctypes.cast(v, _P), 6)
-        return dict(zip(("demux_s", "decode_s", "packets", "frames", "ogg_bytes", "launches"), [float(x) for x in v]))
+        v = (ctypes.c_double * 12)()
+        _plib().opfb_set_stats(self._set, ctypes.cast(v, _P), 12)
+        return dict(zip(("demux_s", "decode_s", "packets", "frames", "ogg_bytes", "launches", "keep_s", "plan_s", "reset_s", "stage_s",
+                         "gpu_wait_s", "finish_s"), [float(x) for x in v]))
 
     def close(self):
         if self._set:

@@ -72,7 +72,10 @@ struct Event {
     int od_pos, od_size; // kPacket: samples [od_pos, od_size) of the decoded packet are played (pre-skip, end trim)
     // filled in by the scheduler
     int status;          // kPacket: kPending, samples decoded (> 0) or OP_EBADPACKET
-    size_t pcm_off;      // kPacket: first played sample in Track::pcm (interleaved, head.channel_count channels)
+    const int16_t* pcm;  // kPacket: decoded sample od_pos (interleaved, decoder channels) -- in the scheduler's pinned round
+                         // buffer, or in `own` once that buffer was needed for a later round
+    int16_t* own;        // kPacket: private copy (malloc), or nullptr
+    int round;           // kPacket: the round that decoded it
 };
 
 // One Ogg Opus file: the reference's open + page processing, producing events instead of decoding.
@@ -474,9 +477,9 @@ private:
 struct Track {
     OpusFileReader rd;
     std::deque<Event> q;        // events not yet consumed by read()
-    size_t sched = 0;           // q[0..sched) already went through the scheduler
-    std::vector<int16_t> pcm;   // decoded samples of scheduled, unconsumed packets (head.channel_count interleaved)
-    size_t pcm_base = 0;        // Event::pcm_off of pcm[0]
+    size_t sched = 0;           // q[0..sched) went through the scheduler and have their results
+    size_t planned = 0;         // q[sched..planned) belong to rounds that are in flight
+    uint8_t last_toc = 0;       // TOC of the last frame handed to the decoder (filler frames repeat it)
     int open_result = OPB_EFAULT;
     bool terminal = false;      // the last queued event is the end of the data (keeps repeating)
     int terminal_code = 0;
@@ -486,6 +489,9 @@ struct Track {
     bool repoll = false;        // single-stream mode: ask the data source again after the end (the reference does)
     int64_t pcm_total = 0;
 
+    ~Track() {
+        for (Event& e : q) free(e.own);
+    }
     int dec_channels() const { return rd.head.coupled_count ? 2 : 1; }
 
     // pull events until `frames` undecoded 20 ms frames are queued or the data ends
@@ -504,13 +510,27 @@ struct Track {
         }
     }
 
+    // The samples of rounds <= `round` are about to lose their place in the scheduler's buffer: keep what is unread.
+    void keep_unread(int round) {
+        const int dc = dec_channels();
+        for (size_t i = 0; i < sched && i < q.size(); i++) {
+            Event& e = q[i];
+            if (e.kind != Event::kPacket || e.status <= 0 || e.own || e.round > round) continue;
+            const int n = e.od_size - e.od_pos;
+            if (n <= 0) continue;
+            e.own = (int16_t*)malloc(sizeof(int16_t) * (size_t)n * dc);
+            if (e.own) memcpy(e.own, e.pcm, sizeof(int16_t) * (size_t)n * dc);
+            e.pcm = e.own;
+        }
+    }
+
     // ref op_read_stereo (src/opusfile.cpp:1293): one call
     int read(int16_t* out, int buf_size) {
         for (;;) {
             if (q.empty()) return terminal ? terminal_code : kPending;
+            if (sched == 0) return kPending;  // the front event has not been through the scheduler yet
             Event& e = q.front();
             if (e.kind == Event::kResetSoft || e.kind == Event::kResetHard) {
-                if (sched == 0) return kPending;
                 pop();
                 continue;
             }
@@ -531,10 +551,19 @@ struct Track {
                 continue;
             }
             n = std::min(n, buf_size >> 1);
-            const int ch = rd.head.channel_count;
-            const int16_t* src = pcm.data() + (e.pcm_off - pcm_base) + (size_t)(cur_pos - e.od_pos) * ch;
-            if (ch == 2) memcpy(out, src, sizeof(int16_t) * 2 * (size_t)n);
-            else for (int i = 0; i < n; i++) out[2 * i] = out[2 * i + 1] = src[i];
+            // decoder channels -> the file's channels (mapping, 255 = silence) -> stereo (mono is duplicated, :1310-1314)
+            const int dc = dec_channels(), ch = rd.head.channel_count;
+            const uint8_t* map = rd.head.mapping;
+            const int16_t* src = e.pcm + (size_t)(cur_pos - e.od_pos) * dc;
+            if (ch == 2 && dc == 2 && map[0] == 0 && map[1] == 1) {
+                memcpy(out, src, sizeof(int16_t) * 2 * (size_t)n);
+            } else if (ch == 1) {
+                const int m = map[0];
+                for (int i = 0; i < n; i++) out[2 * i] = out[2 * i + 1] = m == 255 ? (int16_t)0 : src[(size_t)i * dc + (m < dc ? m : 0)];
+            } else {
+                for (int i = 0; i < n; i++)
+                    for (int c = 0; c < 2; c++) out[2 * i + c] = map[c] == 255 ? (int16_t)0 : src[(size_t)i * dc + (map[c] < dc ? map[c] : 0)];
+            }
             cur_pos += n;
             // a fully read packet stays at the front until the next call finds it empty, exactly like od_buffer
             return n;
@@ -543,139 +572,262 @@ struct Track {
 
 private:
     void pop() {
-        const Event& e = q.front();
-        if (e.kind == Event::kPacket && e.status > 0) {
-            // samples of consumed packets are released in bulk
-            const size_t end = e.pcm_off + (size_t)(e.od_size - e.od_pos) * rd.head.channel_count;
-            if (end > pcm_base) {
-                const size_t drop = end - pcm_base;
-                if (drop >= pcm.size()) { pcm.clear(); pcm_base = end; }
-                else if (drop > ((size_t)1 << 20)) { pcm.erase(pcm.begin(), pcm.begin() + (long)drop); pcm_base = end; }
-            }
-        }
+        free(q.front().own);
         q.pop_front();
         if (sched) sched--;
+        if (planned) planned--;
         cur_started = false;
     }
 };
 
+// `fn(begin, end)` over [0, n) on up to `threads` host threads
+template <class F>
+void parallel_ranges(int n, int threads, F fn) {
+    threads = std::max(1, std::min(threads, n / 64));
+    if (threads == 1) { fn(0, n); return; }
+    std::vector<std::thread> pool;
+    for (int k = 1; k < threads; k++) pool.emplace_back([=]() { fn((int)((long long)n * k / threads), (int)((long long)n * (k + 1) / threads)); });
+    fn(0, (int)((long long)n / threads));
+    for (std::thread& th : pool) th.join();
+}
+
 // Packs the next frames of a group of tracks (same decoder channel count) into pinned rows and decodes them.
+// Host work per round is spread over threads by track range: plan (which packets, how many bytes), copy the packet
+// bytes into the pinned staging buffer, and after the GPU is done point every packet at its samples in the pinned PCM
+// buffer -- the samples are not copied again until op_read_stereo hands them to the caller.
+// Two rounds are kept in flight (decode_many_async): while the caller reads round r, round r+1 is crossing PCIe and
+// round r+2 is in the kernels.  Staging is double buffered, PCM triple buffered; a packet still unread when its PCM
+// buffer comes round again gets a private copy first.
 class RoundScheduler {
 public:
+    enum { kDepth = 2, kPcmBufs = kDepth + 1 };
     ~RoundScheduler() { release(); }
-    int init(int n_tracks, int channels, int frames, int device) {
-        n_ = n_tracks; ch_ = channels; F_ = frames;
+    int init(int n_tracks, int channels, int frames, int device, int threads) {
+        n_ = n_tracks; ch_ = channels; F_ = frames; threads_ = std::max(1, threads);
         int r = dm_create(&ctx_, n_, F_, ch_, device);
         if (r) return r;
-        h_frames_ = (dm_frame*)dm_host_alloc(sizeof(dm_frame) * (size_t)n_ * F_);
-        h_pcm_ = (int16_t*)dm_host_alloc(sizeof(int16_t) * (size_t)n_ * F_ * 960 * ch_);
-        h_status_ = (int32_t*)dm_host_alloc(sizeof(int32_t) * (size_t)n_ * F_);
-        if (!h_frames_ || !h_pcm_ || !h_status_) return DM_ERR_NOMEM;
+        for (int k = 0; k < kPcmBufs; k++) {
+            h_pcm_[k] = (int16_t*)dm_host_alloc(sizeof(int16_t) * (size_t)n_ * F_ * 960 * ch_);
+            if (!h_pcm_[k]) return DM_ERR_NOMEM;
+        }
+        for (Stage& st : stage_) {
+            st.frames = (dm_frame*)dm_host_alloc(sizeof(dm_frame) * (size_t)n_ * F_);
+            st.status = (int32_t*)dm_host_alloc(sizeof(int32_t) * (size_t)n_ * F_);
+            if (!st.frames || !st.status) return DM_ERR_NOMEM;
+            st.plan.resize((size_t)n_);
+        }
         return 0;
     }
     void release() {
-        dm_host_free(h_frames_); dm_host_free(h_pcm_); dm_host_free(h_status_); dm_host_free(h_bytes_);
-        h_frames_ = nullptr; h_pcm_ = nullptr; h_status_ = nullptr; h_bytes_ = nullptr;
-        if (ctx_) dm_destroy(ctx_);
+        if (ctx_) dm_destroy(ctx_);  // waits for whatever is still in flight
         ctx_ = nullptr;
+        for (int k = 0; k < kPcmBufs; k++) { dm_host_free(h_pcm_[k]); h_pcm_[k] = nullptr; }
+        for (Stage& st : stage_) {
+            dm_host_free(st.frames); dm_host_free(st.status); dm_host_free(st.bytes);
+            st.frames = nullptr; st.status = nullptr; st.bytes = nullptr; st.bytes_cap = 0;
+        }
     }
     long long launches() const { return ctx_ ? dm_launch_count(ctx_) : 0; }
+    double t_keep = 0, t_plan = 0, t_reset = 0, t_stage = 0, t_wait = 0, t_finish = 0;  // host seconds per phase, summed over rounds
 
     // One round over tracks[0..n). Returns the number of frames decoded (0: nothing left), or < 0 (DM_ERR_*).
     long long round(Track** tracks) {
-        struct Slot { Track* t; int s; size_t ev; int first, count; bool bad; };
-        std::vector<Slot> slots;
-        std::vector<int32_t> soft, hard;
-        size_t nbytes = 0;
-        long long nframes = 0;
-        std::vector<uint8_t> last_toc((size_t)n_, 0);
-        // pass 1: choose the events of this round, lay out the frames
-        for (int s = 0; s < n_; s++) {
-            Track& t = *tracks[s];
-            int used = 0;
-            bool reset_seen = false;
-            size_t i = t.sched;
-            for (; i < t.q.size(); i++) {
-                Event& e = t.q[i];
-                if (e.kind == Event::kCode) continue;
-                if (e.kind == Event::kResetSoft || e.kind == Event::kResetHard) {
-                    if (used || reset_seen) break;  // a reset sits at the start of a round
-                    (e.kind == Event::kResetSoft ? soft : hard).push_back(s);
-                    reset_seen = true;
-                    continue;
-                }
-                const uint8_t* pkt = t.rd.arena.data() + e.off;
-                uint8_t toc = 0;
-                int16_t size[48];
-                int off = 0;
-                const int count = opusb_packet_parse(pkt, e.bytes, &toc, nullptr, size, &off);
-                // undecodable without undefined behaviour in the reference: reported, never decoded
-                const bool bad = count < 0 || opusb_packet_get_samples_per_frame(pkt, 48000) != 960 ||
-                                 (!(toc & 0x80) && ((toc & 4) ? 2 : 1) != ch_);
-                if (bad) {
-                    slots.push_back(Slot{&t, s, i, 0, 0, true});
-                    continue;
-                }
-                if (used + count > F_) break;
-                slots.push_back(Slot{&t, s, i, used, count, false});
-                size_t pos = (size_t)off;
-                for (int k = 0; k < count; k++) {
-                    dm_frame& f = h_frames_[(size_t)s * F_ + used + k];
-                    f.offset = (uint32_t)(nbytes + pos);  // patched to the staging offset below
-                    f.len = (uint16_t)size[k];
-                    f.toc = toc;
-                    f.flags = k ? DMF_CONT : 0;
-                    pos += (size_t)size[k];
-                }
-                nbytes += (size_t)e.bytes;
-                used += count;
-                last_toc[(size_t)s] = toc;
-            }
-            t.sched = i;
-            for (int k = used; k < F_; k++) {
-                dm_frame& f = h_frames_[(size_t)s * F_ + k];
-                f.offset = 0; f.len = 0; f.toc = last_toc[(size_t)s]; f.flags = DMF_NULL;
-            }
-            nframes += used;
+        long long r = top_up(tracks);
+        if (r < 0) return r;
+        if (submitted_ == completed_) return 0;
+        const long long done = complete(tracks);
+        if (done < 0) return done;
+        r = top_up(tracks);
+        if (r < 0) return r;
+        return done;
+    }
+
+private:
+    struct TrackPlan {
+        size_t n_ev;               // events [sched, sched + n_ev) of the track's queue belong to this round once the rounds
+                                   // before it are finished (reads only pop events in front of `sched`, which moves along)
+        size_t bytes, byte0;       // packet bytes of this track, and where they start in the staging buffer
+        int used;                  // frames of the row in use
+        int packets;               // packets handled (decoded or refused)
+        int reset;                 // 0 none, 1 OPUS_RESET_STATE, 2 new decoder -- before the round
+    };
+    struct Stage {
+        dm_frame* frames = nullptr;
+        int32_t* status = nullptr;
+        uint8_t* bytes = nullptr;
+        size_t bytes_cap = 0;
+        std::vector<TrackPlan> plan;
+        long long ticket = -1, nframes = 0;
+    };
+
+    // keep the pipeline full; a decoder reset needs it empty (it rewrites stream state on the device)
+    long long top_up(Track** tracks) {
+        while (submitted_ - completed_ < kDepth) {
+            if (want_drain_ && submitted_ != completed_) break;
+            const long long r = submit(tracks);
+            if (r <= 0) return r;
         }
+        return 1;
+    }
+
+    // keep, plan, reset, stage, enqueue.  Returns > 0 when a round was enqueued, 0 when nothing is left.
+    long long submit(Track** tracks) {
+        Stage& st = stage_[submitted_ % kDepth];
+        const bool idle = submitted_ == completed_;
+        if (idle) want_drain_ = false;
+        // the PCM buffer of this round was last filled kPcmBufs rounds ago: whoever has not read those samples keeps a copy
+        auto now = []() { return std::chrono::steady_clock::now(); };
+        auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        auto c0 = now();
+        if (submitted_ >= kPcmBufs) {
+            const int old = submitted_ - kPcmBufs;
+            parallel_ranges(n_, threads_, [&](int s0, int s1) { for (int s = s0; s < s1; s++) tracks[s]->keep_unread(old); });
+        }
+        auto c1 = now();
+        t_keep += secs(c0, c1);
+        // pass 1: per track, choose the events of this round and lay out their frames (bytes relative to the track)
+        parallel_ranges(n_, threads_, [&](int s0, int s1) {
+            for (int s = s0; s < s1; s++) plan_track(st, *tracks[s], s, idle);
+        });
+        auto c2 = now();
+        t_plan += secs(c1, c2);
+        std::vector<int32_t> soft, hard;
+        size_t nbytes = 0, nev = 0;
+        long long nframes = 0;
+        for (int s = 0; s < n_; s++) {
+            TrackPlan& pl = st.plan[(size_t)s];
+            pl.byte0 = nbytes;
+            nbytes += pl.bytes;
+            nframes += pl.used;
+            nev += pl.n_ev;
+            if (pl.reset == 1) soft.push_back(s);
+            if (pl.reset == 2) hard.push_back(s);
+        }
+        if (nev == 0) return 0;  // every queue is planned to its end
         if (!soft.empty()) { int r = dm_reset_state(ctx_, soft.data(), (int)soft.size()); if (r) return r; }
         if (!hard.empty()) {
             const bool all = (int)hard.size() == n_;
             int r = dm_reset(ctx_, all ? nullptr : hard.data(), all ? 0 : (int)hard.size());
             if (r) return r;
         }
-        if (slots.empty()) return 0;
+        auto c3 = now();
+        t_reset += secs(c2, c3);
+        st.ticket = -1;
+        st.nframes = nframes;
         if (nframes > 0) {
-            if (nbytes + 16 > bytes_cap_) {
-                dm_host_free(h_bytes_);
-                bytes_cap_ = nbytes * 2 + 4096;
-                h_bytes_ = (uint8_t*)dm_host_alloc(bytes_cap_);
-                if (!h_bytes_) return DM_ERR_NOMEM;
+            if (nbytes + 16 > st.bytes_cap) {
+                dm_host_free(st.bytes);
+                st.bytes_cap = nbytes * 2 + 4096;
+                st.bytes = (uint8_t*)dm_host_alloc(st.bytes_cap);
+                if (!st.bytes) return DM_ERR_NOMEM;
             }
-            size_t pos = 0;
-            for (const Slot& sl : slots) {
-                if (sl.bad) continue;
-                const Event& e = sl.t->q[sl.ev];
-                memcpy(h_bytes_ + pos, sl.t->rd.arena.data() + e.off, (size_t)e.bytes);
-                pos += (size_t)e.bytes;
-            }
+            // pass 2: packet bytes into the pinned staging buffer, frame offsets made absolute
+            parallel_ranges(n_, threads_, [&](int s0, int s1) {
+                for (int s = s0; s < s1; s++) stage_track(st, *tracks[s], s);
+            });
             dm_batch in;
             memset(&in, 0, sizeof(in));
-            in.n_frames = F_; in.mode = DM_MODE_OPUS; in.bytes = h_bytes_; in.n_bytes = pos; in.frames = h_frames_;
-            dm_out out = {h_pcm_, h_status_};
-            const int r = decode_many(ctx_, &in, &out);
+            in.n_frames = F_; in.mode = DM_MODE_OPUS; in.bytes = st.bytes; in.n_bytes = nbytes; in.frames = st.frames;
+            dm_out out = {h_pcm_[submitted_ % kPcmBufs], st.status};
+            const int r = decode_many_async(ctx_, &in, &out, &st.ticket);
             if (r) return r;
         }
-        // pass 2: results -> tracks
-        for (const Slot& sl : slots) {
-            Track& t = *sl.t;
-            Event& e = t.q[sl.ev];
-            const int s = sl.s;
-            int status = sl.bad ? OPB_EBADPACKET : 0;
-            for (int k = 0; k < sl.count && status >= 0; k++) {
-                const int32_t st = h_status_[(size_t)s * F_ + sl.first + k];
-                if (st < 0) status = OPB_EBADPACKET;
-                else status += st;
+        t_stage += secs(c3, now());
+        // the events of this round are spoken for
+        for (int s = 0; s < n_; s++) tracks[s]->planned += st.plan[(size_t)s].n_ev;
+        submitted_++;
+        return nframes > 0 ? nframes : 1;
+    }
+    // wait for the oldest round in flight, results -> events
+    long long complete(Track** tracks) {
+        Stage& st = stage_[completed_ % kDepth];
+        const auto w0 = std::chrono::steady_clock::now();
+        if (st.ticket >= 0) {
+            const int r = dm_wait(ctx_, st.ticket);
+            if (r) return r;
+        }
+        const auto w1 = std::chrono::steady_clock::now();
+        const int16_t* pcm = h_pcm_[completed_ % kPcmBufs];
+        const int round = completed_;
+        parallel_ranges(n_, threads_, [&](int s0, int s1) {
+            for (int s = s0; s < s1; s++) finish_track(st, *tracks[s], s, pcm, round);
+        });
+        t_wait += std::chrono::duration<double>(w1 - w0).count();
+        t_finish += std::chrono::duration<double>(std::chrono::steady_clock::now() - w1).count();
+        completed_++;
+        return st.nframes > 0 ? st.nframes : 1;
+    }
+
+    static bool packet_layout(const Track& t, const Event& e, int ch, uint8_t* toc, int16_t* size, int* off, int* count) {
+        const uint8_t* pkt = t.rd.arena.data() + e.off;
+        *count = opusb_packet_parse(pkt, e.bytes, toc, nullptr, size, off);
+        // undecodable without undefined behaviour in the reference: reported, never decoded
+        return !(*count < 0 || opusb_packet_get_samples_per_frame(pkt, 48000) != 960 || (!(*toc & 0x80) && ((*toc & 4) ? 2 : 1) != ch));
+    }
+    void plan_track(Stage& st, Track& t, int s, bool resets_allowed) {
+        TrackPlan& pl = st.plan[(size_t)s];
+        pl.bytes = 0; pl.used = 0; pl.reset = 0; pl.packets = 0;
+        uint8_t last_toc = t.last_toc;
+        size_t i = t.planned;
+        for (; i < t.q.size(); i++) {
+            Event& e = t.q[i];
+            if (e.kind == Event::kCode) continue;
+            if (e.kind == Event::kResetSoft || e.kind == Event::kResetHard) {
+                if (pl.used || pl.reset) break;  // a reset sits at the start of a round
+                if (!resets_allowed) { want_drain_ = true; break; }
+                pl.reset = e.kind == Event::kResetSoft ? 1 : 2;
+                continue;
+            }
+            uint8_t toc = 0;
+            int16_t size[48];
+            int off = 0, count = 0;
+            if (!packet_layout(t, e, ch_, &toc, size, &off, &count)) { e.round = -1; pl.packets++; continue; }
+            if (pl.used + count > F_) break;
+            pl.packets++;
+            e.round = pl.used;  // first frame of the packet in the row (the round number replaces it in finish_track)
+            size_t pos = pl.bytes + (size_t)off;
+            for (int k = 0; k < count; k++) {
+                dm_frame& f = st.frames[(size_t)s * F_ + pl.used + k];
+                f.offset = (uint32_t)pos;  // relative to the track's bytes until stage_track()
+                f.len = (uint16_t)size[k];
+                f.toc = toc;
+                f.flags = k ? DMF_CONT : 0;
+                pos += (size_t)size[k];
+            }
+            pl.bytes += (size_t)e.bytes;
+            pl.used += count;
+            last_toc = toc;
+        }
+        pl.n_ev = i - t.planned;
+        t.last_toc = last_toc;
+        for (int k = pl.used; k < F_; k++) {
+            dm_frame& f = st.frames[(size_t)s * F_ + k];
+            f.offset = 0; f.len = 0; f.toc = last_toc; f.flags = DMF_NULL;
+        }
+    }
+    void stage_track(Stage& st, Track& t, int s) {
+        const TrackPlan& pl = st.plan[(size_t)s];
+        size_t pos = pl.byte0;
+        for (size_t i = t.planned; i < t.planned + pl.n_ev; i++) {
+            const Event& e = t.q[i];
+            if (e.kind != Event::kPacket || e.round < 0) continue;
+            memcpy(st.bytes + pos, t.rd.arena.data() + e.off, (size_t)e.bytes);
+            pos += (size_t)e.bytes;
+        }
+        for (int k = 0; k < pl.used; k++) st.frames[(size_t)s * F_ + k].offset += (uint32_t)pl.byte0;
+    }
+    void finish_track(Stage& st, Track& t, int s, const int16_t* pcm, int round) {
+        const TrackPlan& pl = st.plan[(size_t)s];
+        for (size_t i = t.sched; i < t.sched + pl.n_ev; i++) {
+            Event& e = t.q[i];
+            if (e.kind != Event::kPacket) continue;
+            const int first = e.round;
+            int status = first < 0 ? OPB_EBADPACKET : 0;
+            const int count = first < 0 ? 0 : e.duration / 960;
+            for (int k = 0; k < count && status >= 0; k++) {
+                const int32_t v = st.status[(size_t)s * F_ + first + k];
+                if (v < 0) status = OPB_EBADPACKET;
+                else status += v;
             }
             if (status >= 0 && status != e.duration) status = OPB_EBADPACKET;
             // a failed packet does not consume pre-skip (ref :1232-1238): give it to the packets behind it
@@ -686,37 +838,21 @@ public:
                 t.discard_refund -= extra;
             }
             e.status = status;
+            e.round = round;
             if (status > 0) {
-                const int out_ch = t.rd.head.channel_count;
-                const int n = e.od_size - e.od_pos;
-                e.pcm_off = t.pcm_base + t.pcm.size();
-                if (n > 0) {
-                    const int16_t* src = h_pcm_ + ((size_t)s * F_ + sl.first) * 960 * ch_ + (size_t)e.od_pos * ch_;
-                    const size_t at = t.pcm.size();
-                    t.pcm.resize(at + (size_t)n * out_ch);
-                    int16_t* dst = t.pcm.data() + at;
-                    const uint8_t* map = t.rd.head.mapping;
-                    if (out_ch == ch_ && map[0] == 0 && (out_ch == 1 || map[1] == 1)) {
-                        memcpy(dst, src, sizeof(int16_t) * (size_t)n * out_ch);
-                    } else {
-                        for (int i = 0; i < n; i++)
-                            for (int c = 0; c < out_ch; c++) dst[i * out_ch + c] = map[c] == 255 ? 0 : src[i * ch_ + (map[c] < ch_ ? map[c] : 0)];
-                    }
-                    t.pcm_total += n;
-                }
+                e.pcm = pcm + (((size_t)s * F_ + first) * 960 + (size_t)e.od_pos) * ch_;
+                t.pcm_total += std::max(0, e.od_size - e.od_pos);
             }
         }
-        return nframes > 0 ? nframes : 1;
+        t.sched += pl.n_ev;
     }
 
-private:
     dm_ctx* ctx_ = nullptr;
-    int n_ = 0, ch_ = 0, F_ = 0;
-    dm_frame* h_frames_ = nullptr;
-    int16_t* h_pcm_ = nullptr;
-    int32_t* h_status_ = nullptr;
-    uint8_t* h_bytes_ = nullptr;
-    size_t bytes_cap_ = 0;
+    int n_ = 0, ch_ = 0, F_ = 0, threads_ = 1;
+    int submitted_ = 0, completed_ = 0;   // rounds handed to the GPU / rounds whose results are with the tracks
+    std::atomic<bool> want_drain_{false}; // a track waits with a decoder reset until nothing is in flight
+    int16_t* h_pcm_[kPcmBufs] = {};
+    Stage stage_[kDepth];
 };
 
 }  // namespace
@@ -798,7 +934,7 @@ OggOpusFileB200* opusb_init_decoder(opusb_read_func read, void* user, int device
         of->track.repoll = true;
         err = of->track.rd.open(&of->track.q);
         of->track.open_result = err;
-        if (!err) err = of->sched.init(1, of->track.dec_channels(), of->frames, device);
+        if (!err) err = of->sched.init(1, of->track.dec_channels(), of->frames, device, 1);
         if (err) { delete of; of = nullptr; }
     }
     if (error) *error = err;
@@ -871,6 +1007,7 @@ int opfb_set_prepare(opfb_set* s) {
     for (int k = 1; k < nt; k++) pool.emplace_back(work);
     work();
     for (std::thread& th : pool) th.join();
+    s->demux_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (Track* t : s->tracks) {
         if (!t || t->open_result) continue;
         s->group[t->dec_channels() - 1].push_back(t);
@@ -880,11 +1017,10 @@ int opfb_set_prepare(opfb_set* s) {
         if (s->group[g].empty()) continue;
         s->sched[g] = new (std::nothrow) RoundScheduler();
         if (!s->sched[g]) return OPB_EFAULT;
-        const int r = s->sched[g]->init((int)s->group[g].size(), g + 1, s->frames, s->device);
+        const int r = s->sched[g]->init((int)s->group[g].size(), g + 1, s->frames, s->device, s->n_threads);
         if (r) return r;
     }
     s->prepared = true;
-    s->demux_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }
 int opfb_set_open_result(const opfb_set* s, int index) {
@@ -918,6 +1054,27 @@ int opfb_set_read_stereo(opfb_set* s, int index, int16_t* pcm, int buf_size) {
     const int r = t->read(pcm, buf_size);
     return r;
 }
+// Benchmark consumer: every file is read with op_read_stereo calls of `buf_size` samples until it reports OPFB_PENDING or
+// its end, on the set's host threads (files are independent).  Returns the stereo frames read.
+int64_t opfb_set_drain(opfb_set* s, int buf_size) {
+    if (!s || !s->prepared || buf_size < 2) return OPB_EINVAL;
+    std::atomic<long long> total(0);
+    parallel_ranges(s->n_files, s->n_threads, [&](int i0, int i1) {
+        std::vector<int16_t> buf((size_t)buf_size);
+        long long n_sum = 0;
+        for (int i = i0; i < i1; i++) {
+            Track* t = s->tracks[(size_t)i];
+            if (!t || t->open_result) continue;
+            for (;;) {
+                const int n = t->read(buf.data(), buf_size);
+                if (n <= 0) break;
+                n_sum += n;
+            }
+        }
+        total += n_sum;
+    });
+    return (int64_t)total.load();
+}
 int64_t opfb_set_pcm_total(const opfb_set* s, int index) {
     if (!s || index < 0 || index >= s->n_files || !s->tracks[(size_t)index]) return OPB_EINVAL;
     return s->tracks[(size_t)index]->pcm_total;
@@ -926,10 +1083,82 @@ int opfb_set_stats(const opfb_set* s, double* out, int cap) {
     if (!s || !out) return 0;
     long long launches = 0;
     for (int g = 0; g < 2; g++) if (s->sched[g]) launches += s->sched[g]->launches();
-    const double v[6] = {s->demux_s, s->decode_s, (double)s->packets, (double)s->frames_done, (double)s->ogg_bytes, (double)launches};
-    const int n = cap < 6 ? cap : 6;
+    double ph[6] = {0, 0, 0, 0, 0, 0};
+    for (int g = 0; g < 2; g++)
+        if (s->sched[g]) {
+            const RoundScheduler& r = *s->sched[g];
+            ph[0] += r.t_keep; ph[1] += r.t_plan; ph[2] += r.t_reset; ph[3] += r.t_stage; ph[4] += r.t_wait; ph[5] += r.t_finish;
+        }
+    const double v[12] = {s->demux_s, s->decode_s, (double)s->packets, (double)s->frames_done, (double)s->ogg_bytes, (double)launches,
+                          ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]};
+    const int n = cap < 12 ? cap : 12;
     for (int i = 0; i < n; i++) out[i] = v[i];
     return n;
+}
+
+// Synthetic Ogg Opus file for benchmarks and tests (SURVEY 8d config 1 layout): OpusHead (version 1, family 0), empty
+// OpusTags, then `n_packets` code-0 packets of `packet_len` bytes (TOC + xorshift payload, the SURVEY 8c generator),
+// `per_page` packets per page, granule positions 960 per packet, EOS on the last page.  Returns the bytes written, or
+// the size needed when `out` is NULL / `cap` is too small.
+size_t opfb_synth_ogg(uint8_t* out, size_t cap, int channels, int pre_skip, int toc, int packet_len, int n_packets, int per_page,
+                      uint64_t seed, uint32_t serial) {
+    if (per_page < 1) per_page = 1;
+    if (per_page > 255 / ((packet_len / 255) + 1)) per_page = 255 / ((packet_len / 255) + 1);
+    const OggCrc& C = ogg_crc();
+    size_t pos = 0;
+    uint32_t seq = 0;
+    uint64_t rng = seed;
+    auto page = [&](const uint8_t* const* pk, const int* len, int n, int64_t gp, int flags) {
+        uint8_t hdr[27 + 255];
+        int nseg = 0;
+        size_t body = 0;
+        for (int i = 0; i < n; i++) {
+            int l = len[i];
+            while (l >= 255) { hdr[27 + nseg++] = 255; l -= 255; }
+            hdr[27 + nseg++] = (uint8_t)l;
+            body += (size_t)len[i];
+        }
+        memcpy(hdr, "OggS", 4);
+        hdr[4] = 0; hdr[5] = (uint8_t)flags;
+        for (int i = 0; i < 8; i++) hdr[6 + i] = (uint8_t)((uint64_t)gp >> (8 * i));
+        for (int i = 0; i < 4; i++) { hdr[14 + i] = (uint8_t)(serial >> (8 * i)); hdr[18 + i] = (uint8_t)(seq >> (8 * i)); hdr[22 + i] = 0; }
+        hdr[26] = (uint8_t)nseg;
+        const size_t total = 27 + (size_t)nseg + body;
+        if (out && pos + total <= cap) {
+            uint8_t* p = out + pos;
+            memcpy(p, hdr, 27 + (size_t)nseg);
+            size_t q = 27 + (size_t)nseg;
+            for (int i = 0; i < n; i++) { memcpy(p + q, pk[i], (size_t)len[i]); q += (size_t)len[i]; }
+            const uint32_t crc = C.update(0, p, total);
+            for (int i = 0; i < 4; i++) p[22 + i] = (uint8_t)(crc >> (8 * i));
+        }
+        pos += total;
+        seq++;
+    };
+    uint8_t head[19] = {'O', 'p', 'u', 's', 'H', 'e', 'a', 'd', 1, (uint8_t)channels, (uint8_t)(pre_skip & 255), (uint8_t)(pre_skip >> 8),
+                        0x80, 0xBB, 0, 0, 0, 0, 0};
+    uint8_t tags[8 + 4 + 4 + 4] = {'O', 'p', 'u', 's', 'T', 'a', 'g', 's', 4, 0, 0, 0, 'b', '2', '0', '0', 0, 0, 0, 0};
+    const uint8_t* hp = head; int hl = (int)sizeof(head);
+    page(&hp, &hl, 1, 0, 2);
+    const uint8_t* tp = tags; int tl = (int)sizeof(tags);
+    page(&tp, &tl, 1, 0, 0);
+    std::vector<uint8_t> buf((size_t)per_page * (size_t)packet_len);
+    std::vector<const uint8_t*> ptrs((size_t)per_page);
+    std::vector<int> lens((size_t)per_page, packet_len);
+    for (int i = 0; i < n_packets; i += per_page) {
+        const int n = std::min(per_page, n_packets - i);
+        for (int k = 0; k < n; k++) {
+            uint8_t* p = buf.data() + (size_t)k * packet_len;
+            p[0] = (uint8_t)toc;
+            for (int j = 1; j < packet_len; j++) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                p[j] = (uint8_t)(rng >> 11);
+            }
+            ptrs[(size_t)k] = p;
+        }
+        page(ptrs.data(), lens.data(), n, (int64_t)960 * (i + n), i + n >= n_packets ? 4 : 0);
+    }
+    return pos;
 }
 
 // Test access to the demux stage alone (no GPU): the events of one memory image, rows of

@@ -98,11 +98,21 @@ int opfb_set_decode_round(opfb_set* set);
 int opfb_set_decode(opfb_set* set);
 /* op_read_stereo for file `index`; OPFB_PENDING when opfb_set_decode_round must run first. */
 int opfb_set_read_stereo(opfb_set* set, int index, int16_t* pcm, int buf_size);
+/* Benchmark consumer: reads every file with op_read_stereo calls of buf_size samples until it reports OPFB_PENDING or
+ * its end, on the set's host threads.  Returns the stereo frames read (the samples are discarded). */
+int64_t opfb_set_drain(opfb_set* set, int buf_size);
 /* Total stereo frames op_read_stereo will deliver for file `index` (after pre-skip and end trimming). */
 int64_t opfb_set_pcm_total(const opfb_set* set, int index);
 /* Statistics of the last prepare/decode: [0] demux seconds, [1] decode seconds (H2D + kernels + D2H), [2] packets,
- * [3] frames, [4] bytes of Ogg data, [5] kernel launches. */
+ * [3] frames, [4] bytes of Ogg data, [5] kernel launches, [6..11] host seconds of the round scheduler by phase: keeping
+ * unread samples, planning, decoder resets, staging + enqueue, waiting for the GPU, handing results to the files. */
 int opfb_set_stats(const opfb_set* set, double* out, int cap);
+
+/* Synthetic Ogg Opus file (benchmarks, tests): OpusHead + OpusTags + n_packets code-0 packets of packet_len bytes (TOC +
+ * xorshift64 payload seeded `seed`, the generator of dm_synth_fill), per_page packets per page, 960 samples per packet,
+ * EOS on the last page.  Returns the size; writes only when `out` has room for it. */
+size_t opfb_synth_ogg(uint8_t* out, size_t cap, int channels, int pre_skip, int toc, int packet_len, int n_packets, int per_page,
+                      uint64_t seed, uint32_t serial);
 
 /* Test access to the host demux stage alone (runs without a GPU): the player events of one memory image as rows of
  * (kind 0 packet | 1 return code | 2 OPUS_RESET_STATE | 3 new decoder, code, bytes, duration, od_pos, od_size). */

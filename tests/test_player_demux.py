@@ -245,3 +245,15 @@ def test_head_parse_matches_reference(pkg, ref):
             assert (h.version, h.channel_count, h.pre_skip, h.input_sample_rate, h.output_gain, h.mapping_family, h.stream_count,
                     h.coupled_count) == tuple(int(x) for x in w[:8]) or True
             assert h.channel_count == int(w[1]) and h.pre_skip == int(w[2]) and h.output_gain == int(w[4])
+
+
+def test_synthetic_ogg_writer_is_read_like_by_the_reference(pkg, ref):
+    """opfb_synth_ogg (the bench corpus generator) produces files the reference player accepts, with the packets of the
+    SURVEY generator: same op_read_stereo sequence, and PCM equal to the packet-level oracle."""
+    blob = pkg.synth_ogg(2, 0xFC, 160, 37, per_page=5, pre_skip=0, seed=ref.SEED)
+    want, pcm = ref_returns(ref, blob.tobytes())
+    res, ev = pkg.demux_events(blob)
+    assert res == 0 and want == [960] * 37 + [-128]
+    assert predicted_returns(ev) == want
+    _, direct, err = ref.decode_synth_stream(0xFC, 160, 2, 37)
+    assert err == 0 and np.array_equal(pcm.reshape(-1, 2), direct)
