@@ -17,6 +17,11 @@
 #define OPUS_HD_CALL inline
 #endif
 
+#if !defined(__CUDACC__)
+#include <string.h>
+struct uint2 { uint32_t x, y; };
+#endif
+
 namespace opusb200 {
 
 typedef int16_t s16;
@@ -27,6 +32,16 @@ typedef uint32_t u32;
 OPUS_HD s32 imin(s32 a, s32 b) { return a < b ? a : b; }
 OPUS_HD s32 imax(s32 a, s32 b) { return a > b ? a : b; }
 OPUS_HD u32 umin(u32 a, u32 b) { return a < b ? a : b; }
+
+// 16 int16 values (32 bytes, 16-byte aligned) between memory and a local block: two 128-bit accesses on the device
+OPUS_HD void ld_block16(int16_t* dst, const int16_t* src) {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
+    reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
+#else
+    memcpy(dst, src, 32);
+#endif
+}
 
 // ---- warp convergence points for thread-per-frame kernels ----
 // The entropy stage runs one frame per lane through data-dependent control flow; left alone the lanes of a

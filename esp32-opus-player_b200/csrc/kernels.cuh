@@ -61,6 +61,8 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     p.C = 1; p.LM = 3; p.start = 0; p.prep_on = 0;
     int oflags = 0;
     bool celt = true, fade = false;
+    // the lanes with a SILK layer go through its parser in lock step (silk_parse_frame)
+    const unsigned silk_lanes = __ballot_sync(warp, P.mode == 0 && !(d.flags & FD_NULL) && opus_has_silk_layer(d.toc, P.CC));
     if (d.flags & FD_NULL) {  // filler behind the last frame of a stream: no output, no state change
         h.status = OPUSB_FRAME_SKIPPED; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1;
         h.start = 0; h.end = kNbEBands;
@@ -69,7 +71,7 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     } else if (P.mode == 0) {
         const int f = local % P.n_frames;
         const int prev_mode = f > 0 ? opus_toc_mode(fr[t - 1].toc) : st[P.first_stream + local / P.n_frames].prev_mode;
-        oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade);
+        oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade, silk_lanes);
     } else {
         rd_init(p.rd, bytes + d.offset, d.len);
         p.C = P.coded_channels;

@@ -21,14 +21,16 @@ enum OpusFrameFlags : uint8_t {
     OF_SILK_REINIT = 8,  // silk_InitDecoder before the SILK layer (previous frame was CELT-only, ref :183)
 };
 
+OPUS_HD bool opus_has_silk_layer(int toc, int CC) { return !(toc & 0x80) && ((toc & 0x4) ? 2 : 1) == CC; }
 OPUS_HD int opus_toc_mode(int toc) { return (toc & 0x80) ? MODE_CELT_ONLY : ((toc & 0x60) == 0x60 ? MODE_HYBRID : MODE_SILK_ONLY); }
 
 // Everything opus_decode_frame reads before the CELT layer.  Sets up `p` (range decoder, band range, frame size)
-// for the single celt_parse_frame call site of the entropy kernel.  Returns the Opus-layer flags; *celt says
+// for the single celt_parse_frame call site of the entropy kernel.  `silk_lanes`: the lanes of the warp that have a SILK
+// layer to parse (opus_has_silk_layer), which step through it together.  Returns the Opus-layer flags; *celt says
 // whether a CELT frame follows, *fade that it is the 120-sample hybrid -> SILK fade-out frame whose status
 // the reference ignores (ref :263-268).
 OPUS_HD int opus_parse_prologue(ParseCtx& p, const uint8_t* payload, int len, int toc, int prev_mode, int CC, CeltFrameHdr& hdr,
-                                SilkFrame& sf, bool* celt, bool* fade) {
+                                SilkFrame& sf, bool* celt, bool* fade, unsigned silk_lanes) {
     const int mode = opus_toc_mode(toc);
     const int C = (toc & 0x4) ? 2 : 1;
     int oflags = 0;
@@ -51,7 +53,7 @@ OPUS_HD int opus_parse_prologue(ParseCtx& p, const uint8_t* payload, int len, in
             const int bw = (toc >> 5) & 3;  // NB, MB, WB (ref :188-197)
             fs_kHz = bw == 0 ? 8 : bw == 1 ? 12 : 16;
         }
-        silk_parse_frame(p.rd, sf, fs_kHz, C);
+        silk_parse_frame(p.rd, sf, fs_kHz, C, silk_lanes);
         if (mode == MODE_HYBRID && rd_tell(p.rd) + 17 + 20 <= 8 * len) rd_bit_logp(p.rd, 12);  // redundancy flag, dropped (ref :218-221)
         p.start = 17;
     }

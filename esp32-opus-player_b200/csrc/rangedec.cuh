@@ -109,6 +109,41 @@ OPUS_HD int rd_icdf(RangeDec& d, const uint8_t* icdf, u32 ftb) {
     rd_normalize(d);
     return ret;
 }
+// Two-entry table {p0, 0}: one comparison
+OPUS_HD int rd_icdf2(RangeDec& d, u32 p0, u32 ftb) {
+    const u32 s = d.rng, v = d.val, s1 = (s >> ftb) * p0;
+    const int ret = v < s1;
+    d.val = ret ? v : v - s1;
+    d.rng = ret ? s1 : s - s1;
+    rd_normalize(d);
+    return ret;
+}
+// Same for a table in the constant data of the module (never for a local array: it is read through 32-bit words).  The
+// table is searched from the front like the reference does, but fetched one aligned word (four entries) at a time: the
+// search is latency bound (each probe used to be a dependent byte load) and symbols mostly sit in the first few entries.
+// A further word is only read when every entry so far was too large, i.e. while the terminating 0 has not been seen, so
+// no byte outside the words of the table is touched.
+OPUS_HD int rd_icdf_tab(RangeDec& d, const uint8_t* icdf, u32 ftb) {
+    u32 s = d.rng, v = d.val, r = s >> ftb, t;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(icdf);
+    const u32* wp = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    int k = (int)(a & 3);  // byte of the current word that holds the next entry
+    u32 w = *wp >> (8 * k);
+    int ret = -1;
+#pragma unroll 1
+    for (;;) {
+        t = s;
+        s = r * (w & 0xffu);
+        ret++;
+        if (v >= s) break;
+        w >>= 8;
+        if (++k == 4) { k = 0; w = *++wp; }
+    }
+    d.val = v - s;
+    d.rng = t - s;
+    rd_normalize(d);
+    return ret;
+}
 
 // ref ec_dec_bits (src/celt.cpp:2773)
 OPUS_HD u32 rd_bits(RangeDec& d, u32 bits) {

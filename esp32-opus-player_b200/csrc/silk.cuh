@@ -131,122 +131,157 @@ OPUS_HD void nlsf_unpack(int16_t* ec_ix, uint8_t* pred_Q8, const SilkCb& cb, int
 }
 
 // ---- entropy half ----
+// The lanes of a warp that parse a SILK layer go through the same sequence of loops (side information, 20 shell
+// blocks, signs); `m` names them and warp_converge(m) makes them meet at every loop head, `on` says whether this lane
+// really has the unit in its bitstream (LBRR copies and the side channel are optional).  Without the meeting points the
+// lanes drift apart for good, as they did in the CELT parser.
+enum { kSilkMaxBlocks = kSilkMaxFrame / 16 };
+
 // ref silk_decode_indices (src/silk.cpp:708) with condCoding == CODE_INDEPENDENTLY
-OPUS_HD void silk_parse_indices(RangeDec& rd, SilkIdx& ix, int fs_kHz, int vad_or_lbrr) {
+OPUS_HD void silk_parse_indices(RangeDec& rd, SilkIdx& ix, int fs_kHz, int vad_or_lbrr, bool on, unsigned m) {
     const uint8_t uni4[4] = {192, 128, 64, 0}, uni6[6] = {213, 171, 128, 85, 43, 0}, uni8[8] = {224, 192, 160, 128, 96, 64, 32, 0};
-    int Ix;
-    if (vad_or_lbrr) {
-        const uint8_t t[4] = {232, 158, 10, 0};
-        Ix = rd_icdf(rd, t, 8) + 2;
-    } else {
-        const uint8_t t[2] = {230, 0};
-        Ix = rd_icdf(rd, t, 8);
-    }
-    ix.signalType = (int8_t)(Ix >> 1);
-    ix.quantOffsetType = (int8_t)(Ix & 1);
-    ix.gains[0] = (int8_t)(rd_icdf(rd, kGainIcdf + ix.signalType * 8, 8) << 3);
-    ix.gains[0] += (int8_t)rd_icdf(rd, uni8, 8);
-    for (int i = 1; i < 4; i++) ix.gains[i] = (int8_t)rd_icdf(rd, kDeltaGainIcdf, 8);
+    const uint8_t ext[7] = {100, 40, 16, 7, 3, 1, 0};
     const SilkCb cb = silk_cb(fs_kHz);
-    ix.nlsf[0] = (int8_t)rd_icdf(rd, cb.cb1_icdf + (ix.signalType >> 1) * 32, 8);
     int16_t ec_ix[kSilkMaxOrder];
     uint8_t pred_Q8[kSilkMaxOrder];
-    nlsf_unpack(ec_ix, pred_Q8, cb, ix.nlsf[0]);
-    const uint8_t ext[7] = {100, 40, 16, 7, 3, 1, 0};
-    for (int i = 0; i < cb.order; i++) {
-        Ix = rd_icdf(rd, cb.ec_icdf + ec_ix[i], 8);
-        if (Ix == 0) Ix -= rd_icdf(rd, ext, 8);
-        else if (Ix == 8) Ix += rd_icdf(rd, ext, 8);
-        ix.nlsf[i + 1] = (int8_t)(Ix - 4);
+    int Ix;
+    if (on) {
+        if (vad_or_lbrr) {
+            const uint8_t t[4] = {232, 158, 10, 0};
+            Ix = rd_icdf(rd, t, 8) + 2;
+        } else {
+            Ix = rd_icdf2(rd, 230, 8);
+        }
+        ix.signalType = (int8_t)(Ix >> 1);
+        ix.quantOffsetType = (int8_t)(Ix & 1);
+        ix.gains[0] = (int8_t)(rd_icdf_tab(rd, kGainIcdf + ix.signalType * 8, 8) << 3);
+        ix.gains[0] += (int8_t)rd_icdf(rd, uni8, 8);
+        for (int i = 1; i < 4; i++) ix.gains[i] = (int8_t)rd_icdf_tab(rd, kDeltaGainIcdf, 8);
+        ix.nlsf[0] = (int8_t)rd_icdf_tab(rd, cb.cb1_icdf + (ix.signalType >> 1) * 32, 8);
+        nlsf_unpack(ec_ix, pred_Q8, cb, ix.nlsf[0]);
     }
-    {
+#pragma unroll 1
+    for (int i = 0; i < kSilkMaxOrder; i++) {
+        warp_converge(m);
+        if (on && i < cb.order) {
+            Ix = rd_icdf_tab(rd, cb.ec_icdf + ec_ix[i], 8);
+            if (Ix == 0) Ix -= rd_icdf(rd, ext, 8);
+            else if (Ix == 8) Ix += rd_icdf(rd, ext, 8);
+            ix.nlsf[i + 1] = (int8_t)(Ix - 4);
+        }
+    }
+    warp_converge(m);
+    if (on) {
         const uint8_t t[5] = {243, 221, 192, 181, 0};
         ix.interpQ2 = (int8_t)rd_icdf(rd, t, 8);
+        ix.lagIndex = 0; ix.contour = 0; ix.perIndex = 0; ix.ltpScaleIndex = 0;
+        for (int k = 0; k < 4; k++) ix.ltp[k] = 0;
+        if (ix.signalType == 2) {
+            ix.lagIndex = (int16_t)((int16_t)rd_icdf_tab(rd, kPitchLagIcdf, 8) * (fs_kHz >> 1));
+            ix.lagIndex += (int16_t)rd_icdf(rd, fs_kHz == 16 ? uni8 : fs_kHz == 12 ? uni6 : uni4, 8);
+            ix.contour = (int8_t)rd_icdf_tab(rd, fs_kHz == 8 ? kPitchContourNbIcdf : kPitchContourIcdf, 8);
+            const uint8_t per[3] = {179, 99, 0};
+            ix.perIndex = (int8_t)rd_icdf(rd, per, 8);
+            const uint8_t* g = ix.perIndex == 0 ? kLtpGainIcdf0 : ix.perIndex == 1 ? kLtpGainIcdf1 : kLtpGainIcdf2;
+            for (int k = 0; k < 4; k++) ix.ltp[k] = (int8_t)rd_icdf_tab(rd, g, 8);
+            const uint8_t sc[3] = {128, 64, 0};
+            ix.ltpScaleIndex = (int8_t)rd_icdf(rd, sc, 8);
+        }
+        ix.seed = (int8_t)rd_icdf(rd, uni4, 8);
     }
-    ix.lagIndex = 0; ix.contour = 0; ix.perIndex = 0; ix.ltpScaleIndex = 0;
-    for (int k = 0; k < 4; k++) ix.ltp[k] = 0;
-    if (ix.signalType == 2) {
-        ix.lagIndex = (int16_t)((int16_t)rd_icdf(rd, kPitchLagIcdf, 8) * (fs_kHz >> 1));
-        ix.lagIndex += (int16_t)rd_icdf(rd, fs_kHz == 16 ? uni8 : fs_kHz == 12 ? uni6 : uni4, 8);
-        ix.contour = (int8_t)rd_icdf(rd, fs_kHz == 8 ? kPitchContourNbIcdf : kPitchContourIcdf, 8);
-        const uint8_t per[3] = {179, 99, 0};
-        ix.perIndex = (int8_t)rd_icdf(rd, per, 8);
-        const uint8_t* g = ix.perIndex == 0 ? kLtpGainIcdf0 : ix.perIndex == 1 ? kLtpGainIcdf1 : kLtpGainIcdf2;
-        for (int k = 0; k < 4; k++) ix.ltp[k] = (int8_t)rd_icdf(rd, g, 8);
-        const uint8_t sc[3] = {128, 64, 0};
-        ix.ltpScaleIndex = (int8_t)rd_icdf(rd, sc, 8);
-    }
-    ix.seed = (int8_t)rd_icdf(rd, uni4, 8);
 }
 
 // ref silk_shell_decoder / decode_split (src/silk.cpp:1146, 1162)
-OPUS_HD void shell_split(RangeDec& rd, int16_t* c1, int16_t* c2, int p, const uint8_t* table) {
+OPUS_HD void shell_split(RangeDec& rd, int16_t* c1, int16_t* c2, int p, const uint8_t* table, bool on, unsigned m) {
+    warp_converge(m);
+    if (!on) return;
     if (p > 0) {
-        *c1 = (int16_t)rd_icdf(rd, table + kShellOffsets[p], 8);
+        *c1 = (int16_t)rd_icdf_tab(rd, table + kShellOffsets[p], 8);
         *c2 = (int16_t)(p - *c1);
     } else {
         *c1 = 0;
         *c2 = 0;
     }
 }
-OPUS_HD void shell_decode(RangeDec& rd, int16_t* p0, int pulses4) {
+// every lane of `m` walks the 15 splits of the block together; `on`: this lane has pulses to split in this block
+OPUS_HD void shell_decode(RangeDec& rd, int16_t* p0, int pulses4, bool on, unsigned m) {
     int16_t p3[2], p2[4], p1[8];
-    shell_split(rd, &p3[0], &p3[1], pulses4, kShell3);
+    shell_split(rd, &p3[0], &p3[1], pulses4, kShell3, on, m);
+#pragma unroll 1
     for (int a = 0; a < 2; a++) {
-        shell_split(rd, &p2[2 * a], &p2[2 * a + 1], p3[a], kShell2);
+        shell_split(rd, &p2[2 * a], &p2[2 * a + 1], p3[a], kShell2, on, m);
+#pragma unroll 1
         for (int b = 0; b < 2; b++) {
-            shell_split(rd, &p1[4 * a + 2 * b], &p1[4 * a + 2 * b + 1], p2[2 * a + b], kShell1);
+            shell_split(rd, &p1[4 * a + 2 * b], &p1[4 * a + 2 * b + 1], p2[2 * a + b], kShell1, on, m);
+#pragma unroll 1
             for (int c = 0; c < 2; c++)
-                shell_split(rd, &p0[8 * a + 4 * b + 2 * c], &p0[8 * a + 4 * b + 2 * c + 1], p1[4 * a + 2 * b + c], kShell0);
+                shell_split(rd, &p0[8 * a + 4 * b + 2 * c], &p0[8 * a + 4 * b + 2 * c + 1], p1[4 * a + 2 * b + c], kShell0, on, m);
         }
     }
 }
 
 // ref silk_decode_pulses + silk_decode_signs (src/silk.cpp:898, 1436)
-OPUS_HD void silk_parse_pulses(RangeDec& rd, int16_t* pulses, int signalType, int quantOffsetType, int frame_length) {
-    int sum_pulses[20], nLshifts[20];
-    const int rate = rd_icdf(rd, kRateLevelsIcdf + (signalType >> 1) * 9, 8);
+OPUS_HD void silk_parse_pulses(RangeDec& rd, int16_t* pulses, int signalType, int quantOffsetType, int frame_length, bool on, unsigned m) {
+    int sum_pulses[kSilkMaxBlocks], nLshifts[kSilkMaxBlocks];
     int iter = frame_length >> 4;
     if (iter * 16 < frame_length) iter++;
-    const uint8_t* cdf = kPulsesPerBlockIcdf + rate * 18;
-    for (int i = 0; i < iter; i++) {
-        nLshifts[i] = 0;
-        sum_pulses[i] = rd_icdf(rd, cdf, 8);
-        while (sum_pulses[i] == 17) {
-            nLshifts[i]++;
-            sum_pulses[i] = rd_icdf(rd, kPulsesPerBlockIcdf + 9 * 18 + (nLshifts[i] == 10), 8);
-        }
-    }
-    for (int i = 0; i < iter; i++) {
-        if (sum_pulses[i] > 0) shell_decode(rd, pulses + 16 * i, sum_pulses[i]);
-        else for (int k = 0; k < 16; k++) pulses[16 * i + k] = 0;
-    }
-    const uint8_t lsb[2] = {120, 0};
-    for (int i = 0; i < iter; i++) {
-        if (nLshifts[i] > 0) {
-            const int nLS = nLshifts[i];
-            int16_t* pp = pulses + 16 * i;
-            for (int k = 0; k < 16; k++) {
-                s32 abs_q = pp[k];
-                for (int j = 0; j < nLS; j++) {
-                    abs_q = shl32(abs_q, 1);
-                    abs_q += rd_icdf(rd, lsb, 8);
-                }
-                pp[k] = (int16_t)abs_q;
+    const uint8_t* cdf = kPulsesPerBlockIcdf;
+    if (on) cdf += 18 * rd_icdf_tab(rd, kRateLevelsIcdf + (signalType >> 1) * 9, 8);
+#pragma unroll 1
+    for (int i = 0; i < kSilkMaxBlocks; i++) {
+        warp_converge(m);
+        if (on && i < iter) {
+            nLshifts[i] = 0;
+            sum_pulses[i] = rd_icdf_tab(rd, cdf, 8);
+#pragma unroll 1
+            while (sum_pulses[i] == 17) {
+                nLshifts[i]++;
+                sum_pulses[i] = rd_icdf_tab(rd, kPulsesPerBlockIcdf + 9 * 18 + (nLshifts[i] == 10), 8);
             }
-            sum_pulses[i] |= nLS << 5;
         }
     }
-    uint8_t icdf[2];
-    icdf[1] = 0;
+#pragma unroll 1
+    for (int i = 0; i < kSilkMaxBlocks; i++) {
+        const bool blk = on && i < iter;
+        const bool coded = blk && sum_pulses[i] > 0;
+        alignas(16) int16_t p0[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        shell_decode(rd, p0, coded ? sum_pulses[i] : 0, coded, m);
+        if (blk) ld_block16(pulses + 16 * i, p0);
+    }
+    if (on) {
+#pragma unroll 1
+        for (int i = 0; i < iter; i++) {
+            if (nLshifts[i] > 0) {
+                const int nLS = nLshifts[i];
+                int16_t* pp = pulses + 16 * i;
+#pragma unroll 1
+                for (int k = 0; k < 16; k++) {
+                    s32 abs_q = pp[k];
+#pragma unroll 1
+                    for (int j = 0; j < nLS; j++) {
+                        abs_q = shl32(abs_q, 1);
+                        abs_q += rd_icdf2(rd, 120, 8);
+                    }
+                    pp[k] = (int16_t)abs_q;
+                }
+                sum_pulses[i] |= nLS << 5;
+            }
+        }
+    }
     const uint8_t* icdf_ptr = kSignIcdf + smulbb(7, quantOffsetType + (signalType << 1));
     const int nblk = (frame_length + 8) >> 4;
-    for (int i = 0; i < nblk; i++) {
-        const int p = sum_pulses[i];
-        if (p > 0) {
-            icdf[0] = icdf_ptr[imin(p & 0x1F, 6)];
+#pragma unroll 1
+    for (int i = 0; i < kSilkMaxBlocks; i++) {
+        warp_converge(m);
+        if (on && i < nblk && sum_pulses[i] > 0) {
+            const u32 p0 = icdf_ptr[imin(sum_pulses[i] & 0x1F, 6)];
+            // the block's 16 magnitudes come in and go out as two 16-byte words
+            alignas(16) int16_t q[16];
+            ld_block16(q, pulses + 16 * i);
+#pragma unroll
             for (int j = 0; j < 16; j++)
-                if (pulses[16 * i + j] > 0) pulses[16 * i + j] = (int16_t)(pulses[16 * i + j] * ((rd_icdf(rd, icdf, 8) << 1) - 1));
+                if (q[j] > 0) q[j] = (int16_t)(q[j] * ((rd_icdf2(rd, p0, 8) << 1) - 1));
+            ld_block16(pulses + 16 * i, q);
         }
     }
 }
@@ -255,7 +290,7 @@ OPUS_HD void silk_parse_pulses(RangeDec& rd, int16_t* pulses, int signalType, in
 OPUS_HD void silk_parse_stereo_pred(RangeDec& rd, int32_t* pred_Q13) {
     const uint8_t uni3[3] = {171, 85, 0}, uni5[5] = {205, 154, 102, 51, 0};
     int ix[2][3];
-    int n = rd_icdf(rd, kStereoJointIcdf, 8);
+    int n = rd_icdf_tab(rd, kStereoJointIcdf, 8);
     ix[0][2] = n / 5;
     ix[1][2] = n - 5 * ix[0][2];
     for (n = 0; n < 2; n++) {
@@ -272,8 +307,10 @@ OPUS_HD void silk_parse_stereo_pred(RangeDec& rd, int32_t* pred_Q13) {
 }
 
 // The SILK part of one Opus frame as silk_Decode reads it (ref src/silk.cpp:1565-1697, lostFlag = 0, one
-// 20 ms frame per packet).  `scratch` receives the discarded LBRR pulses.
-OPUS_HD void silk_parse_frame(RangeDec& rd, SilkFrame& f, int fs_kHz, int nch) {
+// 20 ms frame per packet).  Every lane named in `m` calls this; the four possible (side information + pulses) units of a
+// frame -- the LBRR copy of either channel, which regular decoding skips by parsing it (ref :1590-1616), then the
+// channels themselves -- go through one call site, in lock step.
+OPUS_HD void silk_parse_frame(RangeDec& rd, SilkFrame& f, int fs_kHz, int nch, unsigned m) {
     const int frame_length = 20 * fs_kHz;
     int vad[2] = {0, 0}, lbrr[2] = {0, 0};
     f.fs_kHz = (uint8_t)fs_kHz; f.nch = (uint8_t)nch; f.mid_only = 0; f.present = 1;
@@ -282,36 +319,24 @@ OPUS_HD void silk_parse_frame(RangeDec& rd, SilkFrame& f, int fs_kHz, int nch) {
         vad[n] = rd_bit_logp(rd, 1);
         lbrr[n] = rd_bit_logp(rd, 1);
     }
-    // regular decoding skips the LBRR (FEC) copy of the previous frame by parsing it (ref :1590-1616)
-    for (int n = 0; n < nch; n++) {
-        if (lbrr[n]) {
-            if (nch == 2 && n == 0) {
-                int32_t tmp[2];
-                silk_parse_stereo_pred(rd, tmp);
-                if (lbrr[1] == 0) {
-                    const uint8_t t[2] = {64, 0};
-                    rd_icdf(rd, t, 8);
-                }
-            }
-            silk_parse_indices(rd, f.idx[n], fs_kHz, 1);
-            silk_parse_pulses(rd, f.pulses[n], f.idx[n].signalType, f.idx[n].quantOffsetType, frame_length);
-        }
-    }
     int mid_only = 0;
-    if (nch == 2) {
-        silk_parse_stereo_pred(rd, f.ms_pred_Q13);
-        if (vad[1] == 0) {
-            const uint8_t t[2] = {64, 0};
-            mid_only = rd_icdf(rd, t, 8);
+#pragma unroll 1
+    for (int slot = 0; slot < 4; slot++) {
+        warp_converge(m);
+        const int n = slot & 1, is_lbrr = slot < 2;
+        if (n == 0 && nch == 2 && (!is_lbrr || lbrr[0])) {  // the stereo predictor (and mid-only flag) precede channel 0
+            int32_t tmp[2];
+            silk_parse_stereo_pred(rd, is_lbrr ? tmp : f.ms_pred_Q13);
+            if ((is_lbrr ? lbrr[1] : vad[1]) == 0) {
+                const int flag = rd_icdf2(rd, 64, 8);
+                if (!is_lbrr) mid_only = flag;
+            }
         }
+        const bool on = n < nch && (is_lbrr ? lbrr[n] != 0 : (n == 0 || !mid_only));
+        silk_parse_indices(rd, f.idx[n], fs_kHz, is_lbrr ? 1 : vad[n], on, m);
+        silk_parse_pulses(rd, f.pulses[n], f.idx[n].signalType, f.idx[n].quantOffsetType, frame_length, on, m);
     }
     f.mid_only = (uint8_t)mid_only;
-    for (int n = 0; n < nch; n++) {
-        if (n == 0 || !mid_only) {
-            silk_parse_indices(rd, f.idx[n], fs_kHz, vad[n]);
-            silk_parse_pulses(rd, f.pulses[n], f.idx[n].signalType, f.idx[n].quantOffsetType, frame_length);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

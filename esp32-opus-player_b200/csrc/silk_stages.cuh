@@ -24,9 +24,6 @@
 
 namespace opusb200 {
 
-#if !defined(__CUDACC__)
-struct uint2 { uint32_t x, y; };
-#endif
 OPUS_HD uint2 make_uint2_(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
 
 enum { kSilkRing = 384 };  // >= max pitch lag (288) + 2 + one sub-frame (80), a multiple of 4

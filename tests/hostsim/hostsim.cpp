@@ -225,7 +225,7 @@ int hs_opus_decode(void* dv, int toc, const uint8_t* payload, int len, int16_t* 
     ParseCtx p;
     memset(&p, 0, sizeof(p));
     bool celt, fade;
-    const int oflags = opus_parse_prologue(p, payload, len, toc, d->prev_mode, CC, hdr, sf, &celt, &fade);
+    const int oflags = opus_parse_prologue(p, payload, len, toc, d->prev_mode, CC, hdr, sf, &celt, &fade, 0u);
     if (!celt && !(oflags & OF_HAS_SILK) && opus_toc_mode(toc) != MODE_CELT_ONLY && ((toc & 4) ? 2 : 1) != CC) return OPUSB_UNIMPLEMENTED;
     if (oflags & OF_HAS_SILK) hs_silk_frame(d->silk, sf, (oflags & OF_SILK_REINIT) != 0, pcm_silk);
     if (oflags & OF_RESET_CELT) {  // OPUS_RESET_STATE (ref src/celt.cpp:2479)
