@@ -201,37 +201,30 @@ OPUS_HD void bfly5(Cpx* f, int i, int u, const FftStage& s) {
     F[3 * m] = csub(s11, s12);
 }
 
-// FFT plans for nfft = 480, 240, 120, 60 (shift 0..3), in execution order (ref opus_fft_impl :2997 with the
-// factor lists of fft_state48000_960_{0..3}, :589-626).  fstride already includes << shift.
-OPUS_HD int fft_plan(int shift, FftStage* st) {
-    int n = 0;
-    if (shift == 0) {
-        st[n++] = FftStage{4, 1, 120, 120, 4};
-        st[n++] = FftStage{2, 4, 60, 0, 0};
-        st[n++] = FftStage{4, 8, 15, 15, 32};
-        st[n++] = FftStage{3, 32, 5, 5, 96};
-        st[n++] = FftStage{5, 96, 1, 1, 1};
-    } else if (shift == 1) {
-        st[n++] = FftStage{4, 1, 60, 120, 4};
-        st[n++] = FftStage{4, 4, 15, 30, 16};
-        st[n++] = FftStage{3, 16, 5, 10, 48};
-        st[n++] = FftStage{5, 48, 1, 2, 1};
-    } else if (shift == 2) {
-        st[n++] = FftStage{4, 1, 30, 120, 4};
-        st[n++] = FftStage{2, 4, 15, 0, 0};
-        st[n++] = FftStage{3, 8, 5, 20, 24};
-        st[n++] = FftStage{5, 24, 1, 4, 1};
-    } else {
-        st[n++] = FftStage{4, 1, 15, 120, 4};
-        st[n++] = FftStage{3, 4, 5, 40, 12};
-        st[n++] = FftStage{5, 12, 1, 8, 1};
+// One FFT stage with its shape known at compile time: the unit -> (block, i, j) arithmetic folds into shifts and
+// multiply-highs, and each butterfly is compiled for its own m / twiddle stride.
+template <int kRadix, int kM, int kN, int kFstride, int kMM>
+OPUS_HD void fft_stage(const Lanes& L, int32_t* work, int N2, int nblk) {
+    constexpr int units = kRadix == 2 ? kN * 4 : kN * kM;
+    const FftStage g = FftStage{(uint8_t)kRadix, (uint8_t)kM, (uint8_t)kN, (uint8_t)kFstride, (uint8_t)kMM};
+    for (int t = L.lane; t < nblk * units; t += kLanes) {
+        const int blk = nblk > 1 ? t / units : 0;
+        Cpx* f = (Cpx*)(work + blk * N2);
+        const int u = t - blk * units;
+        const int i = u / kM, j = u - i * kM;
+        if (kRadix == 4) bfly4(f, i, j, g);
+        else if (kRadix == 2) bfly2(f, u);
+        else if (kRadix == 3) bfly3(f, i, j, g);
+        else bfly5(f, i, j, g);
     }
-    return n;
+    L.sync();
 }
 
 // Inverse MDCT of `nblk` interleaved blocks (ref clt_mdct_backward :3204 without the TDAC mirror, which
 // needs the previous block and is done by tdac_* below).  freq: N coefficients, block b at freq[b + k*nblk].
 // work: N int32 (nblk FFTs of N4 complex points).  On return work[b*N2 + k] = raw post-rotated y_b[k].
+// FFT plans for nfft = 480, 240, 120, 60 (shift 0..3), in execution order (ref opus_fft_impl :2997 with the
+// factor lists of fft_state48000_960_{0..3}, :589-626); the twiddle stride already includes << shift.
 OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int shift, int nblk) {
     const int Nm = 1920 >> shift, N2 = Nm >> 1, N4 = Nm >> 2;
     const int16_t* trig = kMdctTrig + (shift == 0 ? 0 : shift == 1 ? 960 : shift == 2 ? 1440 : 1680);
@@ -250,23 +243,26 @@ OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int s
         work[b * N2 + 2 * rev] = yi;
     }
     L.sync();
-    FftStage st[5];
-    const int ns = fft_plan(shift, st);
-    for (int s = 0; s < ns; s++) {
-        const FftStage g = st[s];
-        const int units = (g.radix == 2 ? g.N * 4 : g.N * g.m);
-        const SmallDiv byUnits(units), byM(g.m);
-        for (int t = L.lane; t < nblk * units; t += kLanes) {
-            const int blk = nblk > 1 ? byUnits.div(t) : 0;
-            Cpx* f = (Cpx*)(work + blk * N2);
-            const int u = t - blk * units;
-            const int i = byM.div(u), j = u - i * g.m;
-            if (g.radix == 4) bfly4(f, i, j, g);
-            else if (g.radix == 2) bfly2(f, u);
-            else if (g.radix == 3) bfly3(f, i, j, g);
-            else bfly5(f, i, j, g);
-        }
-        L.sync();
+    if (shift == 0) {
+        fft_stage<4, 1, 120, 120, 4>(L, work, N2, nblk);
+        fft_stage<2, 4, 60, 0, 0>(L, work, N2, nblk);
+        fft_stage<4, 8, 15, 15, 32>(L, work, N2, nblk);
+        fft_stage<3, 32, 5, 5, 96>(L, work, N2, nblk);
+        fft_stage<5, 96, 1, 1, 1>(L, work, N2, nblk);
+    } else if (shift == 1) {
+        fft_stage<4, 1, 60, 120, 4>(L, work, N2, nblk);
+        fft_stage<4, 4, 15, 30, 16>(L, work, N2, nblk);
+        fft_stage<3, 16, 5, 10, 48>(L, work, N2, nblk);
+        fft_stage<5, 48, 1, 2, 1>(L, work, N2, nblk);
+    } else if (shift == 2) {
+        fft_stage<4, 1, 30, 120, 4>(L, work, N2, nblk);
+        fft_stage<2, 4, 15, 0, 0>(L, work, N2, nblk);
+        fft_stage<3, 8, 5, 20, 24>(L, work, N2, nblk);
+        fft_stage<5, 24, 1, 4, 1>(L, work, N2, nblk);
+    } else {
+        fft_stage<4, 1, 15, 120, 4>(L, work, N2, nblk);
+        fft_stage<3, 4, 5, 40, 12>(L, work, N2, nblk);
+        fft_stage<5, 12, 1, 8, 1>(L, work, N2, nblk);
     }
     // post-rotation, in place from both ends (ref :3244-3277)
     const int half = (N4 + 1) >> 1;
