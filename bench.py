@@ -40,10 +40,9 @@ WORKLOADS = {
     "hybrid_swb": (0x68, 99, 1, 8192, 0.6, "configs[3]: %d concurrent hybrid SWB mono 20 ms streams per GPU, 100 B packets"),
 }
 TOC, PAYLOAD, CHANNELS = 0xFC, 159, 2
-# dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full captures of the
-# 20 480-frame run (profiles/r01_v2_ncu_summary_entropy_bands.txt, profiles/r01_v3_ncu_summary_bands_imdct_postfilter.txt);
-# one launch of the bench step moves this times its frame count
-NCU_DRAM_BYTES_PER_FRAME = {"entropy": 57.81e6 / 20480, "bands": 93.56e6 / 20480, "imdct": 178.24e6 / 20480, "postfilter": 293.44e6 / 20480}
+# dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full capture of the
+# 20 480-frame run (profiles/r01_v8_ncu_summary_celt.txt); one launch of the bench step moves this times its frame count
+NCU_DRAM_BYTES_PER_FRAME = {"entropy": 47.59e6 / 20480, "bands": 91.98e6 / 20480, "imdct": 189.06e6 / 20480, "postfilter": 294.03e6 / 20480}
 
 
 def peaks():

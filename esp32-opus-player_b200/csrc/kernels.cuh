@@ -44,7 +44,7 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 6)  // 80 registers: 24 warps per SM measured faster than 16 (128 regs) or 32 (64 regs, spills)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
           BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
