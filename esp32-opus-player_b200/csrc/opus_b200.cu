@@ -274,7 +274,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
         const int chains = n_sel * P.CC;
         const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs five empty launches
-        k_silk_params<<<wide, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P);
+        k_silk_params<<<c->n_sm * 12, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P);
         k_silk_core<<<(chains + 31) / 32, 32, kSilkCoreSmem, s>>>(c->d_hdr, c->d_fe, B, P);
         k_silk_unmix<<<wide, 256, 0, s>>>(B, P);
         k_silk_up2<<<(chains + 31) / 32, 32, 0, s>>>(B, P);

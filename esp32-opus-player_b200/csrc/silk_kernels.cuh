@@ -177,8 +177,11 @@ __device__ __forceinline__ SilkHist silk_hist(const SilkBufs& B, size_t t, int s
 __global__ void __launch_bounds__(256)
 k_silk_unmix(SilkBufs B, DevParams P) {
     if (*B.any_silk == 0) return;
+    // one warp per frame: the frames are independent and each is a few hundred samples, a block per frame would spend
+    // its time waiting for the handful of dependent loads in front of every frame
     const int nfr = P.n_sel * P.n_frames;
-    for (int local = blockIdx.x; local < nfr; local += gridDim.x) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int local = blockIdx.x * wpb + (threadIdx.x >> 5); local < nfr; local += gridDim.x * wpb) {
         const int s = P.first_stream + local / P.n_frames;
         const size_t t = (size_t)P.first_stream * P.n_frames + local;
         const SilkPost& post = B.post[t];
@@ -188,7 +191,7 @@ k_silk_unmix(SilkBufs B, DevParams P) {
         const int16_t* mid = B.xq + (t * 2) * kXqRow;
         if (P.CC == 1) {
             int16_t* o = B.lr + (t * 2) * kXqRow;
-            for (int i = threadIdx.x; i < L; i += blockDim.x) o[i] = i == 0 ? (int16_t)h.m1 : mid[i - 1];
+            for (int i = lane; i < L; i += 32) o[i] = i == 0 ? (int16_t)h.m1 : mid[i - 1];
         } else {
             const int16_t* side = B.xq + (t * 2 + 1) * kXqRow;
             const bool has_side = post.dec_mask & 2;
@@ -196,7 +199,7 @@ k_silk_unmix(SilkBufs B, DevParams P) {
             U.setup(B.frames[t].ms_pred_Q13, h.p0, h.p1, fs);
             int16_t* ol = B.lr + (t * 2) * kXqRow;
             int16_t* orr = B.lr + (t * 2 + 1) * kXqRow;
-            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            for (int i = lane; i < L; i += 32) {
                 const s32 x1a = i >= 2 ? mid[i - 2] : (i == 1 ? h.m1 : h.m2);
                 const s32 x1b = i >= 1 ? mid[i - 1] : h.m1;
                 const s32 x1c = mid[i];
