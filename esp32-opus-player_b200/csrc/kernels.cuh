@@ -326,11 +326,15 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     for (int q = 0; q < DE_STAGES - 1; q++) prefetch();
 
     int f = 0, j0 = 0, my_n = 0;
+    bool silk_only = false;
     for (int q = 0; q < T; q++) {
         const int w = min(DE_TW, N - j0);
         if (j0 == 0) {
             const size_t my_t = (size_t)my_s * P.n_frames + f;
             my_n = live ? fe[my_t].celt_n : 0;  // samples of this frame that carry CELT output (0, or 120 for a fade-out frame)
+            // a frame with no CELT layer whose SILK layer is decoded gets its PCM from k_silk_fir alone: nothing to store here
+            const int sk = live ? fe[my_t].skip : 0;
+            silk_only = live && my_n == 0 && (sk & FS_HAS_SILK) && !(sk & FS_DROPPED);
             if (live && my_c == 0) status[my_t] = (fe[my_t].skip & FS_DROPPED) ? OPUSB_FRAME_SKIPPED : hdr[my_t].status;
         }
         prefetch();
@@ -369,7 +373,7 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
                 ow[2 * k] = __byte_perm(l, r, 0x5410);
                 ow[2 * k + 1] = __byte_perm(l, r, 0x7632);
             }
-            if (live) {
+            if (live && !silk_only) {
                 const int h0 = right ? DE_TW / 2 : 0;  // first frame of this lane's half inside the tile
                 uint32_t* dst = reinterpret_cast<uint32_t*>(out0 + (size_t)f * N * 2) + j0 + h0;
                 if (w == DE_TW) {
@@ -382,7 +386,7 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
                         if (h0 + k < w) dst[k] = ow[k];
                 }
             }
-        } else if (live) {
+        } else if (live && !silk_only) {
             uint32_t* dst = reinterpret_cast<uint32_t*>(out0 + (size_t)f * N + j0);  // N and j0 are even: 4-byte aligned
             if (w == DE_TW && (((size_t)f * N + j0) & 7) == 0) {
 #pragma unroll

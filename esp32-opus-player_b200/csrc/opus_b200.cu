@@ -278,7 +278,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         k_silk_core<<<(chains + 31) / 32, 32, kSilkCoreSmem, s>>>(c->d_hdr, c->d_fe, B, P);
         k_silk_unmix<<<wide, 256, 0, s>>>(B, P);
         k_silk_up2<<<(chains + 31) / 32, 32, 0, s>>>(B, P);
-        k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, d_pcm, P);
+        k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, c->d_fe, d_pcm, P);
         c->launches += 5;
     }
     if (timed) cudaEventRecord(c->ev[7], s);

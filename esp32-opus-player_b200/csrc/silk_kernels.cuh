@@ -281,7 +281,7 @@ k_silk_up2(SilkBufs B, DevParams P) {
 // ------------------------------------------------------------------------------------------------
 enum { FIR_WARPS = 8 };
 __global__ void __launch_bounds__(32 * FIR_WARPS)
-k_silk_fir(SilkBufs B, int16_t* __restrict__ pcm, DevParams P) {
+k_silk_fir(SilkBufs B, const FrameEnergy* __restrict__ fe, int16_t* __restrict__ pcm, DevParams P) {
     if (*B.any_silk == 0) return;
     // one warp per frame; the up-sampled rows of the frame are staged in shared memory (every output reads 8
     // neighbouring taps of them), warps run independently of each other
@@ -302,11 +302,12 @@ k_silk_fir(SilkBufs B, int16_t* __restrict__ pcm, DevParams P) {
                 reinterpret_cast<uint4*>(my[n])[w] = reinterpret_cast<const uint4*>(B.up + (t * 2 + n) * kUpRow)[w];
         __syncwarp();
         const s32 inv = silk_inv_ratio_Q16(fs);
+        const bool add = fe[t].celt_n != 0;  // else k_deemph left this frame's PCM to us (no CELT layer)
         // two interleaved int16 samples (one stereo frame, or two mono samples) per lane and store
         uint32_t* o = reinterpret_cast<uint32_t*>(pcm + t * (size_t)(kMaxFrame * CC));
 #pragma unroll 2
         for (int i = lane; i < kMaxFrame * CC / 2; i += 32) {
-            const uint32_t old = o[i];
+            const uint32_t old = add ? o[i] : 0u;
             s32 a, b;
             if (CC == 2) { a = silk_fir_sample(my[0], i, fs, inv); b = silk_fir_sample(my[1], i, fs, inv); }
             else { a = silk_fir_sample(my[0], 2 * i, fs, inv); b = silk_fir_sample(my[0], 2 * i + 1, fs, inv); }
