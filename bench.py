@@ -38,8 +38,15 @@ WORKLOADS = {
     "silk": (0x48, 59, 1, 16384, 0.4, "configs[2]: %d concurrent SILK-only WB mono 20 ms streams per GPU, 60 B packets"),
     "hybrid": (0x7C, 159, 2, 4096, 1.1, "configs[3]: %d concurrent hybrid FB stereo 20 ms streams per GPU, 160 B packets"),
     "hybrid_swb": (0x68, 99, 1, 8192, 0.6, "configs[3]: %d concurrent hybrid SWB mono 20 ms streams per GPU, 100 B packets"),
+    # configs[4]: a quarter each of CELT FB stereo / SILK WB mono / hybrid FB stereo / hybrid SWB mono, the stereo and the mono streams in a decoder context each
+    # (the reference plays 20 ms frames only, SURVEY F1, so the short-CELT quarter of SURVEY 8d config 5 is hybrid SWB here);
+    # 65 536 streams over 8 GPUs = 8192 per GPU.  TOC/payload/ops below are placeholders: MIX gives the components.
+    "mix": (0xFC, 159, 2, 8192, 0.775, "configs[4]: %d concurrent mixed-mode streams per GPU (25%% each CELT FB stereo 160 B, SILK WB mono 60 B, "
+            "hybrid FB stereo 160 B, hybrid SWB mono 100 B; one decoder context per channel count)"),
 }
+MIX = [(0xFC, 159, 1.0), (0x48, 59, 0.4), (0x7C, 159, 1.1), (0x68, 99, 0.6)]  # (TOC, payload bytes, relative ops per frame)
 TOC, PAYLOAD, CHANNELS = 0xFC, 159, 2
+COMPONENTS = None  # mixed workload: [(toc, payload, ops_rel)]
 # dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full capture of the
 # 20 480-frame run (profiles/r01_v8_ncu_summary_celt.txt); one launch of the bench step moves this times its frame count
 NCU_DRAM_BYTES_PER_FRAME = {"entropy": 47.59e6 / 20480, "bands": 91.98e6 / 20480, "imdct": 189.06e6 / 20480, "postfilter": 294.03e6 / 20480}
@@ -104,16 +111,23 @@ def cpu_reference(n_frames, target_s, jobs=None):
     from oracle import ref
 
     cores = jobs or os.cpu_count() or 1
-    t0 = time.perf_counter()
-    ref.decode_synth_stream(TOC, PAYLOAD + 1, CHANNELS, 250, want_pcm=False)
-    rate1 = 250 * 0.02 / max(time.perf_counter() - t0, 1e-6)  # x realtime on one core
-    per_core = max(1, int(round(target_s * rate1 / (n_frames * 0.02))))
-    n_streams = cores * per_core
-    wall, hashes = ref.bench_fork(TOC, PAYLOAD + 1, CHANNELS, n_streams, n_frames, jobs=cores)
-    audio = n_streams * n_frames * 0.02
-    return {"value": audio / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+    parts = COMPONENTS or [(TOC, PAYLOAD, 1.0)]
+    wall_t, audio_t, streams_t = 0.0, 0.0, 0
+    for toc, payload, _ in parts:  # a mixed workload is timed one mode after the other, an equal number of streams each
+        t0 = time.perf_counter()
+        ref.decode_synth_stream(toc, payload + 1, 2 if toc & 4 else 1, 250, want_pcm=False)
+        rate1 = 250 * 0.02 / max(time.perf_counter() - t0, 1e-6)  # x realtime on one core
+        if len(parts) > 1:
+            rate1 = 400.0  # a mixed workload: the same stream count for every mode
+        per_core = max(1, int(round(target_s / len(parts) * rate1 / (n_frames * 0.02))))
+        n_streams = cores * per_core
+        wall, hashes = ref.bench_fork(toc, payload + 1, 2 if toc & 4 else 1, n_streams, n_frames, jobs=cores)
+        wall_t += wall
+        audio_t += n_streams * n_frames * 0.02
+        streams_t += n_streams
+    return {"value": audio_t / wall_t, "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": "%d streams x %d frames (%.0f audio-s) of the same corpus, one forked reference decoder per core, %.1f s wall"
-                      % (n_streams, n_frames, audio, wall), "wall_s": wall, "audio_s": audio}
+                      % (streams_t, n_frames, audio_t, wall_t), "wall_s": wall_t, "audio_s": audio_t}
 
 
 def run_reference(args, rank, world):
@@ -146,12 +160,15 @@ def main():
     ap.add_argument("--workload", default="celt", choices=sorted(WORKLOADS), help="celt = BASELINE.json's metric config (default)")
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
     ap.add_argument("--frames", type=int, default=50, help="frames per stream per step (50 = 1 s of audio)")
+    ap.add_argument("--mix-order", default="grouped", choices=["grouped", "interleaved"],
+                    help="mix workload: streams of one mode contiguous in the decoder context (what the host scheduler does) or mode = index mod 4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    global TOC, PAYLOAD, CHANNELS, METRIC
+    global TOC, PAYLOAD, CHANNELS, METRIC, COMPONENTS
     TOC, PAYLOAD, CHANNELS, def_streams, ops_rel, wl_desc = WORKLOADS[args.workload]
+    COMPONENTS = MIX if args.workload == "mix" else None
     args.streams = args.streams or def_streams
     if args.workload != "celt":
         METRIC = "decoded audio-sec/sec (x realtime), %s workload (not the BASELINE.json headline)" % args.workload
@@ -179,40 +196,81 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     S, F, K, W = args.streams, args.frames, args.steps, args.warmup
     n_steps = W + K
-    CC = CHANNELS
-    bytes_per_frame_algo = (PAYLOAD + 1) + 960 * CC * 2  # packet in + int16 PCM out
+    lib = pkg.lib()
+
+    # ---- synthetic corpus: global stream g = rank + world * s (round-robin shard), n_steps*F frames each.
+    # A decoder context has ONE output channel count (opus_decoder_init's `channels`), so a mixed workload becomes one
+    # part per channel count -- what the player layer does with mono and stereo files (opus_player.cpp RoundScheduler).
+    if COMPONENTS:
+        nm = len(COMPONENTS)
+        mode_of = [(s % nm) if args.mix_order == "interleaved" else min(nm - 1, s * nm // S) for s in range(S)]
+    else:
+        mode_of = [0] * S
+    comps = COMPONENTS or [(TOC, PAYLOAD, ops_rel)]
+    ops_rel = float(np.mean([comps[m][2] for m in mode_of]))
     ops_per_frame = OPS_PER_FRAME * ops_rel
 
-    # ---- synthetic corpus: global stream g = rank + world * s (round-robin shard), n_steps*F frames each
-    lib = pkg.lib()
-    nb_step = S * F * PAYLOAD
-    h_bytes = [pkg.api.PinnedArray(nb_step, np.uint8) for _ in range(n_steps)]
-    h_frames = [pkg.api.PinnedArray((S, F), pkg.FRAME_DTYPE) for _ in range(n_steps)]
-    # stream ids are interleaved across ranks (shard.rank_corpus seeds every stream by its GLOBAL id)
-    full, fr_full = pkg.shard.rank_corpus(pkg.api, rank, world, S, n_steps * F, PAYLOAD, TOC)
-    full = full.reshape(S, n_steps, F * PAYLOAD)
-    for k in range(n_steps):
-        h_bytes[k].array[:] = full[:, k, :].reshape(-1)
-        fr = h_frames[k].array
-        fr["offset"] = (np.arange(S * F, dtype=np.uint32) * PAYLOAD).reshape(S, F)
-        fr["len"] = PAYLOAD
-        fr["toc"] = TOC
-        fr["flags"] = 0
-    del full, fr_full
-    h_pcm = pkg.api.PinnedArray((S, F, 960, CC), np.int16)
-    h_status = pkg.api.PinnedArray((S, F), np.int32)
+    class Part:
+        """The streams of one output channel count: pinned packets per step, device copies, a decoder context."""
 
-    dec = pkg.BatchDecoder(S, F, channels=CC, device=local_rank)
-    d_bytes = [torch.from_numpy(h_bytes[k].array).cuda() for k in range(n_steps)]
-    d_frames = [torch.from_numpy(h_frames[k].array.view(np.uint8).reshape(-1)).cuda() for k in range(n_steps)]
-    d_pcm = torch.empty(S * F * 960 * CC, dtype=torch.int16, device="cuda")
-    d_status = torch.empty(S * F, dtype=torch.int32, device="cuda")
+        def __init__(self, cc, ids):
+            self.cc, self.ids, self.n = cc, ids, len(ids)
+            self.pay = np.array([comps[mode_of[s]][1] for s in ids], np.int64)
+            self.toc = np.array([comps[mode_of[s]][0] for s in ids], np.uint8)
+            base = np.concatenate([[0], np.cumsum(self.pay * F)])  # byte offset of every stream's F packets inside one step
+            self.nb_step = int(base[-1])
+            self.h_bytes = [pkg.api.PinnedArray(self.nb_step, np.uint8) for _ in range(n_steps)]
+            self.h_frames = [pkg.api.PinnedArray((self.n, F), pkg.FRAME_DTYPE) for _ in range(n_steps)]
+            if len(set(self.pay.tolist())) == 1 and len(set(self.toc.tolist())) == 1 and ids == list(range(S)):
+                full, _ = pkg.shard.rank_corpus(pkg.api, rank, world, S, n_steps * F, int(self.pay[0]), int(self.toc[0]))
+                full = full.reshape(S, n_steps, F * int(self.pay[0]))
+                for k in range(n_steps):
+                    self.h_bytes[k].array[:] = full[:, k, :].reshape(-1)
+                del full
+            else:
+                for j, s in enumerate(ids):  # payload from the SURVEY generator seeded by the GLOBAL stream id
+                    pl = int(self.pay[j])
+                    b1, _ = pkg.api.synth_corpus(1, n_steps * F, pl, int(self.toc[j]), first_stream=pkg.shard.global_id(s, rank, world))
+                    b1 = b1.reshape(n_steps, F * pl)
+                    for k in range(n_steps):
+                        self.h_bytes[k].array[base[j]:base[j + 1]] = b1[k]
+            for k in range(n_steps):
+                fr = self.h_frames[k].array
+                fr["offset"] = (base[:-1, None] + np.arange(F)[None, :] * self.pay[:, None]).astype(np.uint32)
+                fr["len"] = self.pay[:, None].astype(np.uint16)
+                fr["toc"] = self.toc[:, None]
+                fr["flags"] = 0
+            self.dec = pkg.BatchDecoder(self.n, F, channels=cc, device=local_rank)
+            self.d_bytes = [torch.from_numpy(self.h_bytes[k].array).cuda() for k in range(n_steps)]
+            self.d_frames = [torch.from_numpy(self.h_frames[k].array.view(np.uint8).reshape(-1)).cuda() for k in range(n_steps)]
+            self.d_pcm = torch.empty(self.n * F * 960 * cc, dtype=torch.int16, device="cuda")
+            self.d_status = torch.empty(self.n * F, dtype=torch.int32, device="cuda")
+
+        def step_device(self, k, stream):
+            rc = self.dec.decode_device(self.d_bytes[k].data_ptr(), self.nb_step, self.d_frames[k].data_ptr(), F, self.d_pcm.data_ptr(),
+                                        self.d_status.data_ptr(), stream)
+            if rc:
+                raise RuntimeError("dm_decode_device rc=%d" % rc)
+
+        def outs(self):
+            return (pkg.api.PinnedArray((self.n, F, 960, self.cc), np.int16).array, pkg.api.PinnedArray((self.n, F), np.int32).array)
+
+    def out_channels(toc):
+        return 2 if toc & 4 else 1
+
+    parts = []
+    for cc in (2, 1):
+        ids = [s for s in range(S) if out_channels(comps[mode_of[s]][0]) == cc]
+        if ids:
+            parts.append(Part(cc, ids))
+    nb_step = sum(p.nb_step for p in parts)
+    pcm_bytes_step = sum(p.n * F * 960 * p.cc * 2 for p in parts)
+    bytes_per_frame_algo = (nb_step + S * F + pcm_bytes_step) / (S * F)  # packet in (payload + TOC) + int16 PCM out (SURVEY 8d)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_device(k):
-        rc = dec.decode_device(d_bytes[k].data_ptr(), nb_step, d_frames[k].data_ptr(), F, d_pcm.data_ptr(), d_status.data_ptr(), stream)
-        if rc:
-            raise RuntimeError("dm_decode_device rc=%d" % rc)
+        for p in parts:
+            p.step_device(k, stream)
 
     def barrier():
         if world > 1:
@@ -225,9 +283,8 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = dec.launch_count
+    launches0 = sum(p.dec.launch_count for p in parts)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_acc = {}
     ev0.record()
     for k in range(W, n_steps):
         step_device(k)
@@ -235,58 +292,76 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
-    launches = dec.launch_count - launches0
-    st_status = d_status.cpu().numpy()
-    assert (st_status == 960).all(), "decode errors in the timed region"
-    # per-stage times of the last step (events recorded inside the library on the same stream)
-    stage_acc = dec.stage_times()
+    launches = sum(p.dec.launch_count for p in parts) - launches0
+    for p in parts:
+        assert (p.d_status.cpu().numpy() == 960).all(), "decode errors in the timed region"
+    # per-stage times of the last step (events recorded inside the library on the same stream), summed over the parts
+    stage_acc = {}
+    for p in parts:
+        for name, v in p.dec.stage_times().items():
+            stage_acc[name] = stage_acc.get(name, 0.0) + v
+    device_bytes = sum(p.dec.device_bytes for p in parts)
     ms_max = pkg.shard.max_over_ranks(ms, dist if world > 1 else None, "cuda")
     audio_per_step = S * F * 0.02
     value = pkg.shard.aggregate_rate(K * audio_per_step, world, ms_max * 1e-3)
 
-    # ---- e2e: C ABI with pinned host buffers (fresh decoder so that the same packets are legal input)
+    # ---- e2e: C ABI with pinned host buffers (fresh decoders so that the same packets are legal input)
     e2e = None
     if not args.no_e2e:
-        dec2 = pkg.BatchDecoder(S, F, channels=CC, device=local_rank)
-        # three calls in flight: the kernels of step k+1 overlap the PCM read-back of step k, and step k+2 is already
-        # queued when the host wakes up for step k (decode_many_async/dm_wait); every step's packets come from pinned
-        # host memory and its PCM lands in pinned host memory
+        # three calls in flight per context: the kernels of step k+1 overlap the PCM read-back of step k, and step k+2 is
+        # already queued when the host wakes up for step k (decode_many_async/dm_wait); every step's packets come from
+        # pinned host memory and its PCM lands in pinned host memory
         DEPTH = 3
-        outs = [(h_pcm.array, h_status.array)]
-        for _ in range(DEPTH - 1):
-            outs.append((pkg.api.PinnedArray((S, F, 960, CC), np.int16).array, pkg.api.PinnedArray((S, F), np.int32).array))
+        decs = [pkg.BatchDecoder(p.n, F, channels=p.cc, device=local_rank) for p in parts]
+        outs = [[p.outs() for _ in range(DEPTH)] for p in parts]
+
+        def submit(k):
+            t = []
+            for i, p in enumerate(parts):
+                o = outs[i][k % DEPTH]
+                rc, ticket = decs[i].decode_many_async(p.h_bytes[k].array, p.h_frames[k].array, o[0], o[1])
+                assert rc == 0
+                t.append(ticket)
+            return t
+
+        def wait(tickets):
+            for i, t in enumerate(tickets):
+                assert decs[i].wait(t) == 0
+
         for k in range(W):  # warm-up through the same pipelined call (its staging buffers are allocated on first use)
-            rc, ticket = dec2.decode_many_async(h_bytes[k].array, h_frames[k].array, outs[k % DEPTH][0], outs[k % DEPTH][1])
-            assert rc == 0 and dec2.wait(ticket) == 0
+            wait(submit(k))
         barrier()
         t0 = time.perf_counter()
         pending = []
         ok = True
         for k in range(W, n_steps):
-            o = outs[k % DEPTH]
-            rc, ticket = dec2.decode_many_async(h_bytes[k].array, h_frames[k].array, o[0], o[1])
-            assert rc == 0
-            pending.append((ticket, o))
+            pending.append((k, submit(k)))
             if len(pending) == DEPTH:
-                tk, po = pending.pop(0)
-                assert dec2.wait(tk) == 0
-                ok = ok and bool(po[1][0, 0] == 960 and po[1][-1, -1] == 960)  # the step's result is read on the host
-        last = None
-        for tk, po in pending:
-            assert dec2.wait(tk) == 0
-            last = po
+                kk, tk = pending.pop(0)
+                wait(tk)
+                for i in range(len(parts)):  # the step's result is read on the host
+                    st = outs[i][kk % DEPTH][1]
+                    ok = ok and bool(st[0, 0] == 960 and st[-1, -1] == 960)
+        last_k = None
+        for kk, tk in pending:
+            wait(tk)
+            last_k = kk
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        assert ok and (last[1] == 960).all()
-        # the two legs decode the same stream positions: their last step must agree bit for bit
-        same = bool(np.array_equal(last[0].reshape(-1), d_pcm.cpu().numpy()))
+        same = True
+        for i, p in enumerate(parts):
+            lp, ls = outs[i][last_k % DEPTH]
+            assert ok and (ls == 960).all()
+            # the two legs decode the same stream positions: their last step must agree bit for bit
+            same = same and bool(np.array_equal(lp.reshape(-1), p.d_pcm.cpu().numpy()))
         dt_max = pkg.shard.max_over_ranks(dt, dist if world > 1 else None, "cuda")
         e2e = {"value": pkg.shard.aggregate_rate(K * audio_per_step, world, dt_max), "unit": UNIT,
-               "h2d_bytes_per_step": int(nb_step + S * F * 8), "d2h_bytes_per_step": int(S * F * 960 * CC * 2 + S * F * 4),
+               "h2d_bytes_per_step": int(nb_step + S * F * 8), "d2h_bytes_per_step": int(pcm_bytes_step + S * F * 4),
                "ms_per_step": 1e3 * dt_max / K, "matches_device_leg": same,
                "api": "decode_many_async + dm_wait, %d calls in flight, pinned host buffers" % DEPTH,
-               "kernel_ms_last_call": sum(dec2.stage_times().values())}
-        dec2.close()
+               "kernel_ms_last_call": sum(sum(d.stage_times().values()) for d in decs)}
+        for d in decs:
+            d.close()
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
@@ -309,7 +384,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed-point", "data": "synthetic",
                 "config": {"workload": (wl_desc % S) + ", %d frames (%.1f s) per stream per step" % (F, F * 0.02), "streams_per_gpu": S, "frames_per_step": F, "sharding": "stream i -> GPU i mod N, no collective",
-                           "l2": "inputs and intermediates per step (%.1f GB) exceed L2; every step decodes new packets" % (dec.device_bytes / 1e9)},
+                           **({"mix_order": args.mix_order} if COMPONENTS else {}),
+                           "l2": "inputs and intermediates per step (%.1f GB) exceed L2; every step decodes new packets" % (device_bytes / 1e9)},
                 "clocks": clocks, "roofline": roof, "gpu_launches": int(launches)}
         if e2e:
             line["e2e"] = e2e
@@ -317,7 +393,8 @@ def main():
             cb = cpu_reference(3000 if F * n_steps >= 3000 else F * n_steps, 10.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
-    dec.close()
+    for p in parts:
+        p.dec.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -22,6 +22,7 @@ static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdc
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
+    int silk_lanes = 0;  // chains per warp of the SILK lane-per-chain kernels; 0 = silk_chain_lanes() (OPUSB_SILK_LANES overrides, for tuning)
     // per-stream state
     CeltStreamState* d_state;
     SilkStreamState* d_sstate;
@@ -98,6 +99,7 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
     CU_TRY(c, cudaSetDevice(device));
     CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // quant_partition recursion (<= 5 levels) + per-thread allocation arrays live on the local stack
     CU_TRY(c, cudaDeviceSetLimit(cudaLimitStackSize, 6 * 1024));
     const size_t nfr = (size_t)n_streams * max_frames;
@@ -111,7 +113,7 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_slr, nfr * 2 * kXqRow))) return r;
     if ((r = dev_alloc(c, &c->d_sup, nfr * 2 * kUpRow))) return r;
     if ((r = dev_alloc(c, &c->d_any_silk, 1))) return r;
-    CU_TRY(c, cudaFuncSetAttribute(k_silk_core, cudaFuncAttributeMaxDynamicSharedMemorySize, kSilkCoreSmem));
+    CU_TRY(c, cudaFuncSetAttribute(k_silk_core<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, silk_core_smem(32)));
     if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
@@ -275,9 +277,14 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         const int chains = n_sel * P.CC;
         const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs five empty launches
         k_silk_params<<<c->n_sm * 12, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P);
-        k_silk_core<<<(chains + 31) / 32, 32, kSilkCoreSmem, s>>>(c->d_hdr, c->d_fe, B, P);
+        const int lanes = c->silk_lanes > 0 ? c->silk_lanes : silk_chain_lanes(chains, c->n_sm);
+        if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), s>>>(c->d_hdr, c->d_fe, B, P);
+        else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), s>>>(c->d_hdr, c->d_fe, B, P);
+        else k_silk_core<32><<<(chains + 31) / 32, 32, silk_core_smem(32), s>>>(c->d_hdr, c->d_fe, B, P);
         k_silk_unmix<<<wide, 256, 0, s>>>(B, P);
-        k_silk_up2<<<(chains + 31) / 32, 32, 0, s>>>(B, P);
+        if (lanes == 8) k_silk_up2<8><<<(chains + 7) / 8, 32, 0, s>>>(B, P);
+        else if (lanes == 16) k_silk_up2<16><<<(chains + 15) / 16, 32, 0, s>>>(B, P);
+        else k_silk_up2<32><<<(chains + 31) / 32, 32, 0, s>>>(B, P);
         k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, c->d_fe, d_pcm, P);
         c->launches += 5;
     }

@@ -69,21 +69,108 @@ k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp = 32 chains.  Dynamic shared memory: the LTP-state ring (int32) of every lane, lane-interleaved: 48 KB,
-// so four warps share an SM and 16384 chains are resident at once on 148 SMs.  The chain's output history, which the
-// LTP re-whitening reads, is the xq rows this lane wrote earlier (global memory, L1/L2).
-enum { kSilkCoreSmem = kSilkRing * 32 * (int)sizeof(int32_t) };
+// One warp = kLanes chains (lanes beyond that idle).  A chain is one long dependent instruction stream and all warps of
+// a batch are resident at once, so the kernel takes as long as ONE warp takes for its frames: measured on 16384 chains,
+// 16 chains per warp take as long as 32 (6.4 ms) and 8 are slower (8.9 ms, the extra warps then compete for issue
+// slots), so the host uses full warps; the narrower instantiations stay selectable for tuning (OPUSB_SILK_LANES).
+// Dynamic shared memory: the LTP-state ring (int32) of every chain, lane-interleaved: kLanes * 1.5 KB.  The chain's
+// output history, which the LTP re-whitening reads, is the xq rows this lane wrote earlier (global memory, L1/L2).
+inline int silk_chain_lanes(int /*chains*/, int /*n_sm*/) { return 32; }
 
+// SerialCoop's two loops shared out over the warp: one voiced chain after the other, 32 elements per trip.
+// The chain's input window is staged once in shared memory (`win`), so an output costs 17 conflict-free reads instead
+// of 17 selects between the two history spans; the results go to the chain's column of the lane-interleaved ring
+// (a 32-way bank conflict per store, 10 stores per chain: cheap next to what the serial loop cost).
+template <int kLanes>
+struct WarpCoop {
+    int32_t* ring_base;   // chain c of the warp owns ring_base[c + kLanes * i]
+    int16_t* win;         // kSilkWin samples
+    int lane;
+
+    template <class T>
+    __device__ __forceinline__ static T* bcast_ptr(T* p, int src) {
+        return reinterpret_cast<T*>(__shfl_sync(0xffffffffu, (unsigned long long)p, src));
+    }
+    template <class LtpRing>
+    __device__ __forceinline__ void rewhiten(bool on, const ChainHistory& hist, int n_cur, int n_out, int ltp_pos, s32 inv_gain_Q31,
+                                             const int16_t* A_Q12, LtpRing) const {
+        unsigned m = __ballot_sync(0xffffffffu, on);
+        if (m == 0) return;
+        __syncwarp();  // the chains' own earlier writes (xq rows) become visible to the lanes that now read them
+#pragma unroll 1
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int16_t* prev_end = bcast_ptr(hist.prev_end, src);
+            const int16_t* cur = bcast_ptr(hist.cur, src);
+            const int16_t* a = bcast_ptr(A_Q12, src);
+            const int nc = __shfl_sync(0xffffffffu, n_cur, src), no = __shfl_sync(0xffffffffu, n_out, src);
+            const int pos = __shfl_sync(0xffffffffu, ltp_pos, src);
+            const s32 ig = __shfl_sync(0xffffffffu, inv_gain_Q31, src);
+            // window: history positions [nc - no - 16, nc) relative to this frame's row
+            const int p0 = nc - no - kSilkMaxOrder;
+#pragma unroll 1
+            for (int i = lane; i < no + kSilkMaxOrder; i += 32) {
+                const int p = p0 + i;
+                win[i] = p >= 0 ? cur[p] : (prev_end ? prev_end[p] : (int16_t)0);
+            }
+            const uint4 a0 = *reinterpret_cast<const uint4*>(a), a1 = *reinterpret_cast<const uint4*>(a + 8);
+            const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            s32 a16[kSilkMaxOrder];
+#pragma unroll
+            for (int j = 0; j < kSilkMaxOrder; j++) a16[j] = (int16_t)(j & 1 ? aw[j >> 1] >> 16 : aw[j >> 1] & 0xffff);
+            __syncwarp();
+            int32_t* ring = ring_base + src;
+#pragma unroll 1
+            for (int o = lane; o < no; o += 32) {
+                const int16_t* x = win + o;  // x[16] is the sample whitened, x[15 - j] the one j + 1 before it
+                s32 acc[4] = {0, 0, 0, 0};   // silk_SMLABB_ovflw: int16 x int16 products, wrapping sum
+#pragma unroll
+                for (int j = 0; j < kSilkMaxOrder; j++) acc[j & 3] = (s32)((u32)acc[j & 3] + (u32)((s32)x[kSilkMaxOrder - 1 - j] * a16[j]));
+                const s32 sum = (s32)(((u32)acc[0] + (u32)acc[1]) + ((u32)acc[2] + (u32)acc[3]));
+                const s32 r = sub_w(shl32((s32)x[kSilkMaxOrder], 12), sum);
+                const s32 white = sat16(rshift_round(r, 12));
+                ring[kLanes * ChainRing<int32_t, kLanes>::wrap(pos - no + o)] = smulwb(ig, white);
+            }
+            __syncwarp();  // win is reused by the next chain; the ring column is read by its owner
+        }
+    }
+    template <class LtpRing>
+    __device__ __forceinline__ void rescale(bool on, int ltp_pos, int count, s32 gain_adj_Q16, LtpRing) const {
+        unsigned m = __ballot_sync(0xffffffffu, on);
+        if (m == 0) return;
+        __syncwarp();
+#pragma unroll 1
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int pos = __shfl_sync(0xffffffffu, ltp_pos, src), cnt = __shfl_sync(0xffffffffu, count, src);
+            const s32 g = __shfl_sync(0xffffffffu, gain_adj_Q16, src);
+            int32_t* ring = ring_base + src;
+#pragma unroll 1
+            for (int i = lane; i < cnt; i += 32) {
+                int32_t& e = ring[kLanes * ChainRing<int32_t, kLanes>::wrap(pos - i - 1)];
+                e = smulww(g, e);
+            }
+        }
+        __syncwarp();
+    }
+};
+enum { kSilkWin = 320 };  // >= max lag (288) + 2 + order (16)
+constexpr int silk_core_smem(int lanes) { return kSilkRing * lanes * (int)sizeof(int32_t) + kSilkWin * (int)sizeof(int16_t); }
+
+template <int kLanes>
 __global__ void __launch_bounds__(32)
 k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkBufs B, DevParams P) {
     if (*B.any_silk == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* ltp_base = reinterpret_cast<int32_t*>(smem_raw);
     const int lane = threadIdx.x;
-    const int chain = blockIdx.x * 32 + lane;
-    if (chain >= P.n_sel * P.CC) return;
-    const int n = chain % P.CC, s = P.first_stream + chain / P.CC;
-    const ChainRing<int32_t, 32> ltp{ltp_base + lane};
+    const int chain = blockIdx.x * kLanes + lane;
+    const bool alive = lane < kLanes && chain < P.n_sel * P.CC;  // the other lanes only help in the coop steps
+    const int n = alive ? chain % P.CC : 0, s = alive ? P.first_stream + chain / P.CC : P.first_stream;
+    const ChainRing<int32_t, kLanes> ltp{ltp_base + (alive ? lane : 0)};
+    const WarpCoop<kLanes> coop{ltp_base, reinterpret_cast<int16_t*>(ltp_base + kSilkRing * kLanes), lane};
     SilkStreamState& S = B.state[s];
     SilkChannel& C = S.ch[n];
     SilkChainRegs R;
@@ -97,32 +184,38 @@ k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict_
     int last_out_f = -1, last_dec_f = -1;
     bool hist_zero = false;  // a re-init happened in this call and no frame has produced output since
     const size_t t0 = (size_t)s * P.n_frames;
+#pragma unroll 1
     for (int f = 0; f < P.n_frames; f++) {
         const size_t t = t0 + f;
         SilkPost& post = B.post[t];
-        if (!silk_frame_live(hdr, fe, t)) {
-            if (n == 0) post.has_out = 0;
-            continue;
-        }
+        const bool live = alive && silk_frame_live(hdr, fe, t);
+        if (alive && !live && n == 0) post.has_out = 0;
         const SilkFrame& F = B.frames[t];
-        const int fs = F.fs_kHz;
-        const bool reinit = (hdr[t].oflags & OF_SILK_REINIT) != 0;
-        if (reinit) { prev_mid_only = 0; hist_zero = true; }
-        bool rs_reset, cleared;
-        const bool decode = silk_chain_begin_frame(K, R, n, reinit, fs, F.mid_only, prev_mid_only, &rs_reset, &cleared);
-        if (cleared) hist_end = nullptr;
+        bool decode = false, rs_reset = false, reinit = false;
+        int fs = 16;
+        s32 gains[4] = {0, 0, 0, 0};
+        int16_t* row = B.xq + (t * 2 + n) * kXqRow;
+        if (live) {
+            fs = F.fs_kHz;
+            reinit = (hdr[t].oflags & OF_SILK_REINIT) != 0;
+            if (reinit) { prev_mid_only = 0; hist_zero = true; }
+            bool cleared;
+            decode = silk_chain_begin_frame(K, R, n, reinit, fs, F.mid_only, prev_mid_only, &rs_reset, &cleared);
+            if (cleared) hist_end = nullptr;
+            if (decode) {
+                int8_t lgi = (int8_t)K.LastGainIndex;
+                silk_gains_dequant(gains, F.idx[n].gains, &lgi);
+                K.LastGainIndex = lgi;
+            }
+        }
+        silk_core_frame(R, ChainHistory{hist_end, row}, ltp, F.pulses[n], &B.ctl[t * 2 + n], gains, decode ? F.idx[n].signalType : 0,
+                        decode ? F.idx[n].quantOffsetType : 0, decode ? F.idx[n].seed : 0, fs, row, decode, coop);
         if (decode) {
-            s32 gains[4];
-            int8_t lgi = (int8_t)K.LastGainIndex;
-            silk_gains_dequant(gains, F.idx[n].gains, &lgi);
-            K.LastGainIndex = lgi;
-            int16_t* row = B.xq + (t * 2 + n) * kXqRow;
-            silk_core_frame(R, ChainHistory{hist_end, row}, ltp, F.pulses[n], B.ctl[t * 2 + n], gains, F.idx[n].signalType,
-                            F.idx[n].quantOffsetType, F.idx[n].seed, fs, row);
             hist_end = row + 20 * fs;
             K.first = 0;
             last_dec_f = f;
         }
+        if (!live) continue;
         post.rs_reset[n] = rs_reset;
         if (n == 0) {
             post.prev = hist_zero ? (int16_t)0 : last_out_f >= 0 ? (int16_t)(last_out_f - f) : (int16_t)1;
@@ -135,6 +228,7 @@ k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict_
         last_out_f = f;
         hist_zero = false;
     }
+    if (!alive) return;
     for (int j = 0; j < kSilkMaxOrder; j++) C.sLPC_Q14_buf[kSilkMaxOrder - 1 - j] = R.h[j];
     C.prev_gain_Q16 = R.prev_gain_Q16;
     if (hist_end != C.outBuf + kSilkMaxFrame) {  // the history moved on: keep its newest frame (zeros after a clear)
@@ -211,11 +305,12 @@ k_silk_unmix(SilkBufs B, DevParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+template <int kLanes>
 __global__ void __launch_bounds__(32)
 k_silk_up2(SilkBufs B, DevParams P) {
     if (*B.any_silk == 0) return;
-    const int chain = blockIdx.x * 32 + threadIdx.x;
-    if (chain >= P.n_sel * P.CC) return;
+    const int chain = blockIdx.x * kLanes + threadIdx.x;
+    if ((int)threadIdx.x >= kLanes || chain >= P.n_sel * P.CC) return;
     const int n = chain % P.CC, s = P.first_stream + chain / P.CC;
     SilkStreamState& S = B.state[s];
     SilkResampler& Rs = S.ch[n].rs;

@@ -129,89 +129,115 @@ struct SilkChainRegs {       // what a chain carries from frame to frame in regi
     int ltp_pos;             // ring index one past the newest LTP state sample, in [0, kSilkRing)
 };
 
+// The two loops of silk_decode_core that run over the LTP state instead of over the frame's samples.  Neither has a
+// dependency from one element to the next, so a warp can share them out over its lanes (WarpCoop, silk_kernels.cuh)
+// instead of leaving each chain's lane to walk up to 290 elements alone while the unvoiced lanes wait; SerialCoop is
+// the chain-local form (host simulation, and the definition of what WarpCoop must compute).
+//
+// rewhiten: the last n_out = lag + 2 output samples, filtered with this half's LPC (ref silk_LPC_analysis_filter
+// :2268) and scaled into the LTP state (ref :1877-1888).  The reference's input window outBuf[start_idx .. ltp_mem)
+// (+ the first two sub-frames when k == 2) is simply the newest lag + order + 2 samples of the output history.
+// rescale: the newest `count` state samples times gain_adj_Q16 (ref :1892-1896).
+struct SerialCoop {
+    template <class LtpRing>
+    OPUS_HD void rewhiten(bool on, const ChainHistory& hist, int n_cur, int n_out, int ltp_pos, s32 inv_gain_Q31, const int16_t* A_Q12,
+                          LtpRing ltp) const {
+        if (!on) return;
+        s32 a16[kSilkMaxOrder];
+#pragma unroll
+        for (int j = 0; j < kSilkMaxOrder; j++) a16[j] = A_Q12[j];
+        s32 w[kSilkMaxOrder];  // w[j] = in[ix - 1 - j]; the sample whitened first lies n_out back
+#pragma unroll
+        for (int j = 0; j < kSilkMaxOrder; j++) w[j] = hist.back(n_cur, n_out + 1 + j);
+#pragma unroll 1
+        for (int o0 = 0; o0 < n_out; o0 += 4) {
+            s32 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) c[u] = o0 + u < n_out ? hist.back(n_cur, n_out - o0 - u) : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                s32 acc[4] = {0, 0, 0, 0};  // silk_SMLABB_ovflw: int16 x int16 products, wrapping sum
+#pragma unroll
+                for (int j = 0; j < kSilkMaxOrder; j++) {
+                    const s32 v = (u - 1 - j >= 0) ? c[(u - 1 - j) & 3] : w[(j - u) & (kSilkMaxOrder - 1)];
+                    acc[j & 3] = (s32)((u32)acc[j & 3] + (u32)(v * a16[j]));
+                }
+                const s32 sum = (s32)(((u32)acc[0] + (u32)acc[1]) + ((u32)acc[2] + (u32)acc[3]));
+                const s32 r = sub_w(shl32(c[u], 12), sum);
+                const s32 white = sat16(rshift_round(r, 12));
+                if (o0 + u < n_out) ltp[ltp_pos - n_out + o0 + u] = smulwb(inv_gain_Q31, white);
+            }
+#pragma unroll
+            for (int j = kSilkMaxOrder - 1; j >= 4; j--) w[j] = w[j - 4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[j] = c[3 - j];
+        }
+    }
+    template <class LtpRing>
+    OPUS_HD void rescale(bool on, int ltp_pos, int count, s32 gain_adj_Q16, LtpRing ltp) const {
+        if (!on) return;
+#pragma unroll 2
+        for (int i = 0; i < count; i++) {
+            s32& e = ltp[ltp_pos - i - 1];
+            e = smulww(gain_adj_Q16, e);
+        }
+    }
+};
+
 // One frame of one chain (ref silk_decode_core, src/silk.cpp:1806).  `hist` is the chain's output history (ref outBuf),
 // `ltp` the LTP state (ref sLTP_Q15); xq receives frame_length samples at the internal rate.
-// A chain runs alone on its lane and a warp has few neighbours on its SM (the rings take 96 KB per warp), so the
+// Every lane of the warp calls this for every frame, `active` or not (no frame to synthesise: nothing is read or
+// written through the arguments), because the coop steps are warp-wide.
+// A chain runs alone on its lane and a warp has few neighbours on its SM (the rings take 48 KB per warp), so the
 // code is written for the latency of one instruction stream: the 16-tap sums are split over four accumulators (the
 // reference's 32-bit wrapping adds are associative), the next block's pulses are loaded before the current block is
 // computed, ring addresses are formed once per block of four samples.
-template <class LtpRing>
-OPUS_HD void silk_core_frame(SilkChainRegs& R, ChainHistory hist, LtpRing ltp, const int16_t* pulses, const SilkCtl& ctl, const s32* Gains_Q16,
-                             int signalType, int quantOffsetType, int seed, int fs_kHz, int16_t* xq) {
+template <class LtpRing, class Coop>
+OPUS_HD void silk_core_frame(SilkChainRegs& R, ChainHistory hist, LtpRing ltp, const int16_t* pulses, const SilkCtl* ctl, const s32* Gains_Q16,
+                             int signalType, int quantOffsetType, int seed, int fs_kHz, int16_t* xq, bool active, const Coop& coop) {
     const int order = fs_kHz == 16 ? 16 : 10;
     const int subfr = 5 * fs_kHz;
     const s32 offs[2][2] = {{100, 240}, {32, 100}};
-    const s32 offset_Q14 = offs[signalType >> 1][quantOffsetType] << 4;
+    const s32 offset_Q14 = active ? offs[signalType >> 1][quantOffsetType] << 4 : 0;
     u32 rand_seed = (u32)(s32)seed;
     int lag = 0;
     const uint2* p4 = reinterpret_cast<const uint2*>(pulses);  // four pulses per load (rows are 16-byte aligned)
     uint2* x4 = reinterpret_cast<uint2*>(xq);
-    uint2 pnext = p4[0];
+    uint2 pnext = make_uint2_(0, 0);
+    if (active) pnext = p4[0];
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
         s32 A[kSilkMaxOrder];  // A_Q12 << 16 (multiply-high form)
-#pragma unroll
-        for (int j = 0; j < kSilkMaxOrder; j++) A[j] = (s32)((u32)(uint16_t)ctl.A_Q12[k >> 1][j] << 16);
-        const s32 gain_Q16 = Gains_Q16[k];
-        const s32 Gain_Q10 = gain_Q16 >> 6;
-        s32 inv_gain_Q31 = inverse32_varq(gain_Q16, 47);
-        s32 gain_adj_Q16 = 1 << 16;
-        if (gain_Q16 != R.prev_gain_Q16) {
-            gain_adj_Q16 = div32_varq(R.prev_gain_Q16, gain_Q16, 16);
-#pragma unroll
-            for (int j = 0; j < kSilkMaxOrder; j++) R.h[j] = smulww(gain_adj_Q16, R.h[j]);
-        }
-        R.prev_gain_Q16 = gain_Q16;
         s32 B[5] = {0, 0, 0, 0, 0};
-        if (signalType == 2) {
-            lag = ctl.pitchL[k];
+        s32 Gain_Q10 = 0, inv_gain_Q31 = 0, gain_adj_Q16 = 1 << 16;
+        bool rewhiten = false, rescale = false;
+        if (active) {
 #pragma unroll
-            for (int t = 0; t < 5; t++) B[t] = (s32)((u32)(uint16_t)ctl.B_Q14[k * 5 + t] << 16);
-            if (k == 0 || (k == 2 && ctl.interp_flag)) {
-                // re-whiten the last lag + 2 output samples with this half's LPC (ref silk_LPC_analysis_filter :2268) and
-                // scale them into the LTP state (ref :1877-1888).  The reference's input window outBuf[start_idx ..
-                // ltp_mem) (+ the first two sub-frames when k == 2) is simply the newest lag + order + 2 samples of the
-                // output ring.
-                if (k == 0) inv_gain_Q31 = shl32(smulwb(inv_gain_Q31, ctl.LTP_scale_Q14), 2);
-                s32 a16[kSilkMaxOrder];
+            for (int j = 0; j < kSilkMaxOrder; j++) A[j] = (s32)((u32)(uint16_t)ctl->A_Q12[k >> 1][j] << 16);
+            const s32 gain_Q16 = Gains_Q16[k];
+            Gain_Q10 = gain_Q16 >> 6;
+            inv_gain_Q31 = inverse32_varq(gain_Q16, 47);
+            if (gain_Q16 != R.prev_gain_Q16) {
+                gain_adj_Q16 = div32_varq(R.prev_gain_Q16, gain_Q16, 16);
 #pragma unroll
-                for (int j = 0; j < kSilkMaxOrder; j++) a16[j] = ctl.A_Q12[k >> 1][j];
-                const int n_out = lag + 2;
-                const int n_cur = k * subfr;        // samples of this frame that already exist
-                s32 w[kSilkMaxOrder];               // w[j] = in[ix - 1 - j]; the sample whitened first lies n_out back
-#pragma unroll
-                for (int j = 0; j < kSilkMaxOrder; j++) w[j] = hist.back(n_cur, n_out + 1 + j);
-#pragma unroll 1
-                for (int o0 = 0; o0 < n_out; o0 += 4) {
-                    s32 c[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) c[u] = o0 + u < n_out ? hist.back(n_cur, n_out - o0 - u) : 0;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        s32 acc[4] = {0, 0, 0, 0};  // silk_SMLABB_ovflw: int16 x int16 products, wrapping sum
-#pragma unroll
-                        for (int j = 0; j < kSilkMaxOrder; j++) {
-                            const s32 v = (u - 1 - j >= 0) ? c[(u - 1 - j) & 3] : w[(j - u) & (kSilkMaxOrder - 1)];
-                            acc[j & 3] = (s32)((u32)acc[j & 3] + (u32)(v * a16[j]));
-                        }
-                        const s32 sum = (s32)(((u32)acc[0] + (u32)acc[1]) + ((u32)acc[2] + (u32)acc[3]));
-                        const s32 r = sub_w(shl32(c[u], 12), sum);
-                        const s32 white = sat16(rshift_round(r, 12));
-                        if (o0 + u < n_out) ltp[R.ltp_pos - n_out + o0 + u] = smulwb(inv_gain_Q31, white);
-                    }
-#pragma unroll
-                    for (int j = kSilkMaxOrder - 1; j >= 4; j--) w[j] = w[j - 4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) w[j] = c[3 - j];
-                }
-            } else if (gain_adj_Q16 != 1 << 16) {
-#pragma unroll 2
-                for (int i = 0; i < lag + 2; i++) {
-                    s32& e = ltp[R.ltp_pos - i - 1];
-                    e = smulww(gain_adj_Q16, e);
-                }
+                for (int j = 0; j < kSilkMaxOrder; j++) R.h[j] = smulww(gain_adj_Q16, R.h[j]);
             }
+            R.prev_gain_Q16 = gain_Q16;
+            if (signalType == 2) {
+                lag = ctl->pitchL[k];
+#pragma unroll
+                for (int t = 0; t < 5; t++) B[t] = (s32)((u32)(uint16_t)ctl->B_Q14[k * 5 + t] << 16);
+                rewhiten = k == 0 || (k == 2 && ctl->interp_flag);
+                rescale = !rewhiten && gain_adj_Q16 != 1 << 16;
+                if (k == 0) inv_gain_Q31 = shl32(smulwb(inv_gain_Q31, ctl->LTP_scale_Q14), 2);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kSilkMaxOrder; j++) A[j] = 0;
         }
+        coop.rewhiten(rewhiten, hist, k * subfr, lag + 2, R.ltp_pos, inv_gain_Q31, rewhiten ? ctl->A_Q12[k >> 1] : nullptr, ltp);
+        coop.rescale(rescale, R.ltp_pos, lag + 2, gain_adj_Q16, ltp);
+        if (!active) continue;
 #pragma unroll 1
         for (int i = 0; i < subfr; i += 4) {
             const uint2 pw = pnext;

@@ -159,8 +159,8 @@ static void hs_silk_frame(HsSilk& h, SilkFrame& F, bool reinit, int16_t* pcm48) 
             silk_gains_dequant(gains, F.idx[n].gains, &lgi);
             h.K[n].LastGainIndex = lgi;
             const ChainHistory hist{h.prev_len[n] ? h.prev_row[n] + h.prev_len[n] : nullptr, xq[n]};
-            silk_core_frame(h.R[n], hist, ltp, F.pulses[n], ctl, gains, F.idx[n].signalType, F.idx[n].quantOffsetType, F.idx[n].seed, fs,
-                            xq[n]);
+            silk_core_frame(h.R[n], hist, ltp, F.pulses[n], &ctl, gains, F.idx[n].signalType, F.idx[n].quantOffsetType, F.idx[n].seed, fs,
+                            xq[n], true, SerialCoop{});
             memcpy(h.prev_row[n], xq[n], sizeof(int16_t) * (size_t)L);
             h.prev_len[n] = L;
             h.K[n].first = 0;

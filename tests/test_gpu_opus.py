@@ -79,6 +79,16 @@ def test_mode_switching_bit_exact(pkg, ref, ch):
     _check(pkg, ref, ch, plans, 900 + ch, calls=3)
 
 
+@pytest.mark.parametrize("ch", [1, 2])
+def test_config5_mixed_modes_side_by_side(pkg, ref, ch):
+    """BASELINE configs[4] shape at oracle-sized scale: the streams of one batch alternate CELT FB, SILK WB, hybrid FB
+    and hybrid SWB (mode = stream index mod 4, so every warp of the entropy kernel holds all four), decoded in two
+    calls; one decoder context per channel count, as the player layer groups its files."""
+    s = 4 if ch == 2 else 0
+    comp = [(0xF8 | s, 159), (0x48 | s, 59), (0x78 | s, 159), (0x68 | s, 99)]
+    _check(pkg, ref, ch, [[comp[k % 4]] * 12 for k in range(132)], 77 + ch, calls=2)
+
+
 @pytest.mark.parametrize("idx", [1, 2, 3, 4])
 def test_survey_hashes_silk_hybrid(pkg, ref, idx):
     """SURVEY 8c golden hashes over 500 frames: SILK WB mono/stereo, hybrid FB stereo, hybrid SWB mono."""
