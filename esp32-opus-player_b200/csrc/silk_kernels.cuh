@@ -69,13 +69,16 @@ k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp = kLanes chains (lanes beyond that idle).  A chain is one long dependent instruction stream and all warps of
-// a batch are resident at once, so the kernel takes as long as ONE warp takes for its frames: measured on 16384 chains,
-// 16 chains per warp take as long as 32 (6.4 ms) and 8 are slower (8.9 ms, the extra warps then compete for issue
-// slots), so the host uses full warps; the narrower instantiations stay selectable for tuning (OPUSB_SILK_LANES).
-// Dynamic shared memory: the LTP-state ring (int32) of every chain, lane-interleaved: kLanes * 1.5 KB.  The chain's
-// output history, which the LTP re-whitening reads, is the xq rows this lane wrote earlier (global memory, L1/L2).
-inline int silk_chain_lanes(int /*chains*/, int /*n_sm*/) { return 32; }
+// One warp = kLanes chains (the other lanes only help in the coop steps).  A chain is one long dependent instruction
+// stream and all warps of a batch are resident at once, so the kernel takes as long as ONE warp takes for its frames,
+// however many warps there are: what shortens it is a shorter stream per warp.  With 16 chains per warp the coop steps
+// serve half as many voiced chains per frame (12.5 -> 12.2 ms for the SILK stages of 16384 chains); with 8 the extra
+// warps compete for issue slots (16.3 ms).  So: 16 while the batch still fits the machine in one wave that way, else
+// 32 (OPUSB_SILK_LANES overrides, for tuning).
+// Dynamic shared memory: the LTP-state ring (int32) of every chain, lane-interleaved (kLanes * 1.5 KB), and the
+// staging window of the coop re-whitening.  The chain's output history, which the re-whitening reads, is the xq rows
+// this lane wrote earlier (global memory, L1/L2).
+inline int silk_chain_lanes(int chains, int n_sm) { return chains <= n_sm * 8 * 16 ? 16 : 32; }
 
 // SerialCoop's two loops shared out over the warp: one voiced chain after the other, 32 elements per trip.
 // The chain's input window is staged once in shared memory (`win`), so an output costs 17 conflict-free reads instead
