@@ -27,17 +27,30 @@ OPUS_HD s32 smlaww(s32 a, s32 b, s32 c) { return (s32)((s64)a + (((s64)b * (s64)
 OPUS_HD s32 smmul(s32 a, s32 b) { return (s32)(((s64)a * (s64)b) >> 32); }                    // silk_SMMUL
 OPUS_HD s32 mul_w(s32 a, s32 b) { return (s32)((u32)a * (u32)b); }                            // silk_MUL (two's complement)
 OPUS_HD s32 rshift_round(s32 a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }  // silk_RSHIFT_ROUND
-OPUS_HD s64 rshift_round64(s64 a, int s) { return s == 1 ? (a >> 1) + (a & 1) : ((a >> (s - 1)) + 1) >> 1; }
+// silk_RSHIFT_ROUND64 for |a| < 2^62 (every caller passes a product of two int32): one add and one shift
+OPUS_HD s64 rshift_round64(s64 a, int s) { return (a + ((s64)1 << (s - 1))) >> s; }
 OPUS_HD s32 limit32(s32 a, s32 lo, s32 hi) {                                                  // silk_LIMIT
     return lo > hi ? (a > lo ? lo : (a < hi ? hi : a)) : (a > hi ? hi : (a < lo ? lo : a));
 }
 OPUS_HD s32 add_sat32(s32 a, s32 b) {                                                         // silk_ADD_SAT32
+#if defined(__CUDA_ARCH__)
+    s32 r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
     s64 r = (s64)a + (s64)b;
     return r > 2147483647LL ? 2147483647 : (r < -2147483648LL ? (s32)(-2147483647 - 1) : (s32)r);
+#endif
 }
 OPUS_HD s32 sub_sat32(s32 a, s32 b) {                                                         // silk_SUB_SAT32
+#if defined(__CUDA_ARCH__)
+    s32 r;
+    asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
     s64 r = (s64)a - (s64)b;
     return r > 2147483647LL ? 2147483647 : (r < -2147483648LL ? (s32)(-2147483647 - 1) : (s32)r);
+#endif
 }
 OPUS_HD s32 lshift_sat32(s32 a, int s) {                                                      // silk_LSHIFT_SAT32
     return shl32(limit32(a, (s32)(-2147483647 - 1) >> s, 2147483647 >> s), s);
@@ -526,10 +539,10 @@ OPUS_HD s32 silk_lpc_inverse_pred_gain(const int16_t* A_Q12, int order) {
         for (int n = 0; n < (k + 1) >> 1; n++) {
             s32 tmp1 = A_QA[n], tmp2 = A_QA[k - n - 1];
             s64 t64 = rshift_round64((s64)sub_sat32(tmp1, (s32)rshift_round64((s64)tmp2 * rc_Q31, 31)) * rc_mult2, mult2Q);
-            if (t64 > 2147483647LL || t64 < -2147483648LL) return 0;
+            if (t64 != (s64)(s32)t64) return 0;
             A_QA[n] = (s32)t64;
             t64 = rshift_round64((s64)sub_sat32(tmp2, (s32)rshift_round64((s64)tmp1 * rc_Q31, 31)) * rc_mult2, mult2Q);
-            if (t64 > 2147483647LL || t64 < -2147483648LL) return 0;
+            if (t64 != (s64)(s32)t64) return 0;
             A_QA[k - n - 1] = (s32)t64;
         }
     }
