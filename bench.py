@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--workload", default="celt", choices=sorted(WORKLOADS), help="celt = BASELINE.json's metric config (default)")
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
     ap.add_argument("--frames", type=int, default=50, help="frames per stream per step (50 = 1 s of audio)")
+    ap.add_argument("--payload", type=int, default=0, help="payload bytes per packet behind the TOC (default: the workload's; SURVEY 8d length sensitivity)")
     ap.add_argument("--mix-order", default="grouped", choices=["grouped", "interleaved"],
                     help="mix workload: streams of one mode contiguous in the decoder context (what the host scheduler does) or mode = index mod 4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -169,8 +170,11 @@ def main():
     global TOC, PAYLOAD, CHANNELS, METRIC, COMPONENTS
     TOC, PAYLOAD, CHANNELS, def_streams, ops_rel, wl_desc = WORKLOADS[args.workload]
     COMPONENTS = MIX if args.workload == "mix" else None
+    if args.payload and not COMPONENTS:
+        PAYLOAD = args.payload
+        wl_desc = wl_desc.rsplit(",", 1)[0] + ", %d B packets" % (PAYLOAD + 1)
     args.streams = args.streams or def_streams
-    if args.workload != "celt":
+    if args.workload != "celt" or (args.payload and args.payload != 159):
         METRIC = "decoded audio-sec/sec (x realtime), %s workload (not the BASELINE.json headline)" % args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
