@@ -99,7 +99,7 @@ OPUS_HD void denormalise(const Lanes& L, const int16_t* X, int32_t* freq, const 
 }
 
 // ---- fixed-point FFT butterflies (ref kf_bfly2/3/4/5, src/celt.cpp:2794-2995) ----
-struct Cpx { s32 r, i; };
+struct alignas(8) Cpx { s32 r, i; };  // one 64-bit shared-memory access per complex value (work buffers are 16-byte aligned)
 OPUS_HD s32 smul(s32 a, s16 b) { return mul16x32_q15(b, a); }  // ref S_MUL(a,b), src/celt.h:192
 OPUS_HD Cpx cmul(Cpx a, int tw) {                                // ref C_MUL with twiddle index tw
     const s16 br = kFftTwRe[tw], bi = kFftTwIm[tw];

@@ -179,7 +179,7 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
 __global__ void __launch_bounds__(32 * KW_WARPS)
 k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int16_t* __restrict__ X,
         int32_t* __restrict__ raw, DevParams P) {
-    __shared__ int32_t fsm[KW_WARPS][2][kMaxFrame];
+    __shared__ __align__(16) int32_t fsm[KW_WARPS][2][kMaxFrame];
     __shared__ int32_t gsm[KW_WARPS][kNbEBands + 1];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.n_frames * P.CC) return;

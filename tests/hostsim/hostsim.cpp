@@ -80,7 +80,7 @@ static int celt_decode_rd(HsCelt* d, const RangeDec& rd, int C, int frame_size, 
     if (hdr.flags & FF_ANTICOLLAPSE) band_stage_anti_collapse(L, W, hdr, fe, seed);
     const int transient = (hdr.flags & FF_TRANSIENT) != 0, silence = (hdr.flags & FF_SILENCE) != 0;
     const int nblk = transient ? M : 1, shift = transient ? 3 : 3 - LM, N2 = N / nblk;
-    static int32_t freq[kMaxFrame], freq2[kMaxFrame], work[kMaxFrame], buf[kCombHist + kMaxFrame], gs[kNbEBands + 1];
+    alignas(16) static int32_t freq[kMaxFrame], freq2[kMaxFrame], work[kMaxFrame], buf[kCombHist + kMaxFrame], gs[kNbEBands + 1];
     for (int c = 0; c < CC; c++) {
         if (CC == 2 && C == 1) {
             denormalise(L, W + W_XY, freq, fe.E[0], hdr.start, hdr.end, M, silence, gs);
