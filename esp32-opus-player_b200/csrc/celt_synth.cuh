@@ -238,9 +238,9 @@ OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int s
         s16 t0 = trig[i], t1 = trig[N4 + i];
         s32 yr = add_w(smul(x2, t0), smul(x1, t1));
         s32 yi = sub_w(smul(x1, t0), smul(x2, t1));
-        int rev = bitrev[i];
-        work[b * N2 + 2 * rev + 1] = yr;
-        work[b * N2 + 2 * rev] = yi;
+        Cpx y;
+        y.r = yi; y.i = yr;  // the FFT input has real and imaginary parts swapped (ref :3236-3237)
+        reinterpret_cast<Cpx*>(work + b * N2)[bitrev[i]] = y;
     }
     L.sync();
     if (shift == 0) {
@@ -269,22 +269,19 @@ OPUS_HD void imdct_raw(const Lanes& L, const int32_t* freq, int32_t* work, int s
     const SmallDiv byHalf(half);
     for (int t = L.lane; t < nblk * half; t += kLanes) {
         const int b = nblk > 1 ? byHalf.div(t) : 0, i = t - b * half;
-        int32_t* yp0 = work + b * N2 + 2 * i;
-        int32_t* yp1 = work + b * N2 + N2 - 2 - 2 * i;
-        s32 re = yp0[1], im = yp0[0];
+        Cpx* yp0 = reinterpret_cast<Cpx*>(work + b * N2) + i;
+        Cpx* yp1 = reinterpret_cast<Cpx*>(work + b * N2) + N4 - 1 - i;  // never the same element: N4 is even
+        const Cpx a = *yp0, z = *yp1;  // .r = imaginary part, .i = real part (swapped, as above)
         s16 t0 = trig[i], t1 = trig[N4 + i];
-        s32 yr = add_w(smul(re, t0), smul(im, t1));
-        s32 yi = sub_w(smul(re, t1), smul(im, t0));
-        re = yp1[1];
-        im = yp1[0];
-        yp0[0] = yr;
-        yp1[1] = yi;
+        Cpx o0, o1;
+        o0.r = add_w(smul(a.i, t0), smul(a.r, t1));
+        o1.i = sub_w(smul(a.i, t1), smul(a.r, t0));
         t0 = trig[N4 - i - 1];
         t1 = trig[N2 - i - 1];
-        yr = add_w(smul(re, t0), smul(im, t1));
-        yi = sub_w(smul(re, t1), smul(im, t0));
-        yp1[0] = yr;
-        yp0[1] = yi;
+        o1.r = add_w(smul(z.i, t0), smul(z.r, t1));
+        o0.i = sub_w(smul(z.i, t1), smul(z.r, t0));
+        *yp0 = o0;
+        *yp1 = o1;
     }
     L.sync();
 }
