@@ -192,6 +192,28 @@ OPUS_HD s32 pvq_expand(int n, int k, u32 i, int16_t* y) {
 // recurrence with per-step rounding: serial along the vector, so a lane keeps the carried value in a register.
 OPUS_HD void leaf_rotate1(int16_t* X, int len, int stride, s16 c, s16 s) {
     const s16 ms = (s16)(-(s32)s);
+    if (stride == 1) {
+        // the value a step hands to the next one stays in a register: one load and one store per step
+        if (len < 2) return;
+        s16 v = X[0];
+#pragma unroll 1
+        for (int i = 0; i < len - 1; i++) {
+            const s16 x2 = X[i + 1];
+            X[i] = (s16)pshr32(mul16(c, v) + mul16(ms, x2), 15);
+            v = (s16)pshr32(mul16(c, x2) + mul16(s, v), 15);
+        }
+        X[len - 1] = v;
+        if (len < 3) return;
+        s16 w = X[len - 2];
+#pragma unroll 1
+        for (int i = len - 3; i >= 0; i--) {
+            const s16 x1 = X[i];
+            X[i + 1] = (s16)pshr32(mul16(c, w) + mul16(s, x1), 15);
+            w = (s16)pshr32(mul16(c, x1) + mul16(ms, w), 15);
+        }
+        X[0] = w;
+        return;
+    }
 #pragma unroll 1
     for (int i = 0; i < len - stride; i++) {
         s16 x1 = X[i], x2 = X[i + stride];
