@@ -47,9 +47,11 @@ WORKLOADS = {
 MIX = [(0xFC, 159, 1.0), (0x48, 59, 0.4), (0x7C, 159, 1.1), (0x68, 99, 0.6)]  # (TOC, payload bytes, relative ops per frame)
 TOC, PAYLOAD, CHANNELS = 0xFC, 159, 2
 COMPONENTS = None  # mixed workload: [(toc, payload, ops_rel)]
-# dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full capture of the
-# 20 480-frame run (profiles/r01_v8_ncu_summary_celt.txt); one launch of the bench step moves this times its frame count
-NCU_DRAM_BYTES_PER_FRAME = {"entropy": 47.59e6 / 20480, "bands": 91.98e6 / 20480, "imdct": 189.06e6 / 20480, "postfilter": 294.03e6 / 20480}
+# dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full capture of one
+# full bench step (204 800 frames per launch, profiles/r01_v12_ncu_summary_celt.txt); a launch moves this times its frame count
+NCU_DRAM_BYTES_PER_FRAME = {"entropy": (0.687646e9 + 1.858288e9) / 204800, "bands": (0.602288e9 + 0.746244e9) / 204800,
+                            "imdct": (0.852107e9 + 1.518223e9) / 204800, "postfilter": (1.667434e9 + 1.567839e9) / 204800,
+                            "deemph": (1.626922e9 + 0.761536e9) / 204800, "sequence": (0.083953e9 + 0.015214e9) / 204800}
 
 
 def peaks():
@@ -380,7 +382,7 @@ def main():
         roof = {"bound": "hbm", "kernel": "k_" + str(top), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None,
                 "traffic": (NCU_DRAM_BYTES_PER_FRAME[top] * S * F) if (args.workload == "celt" and top in NCU_DRAM_BYTES_PER_FRAME) else None,
-                "traffic_source": "ncu dram bytes per frame at 20 480 frames (profiles/) x frames per launch", "peak_source": peak_src,
+                "traffic_source": "ncu dram bytes per frame of a full 204 800-frame launch (profiles/r01_v12_ncu_summary_celt.txt) x frames per launch", "peak_source": peak_src,
                 "kernel_ms": top_ms, "stage_ms": stage_acc,
                 "issue": {"note": "the path is issue bound (SURVEY 8d): algorithmic integer ops vs SM issue peak over the whole step",
                           "achieved_lane_ops_per_s": S * F * ops_per_frame / step_s, "peak_lane_ops_per_s": issue_peak,
