@@ -36,7 +36,21 @@ struct DevParams {
     int first_stream, n_sel;  // stream range handled by this launch
 };
 
-enum { K1_THREADS = 128, KW_WARPS = 4 };
+#ifndef K1_THREADS
+#define K1_THREADS 128
+#endif
+#ifndef K1_BLOCKS
+#define K1_BLOCKS 6
+#endif
+enum { KW_WARPS = 4 };
+// warps per block of the warp-per-frame kernels: a block keeps its shared memory until its slowest warp is done, so the
+// band kernel (frames of very different length) runs better in pairs than in fours: 4.83 -> 4.54 ms
+#ifndef KB_WARPS
+#define KB_WARPS 2
+#endif
+#ifndef KI_WARPS
+#define KI_WARPS 4
+#endif
 enum { FD_CONT = 1, FD_NULL = 2 };  // dm_frame.flags (include/opus_b200.h)
 
 __device__ __forceinline__ bool frame_skipped(int status) {
@@ -44,7 +58,7 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K1_THREADS, 6)  // 80 registers: 24 warps per SM measured faster than 16 (128 regs) or 32 (64 regs, spills)
+__global__ void __launch_bounds__(K1_THREADS, K1_BLOCKS)  // 80 registers: 24 warps per SM measured faster than 16 (128 regs) or 32 (64 regs, spills)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
           BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
@@ -152,10 +166,10 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ f
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * KW_WARPS)
+__global__ void __launch_bounds__(32 * KB_WARPS)
 k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, const FrameEnergy* __restrict__ fe,
         int16_t* __restrict__ X, DevParams P) {
-    __shared__ __align__(16) int16_t Wsm[KW_WARPS][W_SIZE];
+    __shared__ __align__(16) int16_t Wsm[KB_WARPS][W_SIZE];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.n_frames) return;
     const size_t t = (size_t)P.first_stream * P.n_frames + local;
@@ -176,11 +190,11 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * KW_WARPS)
+__global__ void __launch_bounds__(32 * KI_WARPS)
 k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int16_t* __restrict__ X,
         int32_t* __restrict__ raw, DevParams P) {
-    __shared__ __align__(16) int32_t fsm[KW_WARPS][2][kMaxFrame];
-    __shared__ int32_t gsm[KW_WARPS][kNbEBands + 1];
+    __shared__ __align__(16) int32_t fsm[KI_WARPS][2][kMaxFrame];
+    __shared__ int32_t gsm[KI_WARPS][kNbEBands + 1];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.n_frames * P.CC) return;
     const int c = local % P.CC;
@@ -215,7 +229,9 @@ k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe
 // into (<= 1026 samples) and the frame being filtered live in a 2048-entry ring in shared memory, so nothing is
 // moved between frames; the next frame's raw IMDCT output is fetched with cp.async into a staging row while the
 // current frame is being filtered (the warp has nothing else to overlap a global-memory round trip with).
-enum { PF_WARPS = 4 };
+#ifndef PF_WARPS
+#define PF_WARPS 4
+#endif
 
 __global__ void __launch_bounds__(32 * PF_WARPS)
 k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ raw,

@@ -264,9 +264,9 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (parsed) cudaEventRecord(parsed, s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[2], s);
-    k_bands<<<(nfr + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, P);
+    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, P);
     if (timed) cudaEventRecord(c->ev[3], s);
-    k_imdct<<<(nfr * P.CC + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
+    k_imdct<<<(nfr * P.CC + KI_WARPS - 1) / KI_WARPS, 32 * KI_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
     if (timed) cudaEventRecord(c->ev[4], s);
     k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[5], s);
