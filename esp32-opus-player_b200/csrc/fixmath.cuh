@@ -11,10 +11,8 @@
 // C++ compiler sees them as ordinary inline functions, which is how tests/hostsim checks their logic.
 #if defined(__CUDACC__)
 #define OPUS_HD __device__ __forceinline__
-#define OPUS_HD_CALL __device__ __noinline__   // large bodies reached from several places: one copy, called
 #else
 #define OPUS_HD inline
-#define OPUS_HD_CALL inline
 #endif
 
 #if !defined(__CUDACC__)
