@@ -400,7 +400,7 @@ def main():
                 "clocks": clocks, "roofline": roof, "gpu_launches": int(launches)}
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             cb = cpu_reference(3000 if F * n_steps >= 3000 else F * n_steps, 10.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
