@@ -65,17 +65,21 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi takes up to a
+    second to produce its first line, so the sampler is started early (start) and only the lines read between begin() and
+    end() -- the timed region -- are used; if the region was too short to catch one, the lines of the warm-up steps
+    just before it count instead (the GPU is under the same load) and the result says so."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_load = self.t_begin = self.t_end = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,30 +88,49 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def load_begins(self):
+        self.t_load = time.perf_counter()
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
+
+        def collect(t0, t1):
+            sm, mx, reasons = [], [], set()
+            for ts, r in self.rows:
+                if ts < t0 or ts > t1:
+                    continue
+                try:
+                    sm.append(float(r[0]))
+                    mx.append(float(r[1]))
+                    for k, nm in enumerate(names):
+                        if r[3 + k].lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    pass
+            return sm, mx, reasons
+
+        window = "timed region"
+        sm, mx, reasons = collect(self.t_begin, self.t_end + 0.02)  # a line is read up to one period after it was sampled
+        if not sm and self.t_load is not None:
+            window = "warm-up steps and timed region"
+            sm, mx, reasons = collect(self.t_load, self.t_end + 0.02)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_reference(n_frames, target_s, jobs=None):
@@ -205,6 +228,8 @@ def main():
     S, F, K, W = args.streams, args.frames, args.steps, args.warmup
     n_steps = W + K
     lib = pkg.lib()
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # early: its first line takes a while, the corpus below takes longer
 
     # ---- synthetic corpus: global stream g = rank + world * s (round-robin shard), n_steps*F frames each.
     # A decoder context has ONE output channel count (opus_decoder_init's `channels`), so a mixed workload becomes one
@@ -286,18 +311,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident, CUDA events
+    sampler.load_begins()
     for k in range(W):
         step_device(k)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = sum(p.dec.launch_count for p in parts)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     ev0.record()
     for k in range(W, n_steps):
         step_device(k)
     ev1.record()
     barrier()
+    sampler.end()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = sum(p.dec.launch_count for p in parts) - launches0
