@@ -63,6 +63,33 @@ def test_config2_streams_bit_exact(pkg, ref):
     dec.close()
 
 
+def test_config2_full_size_properties(pkg, ref):
+    """BASELINE configs[1] at its full per-GPU size (4096 streams x 50 frames, two consecutive calls), checked through
+    properties that do not need the oracle on every stream: (1) a sample of streams spread over the batch is bit-exact
+    against the oracle across both calls, (2) stream i's PCM does not depend on the batch it is decoded in -- a decoder
+    holding only every 64th stream reproduces those rows exactly, (3) every status is 960."""
+    n_streams, n_frames, calls = 4096, 50, 2
+    data, frames = pkg.synth_corpus(n_streams, n_frames * calls, 159, 0xFC)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+    rows = list(range(0, n_streams, 64)) + [n_streams - 1]
+    got = np.zeros((len(rows), n_frames * calls, 960, 2), np.int16)
+    for k in range(calls):
+        rc, pcm, status = dec.decode_many(data, np.ascontiguousarray(frames[:, k * n_frames:(k + 1) * n_frames]))
+        assert rc == 0 and (status == 960).all()
+        got[:, k * n_frames:(k + 1) * n_frames] = pcm[rows]
+    dec.close()
+    for j, s in enumerate(rows[::8]):
+        _, want, err = ref.decode_synth_stream(0xFC, 160, 2, n_frames * calls, seed=ref.SEED ^ s)
+        assert err == 0
+        assert np.array_equal(got[j * 8].reshape(-1, 2), want), "stream %d" % s
+    small = pkg.BatchDecoder(len(rows), n_frames * calls, channels=2)
+    sub = np.ascontiguousarray(frames[rows])
+    rc, pcm2, status2 = small.decode_many(data, sub)
+    assert rc == 0 and (status2 == 960).all()
+    assert np.array_equal(pcm2, got)
+    small.close()
+
+
 def test_survey_hash_celt_fb_stereo_500_frames(pkg, ref):
     e = GOLD["packet_level"][0]
     data, frames = pkg.synth_corpus(1, 500, e["len"] - 1, e["toc"])

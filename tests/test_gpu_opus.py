@@ -116,6 +116,30 @@ def test_config3_silk_wb_mono_streams(pkg, ref):
     dec.close()
 
 
+def test_config3_full_size_properties(pkg, ref):
+    """BASELINE configs[2] at its full per-GPU size (16 384 SILK WB mono streams x 50 frames): every status is 960, a
+    sample of streams spread over the batch is bit-exact against the oracle, and those streams decoded alone in a small
+    context give the same PCM (a stream's output does not depend on its neighbours in the batch)."""
+    n_streams, n_frames = 16384, 50
+    data, frames = pkg.synth_corpus(n_streams, n_frames, 59, 0x48)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=1)
+    rc, pcm, status = dec.decode_many(data, frames)
+    assert rc == 0 and (status == 960).all()
+    rows = list(range(0, n_streams, 512)) + [n_streams - 1]
+    got = pcm[rows].copy()
+    del pcm
+    dec.close()
+    for j, s in enumerate(rows[::4]):
+        _, want, err = ref.decode_synth_stream(0x48, 60, 1, n_frames, seed=ref.SEED ^ s)
+        assert err == 0
+        assert np.array_equal(got[j * 4].reshape(-1, 1), want), "stream %d" % s
+    small = pkg.BatchDecoder(len(rows), n_frames, channels=1)
+    rc, pcm2, status2 = small.decode_many(data, np.ascontiguousarray(frames[rows]))
+    assert rc == 0 and (status2 == 960).all()
+    assert np.array_equal(pcm2, got)
+    small.close()
+
+
 def test_single_stream_dropin_silk_and_hybrid(pkg, ref):
     """opus_decode()-shaped single-stream API over mixed packets (ref src/opus_decoder.cpp:351)."""
     rng = np.random.default_rng(3)
