@@ -206,7 +206,6 @@ OPUS_HD void silk_parse_indices(RangeDec& rd, SilkIdx& ix, int fs_kHz, int vad_o
 
 // ref silk_shell_decoder / decode_split (src/silk.cpp:1146, 1162)
 OPUS_HD void shell_split(RangeDec& rd, int16_t* c1, int16_t* c2, int p, const uint8_t* table, bool on, unsigned m) {
-    warp_converge(m);
     if (!on) return;
     if (p > 0) {
         *c1 = (int16_t)rd_icdf_tab(rd, table + kShellOffsets[p], 8);
@@ -219,6 +218,7 @@ OPUS_HD void shell_split(RangeDec& rd, int16_t* c1, int16_t* c2, int p, const ui
 // every lane of `m` walks the 15 splits of the block together; `on`: this lane has pulses to split in this block
 OPUS_HD void shell_decode(RangeDec& rd, int16_t* p0, int pulses4, bool on, unsigned m) {
     int16_t p3[2], p2[4], p1[8];
+    warp_converge(m);
     shell_split(rd, &p3[0], &p3[1], pulses4, kShell3, on, m);
 #pragma unroll 1
     for (int a = 0; a < 2; a++) {
