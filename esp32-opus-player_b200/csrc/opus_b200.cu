@@ -35,7 +35,9 @@ struct dm_ctx {
     int16_t* d_sxq;
     int16_t* d_slr;
     int16_t* d_sup;
-    int* d_any_silk;
+    int* d_any_silk;         // a frame of the call has a SILK layer
+    int* d_fix_count;        // per stream range of a call (kMaxChunks): filters queued for k_silk_fix
+    FixEntry* d_sfix;        // LPC filters that failed their first stability check (two per SILK frame-channel at most)
     int16_t* d_X;
     FrameEnergy* d_fe;
     int32_t* d_raw;
@@ -113,6 +115,8 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_slr, nfr * 2 * kXqRow))) return r;
     if ((r = dev_alloc(c, &c->d_sup, nfr * 2 * kUpRow))) return r;
     if ((r = dev_alloc(c, &c->d_any_silk, 1))) return r;
+    if ((r = dev_alloc(c, &c->d_fix_count, kMaxChunks))) return r;
+    if ((r = dev_alloc(c, &c->d_sfix, nfr * 4))) return r;
     CU_TRY(c, cudaFuncSetAttribute(k_silk_core<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, silk_core_smem(32)));
     if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
@@ -144,7 +148,7 @@ void dm_destroy(dm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_silk); cudaFree(c->d_sctl); cudaFree(c->d_spost); cudaFree(c->d_sxq); cudaFree(c->d_slr);
-    cudaFree(c->d_sup); cudaFree(c->d_any_silk); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
+    cudaFree(c->d_sup); cudaFree(c->d_any_silk); cudaFree(c->d_sfix); cudaFree(c->d_fix_count); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
     cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames); cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status2);
     cudaFree(c->d_status);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -249,7 +253,8 @@ static int reserve_bytes(dm_ctx* c, int bi, size_t n) {
 
 // Enqueue the six kernels for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
 static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
-                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, bool clear_flag = true) {
+                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, bool clear_flag = true,
+                           int chunk = 0) {
     DevParams P;
     P.n_streams = c->n_streams; P.n_frames = in->n_frames; P.mode = in->mode;
     P.frame_size = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
@@ -276,7 +281,11 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
         const int chains = n_sel * P.CC;
         const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs five empty launches
-        k_silk_params<<<c->n_sm * 12, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P);
+        // the stream range's own slice of the fix queue (at most two filters per frame and channel) and its own counter
+        FixEntry* fq = c->d_sfix + (size_t)first * in->n_frames * 4;
+        cudaMemsetAsync(c->d_fix_count + chunk, 0, sizeof(int), s);
+        k_silk_params<<<c->n_sm * 12, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P, fq, c->d_fix_count + chunk);
+        k_silk_fix<<<c->n_sm * 8, 128, 0, s>>>(c->d_any_silk, fq, c->d_fix_count + chunk);
         const int lanes = c->silk_lanes > 0 ? c->silk_lanes : silk_chain_lanes(chains, c->n_sm);
         if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), s>>>(c->d_hdr, c->d_fe, B, P);
         else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), s>>>(c->d_hdr, c->d_fe, B, P);
@@ -286,7 +295,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         else if (lanes == 16) k_silk_up2<16><<<(chains + 15) / 16, 32, 0, s>>>(B, P);
         else k_silk_up2<32><<<(chains + 31) / 32, 32, 0, s>>>(B, P);
         k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, c->d_fe, d_pcm, P);
-        c->launches += 5;
+        c->launches += 6;
     }
     if (timed) cudaEventRecord(c->ev[7], s);
     c->launches += kStages - 1;
@@ -327,7 +336,7 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
         const size_t f0 = (size_t)first * nf, fn = (size_t)n_sel * nf;
         if (k) CU_TRY(c, cudaStreamWaitEvent(s, c->bytes_ready, 0));
         CU_TRY(c, cudaMemcpyAsync(c->d_frames + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
-        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false, nullptr, false);
+        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false, nullptr, false, k);
         if (r) return r;
         CU_TRY(c, cudaMemcpyAsync(out->pcm + f0 * fs * CC, c->d_pcm + f0 * fs * CC, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(out->status + f0, c->d_status + f0, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -564,11 +564,15 @@ OPUS_HD void silk_nlsf2a_find_poly(s32* out, const s32* cLSF, int dd) {
         out[1] -= ftmp;
     }
 }
-OPUS_HD void silk_nlsf2a(int16_t* a_Q12, const int16_t* NLSF, int d) {
+// silk_NLSF2A in two halves: everything up to and including the first stability check, and the bandwidth-expansion
+// loop that runs only for filters that fail it (ref :665-672).  Those take up to 16 rounds of expansion + re-check
+// while the rest of their warp waits, so the params kernel queues them and a second kernel runs the loop one failed
+// filter per thread (k_silk_fix).  Returns whether the filter is stable as it is.
+OPUS_HD bool silk_nlsf2a_first(int16_t* a_Q12, s32* a32_QA1, const int16_t* NLSF, int d) {
     const uint8_t ordering16[16] = {0, 15, 8, 7, 4, 11, 12, 3, 2, 13, 10, 5, 6, 9, 14, 1};
     const uint8_t ordering10[10] = {0, 9, 6, 3, 4, 5, 8, 1, 2, 7};
     const uint8_t* ordering = d == 16 ? ordering16 : ordering10;
-    s32 cos_LSF_QA[kSilkMaxOrder], P[kSilkMaxOrder / 2 + 1], Q[kSilkMaxOrder / 2 + 1], a32_QA1[kSilkMaxOrder];
+    s32 cos_LSF_QA[kSilkMaxOrder], P[kSilkMaxOrder / 2 + 1], Q[kSilkMaxOrder / 2 + 1];
     for (int k = 0; k < d; k++) {
         s32 f_int = NLSF[k] >> 8;
         s32 f_frac = NLSF[k] - shl32(f_int, 8);
@@ -586,10 +590,19 @@ OPUS_HD void silk_nlsf2a(int16_t* a_Q12, const int16_t* NLSF, int d) {
         a32_QA1[d - k - 1] = Qtmp - Ptmp;
     }
     silk_lpc_fit(a_Q12, a32_QA1, d);
-    for (int i = 0; silk_lpc_inverse_pred_gain(a_Q12, d) == 0 && i < 16; i++) {
+    return silk_lpc_inverse_pred_gain(a_Q12, d) != 0;
+}
+// the loop for a filter that failed the check; a_Q12 is rebuilt from a32_QA1 in every round
+OPUS_HD void silk_nlsf2a_fix(int16_t* a_Q12, s32* a32_QA1, int d) {
+    for (int i = 0; i < 16; i++) {
         silk_bwexpander_32(a32_QA1, d, 65536 - shl32(2, i));
         for (int k = 0; k < d; k++) a_Q12[k] = (int16_t)rshift_round(a32_QA1[k], 5);
+        if (silk_lpc_inverse_pred_gain(a_Q12, d) != 0) break;
     }
+}
+OPUS_HD void silk_nlsf2a(int16_t* a_Q12, const int16_t* NLSF, int d) {
+    s32 a32_QA1[kSilkMaxOrder];
+    if (!silk_nlsf2a_first(a_Q12, a32_QA1, NLSF, d)) silk_nlsf2a_fix(a_Q12, a32_QA1, d);
 }
 
 }  // namespace opusb200

@@ -30,9 +30,51 @@ __device__ __forceinline__ bool silk_frame_live(const CeltFrameHdr* hdr, const F
 }
 
 // ------------------------------------------------------------------------------------------------
+// Thread per (frame, channel).  NLSF -> LPC ends in a stability check; the filters that fail it need up to 16 rounds
+// of bandwidth expansion + re-check (each an O(order^2) recursion in 64-bit arithmetic).  Done in place, every warp
+// waited for its unluckiest lane with 5 of 32 lanes busy.  So k_silk_params queues the failing filters (global memory,
+// one atomic per warp) and k_silk_fix runs the expansion loop with one queued filter per thread: the warps there are
+// full and differ only in trip count (params 2.7 ms -> 1.9 + 0.2 ms per 819 200 frames; moving the first check into
+// the second kernel as well was measured too: 1.1 + 1.6 ms, no better than in place).
+struct FixEntry { s32 a32[kSilkMaxOrder]; int16_t* dst0; int16_t* dst1; int order; int pad; };
+struct GlobalFixQueue {
+    FixEntry* ents;
+    int* count;
+    __device__ __forceinline__ void push(int16_t* dst0, int16_t* dst1, const s32* a32, int order) const {
+        // warp-aggregated slot allocation: the lanes that push right now share one atomic
+        const unsigned m = __activemask();
+        const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(count, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        FixEntry& e = ents[base + __popc(m & ((1u << lane) - 1u))];
+#pragma unroll
+        for (int i = 0; i < kSilkMaxOrder; i++) e.a32[i] = a32[i];
+        e.dst0 = dst0; e.dst1 = dst1; e.order = order;
+    }
+    __device__ __forceinline__ void operator()(int16_t* dst, int16_t* a, s32* a32, int order, bool stable) const {
+        if (stable) {
+#pragma unroll 1
+            for (int i = 0; i < kSilkMaxOrder; i++) dst[i] = i < order ? a[i] : (int16_t)0;
+        } else {
+            push(dst, nullptr, a32, order);
+        }
+    }
+    __device__ __forceinline__ void both(int16_t* dst0, int16_t* dst1, int16_t* a, s32* a32, int order, bool stable) const {
+        if (stable) {
+#pragma unroll 1
+            for (int i = 0; i < kSilkMaxOrder; i++) dst0[i] = dst1[i] = i < order ? a[i] : (int16_t)0;
+        } else {
+            push(dst0, dst1, a32, order);
+        }
+    }
+};
+
 __global__ void __launch_bounds__(128)
-k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkBufs B, DevParams P) {
+k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, SilkBufs B, DevParams P, FixEntry* fix_ents,
+              int* fix_count) {
     if (*B.any_silk == 0) return;
+    const GlobalFixQueue queue{fix_ents, fix_count};
     const int total = P.n_sel * P.n_frames * 2;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int local = idx >> 1, n = idx & 1;
@@ -64,7 +106,28 @@ k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restric
                 }
             }
         }
-        silk_params_item(F.idx[n], fs, have_prev ? prev : nullptr, B.ctl[t * 2 + n]);
+        silk_params_item(F.idx[n], fs, have_prev ? prev : nullptr, B.ctl[t * 2 + n], queue);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_silk_fix(const int* __restrict__ any_silk, FixEntry* __restrict__ ents, const int* __restrict__ count) {
+    if (*any_silk == 0) return;
+    const int qn = *count;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < qn; e += gridDim.x * blockDim.x) {
+        const FixEntry& E = ents[e];
+        s32 a32[kSilkMaxOrder];
+        int16_t a[kSilkMaxOrder];
+#pragma unroll
+        for (int i = 0; i < kSilkMaxOrder; i++) a32[i] = E.a32[i];
+        const int order = E.order;
+        silk_nlsf2a_fix(a, a32, order);
+#pragma unroll 1
+        for (int i = 0; i < kSilkMaxOrder; i++) {
+            const int16_t v = i < order ? a[i] : (int16_t)0;
+            E.dst0[i] = v;
+            if (E.dst1) E.dst1[i] = v;
+        }
     }
 }
 
@@ -377,7 +440,9 @@ k_silk_up2(SilkBufs B, DevParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-enum { FIR_WARPS = 8 };
+#ifndef FIR_WARPS
+#define FIR_WARPS 16
+#endif
 __global__ void __launch_bounds__(32 * FIR_WARPS)
 k_silk_fir(SilkBufs B, const FrameEnergy* __restrict__ fe, int16_t* __restrict__ pcm, DevParams P) {
     if (*B.any_silk == 0) return;

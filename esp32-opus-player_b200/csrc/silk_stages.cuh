@@ -74,27 +74,43 @@ struct SilkPost {
 };
 
 // ---- params ----
+// An LPC filter that fails its first stability check goes to `fix`: SerialFix runs the bandwidth-expansion loop on the
+// spot (host simulation), the params kernel queues the filter for k_silk_fix.
+struct SerialFix {
+    OPUS_HD void operator()(int16_t* dst, int16_t* a, s32* a32_QA1, int order, bool stable) const {
+        if (!stable) silk_nlsf2a_fix(a, a32_QA1, order);
+#pragma unroll 1
+        for (int i = 0; i < kSilkMaxOrder; i++) dst[i] = i < order ? a[i] : (int16_t)0;
+    }
+    OPUS_HD void both(int16_t* dst0, int16_t* dst1, int16_t* a, s32* a32_QA1, int order, bool stable) const {
+        (*this)(dst1, a, a32_QA1, order, stable);
+#pragma unroll 1
+        for (int i = 0; i < kSilkMaxOrder; i++) dst0[i] = dst1[i];
+    }
+};
+
 // prevNLSF == nullptr: first frame after a reset (no interpolation, ref :838)
-OPUS_HD void silk_params_item(const SilkIdx& ix, int fs_kHz, const int16_t* prevNLSF, SilkCtl& o) {
+template <class Fix>
+OPUS_HD void silk_params_item(const SilkIdx& ix, int fs_kHz, const int16_t* prevNLSF, SilkCtl& o, const Fix& fix) {
     const SilkCb cb = silk_cb(fs_kHz);
     const int order = cb.order;
     int16_t cur[kSilkMaxOrder], a[kSilkMaxOrder];
+    s32 a32[kSilkMaxOrder];
     silk_nlsf_decode(cur, ix.nlsf, cb);
-    silk_nlsf2a(a, cur, order);
+    bool stable = silk_nlsf2a_first(a, a32, cur, order);
 #pragma unroll 1
-    for (int i = 0; i < kSilkMaxOrder; i++) {
-        o.nlsf_Q15[i] = i < order ? cur[i] : (int16_t)0;
-        o.A_Q12[1][i] = i < order ? a[i] : (int16_t)0;
-    }
+    for (int i = 0; i < kSilkMaxOrder; i++) o.nlsf_Q15[i] = i < order ? cur[i] : (int16_t)0;
     const int interpQ2 = prevNLSF ? ix.interpQ2 : 4;
     if (interpQ2 < 4) {
+        fix(o.A_Q12[1], a, a32, order, stable);
         int16_t n0[kSilkMaxOrder];
 #pragma unroll 1
         for (int i = 0; i < order; i++) n0[i] = (int16_t)(prevNLSF[i] + (mul_w(interpQ2, cur[i] - prevNLSF[i]) >> 2));
-        silk_nlsf2a(a, n0, order);
+        stable = silk_nlsf2a_first(a, a32, n0, order);
+        fix(o.A_Q12[0], a, a32, order, stable);
+    } else {
+        fix.both(o.A_Q12[0], o.A_Q12[1], a, a32, order, stable);  // no interpolation: both halves use the same filter
     }
-#pragma unroll 1
-    for (int i = 0; i < kSilkMaxOrder; i++) o.A_Q12[0][i] = i < order ? a[i] : (int16_t)0;
     o.interp_flag = interpQ2 < 4;
     if (ix.signalType == 2) {  // ref silk_decode_pitch :2055 and the LTP codebooks :871-886
         const int8_t* cbk = fs_kHz == 8 ? kCbLagsStage2 : kCbLagsStage3;

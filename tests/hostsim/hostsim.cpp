@@ -153,7 +153,7 @@ static void hs_silk_frame(HsSilk& h, SilkFrame& F, bool reinit, int16_t* pcm48) 
         if (cleared) h.prev_len[n] = 0;
         if (dec[n]) {
             SilkCtl ctl;
-            silk_params_item(F.idx[n], fs, h.K[n].first ? nullptr : h.prevNLSF[n], ctl);
+            silk_params_item(F.idx[n], fs, h.K[n].first ? nullptr : h.prevNLSF[n], ctl, SerialFix{});
             s32 gains[4];
             int8_t lgi = (int8_t)h.K[n].LastGainIndex;
             silk_gains_dequant(gains, F.idx[n].gains, &lgi);
