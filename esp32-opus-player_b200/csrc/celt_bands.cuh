@@ -247,24 +247,41 @@ OPUS_HD void leaf_rotate(int16_t* X, int len, int stride, int K, int spread) {
     }
 }
 
-// ref alg_unquant (src/celt.cpp:782) for every coded leaf of the frame.  `last` points at the first leaf
-// record (leaves are stored downwards from the end of the frame's op buffer).
+// ref alg_unquant (src/celt.cpp:782) for one coded leaf: codeword index -> pulses -> unit-norm, spread-rotated vector
+// in y[0 .. o.n).
+OPUS_HD void leaf_expand(const BandOp& o, int spread, int16_t* y) {
+    const int N = o.n, K = o.off2, B = o.a;
+    const s32 Ryy = pvq_expand(N, K, o.aux, y);
+    // normalise_residual (ref :745)
+    const int k = ilog2p(Ryy) >> 1;
+    const s32 t = vshr32(Ryy, 2 * (k - 7));
+    const s16 g = (s16)mul16_p15(rsqrt_norm(t), o.g);
+#pragma unroll 1
+    for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
+    leaf_rotate(y, N, B, K, spread);
+}
+// Cost class of leaf_expand, 0 .. kLeafClasses-1 in half-octaves of its approximate trip count (the codeword walk, the
+// scaling, the rotation passes): leaves of one class take within ~1.4x of each other.
+enum { kLeafClasses = 16 };
+OPUS_HD int leaf_class(const BandOp& o, int spread) {
+    const int N = o.n, K = o.off2;
+    const bool rotates = !(2 * K >= N || spread == 0);
+    const int cost = 2 * N + K + (rotates ? 4 * N : 0);  // >= 5
+    const int lg = ilog2p(cost);
+    const int c = 2 * lg + ((cost >> (lg - 1)) & 1) - 4;
+    return c < 0 ? 0 : (c >= kLeafClasses ? kLeafClasses - 1 : c);
+}
+
+// Every coded leaf of the frame, one lane per leaf, straight into the workspace (host simulation, and the GPU fallback
+// when a step has more leaves than the sorted list holds).  `last` points at the first leaf record (leaves are stored
+// downwards from the end of the frame's op buffer).
 OPUS_HD void leaf_stage(const Lanes& L, int16_t* W, const BandOp* last, int n_leaves, int spread) {
 #pragma unroll 1
     for (int l0 = 0; l0 < n_leaves; l0 += kLanes) {
         const int l = l0 + L.lane;
         if (l < n_leaves) {
             const BandOp o = last[-l];
-            int16_t* y = W + o.off;
-            const int N = o.n, K = o.off2, B = o.a;
-            const s32 Ryy = pvq_expand(N, K, o.aux, y);
-            // normalise_residual (ref :745)
-            const int k = ilog2p(Ryy) >> 1;
-            const s32 t = vshr32(Ryy, 2 * (k - 7));
-            const s16 g = (s16)mul16_p15(rsqrt_norm(t), o.g);
-#pragma unroll 1
-            for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
-            leaf_rotate(y, N, B, K, spread);
+            leaf_expand(o, spread, W + o.off);
         }
     }
     L.sync();

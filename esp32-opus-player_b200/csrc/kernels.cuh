@@ -108,6 +108,100 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coded PVQ leaves (alg_unquant, a5).  A leaf is serial work of very uneven length (cwrsi is O(N + K), the spreading
+// rotation a recurrence over N; a frame has ~30 leaves of 2 .. 176 coefficients), so with a lane per leaf of ONE frame
+// a warp waits for its longest leaf with 3.8 of 32 lanes active.  Here all leaf records of a step are sorted by cost
+// class (counting sort: k_leaf_count, k_leaf_place; per-block counts in shared memory, one global atomic per class and
+// block) and k_leaf_expand takes them in that order, one leaf per thread: the leaves of a warp cost about the same.
+// The vectors go to the frames' X rows, where the band kernel picks them up.
+// LeafSort.n[c]: leaves of class c; cursor[c]: next free slot of class c; total / overflow (more leaves than the list
+// holds: the band kernel expands its own leaves, as the host simulation does).
+struct LeafSort { int n[kLeafClasses], cursor[kLeafClasses], total, overflow; };
+enum { kLeafSlotsPerFrame = 48 };  // capacity of the sorted list per frame of the context (a 64 kb/s stereo frame has ~30 leaves)
+enum { KL_THREADS = 128 };
+
+__global__ void __launch_bounds__(KL_THREADS)
+k_leaf_count(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, LeafSort* __restrict__ ls, DevParams P) {
+    __shared__ int cnt[kLeafClasses];
+    if (threadIdx.x < kLeafClasses) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int local = blockIdx.x * KL_THREADS + threadIdx.x;
+    if (local < P.n_sel * P.n_frames) {
+        const size_t t = (size_t)P.first_stream * P.n_frames + local;
+        const int n = hdr[t].n_leaves, spread = hdr[t].spread;
+        const BandOp* last = ops + t * kMaxOps + (kMaxOps - 1);
+#pragma unroll 1
+        for (int l = 0; l < n; l++) atomicAdd(&cnt[leaf_class(last[-l], spread)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < kLeafClasses && cnt[threadIdx.x]) atomicAdd(&ls->n[threadIdx.x], cnt[threadIdx.x]);
+}
+
+// order[] entry: frame index relative to the launch's first frame << 11 | leaf index (kMaxOps < 2048)
+__global__ void __launch_bounds__(KL_THREADS)
+k_leaf_place(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, LeafSort* __restrict__ ls, uint32_t* __restrict__ order,
+             int cap, DevParams P) {
+    __shared__ int cnt[kLeafClasses], base[kLeafClasses];
+    if (threadIdx.x < kLeafClasses) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int c = 0; c < kLeafClasses; c++) total += ls->n[c];
+    if (total > cap || P.n_sel * P.n_frames > (1 << 21)) {  // the list is full, or a frame index does not fit an entry
+        if (blockIdx.x == 0 && threadIdx.x == 0) { ls->overflow = 1; ls->total = 0; }
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ls->total = total;
+    const int local = blockIdx.x * KL_THREADS + threadIdx.x;
+    const bool in = local < P.n_sel * P.n_frames;
+    const size_t t = (size_t)P.first_stream * P.n_frames + (in ? local : 0);
+    const int n = in ? hdr[t].n_leaves : 0, spread = hdr[t].spread;
+    const BandOp* last = ops + t * kMaxOps + (kMaxOps - 1);
+#pragma unroll 1
+    for (int l = 0; l < n; l++) atomicAdd(&cnt[leaf_class(last[-l], spread)], 1);
+    __syncthreads();
+    if (threadIdx.x < kLeafClasses) {
+        // class c starts behind all more expensive classes; this block's share of it
+        int start = 0;
+        for (int c = kLeafClasses - 1; c > (int)threadIdx.x; c--) start += ls->n[c];
+        base[threadIdx.x] = start + (cnt[threadIdx.x] ? atomicAdd(&ls->cursor[threadIdx.x], cnt[threadIdx.x]) : 0);
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < n; l++) {
+        const int c = leaf_class(last[-l], spread);
+        order[base[c] + atomicAdd(&cnt[c], 1)] = (uint32_t)local << 11 | (uint32_t)l;
+    }
+}
+
+__global__ void __launch_bounds__(KL_THREADS)
+k_leaf_expand(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, const LeafSort* __restrict__ ls,
+              const uint32_t* __restrict__ order, int16_t* __restrict__ X, DevParams P) {
+    const int total = ls->total;
+    __align__(16) int16_t y[kMaxLeaf];
+#pragma unroll 1
+    for (int k = blockIdx.x * KL_THREADS + threadIdx.x; k < total; k += gridDim.x * KL_THREADS) {
+        const uint32_t ent = order[k];
+        const size_t t = (size_t)P.first_stream * P.n_frames + (ent >> 11);
+        const BandOp o = ops[t * kMaxOps + (kMaxOps - 1) - (ent & 2047u)];
+        leaf_expand(o, hdr[t].spread, y);
+        int16_t* dst = X + t * (2 * kMaxFrame) + o.off;
+        const int N = o.n;
+        if (((o.off | N) & 7) == 0) {
+#pragma unroll 1
+            for (int i = 0; i < N; i += 8) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(y + i);
+        } else if (((o.off | N) & 1) == 0) {
+#pragma unroll 1
+            for (int i = 0; i < N; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = *reinterpret_cast<const uint32_t*>(y + i);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < N; i++) dst[i] = y[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * KW_WARPS)
 k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ fr, FrameEnergy* __restrict__ fe,
            CeltStreamState* __restrict__ st, DevParams P) {
@@ -168,7 +262,7 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ f
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * KB_WARPS)
 k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, const FrameEnergy* __restrict__ fe,
-        int16_t* __restrict__ X, DevParams P) {
+        int16_t* __restrict__ X, const LeafSort* __restrict__ ls, DevParams P) {
     __shared__ __align__(16) int16_t Wsm[KB_WARPS][W_SIZE];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.n_frames) return;
@@ -182,7 +276,13 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
     int32_t* Xw = reinterpret_cast<int32_t*>(X + t * (2 * kMaxFrame));
     int32_t* Ww = reinterpret_cast<int32_t*>(W);
     const BandOp* fops = ops + t * kMaxOps;
-    leaf_stage(L, W, fops + kMaxOps - 1, h.n_leaves, h.spread);
+    if (ls->overflow) {
+        leaf_stage(L, W, fops + kMaxOps - 1, h.n_leaves, h.spread);
+    } else {
+        // the coded leaves are already in the frame's X row (k_leaf_expand); everything else in it is overwritten by the ops
+        for (int j = L.lane; j < words; j += 32) Ww[j] = Xw[j];
+        L.sync();
+    }
     u32 seed = band_stage_ops(L, W, fops, h.n_ops, e.seed);
     if (h.flags & FF_ANTICOLLAPSE) band_stage_anti_collapse(L, W, h, e, seed);
     L.sync();

@@ -39,6 +39,8 @@ struct dm_ctx {
     int* d_fix_count;        // per stream range of a call (kMaxChunks): filters queued for k_silk_fix
     FixEntry* d_sfix;        // LPC filters that failed their first stability check (two per SILK frame-channel at most)
     int16_t* d_X;
+    LeafSort* d_leafsort;    // [kMaxChunks]: counting sort of the coded leaves of a launch by cost class
+    uint32_t* d_leaf_order;  // the sorted leaf list, kLeafSlotsPerFrame entries per frame of the context
     FrameEnergy* d_fe;
     int32_t* d_raw;
     int32_t* d_syn;
@@ -121,6 +123,8 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &c->d_leafsort, (size_t)kMaxChunks))) return r;
+    if ((r = dev_alloc(c, &c->d_leaf_order, nfr * kLeafSlotsPerFrame))) return r;
     if ((r = dev_alloc(c, &c->d_fe, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_raw, nfr * channels * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_syn, nfr * channels * kMaxFrame))) return r;
@@ -148,7 +152,7 @@ void dm_destroy(dm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_silk); cudaFree(c->d_sctl); cudaFree(c->d_spost); cudaFree(c->d_sxq); cudaFree(c->d_slr);
-    cudaFree(c->d_sup); cudaFree(c->d_any_silk); cudaFree(c->d_sfix); cudaFree(c->d_fix_count); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_fe);
+    cudaFree(c->d_sup); cudaFree(c->d_any_silk); cudaFree(c->d_sfix); cudaFree(c->d_fix_count); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_fe);
     cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames); cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status2);
     cudaFree(c->d_status);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -267,9 +271,16 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, c->d_any_silk);
     if (timed) cudaEventRecord(c->ev[1], s);
     if (parsed) cudaEventRecord(parsed, s);
+    // coded leaves: sort by cost class, expand one per thread (counted into the "sequence" stage time, with k_sequence)
+    LeafSort* ls = c->d_leafsort + chunk;
+    uint32_t* order = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
+    cudaMemsetAsync(ls, 0, sizeof(LeafSort), s);
+    k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, P);
+    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * kLeafSlotsPerFrame, P);
+    k_leaf_expand<<<c->n_sm * 16, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[2], s);
-    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, P);
+    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, ls, P);
     if (timed) cudaEventRecord(c->ev[3], s);
     k_imdct<<<(nfr * P.CC + KI_WARPS - 1) / KI_WARPS, 32 * KI_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
     if (timed) cudaEventRecord(c->ev[4], s);
@@ -298,7 +309,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         c->launches += 6;
     }
     if (timed) cudaEventRecord(c->ev[7], s);
-    c->launches += kStages - 1;
+    c->launches += kStages - 1 + 3;
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
