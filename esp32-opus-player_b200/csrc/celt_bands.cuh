@@ -131,48 +131,34 @@ OPUS_HD void w_stereo_merge(const Lanes& L, int16_t* X, int16_t* Y, s16 mid, int
 
 // ---- coded PVQ leaves: one lane expands one leaf (index -> pulses -> unit-norm rotated vector) ----
 // ref cwrsi (src/celt.cpp:2545): codeword index -> signed pulses y[0..n), returns sum y^2
+// One flat loop, one table probe per trip: at a fresh coefficient strip the sign (index >= U(n, k+1)) and start the
+// search for the largest k' <= k with U(n, k') <= index; the coefficient holds k - k' pulses.  (The reference nests a
+// search loop inside the coefficient loop; flat, the lanes of a warp that expand leaves of similar size differ only in
+// their total trip count, not at every coefficient.)
 OPUS_HD s32 pvq_expand(int n, int k, u32 i, int16_t* y) {
-    u32 p;
-    int s, k0;
     s32 yy = 0;
+    int s = 0, k0 = k;
+    bool fresh = true;
+#pragma unroll 1
     while (n > 2) {
-        u32 q;
-        s16 val;
-        if (k >= n) {  // lots of pulses
-            const u32* row = kPvqU + kPvqRow[n];
-            p = row[k + 1];
-            s = -(int)(i >= p);
-            i -= p & (u32)s;
+        if (fresh) {
+            const u32 p1 = n <= k ? kPvqU[kPvqRow[n] + k + 1] : kPvqU[kPvqRow[k + 1] + n];  // U(n, k + 1)
+            s = -(int)(i >= p1);
+            i -= p1 & (u32)s;
             k0 = k;
-            q = row[n];
-            if (q > i) {
-                k = n;
-                do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
-            } else {
-                for (p = row[k]; p > i; p = row[k]) k--;
-            }
-            i -= p;
-            val = (s16)((k0 - k + s) ^ s);
-        } else {  // lots of dimensions
-            p = kPvqU[kPvqRow[k] + n];
-            q = kPvqU[kPvqRow[k + 1] + n];
-            if (p <= i && i < q) {
-                i -= p;
-                val = 0;
-            } else {
-                s = -(int)(i >= q);
-                i -= q & (u32)s;
-                k0 = k;
-                do p = kPvqU[kPvqRow[--k] + n]; while (p > i);
-                i -= p;
-                val = (s16)((k0 - k + s) ^ s);
-            }
+            if (k >= n && kPvqU[kPvqRow[n] + n] > i) k = n - 1;  // lots of pulses, but fewer than n remain: skip to U(n, n-1)
+            fresh = false;
         }
+        const u32 p = n <= k ? kPvqU[kPvqRow[n] + k] : kPvqU[kPvqRow[k] + n];  // U(n, k)
+        if (p > i) { k--; continue; }
+        i -= p;
+        const s16 val = (s16)((k0 - k + s) ^ s);
         *y++ = val;
         yy += mul16(val, val);
         n--;
+        fresh = true;
     }
-    p = 2 * (u32)k + 1;
+    u32 p = 2 * (u32)k + 1;
     s = -(int)(i >= p);
     i -= p & (u32)s;
     k0 = k;

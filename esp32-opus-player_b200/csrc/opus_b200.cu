@@ -17,8 +17,8 @@ using namespace opusb200;
 static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
 static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
-enum { kStages = 7, kMaxChunks = 4, kRing = 4 };
-static const char* kStageNames[kStages] = {"entropy", "sequence", "bands", "imdct", "postfilter", "deemph", "silk"};
+enum { kStages = 8, kMaxChunks = 4, kRing = 4 };
+static const char* kStageNames[kStages] = {"entropy", "leaves", "sequence", "bands", "imdct", "postfilter", "deemph", "silk"};
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
@@ -255,7 +255,7 @@ static int reserve_bytes(dm_ctx* c, int bi, size_t n) {
     return 0;
 }
 
-// Enqueue the six kernels for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
+// Enqueue the kernels of one call for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
 static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
                            int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, bool clear_flag = true,
                            int chunk = 0) {
@@ -271,23 +271,24 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, c->d_any_silk);
     if (timed) cudaEventRecord(c->ev[1], s);
     if (parsed) cudaEventRecord(parsed, s);
-    // coded leaves: sort by cost class, expand one per thread (counted into the "sequence" stage time, with k_sequence)
+    // coded leaves: sort by cost class, expand one per thread
     LeafSort* ls = c->d_leafsort + chunk;
     uint32_t* order = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
     cudaMemsetAsync(ls, 0, sizeof(LeafSort), s);
     k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, P);
     k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * kLeafSlotsPerFrame, P);
     k_leaf_expand<<<c->n_sm * 16, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
-    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[2], s);
-    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, ls, P);
+    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[3], s);
-    k_imdct<<<(nfr * P.CC + KI_WARPS - 1) / KI_WARPS, 32 * KI_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
+    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, ls, P);
     if (timed) cudaEventRecord(c->ev[4], s);
-    k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
+    k_imdct<<<(nfr * P.CC + KI_WARPS - 1) / KI_WARPS, 32 * KI_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
     if (timed) cudaEventRecord(c->ev[5], s);
-    k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
+    k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[6], s);
+    k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
+    if (timed) cudaEventRecord(c->ev[7], s);
     if (in->mode == DM_MODE_OPUS) {  // every one of these returns at once unless k_entropy saw a frame with a SILK layer
         SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
         const int chains = n_sel * P.CC;
@@ -308,8 +309,8 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, c->d_fe, d_pcm, P);
         c->launches += 6;
     }
-    if (timed) cudaEventRecord(c->ev[7], s);
-    c->launches += kStages - 1 + 3;
+    if (timed) cudaEventRecord(c->ev[8], s);
+    c->launches += 9;  // entropy, 3 leaf kernels, sequence, bands, imdct, postfilter, deemph
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
