@@ -22,6 +22,7 @@ static const char* kStageNames[kStages] = {"entropy", "leaves", "sequence", "ban
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
+    int leaf_slots = kLeafSlotsPerFrame;  // capacity of the sorted leaf list per frame (OPUSB_LEAF_SLOTS lowers it: tests of the overflow path)
     int silk_lanes = 0;  // chains per warp of the SILK lane-per-chain kernels; 0 = silk_chain_lanes() (OPUSB_SILK_LANES overrides, for tuning)
     // per-stream state
     CeltStreamState* d_state;
@@ -103,6 +104,7 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
     CU_TRY(c, cudaSetDevice(device));
     CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (const char* e = getenv("OPUSB_LEAF_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= kLeafSlotsPerFrame) c->leaf_slots = v; }
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // quant_partition recursion (<= 5 levels) + per-thread allocation arrays live on the local stack
     CU_TRY(c, cudaDeviceSetLimit(cudaLimitStackSize, 6 * 1024));
@@ -276,7 +278,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     uint32_t* order = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
     cudaMemsetAsync(ls, 0, sizeof(LeafSort), s);
     k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, P);
-    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * kLeafSlotsPerFrame, P);
+    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * c->leaf_slots, P);
     k_leaf_expand<<<c->n_sm * 16, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
     if (timed) cudaEventRecord(c->ev[2], s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);

@@ -90,6 +90,22 @@ def test_config2_full_size_properties(pkg, ref):
     small.close()
 
 
+def test_leaf_list_overflow_falls_back(pkg, ref, monkeypatch):
+    """The sorted leaf list has a fixed capacity per frame; a step with more coded leaves than it holds must take the
+    band kernel's own leaf expansion.  OPUSB_LEAF_SLOTS=1 forces that path; the result is the same PCM."""
+    monkeypatch.setenv("OPUSB_LEAF_SLOTS", "1")
+    n_streams, n_frames = 40, 12
+    data, frames = pkg.synth_corpus(n_streams, n_frames, 159, 0xFC)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+    rc, pcm, status = dec.decode_many(data, frames)
+    dec.close()
+    assert rc == 0 and (status == 960).all()
+    for s in range(0, n_streams, 5):
+        _, want, err = ref.decode_synth_stream(0xFC, 160, 2, n_frames, seed=ref.SEED ^ s)
+        assert err == 0
+        assert np.array_equal(pcm[s].reshape(-1, 2), want), "stream %d" % s
+
+
 def test_survey_hash_celt_fb_stereo_500_frames(pkg, ref):
     e = GOLD["packet_level"][0]
     data, frames = pkg.synth_corpus(1, 500, e["len"] - 1, e["toc"])
