@@ -246,15 +246,15 @@ OPUS_HD void leaf_expand(const BandOp& o, int spread, int16_t* y) {
     for (int i = 0; i < N; i++) y[i] = (s16)pshr32(mul16(g, y[i]), k + 1);
     leaf_rotate(y, N, B, K, spread);
 }
-// Cost class of leaf_expand, 0 .. kLeafClasses-1 in half-octaves of its approximate trip count (the codeword walk, the
-// scaling, the rotation passes): leaves of one class take within ~1.4x of each other.
-enum { kLeafClasses = 16 };
+// Cost class of leaf_expand, 0 .. kLeafClasses-1 in quarter-octaves of its approximate trip count (the codeword walk,
+// the scaling, the rotation passes): leaves of one class take within ~1.2x of each other.
+enum { kLeafClasses = 32 };
 OPUS_HD int leaf_class(const BandOp& o, int spread) {
     const int N = o.n, K = o.off2;
     const bool rotates = !(2 * K >= N || spread == 0);
     const int cost = 2 * N + K + (rotates ? 4 * N : 0);  // >= 5
-    const int lg = ilog2p(cost);
-    const int c = 2 * lg + ((cost >> (lg - 1)) & 1) - 4;
+    const int lg = ilog2p(cost);                         // >= 2
+    const int c = 4 * lg + ((cost >> (lg - 2)) & 3) - 10;
     return c < 0 ? 0 : (c >= kLeafClasses ? kLeafClasses - 1 : c);
 }
 

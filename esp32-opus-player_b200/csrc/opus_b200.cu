@@ -22,8 +22,8 @@ static const char* kStageNames[kStages] = {"entropy", "leaves", "sequence", "ban
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
-    int leaf_slots = kLeafSlotsPerFrame;  // capacity of the sorted leaf list per frame (OPUSB_LEAF_SLOTS lowers it: tests of the overflow path)
-    int silk_lanes = 0;  // chains per warp of the SILK lane-per-chain kernels; 0 = silk_chain_lanes() (OPUSB_SILK_LANES overrides, for tuning)
+    int leaf_slots;  // capacity of the sorted leaf list per frame (OPUSB_LEAF_SLOTS lowers it: tests of the overflow path)
+    int silk_lanes;  // chains per warp of the SILK lane-per-chain kernels; 0 = silk_chain_lanes() (OPUSB_SILK_LANES overrides, for tuning)
     // per-stream state
     CeltStreamState* d_state;
     SilkStreamState* d_sstate;
@@ -104,6 +104,7 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
     CU_TRY(c, cudaSetDevice(device));
     CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+    c->leaf_slots = kLeafSlotsPerFrame;  // (the context was just zeroed)
     if (const char* e = getenv("OPUSB_LEAF_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= kLeafSlotsPerFrame) c->leaf_slots = v; }
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // quant_partition recursion (<= 5 levels) + per-thread allocation arrays live on the local stack
