@@ -46,6 +46,7 @@ def lib():
     L.decode_many.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out)]
     L.decode_many_async.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), ctypes.POINTER(ctypes.c_longlong)]
     L.dm_wait.argtypes = [_P, ctypes.c_longlong]
+    L.dm_debug_leaf_overflow.argtypes = [_P]
     L.dm_decode_device.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), _P]
     L.dm_host_alloc.restype = _P
     L.dm_host_alloc.argtypes = [ctypes.c_size_t]
@@ -199,6 +200,10 @@ class BatchDecoder:
     @property
     def launch_count(self):
         return int(lib().dm_launch_count(self._ctx))
+
+    def leaf_overflow(self):
+        """1 if the last call took the band kernel's own leaf expansion (sorted leaf list full), else 0."""
+        return int(lib().dm_debug_leaf_overflow(self._ctx))
 
     @property
     def device_bytes(self):

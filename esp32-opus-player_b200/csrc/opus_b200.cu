@@ -436,6 +436,16 @@ int dm_stage_times(dm_ctx* c, float* ms, int cap) {
     }
     return n;
 }
+int dm_debug_leaf_overflow(dm_ctx* c) {
+    if (!c) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    LeafSort ls[kMaxChunks];
+    CU_TRY(c, cudaMemcpy(ls, c->d_leafsort, sizeof(ls), cudaMemcpyDeviceToHost));
+    int any = 0;
+    for (int k = 0; k < kMaxChunks; k++) any |= ls[k].overflow;
+    return any;
+}
 size_t dm_stream_state_size(void) { return sizeof(CeltStreamState); }
 int dm_get_stream_state(dm_ctx* c, int stream, void* dst, size_t cap) {
     if (!c || !dst || stream < 0 || stream >= c->n_streams || cap < sizeof(CeltStreamState)) return OPUSB_BAD_ARG;

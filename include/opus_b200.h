@@ -114,6 +114,9 @@ size_t dm_device_bytes(const dm_ctx* ctx);
  * of stages written (names via dm_stage_name). */
 int dm_stage_times(dm_ctx* ctx, float* ms, int cap);
 const char* dm_stage_name(int i);
+/* Debug/test access: 1 if the most recent call had more coded PVQ leaves than the sorted leaf list holds and the band
+ * kernel expanded its own leaves instead (slower, same result), 0 if not, < 0 on error.  Synchronises the device. */
+int dm_debug_leaf_overflow(dm_ctx* ctx);
 /* Debug/test access: copies one stream's CELT state blob to host (checkpoint). */
 int dm_get_stream_state(dm_ctx* ctx, int stream, void* dst, size_t cap);
 size_t dm_stream_state_size(void);

@@ -60,6 +60,7 @@ def test_config2_streams_bit_exact(pkg, ref):
         assert err == 0
         assert np.array_equal(pcm[s].reshape(-1, 2), want), "stream %d" % s
     assert dec.launch_count > 0
+    assert dec.leaf_overflow() == 0  # the sorted leaf path ran, not the fallback
     dec.close()
 
 
@@ -98,6 +99,7 @@ def test_leaf_list_overflow_falls_back(pkg, ref, monkeypatch):
     data, frames = pkg.synth_corpus(n_streams, n_frames, 159, 0xFC)
     dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
     rc, pcm, status = dec.decode_many(data, frames)
+    assert dec.leaf_overflow() == 1
     dec.close()
     assert rc == 0 and (status == 960).all()
     for s in range(0, n_streams, 5):
