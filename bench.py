@@ -48,13 +48,13 @@ MIX = [(0xFC, 159, 1.0), (0x48, 59, 0.4), (0x7C, 159, 1.1), (0x68, 99, 0.6)]  # 
 TOC, PAYLOAD, CHANNELS = 0xFC, 159, 2
 COMPONENTS = None  # mixed workload: [(toc, payload, ops_rel)]
 # dram__bytes_read.sum + dram__bytes_write.sum per decoded CELT FB stereo frame, from the ncu --set full capture of one
-# full bench step (204 800 frames per launch, profiles/r01_v16_ncu_summary_celt.txt); a launch moves this times its frame count
+# full bench step (204 800 frames per launch, profiles/r01_v17_ncu_summary_celt.txt); a launch moves this times its frame count
 NCU_DRAM_BYTES_PER_FRAME = {"entropy": (0.688528e9 + 1.861747e9) / 204800, "bands": (1.223216e9 + 0.746794e9) / 204800,
-                            "leaves": (0.193185e9 + 0.004215e9 + 0.356882e9 + 0.025675e9 + 1.259962e9 + 0.445616e9) / 204800,
+                            "leaves": (0.193186e9 + 0.003928e9 + 0.357798e9 + 0.025795e9 + 1.342981e9 + 0.446985e9) / 204800,
                             "imdct": (0.852076e9 + 1.519578e9) / 204800, "postfilter": (1.667189e9 + 1.568961e9) / 204800,
                             "deemph": (1.626948e9 + 0.761595e9) / 204800, "sequence": (0.084038e9 + 0.014776e9) / 204800}
 # smsp__inst_executed.sum of the same capture, all nine CELT kernels of one step: warp instructions per decoded frame
-NCU_WARP_INST_PER_FRAME = (1.978627e9 + 0.010017e9 + 0.023467e9 + 0.785703e9 + 0.080024e9 + 2.368702e9 + 1.784372e9 + 1.414198e9
+NCU_WARP_INST_PER_FRAME = (1.978627e9 + 0.010017e9 + 0.023592e9 + 0.761288e9 + 0.080024e9 + 2.368702e9 + 1.784372e9 + 1.414198e9
                            + 0.184346e9) / 204800
 
 
@@ -412,14 +412,14 @@ def main():
         roof = {"bound": "hbm", "kernel": "k_" + str(top), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None,
                 "traffic": (NCU_DRAM_BYTES_PER_FRAME[top] * S * F) if (args.workload == "celt" and top in NCU_DRAM_BYTES_PER_FRAME) else None,
-                "traffic_source": "ncu dram bytes per frame of a full 204 800-frame launch (profiles/r01_v16_ncu_summary_celt.txt) x frames per launch", "peak_source": peak_src,
+                "traffic_source": "ncu dram bytes per frame of a full 204 800-frame launch (profiles/r01_v17_ncu_summary_celt.txt) x frames per launch", "peak_source": peak_src,
                 "kernel_ms": top_ms, "stage_ms": stage_acc,
                 "issue": {"note": "the path is issue bound (SURVEY 8d): algorithmic integer ops vs SM issue peak over the whole step",
                           "achieved_lane_ops_per_s": S * F * ops_per_frame / step_s, "peak_lane_ops_per_s": issue_peak,
                           "frac": S * F * ops_per_frame / step_s / issue_peak, "sm_clock_hz_under_load": sm_clock,
                           # SURVEY 8d issue_utilisation: executed warp instructions (ncu) / (t x SMs x 4 x f_max)
                           "issue_utilisation": (NCU_WARP_INST_PER_FRAME * S * F / step_s / (issue_peak / 32)) if args.workload == "celt" and not args.payload else None,
-                          "issue_utilisation_source": "smsp__inst_executed.sum per frame from profiles/r01_v16_ncu_summary_celt.txt x frames per step"}}
+                          "issue_utilisation_source": "smsp__inst_executed.sum per frame from profiles/r01_v17_ncu_summary_celt.txt x frames per step"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 fixed-point", "data": "synthetic",
                 "config": {"workload": (wl_desc % S) + ", %d frames (%.1f s) per stream per step" % (F, F * 0.02), "streams_per_gpu": S, "frames_per_step": F, "sharding": "stream i -> GPU i mod N, no collective",
