@@ -118,7 +118,12 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
 // holds: the band kernel expands its own leaves, as the host simulation does).
 struct LeafSort { int n[kLeafClasses], cursor[kLeafClasses], total, overflow; };
 enum { kLeafSlotsPerFrame = 48 };  // capacity of the sorted list per frame of the context (a 64 kb/s stereo frame has ~30 leaves)
-enum { KL_THREADS = 128 };
+#ifndef KL_THREADS
+#define KL_THREADS 128
+#endif
+#ifndef KL_GRID
+#define KL_GRID 32
+#endif
 
 __global__ void __launch_bounds__(KL_THREADS)
 k_leaf_count(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, LeafSort* __restrict__ ls, DevParams P) {

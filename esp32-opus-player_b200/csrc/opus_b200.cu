@@ -280,7 +280,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     cudaMemsetAsync(ls, 0, sizeof(LeafSort), s);
     k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, P);
     k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * c->leaf_slots, P);
-    k_leaf_expand<<<c->n_sm * 16, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
+    k_leaf_expand<<<c->n_sm * KL_GRID, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
     if (timed) cudaEventRecord(c->ev[2], s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[3], s);
