@@ -18,7 +18,7 @@ static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
 static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
 enum { kStages = 8, kMaxChunks = 4, kRing = 4 };
-static const char* kStageNames[kStages] = {"entropy", "leaves", "sequence", "bands", "imdct", "postfilter", "deemph", "silk"};
+static const char* kStageNames[kStages] = {"entropy", "sequence", "leaves", "bands", "imdct", "postfilter", "deemph", "silk"};
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
@@ -54,6 +54,8 @@ struct dm_ctx {
     int16_t* d_pcm2;         // second output buffer, allocated on the first decode_many_async
     int32_t* d_status2;
     cudaStream_t streams[kMaxChunks];
+    cudaStream_t side[kMaxChunks];        // per stream range: the SILK kernels of a call run beside its CELT kernels
+    cudaEvent_t fork_ev[kMaxChunks], join_ev[kMaxChunks];
     cudaEvent_t bytes_ready;
     // calls in flight (decode_many_async): per chunk stream, "packets parsed" and "results in host memory"
     cudaEvent_t parsed[kRing][kMaxChunks], done[kRing][kMaxChunks];
@@ -135,6 +137,11 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_pcm, nfr * channels * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_status, nfr))) return r;
     for (int i = 0; i < kMaxChunks; i++) CU_TRY(c, cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; i++) {
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
+        CU_TRY(c, cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+    }
     CU_TRY(c, cudaEventCreateWithFlags(&c->bytes_ready, cudaEventDisableTiming));
     for (int r = 0; r < kRing; r++)
         for (int k = 0; k < kMaxChunks; k++) {
@@ -159,6 +166,11 @@ void dm_destroy(dm_ctx* c) {
     cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames); cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status2);
     cudaFree(c->d_status);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    for (int i = 0; i < kMaxChunks; i++) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->fork_ev[i]) cudaEventDestroy(c->fork_ev[i]);
+        if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
+    }
     if (c->bytes_ready) cudaEventDestroy(c->bytes_ready);
     for (int r = 0; r < kRing; r++)
         for (int k = 0; k < kMaxChunks; k++) {
@@ -274,6 +286,35 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, c->d_any_silk);
     if (timed) cudaEventRecord(c->ev[1], s);
     if (parsed) cudaEventRecord(parsed, s);
+    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
+    if (timed) cudaEventRecord(c->ev[2], s);
+    // The SILK layer of a call needs nothing from its CELT layer until the final sum, and its two long kernels (LTP/LPC
+    // synthesis, up-sampler) are single-wave recurrences that leave most issue slots idle: they run on a side stream
+    // beside the issue-bound CELT kernels and meet them again in front of k_silk_fir.  Every one of these returns at
+    // once unless k_entropy saw a frame with a SILK layer.
+    const bool silk = in->mode == DM_MODE_OPUS;
+    SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
+    const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs a few empty launches
+    if (silk) {
+        cudaStream_t ss = c->side[chunk];
+        cudaEventRecord(c->fork_ev[chunk], s);
+        cudaStreamWaitEvent(ss, c->fork_ev[chunk], 0);
+        const int chains = n_sel * P.CC;
+        // the stream range's own slice of the fix queue (at most two filters per frame and channel) and its own counter
+        FixEntry* fq = c->d_sfix + (size_t)first * in->n_frames * 4;
+        cudaMemsetAsync(c->d_fix_count + chunk, 0, sizeof(int), ss);
+        k_silk_params<<<c->n_sm * 12, 128, 0, ss>>>(c->d_hdr, c->d_fe, B, P, fq, c->d_fix_count + chunk);
+        k_silk_fix<<<c->n_sm * 8, 128, 0, ss>>>(c->d_any_silk, fq, c->d_fix_count + chunk);
+        const int lanes = c->silk_lanes > 0 ? c->silk_lanes : silk_chain_lanes(chains, c->n_sm);
+        if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), ss>>>(c->d_hdr, c->d_fe, B, P);
+        else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), ss>>>(c->d_hdr, c->d_fe, B, P);
+        else k_silk_core<32><<<(chains + 31) / 32, 32, silk_core_smem(32), ss>>>(c->d_hdr, c->d_fe, B, P);
+        k_silk_unmix<<<wide, 256, 0, ss>>>(B, P);
+        if (lanes == 8) k_silk_up2<8><<<(chains + 7) / 8, 32, 0, ss>>>(B, P);
+        else if (lanes == 16) k_silk_up2<16><<<(chains + 15) / 16, 32, 0, ss>>>(B, P);
+        else k_silk_up2<32><<<(chains + 31) / 32, 32, 0, ss>>>(B, P);
+        cudaEventRecord(c->join_ev[chunk], ss);
+    }
     // coded leaves: sort by cost class, expand one per thread
     LeafSort* ls = c->d_leafsort + chunk;
     uint32_t* order = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
@@ -281,8 +322,6 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, P);
     k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * c->leaf_slots, P);
     k_leaf_expand<<<c->n_sm * KL_GRID, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
-    if (timed) cudaEventRecord(c->ev[2], s);
-    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[3], s);
     k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, ls, P);
     if (timed) cudaEventRecord(c->ev[4], s);
@@ -292,28 +331,13 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) cudaEventRecord(c->ev[6], s);
     k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
     if (timed) cudaEventRecord(c->ev[7], s);
-    if (in->mode == DM_MODE_OPUS) {  // every one of these returns at once unless k_entropy saw a frame with a SILK layer
-        SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
-        const int chains = n_sel * P.CC;
-        const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs five empty launches
-        // the stream range's own slice of the fix queue (at most two filters per frame and channel) and its own counter
-        FixEntry* fq = c->d_sfix + (size_t)first * in->n_frames * 4;
-        cudaMemsetAsync(c->d_fix_count + chunk, 0, sizeof(int), s);
-        k_silk_params<<<c->n_sm * 12, 128, 0, s>>>(c->d_hdr, c->d_fe, B, P, fq, c->d_fix_count + chunk);
-        k_silk_fix<<<c->n_sm * 8, 128, 0, s>>>(c->d_any_silk, fq, c->d_fix_count + chunk);
-        const int lanes = c->silk_lanes > 0 ? c->silk_lanes : silk_chain_lanes(chains, c->n_sm);
-        if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), s>>>(c->d_hdr, c->d_fe, B, P);
-        else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), s>>>(c->d_hdr, c->d_fe, B, P);
-        else k_silk_core<32><<<(chains + 31) / 32, 32, silk_core_smem(32), s>>>(c->d_hdr, c->d_fe, B, P);
-        k_silk_unmix<<<wide, 256, 0, s>>>(B, P);
-        if (lanes == 8) k_silk_up2<8><<<(chains + 7) / 8, 32, 0, s>>>(B, P);
-        else if (lanes == 16) k_silk_up2<16><<<(chains + 15) / 16, 32, 0, s>>>(B, P);
-        else k_silk_up2<32><<<(chains + 31) / 32, 32, 0, s>>>(B, P);
+    if (silk) {  // "silk" stage time: what is left of the SILK layer once the CELT kernels are done, plus the final sum
+        cudaStreamWaitEvent(s, c->join_ev[chunk], 0);
         k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, c->d_fe, d_pcm, P);
         c->launches += 6;
     }
     if (timed) cudaEventRecord(c->ev[8], s);
-    c->launches += 9;  // entropy, 3 leaf kernels, sequence, bands, imdct, postfilter, deemph
+    c->launches += 9;  // entropy, sequence, 3 leaf kernels, bands, imdct, postfilter, deemph
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
