@@ -138,7 +138,10 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_status, nfr))) return r;
     for (int i = 0; i < kMaxChunks; i++) CU_TRY(c, cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; i++) {
-        CU_TRY(c, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        // the side stream carries few, long-running warps: give its blocks the first free slots
+        int prio_lo = 0, prio_hi = 0;
+        CU_TRY(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU_TRY(c, cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio_hi));
         CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
         CU_TRY(c, cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
     }
