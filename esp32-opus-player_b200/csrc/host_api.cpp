@@ -8,7 +8,7 @@
 
 namespace {
 
-const int kOpusBadArg = -1, kOpusBufferTooSmall = -2, kOpusInvalidPacket = -4;
+const int kOpusBadArg = -1, kOpusBufferTooSmall = -2, kOpusInvalidPacket = -4, kOpusUnimplemented = -5;
 
 // ref parse_size (src/opus_decoder.cpp:524)
 int frame_size_field(const uint8_t* data, int32_t len, int16_t* size) {
@@ -230,7 +230,12 @@ int opusb_decode(OpusB200Decoder* st, const uint8_t* data, int32_t len, int16_t*
     int off;
     const int count = opusb_packet_parse(data, len, &toc, frames, size, &off);
     if (count < 0) return count;
-    if (count * opusb_packet_get_samples_per_frame(data, 48000) > frame_size) return kOpusBufferTooSmall;
+    const int spf = opusb_packet_get_samples_per_frame(data, 48000);
+    if (count * spf > frame_size) return kOpusBufferTooSmall;  // ref src/opus_decoder.cpp:320-321
+    // Every frame is decoded as 960 samples whatever its TOC says.  For a TOC frame size other than 20 ms
+    // the reference trips assert(ret == packet_frame_size) (src/opus_decoder.cpp:341) or, without asserts, overruns
+    // the caller's buffer: such packets are refused here, and nothing is ever written past frame_size samples.
+    if (spf != 960) return kOpusUnimplemented;
     size_t pos = 0;
     for (int i = 0; i < count; i++) {
         memcpy(st->h_bytes + pos, frames[i], (size_t)size[i]);
@@ -250,6 +255,7 @@ int opusb_decode(OpusB200Decoder* st, const uint8_t* data, int32_t len, int16_t*
     int n = 0;
     for (int i = 0; i < count; i++) {
         if (st->h_status[i] < 0) return st->h_status[i];
+        if (n + st->h_status[i] > frame_size) return kOpusBufferTooSmall;  // cannot happen behind the checks above
         memcpy(pcm + (size_t)n * st->channels, st->h_pcm + (size_t)i * 960 * st->channels, sizeof(int16_t) * 960 * st->channels);
         n += st->h_status[i];
     }

@@ -541,6 +541,15 @@ __global__ void k_reset_state(const int32_t* __restrict__ ids, int n, CeltStream
     silk_stream_reinit(sst[ids[i]]);
 }
 
+// opus_decoder_init for a list of streams (ids == nullptr: stream = block index): a pristine CELT and SILK state blob
+// copied word-wise over each of them, one block per stream.
+__global__ void k_init_streams(const int32_t* __restrict__ ids, uint32_t* __restrict__ st, uint32_t* __restrict__ sst,
+                               const uint32_t* __restrict__ tc, const uint32_t* __restrict__ ts, int wc, int ws) {
+    const size_t s = ids ? (size_t)ids[blockIdx.x] : (size_t)blockIdx.x;
+    for (int i = threadIdx.x; i < wc; i += blockDim.x) st[s * wc + i] = tc[i];
+    for (int i = threadIdx.x; i < ws; i += blockDim.x) sst[s * ws + i] = ts[i];
+}
+
 }  // namespace opusb200
 
 #include "silk_kernels.cuh"

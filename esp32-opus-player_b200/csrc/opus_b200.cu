@@ -36,7 +36,7 @@ struct dm_ctx {
     int16_t* d_sxq;
     int16_t* d_slr;
     int16_t* d_sup;
-    int* d_any_silk;         // a frame of the call has a SILK layer
+    int* d_any_silk;         // [kMaxChunks] a frame of the stream range of the call has a SILK layer
     int* d_fix_count;        // per stream range of a call (kMaxChunks): filters queued for k_silk_fix
     FixEntry* d_sfix;        // LPC filters that failed their first stability check (two per SILK frame-channel at most)
     int16_t* d_X;
@@ -92,25 +92,26 @@ static void init_state_host(CeltStreamState& s) {
 
 extern "C" {
 
-int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int device) {
-    if (!out || n_streams < 1 || max_frames < 1 || (channels != 1 && channels != 2)) return OPUSB_BAD_ARG;
-    *out = nullptr;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
-        fprintf(stderr, "opusb200: no usable CUDA device (this library has no CPU path)\n");
-        return DM_ERR_NO_DEVICE;
-    }
-    dm_ctx* c = new (std::nothrow) dm_ctx();
-    if (!c) return DM_ERR_NOMEM;
-    memset(c, 0, sizeof(*c));
-    c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
+}  // extern "C"
+
+// Everything dm_create allocates; on failure the caller tears the half-built context down with dm_destroy.
+static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, int device) {
     CU_TRY(c, cudaSetDevice(device));
     CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     c->leaf_slots = kLeafSlotsPerFrame;  // (the context was just zeroed)
     if (const char* e = getenv("OPUSB_LEAF_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= kLeafSlotsPerFrame) c->leaf_slots = v; }
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
-    // quant_partition recursion (<= 5 levels) + per-thread allocation arrays live on the local stack
-    CU_TRY(c, cudaDeviceSetLimit(cudaLimitStackSize, 6 * 1024));
+    // The entropy kernel keeps its per-thread allocation arrays and the explicit partition stack in local memory.  The
+    // stack limit is a DEVICE-wide setting shared with every other CUDA user of the process (torch): it is only ever
+    // raised, and only as far as this library's largest frame needs (no recursion anywhere, so ptxas knows the size).
+    {
+        cudaFuncAttributes fa;
+        CU_TRY(c, cudaFuncGetAttributes(&fa, k_entropy));
+        size_t cur = 0;
+        CU_TRY(c, cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        const size_t need = (fa.localSizeBytes + 255) / 256 * 256;
+        if (need > cur) CU_TRY(c, cudaDeviceSetLimit(cudaLimitStackSize, need));
+    }
     const size_t nfr = (size_t)n_streams * max_frames;
     int r;
     if ((r = dev_alloc(c, &c->d_state, (size_t)n_streams))) return r;
@@ -121,7 +122,7 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
     if ((r = dev_alloc(c, &c->d_sxq, nfr * 2 * kXqRow))) return r;
     if ((r = dev_alloc(c, &c->d_slr, nfr * 2 * kXqRow))) return r;
     if ((r = dev_alloc(c, &c->d_sup, nfr * 2 * kUpRow))) return r;
-    if ((r = dev_alloc(c, &c->d_any_silk, 1))) return r;
+    if ((r = dev_alloc(c, &c->d_any_silk, kMaxChunks))) return r;
     if ((r = dev_alloc(c, &c->d_fix_count, kMaxChunks))) return r;
     if ((r = dev_alloc(c, &c->d_sfix, nfr * 4))) return r;
     CU_TRY(c, cudaFuncSetAttribute(k_silk_core<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, silk_core_smem(32)));
@@ -156,8 +157,32 @@ int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int dev
         CU_TRY(c, cudaEventCreateWithFlags(&c->kernels_done[r], cudaEventDisableTiming));
     }
     for (int i = 0; i <= kStages; i++) CU_TRY(c, cudaEventCreate(&c->ev[i]));
-    *out = c;
+    CU_TRY(c, cudaMemset(c->d_spost, 0, nfr * sizeof(SilkPost)));  // has_out of frames no SILK kernel has visited yet
+    CU_TRY(c, cudaMemset(c->d_any_silk, 0, kMaxChunks * sizeof(int)));
     return dm_reset(c, nullptr, 0);
+}
+
+extern "C" {
+
+int dm_create(dm_ctx** out, int n_streams, int max_frames, int channels, int device) {
+    if (!out || n_streams < 1 || max_frames < 1 || (channels != 1 && channels != 2)) return OPUSB_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "opusb200: no usable CUDA device (this library has no CPU path)\n");
+        return DM_ERR_NO_DEVICE;
+    }
+    dm_ctx* c = new (std::nothrow) dm_ctx();
+    if (!c) return DM_ERR_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->n_streams = n_streams; c->max_frames = max_frames; c->channels = channels; c->device = device;
+    const int r = create_impl(c, n_streams, max_frames, channels, device);
+    if (r) {
+        dm_destroy(c);  // frees whatever was allocated (every pointer of the zeroed context is null or valid)
+        return r;
+    }
+    *out = c;
+    return 0;
 }
 
 void dm_destroy(dm_ctx* c) {
@@ -195,32 +220,33 @@ int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
     CeltStreamState* init = (CeltStreamState*)malloc(sizeof(CeltStreamState));
     if (!init) return DM_ERR_NOMEM;
     init_state_host(*init);
-    int rc = 0;
-    if (!ids) {
-        std::vector<CeltStreamState> all((size_t)c->n_streams, *init);
-        cudaError_t e = cudaMemcpy(c->d_state, all.data(), all.size() * sizeof(CeltStreamState), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) rc = DM_ERR_CUDA;
-    } else {
-        for (int i = 0; i < n && !rc; i++) {
-            if (ids[i] < 0 || ids[i] >= c->n_streams) { rc = OPUSB_BAD_ARG; break; }
-            if (cudaMemcpy(c->d_state + ids[i], init, sizeof(CeltStreamState), cudaMemcpyHostToDevice) != cudaSuccess) rc = DM_ERR_CUDA;
-        }
-    }
-    free(init);
-    if (rc) return rc;
     // SILK layer: silk_InitDecoder (ref src/silk.cpp:1792) + zeroed resamplers
     SilkStreamState* si = (SilkStreamState*)calloc(1, sizeof(SilkStreamState));
-    if (!si) return DM_ERR_NOMEM;
+    if (!si) { free(init); return DM_ERR_NOMEM; }
     for (int n = 0; n < 2; n++) { si->ch[n].prev_gain_Q16 = 65536; si->ch[n].first_frame_after_reset = 1; }  // ref silk_init_decoder :2192
-    if (!ids) {
-        std::vector<SilkStreamState> all((size_t)c->n_streams, *si);
-        if (cudaMemcpy(c->d_sstate, all.data(), all.size() * sizeof(SilkStreamState), cudaMemcpyHostToDevice) != cudaSuccess) rc = DM_ERR_CUDA;
-    } else {
-        for (int i = 0; i < n && !rc; i++)
-            if (cudaMemcpy(c->d_sstate + ids[i], si, sizeof(SilkStreamState), cudaMemcpyHostToDevice) != cudaSuccess) rc = DM_ERR_CUDA;
+    // one pristine blob of each kind goes to the device, a kernel copies them over the chosen streams
+    const size_t wc = sizeof(CeltStreamState) / 4, ws = sizeof(SilkStreamState) / 4;
+    static_assert(sizeof(CeltStreamState) % 4 == 0 && sizeof(SilkStreamState) % 4 == 0, "state blobs are copied word-wise");
+    if (ids) for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= c->n_streams) { free(init); free(si); return OPUSB_BAD_ARG; }
+    const int count = ids ? n : c->n_streams;
+    uint32_t* d_tmpl = nullptr;
+    int32_t* d_ids = nullptr;
+    cudaError_t e = count > 0 ? cudaMalloc((void**)&d_tmpl, (wc + ws) * 4) : cudaSuccess;
+    if (e == cudaSuccess && count > 0) e = cudaMemcpy(d_tmpl, init, wc * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && count > 0) e = cudaMemcpy(d_tmpl + wc, si, ws * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ids && count > 0) {
+        e = cudaMalloc((void**)&d_ids, sizeof(int32_t) * (size_t)count);
+        if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids, sizeof(int32_t) * (size_t)count, cudaMemcpyHostToDevice);
     }
-    free(si);
-    return rc;
+    if (e == cudaSuccess && count > 0) {
+        k_init_streams<<<count, 256>>>(d_ids, (uint32_t*)c->d_state, (uint32_t*)c->d_sstate, d_tmpl, d_tmpl + wc, (int)wc, (int)ws);
+        c->launches++;
+        e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_tmpl); cudaFree(d_ids);
+    free(init); free(si);
+    CU_TRY(c, e);
+    return 0;
 }
 
 int dm_reset_state(dm_ctx* c, const int32_t* ids, int n) {
@@ -275,8 +301,7 @@ static int reserve_bytes(dm_ctx* c, int bi, size_t n) {
 
 // Enqueue the kernels of one call for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
 static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
-                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, bool clear_flag = true,
-                           int chunk = 0) {
+                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, int chunk = 0) {
     DevParams P;
     P.n_streams = c->n_streams; P.n_frames = in->n_frames; P.mode = in->mode;
     P.frame_size = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
@@ -285,8 +310,9 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     const int nfr = n_sel * in->n_frames;
     const int wb = 32 * KW_WARPS;
     if (timed) cudaEventRecord(c->ev[0], s);
-    if (clear_flag) cudaMemsetAsync(c->d_any_silk, 0, sizeof(int), s);
-    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, c->d_any_silk);
+    int* any_silk = c->d_any_silk + chunk;  // per stream range: ranges of one call run concurrently on their own streams
+    cudaMemsetAsync(any_silk, 0, sizeof(int), s);
+    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, any_silk);
     if (timed) cudaEventRecord(c->ev[1], s);
     if (parsed) cudaEventRecord(parsed, s);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
@@ -296,7 +322,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     // beside the issue-bound CELT kernels and meet them again in front of k_silk_fir.  Every one of these returns at
     // once unless k_entropy saw a frame with a SILK layer.
     const bool silk = in->mode == DM_MODE_OPUS;
-    SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, c->d_any_silk};
+    SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, any_silk};
     const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs a few empty launches
     if (silk) {
         cudaStream_t ss = c->side[chunk];
@@ -307,7 +333,7 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         FixEntry* fq = c->d_sfix + (size_t)first * in->n_frames * 4;
         cudaMemsetAsync(c->d_fix_count + chunk, 0, sizeof(int), ss);
         k_silk_params<<<c->n_sm * 12, 128, 0, ss>>>(c->d_hdr, c->d_fe, B, P, fq, c->d_fix_count + chunk);
-        k_silk_fix<<<c->n_sm * 8, 128, 0, ss>>>(c->d_any_silk, fq, c->d_fix_count + chunk);
+        k_silk_fix<<<c->n_sm * 8, 128, 0, ss>>>(any_silk, fq, c->d_fix_count + chunk);
         const int lanes = c->silk_lanes > 0 ? c->silk_lanes : silk_chain_lanes(chains, c->n_sm);
         if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), ss>>>(c->d_hdr, c->d_fe, B, P);
         else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), ss>>>(c->d_hdr, c->d_fe, B, P);
@@ -368,7 +394,6 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
     const int fs = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
     // packets are small: one copy on stream 0, the other chunk streams wait for it
     CU_TRY(c, cudaMemcpyAsync(c->d_bytes[0], in->bytes, in->n_bytes, cudaMemcpyHostToDevice, c->streams[0]));
-    CU_TRY(c, cudaMemsetAsync(c->d_any_silk, 0, sizeof(int), c->streams[0]));  // one flag for all chunks of the call
     CU_TRY(c, cudaEventRecord(c->bytes_ready, c->streams[0]));
     const int n_chunks = c->n_streams >= 64 * kMaxChunks ? kMaxChunks : 1;
     for (int k = 0; k < n_chunks; k++) {
@@ -378,7 +403,7 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
         const size_t f0 = (size_t)first * nf, fn = (size_t)n_sel * nf;
         if (k) CU_TRY(c, cudaStreamWaitEvent(s, c->bytes_ready, 0));
         CU_TRY(c, cudaMemcpyAsync(c->d_frames + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
-        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false, nullptr, false, k);
+        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false, nullptr, k);
         if (r) return r;
         CU_TRY(c, cudaMemcpyAsync(out->pcm + f0 * fs * CC, c->d_pcm + f0 * fs * CC, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(out->status + f0, c->d_status + f0, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -311,6 +311,10 @@ private:
         if (head.stream_count != 1 || head.channel_count < 1 || head.channel_count > 2) return OPB_EIMPL;
         const bool same = have_dec_ && dec_streams_ == head.stream_count && dec_coupled_ == head.coupled_count &&
                           dec_channels_ == head.channel_count && memcmp(dec_map_, head.mapping, (size_t)head.channel_count) == 0;
+        // A later link of a chain with another channel layout would need another decoder context (the reference creates a
+        // new decoder, src/opusfile.cpp:683-697); the file's slot in a batch context has ONE channel count, and the samples
+        // already queued are mapped with the first link's layout: such chains are refused.
+        if (have_dec_ && !same) return OPB_EIMPL;
         Event e;
         memset(&e, 0, sizeof(e));
         e.kind = same ? Event::kResetSoft : Event::kResetHard;
@@ -519,8 +523,13 @@ struct Track {
             const int n = e.od_size - e.od_pos;
             if (n <= 0) continue;
             e.own = (int16_t*)malloc(sizeof(int16_t) * (size_t)n * dc);
-            if (e.own) memcpy(e.own, e.pcm, sizeof(int16_t) * (size_t)n * dc);
-            e.pcm = e.own;
+            if (e.own) {
+                memcpy(e.own, e.pcm, sizeof(int16_t) * (size_t)n * dc);
+                e.pcm = e.own;
+            } else {  // out of host memory: the packet's samples are lost, read() reports it as a bad packet
+                e.pcm = nullptr;
+                e.status = OPB_EFAULT;
+            }
         }
     }
 

@@ -302,3 +302,42 @@ def test_decoder_ctl_and_multistream_match_reference(pkg, ref):
             assert np.array_equal(got, want)
         ours.close()
         ctypes.CDLL(None).free(ctypes.c_void_p(rst))
+
+
+def test_packets_with_a_toc_frame_size_other_than_20ms_are_refused_without_touching_the_buffer(pkg):
+    """Every frame is decoded as 960 samples whatever the TOC says; the reference asserts / overruns on
+    2.5 / 5 / 10 / 40 / 60 ms TOCs.  The packet API refuses them (OPUS_UNIMPLEMENTED) or reports OPUS_BUFFER_TOO_SMALL
+    by the reference's own rule, and never writes past frame_size samples."""
+    rng = np.random.default_rng(77)
+    r = lambda n: rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    dec = pkg.OpusDecoder(48000, 2)
+    L = pkg.lib()
+    guard = 0x5A5A
+
+    def call(packet, frame_size):
+        p = np.frombuffer(packet, np.uint8).copy()
+        pcm = np.full(8 * 5760 * 2, guard, np.int16)
+        n = L.opusb_decode(dec._st, p.ctypes.data, p.size, pcm.ctypes.data, frame_size)
+        return n, pcm
+
+    for toc in (0xE4, 0xEC, 0xF4, 0x04, 0x54, 0x5C, 0x64):  # CELT 2.5/5/10 ms, SILK 10 ms, SILK 40/60 ms, hybrid 10 ms
+        spf = pkg.opus_packet_get_samples_per_frame(bytes([toc]), 48000)
+        assert spf != 960
+        n, pcm = call(bytes([toc]) + r(60), 5760)
+        assert n == -5 and (pcm == guard).all()
+        n, pcm = call(bytes([toc]) + r(60), spf)       # the advisor's case: one short frame, frame_size = its TOC size
+        assert n in (-5, -2) and (pcm == guard).all()
+    # code 3, 48 x 2.5 ms frames, frame_size 5760
+    n, pcm = call(bytes([0xE4 | 3, 48]) + r(48 * 10), 5760)
+    assert n == -5 and (pcm == guard).all()
+    # 20 ms TOC, 3 frames, buffer for 2: the reference's OPUS_BUFFER_TOO_SMALL (src/opus_decoder.cpp:320)
+    n, pcm = call(bytes([0xFC | 3, 3]) + r(3 * 80), 1920)
+    assert n == -2 and (pcm == guard).all()
+    n, pcm = call(bytes([0xFC | 3, 3]) + r(3 * 80), 2880)
+    assert n == 2880 and (pcm[2880 * 2:] == guard).all() and not (pcm[: 2880 * 2] == guard).all()
+    # multistream wrapper: same rules (its scratch holds 5760 samples per channel)
+    ms = pkg.OpusMSDecoder(48000, 2, 1, 1, [0, 1])
+    n, _ = ms.decode(bytes([0xE4 | 3, 48]) + r(48 * 10))
+    assert n == -5
+    ms.close()
+    dec.close()
