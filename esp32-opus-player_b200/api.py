@@ -48,6 +48,7 @@ def lib():
     L.dm_wait.argtypes = [_P, ctypes.c_longlong]
     L.dm_debug_leaf_overflow.argtypes = [_P]
     L.dm_decode_device.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), _P]
+    L.dm_probe_d2h.argtypes = [_P, _P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_float)]
     L.dm_host_alloc.restype = _P
     L.dm_host_alloc.argtypes = [ctypes.c_size_t]
     L.dm_host_free.argtypes = [_P]
@@ -63,6 +64,8 @@ def lib():
     L.dm_synth_bytes.restype = ctypes.c_size_t
     L.dm_synth_bytes.argtypes = [_I, _I, _I]
     L.dm_synth_fill.argtypes = [_P, _P, _I, _I, _I, _I, ctypes.c_uint64, _I]
+    L.dm_synth_fill_raw.argtypes = [_P, _P, _I, _I, _I, ctypes.c_uint64, _I]
+    L.dm_fnv_update.argtypes = [_P, _P, _I, ctypes.c_size_t, _I, _I, _I]
     for fn in ("opusb_packet_get_mode", "opusb_packet_get_bandwidth", "opusb_packet_get_nb_channels"):
         getattr(L, fn).argtypes = [_P]
     L.opusb_packet_get_samples_per_frame.argtypes = [_P, ctypes.c_int32]
@@ -118,8 +121,22 @@ def synth_corpus(n_streams, n_frames, payload_len, toc, seed_base=0x9E3779B97F4A
     nb = L.dm_synth_bytes(n_streams, n_frames, payload_len)
     b = bytes_out if bytes_out is not None else np.empty(nb, np.uint8)
     f = frames_out if frames_out is not None else make_frames(n_streams, n_frames)
-    L.dm_synth_fill(_ptr(b), _ptr(f), n_streams, n_frames, payload_len, toc, ctypes.c_uint64(seed_base), first_stream)
+    if toc is None or toc < 0:  # raw CELT frames: no TOC, every byte is generator output
+        L.dm_synth_fill_raw(_ptr(b), _ptr(f), n_streams, n_frames, payload_len, ctypes.c_uint64(seed_base), first_stream)
+    else:
+        L.dm_synth_fill(_ptr(b), _ptr(f), n_streams, n_frames, payload_len, toc, ctypes.c_uint64(seed_base), first_stream)
     return b, f
+
+
+FNV_START = 1469598103934665603
+
+
+def fnv_update(hashes, pcm, channels, dup_mono=True, n_threads=0):
+    """Carry the SURVEY 8c stream hashes (uint64[n_streams], start FNV_START) over one more call's PCM
+    (int16[n_streams][...], C-contiguous) on host threads."""
+    assert hashes.dtype == np.uint64 and pcm.dtype == np.int16 and pcm.flags["C_CONTIGUOUS"] and pcm.shape[0] == hashes.size
+    lib().dm_fnv_update(hashes.ctypes.data, pcm.ctypes.data, hashes.size, pcm.size // hashes.size, channels, 1 if dup_mono else 0, n_threads)
+    return hashes
 
 
 class BatchDecoder:
@@ -191,6 +208,14 @@ class BatchDecoder:
         b = self._batch(d_bytes, n_bytes, d_frames, n_frames, mode, frame_size, coded_channels, start_band)
         o = _Out(d_pcm, d_status)
         return lib().dm_decode_device(self._ctx, ctypes.byref(b), ctypes.byref(o), cuda_stream)
+
+    def probe_d2h(self, host_array, nbytes, reps=5):
+        """ms per bare D2H copy of nbytes from the context's PCM buffer into host_array (pinned)."""
+        ms = ctypes.c_float(0)
+        rc = lib().dm_probe_d2h(self._ctx, _ptr(host_array), nbytes, reps, ctypes.byref(ms))
+        if rc:
+            raise RuntimeError("dm_probe_d2h rc=%d" % rc)
+        return ms.value / reps
 
     def stage_times(self):
         ms = (ctypes.c_float * 16)()

@@ -4,6 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 #include "../../include/opus_b200.h"
 
 namespace {
@@ -183,6 +186,37 @@ void dm_synth_fill(uint8_t* bytes, dm_frame* frames, int n_streams, int n_frames
             frames[t].flags = 0;
         }
     }
+}
+
+// Raw CELT frames (DM_MODE_CELT_RAW): every byte of a frame is payload (SURVEY 8c "CELT layer" generator).
+void dm_synth_fill_raw(uint8_t* bytes, dm_frame* frames, int n_streams, int n_frames, int frame_len, uint64_t seed_base, int first_stream) {
+    dm_synth_fill(bytes, frames, n_streams, n_frames, frame_len, 0, seed_base, first_stream);
+}
+
+// Result check of a benchmark or a server: the SURVEY 8c stream hash (FNV-1a over the uint16 view of the interleaved
+// samples; a mono stream counts every sample twice when dup_mono is set, as the packet-level oracle does) carried on
+// over consecutive calls.  pcm is [n_streams][samples_per_stream] with samples_per_stream = frames * frame_size *
+// channels; hashes[n_streams] is updated in place (start value 1469598103934665603).  Streams are shared out over
+// n_threads host threads (0 = one per core).
+void dm_fnv_update(uint64_t* hashes, const int16_t* pcm, int n_streams, size_t samples_per_stream, int channels, int dup_mono, int n_threads) {
+    if (!hashes || !pcm || n_streams <= 0) return;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > n_streams) nt = n_streams;
+    const bool twice = channels == 1 && dup_mono;
+    auto work = [=](int lo, int hi) {
+        for (int s = lo; s < hi; s++) {
+            uint64_t h = hashes[s];
+            const uint16_t* p = reinterpret_cast<const uint16_t*>(pcm + (size_t)s * samples_per_stream);
+            if (twice) for (size_t i = 0; i < samples_per_stream; i++) { h = (h ^ p[i]) * 1099511628211ull; h = (h ^ p[i]) * 1099511628211ull; }
+            else for (size_t i = 0; i < samples_per_stream; i++) h = (h ^ p[i]) * 1099511628211ull;
+            hashes[s] = h;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, (int)((long long)n_streams * t / nt), (int)((long long)n_streams * (t + 1) / nt));
+    work(0, (int)((long long)n_streams / nt));
+    for (auto& t : th) t.join();
 }
 
 // ---- single-stream drop-in (ref opus_decoder_init / opus_decode, src/opus_decoder.cpp:82, 351) ----

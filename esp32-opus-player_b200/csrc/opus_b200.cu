@@ -469,6 +469,24 @@ int dm_wait(dm_ctx* c, long long ticket) {
     return 0;
 }
 
+// The bare read-back of decode_many_async, nothing else: `reps` cudaMemcpyAsync D2H of `bytes` from the context's PCM
+// buffer to `host` on the read-back stream, timed with CUDA events.  What the PCIe link and the host memory system allow.
+int dm_probe_d2h(dm_ctx* c, void* host, size_t bytes, int reps, float* ms_total) {
+    if (!c || !host || reps < 1 || !ms_total) return OPUSB_BAD_ARG;
+    const size_t cap = (size_t)c->n_streams * c->max_frames * c->channels * kMaxFrame * sizeof(int16_t);
+    if (bytes > cap) return DM_ERR_CAPACITY;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    cudaStream_t down = c->streams[1];
+    CU_TRY(c, cudaMemcpyAsync(host, c->d_pcm, bytes, cudaMemcpyDeviceToHost, down));  // warm-up
+    CU_TRY(c, cudaEventRecord(c->ev[0], down));
+    for (int i = 0; i < reps; i++) CU_TRY(c, cudaMemcpyAsync(host, c->d_pcm, bytes, cudaMemcpyDeviceToHost, down));
+    CU_TRY(c, cudaEventRecord(c->ev[1], down));
+    CU_TRY(c, cudaStreamSynchronize(down));
+    CU_TRY(c, cudaEventElapsedTime(ms_total, c->ev[0], c->ev[1]));
+    return 0;
+}
+
 void* dm_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -51,3 +51,19 @@ def max_over_ranks(value, dist=None, device="cpu"):
 def aggregate_rate(units_per_rank, world, seconds_max):
     """Whole-job throughput: the units ALL ranks processed divided by the slowest rank's time."""
     return world * units_per_rank / seconds_max
+
+
+def gather_by_global_id(local, rank, world, dist=None, device="cpu"):
+    """Per-stream values of every rank (uint64[n_local] each, stream s of rank r is global stream r + world * s) as one
+    array indexed by GLOBAL stream id, on every rank.  Verification plumbing (the result hashes of a sharded run), never
+    on the data path."""
+    local = np.ascontiguousarray(local, np.uint64)
+    if dist is None or not dist.is_available() or not dist.is_initialized() or world == 1:
+        return local.copy()
+    import torch
+
+    t = torch.from_numpy(local.view(np.int64).copy()).to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    per_rank = torch.stack(parts).cpu().numpy().view(np.uint64).reshape(world, -1)
+    return np.ascontiguousarray(per_rank.T).reshape(-1)  # [s][r] -> g = r + world * s

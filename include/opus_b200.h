@@ -105,6 +105,9 @@ int dm_decode_device(dm_ctx* ctx, const dm_batch* in_dev, dm_out* out_dev, void*
 void* dm_host_alloc(size_t bytes);
 void dm_host_free(void* p);
 
+/* Measurement aid: `reps` bare device-to-host copies of `bytes` from the context's PCM buffer into `host` (the copy
+ * decode_many_async ends with, and nothing else), timed with CUDA events: the read-back ceiling of this box. */
+int dm_probe_d2h(dm_ctx* ctx, void* host, size_t bytes, int reps, float* ms_total);
 /* Number of kernel launches issued by this library since dm_create (bench evidence). */
 long long dm_launch_count(const dm_ctx* ctx);
 /* Bytes of device memory held by the context. */
@@ -128,6 +131,16 @@ size_t dm_stream_state_size(void);
 size_t dm_synth_bytes(int n_streams, int n_frames, int payload_len);
 void dm_synth_fill(uint8_t* bytes, dm_frame* frames, int n_streams, int n_frames, int payload_len, int toc,
                    uint64_t seed_base, int first_stream);
+
+/* The same for raw CELT frames (DM_MODE_CELT_RAW): all frame_len bytes of a frame are generator output. */
+void dm_synth_fill_raw(uint8_t* bytes, dm_frame* frames, int n_streams, int n_frames, int frame_len, uint64_t seed_base,
+                       int first_stream);
+/* Result check: the SURVEY 8c stream hash (FNV-1a over the uint16 view of the interleaved samples, a mono stream's
+ * samples counted twice when dup_mono != 0, as the packet-level oracle does), carried on across calls.
+ * pcm = [n_streams][samples_per_stream]; hashes[n_streams] is updated in place (start: 1469598103934665603).
+ * n_threads host threads (0 = one per core). */
+void dm_fnv_update(uint64_t* hashes, const int16_t* pcm, int n_streams, size_t samples_per_stream, int channels, int dup_mono,
+                   int n_threads);
 
 /* ------------------------------------------------------------------------------------------------
  * Packet helpers with the reference's semantics (src/opus_decoder.cpp:135, 460-680).

@@ -45,6 +45,8 @@ def lib():
         L.ref_decode_synth_celt.argtypes = [_I, _I, _I, _I, ctypes.c_uint64, _P, _P]
         L.ref_bench_fork.restype = ctypes.c_double
         L.ref_bench_fork.argtypes = [_I, _I, _I, _I, _I, ctypes.c_uint64, _I, _P]
+        L.ref_bench_fork_ids.restype = ctypes.c_double
+        L.ref_bench_fork_ids.argtypes = [_I, _I, _I, _I, _P, _I, _I, ctypes.c_uint64, _I, _P]
         L.ref_ogg_open.argtypes = [_P, ctypes.c_size_t]
         L.ref_ogg_read_stereo.argtypes = [_P, _I]
         L.ref_gen_packet.argtypes = [_P, _I, _I, _P]
@@ -123,4 +125,14 @@ def bench_fork(toc, length, channels, n_streams, n_frames, seed_base=SEED, jobs=
     jobs = jobs or os.cpu_count() or 1
     hashes = np.zeros(n_streams, np.uint64)
     wall = lib().ref_bench_fork(toc, length, channels, n_streams, n_frames, seed_base, jobs, hashes.ctypes.data)
+    return wall, hashes
+
+
+def bench_fork_ids(toc, length, channels, ids, n_frames, frame_size=0, seed_base=SEED, jobs=None):
+    """bench_fork for an explicit list of stream ids; frame_size != 0 decodes at the CELT layer (raw frames of `length`
+    random bytes).  Returns (wall_s, hashes)."""
+    jobs = jobs or os.cpu_count() or 1
+    ids = np.ascontiguousarray(ids, np.int64)
+    hashes = np.zeros(ids.size, np.uint64)
+    wall = lib().ref_bench_fork_ids(toc, length, channels, frame_size, ids.ctypes.data, ids.size, n_frames, seed_base, jobs, hashes.ctypes.data)
     return wall, hashes

@@ -268,4 +268,40 @@ double ref_bench_fork(int toc, int len, int channels, int n_streams, int n_frame
     return wall;
 }
 
+/* Same for an explicit list of stream ids (stream ids[k] uses seed seed_base ^ ids[k]), at packet level (frame_size == 0:
+ * packets of `len` bytes behind `toc`, hash with mono duplicated as ref_decode_synth_stream does) or at the CELT layer
+ * (frame_size 120/240/480/960: `len` random bytes per frame, no TOC, as ref_decode_synth_celt does). */
+double ref_bench_fork_ids(int toc, int len, int channels, int frame_size, const int64_t* ids, int n_streams, int n_frames, uint64_t seed_base,
+                          int jobs, uint64_t* hashes) {
+    if (n_streams <= 0) return 0.0;
+    if (jobs < 1) jobs = 1;
+    if (jobs > n_streams) jobs = n_streams;
+    size_t shm_sz = sizeof(uint64_t) * n_streams;
+    void* shm = mmap(nullptr, shm_sz, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (shm == MAP_FAILED) return -1.0;
+    uint64_t* sh_hash = (uint64_t*)shm;
+    ref_setup();
+    double t0 = now_s();
+    pid_t* pids = (pid_t*)calloc(jobs, sizeof(pid_t));
+    for (int j = 0; j < jobs; j++) {
+        pid_t p = fork();
+        if (p == 0) {
+            int lo = (int)((int64_t)n_streams * j / jobs), hi = (int)((int64_t)n_streams * (j + 1) / jobs);
+            for (int s = lo; s < hi; s++) {
+                const uint64_t seed = seed_base ^ (uint64_t)ids[s];
+                sh_hash[s] = frame_size ? ref_decode_synth_celt(frame_size, channels, len, n_frames, seed, nullptr, nullptr)
+                                        : ref_decode_synth_stream(toc, len, channels, n_frames, seed, nullptr, nullptr);
+            }
+            _exit(0);
+        }
+        pids[j] = p;
+    }
+    for (int j = 0; j < jobs; j++) { int stt; if (pids[j] > 0) waitpid(pids[j], &stt, 0); }
+    double wall = now_s() - t0;
+    if (hashes) memcpy(hashes, sh_hash, sizeof(uint64_t) * n_streams);
+    free(pids);
+    munmap(shm, shm_sz);
+    return wall;
+}
+
 } /* extern "C" */

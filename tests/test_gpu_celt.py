@@ -290,3 +290,30 @@ def test_async_calls_in_flight_match_blocking_calls(pkg):
     for k in range(steps):
         assert np.array_equal(got[k], want[k]), k
     b.close()
+
+
+def test_script_capacity_is_a_true_worst_case(pkg, ref):
+    """OPUSB_SCRIPT_OVERFLOW (-1000) is a status the reference never returns: the per-frame script (kMaxOps entries) must
+    hold the worst case.  Maximum-size frames (1275 B: the most bits per band, the deepest splits) at every frame size,
+    mono and stereo, random payloads (transient 1/8, so short blocks with B = 8 occur), several hundred frames each:
+    no frame overflows and every one equals the reference."""
+    rng = np.random.default_rng(99)
+    worst = 0
+    for fs, ch, ln in [(960, 2, 1275), (960, 1, 1275), (480, 2, 1275), (240, 2, 1275), (120, 2, 1275), (120, 1, 1275), (960, 2, 900), (480, 1, 1000)]:
+        S, F = 24, 12
+        data = rng.integers(0, 256, S * F * ln, dtype=np.uint8)
+        frames = pkg.make_frames(S, F)
+        frames["offset"] = (np.arange(S * F, dtype=np.uint32) * ln).reshape(S, F)
+        frames["len"] = ln
+        dec = pkg.BatchDecoder(S, F, channels=ch)
+        rc, pcm, status = dec.decode_many(data, frames, mode=pkg.DM_MODE_CELT_RAW, frame_size=fs, coded_channels=ch)
+        assert rc == 0
+        assert not (status == -1000).any(), (fs, ch, ln)
+        dec.close()
+        for s in range(0, S, 5):
+            o = ref.CeltLayer(ch)
+            for f in range(F):
+                n, want = o.decode(data[(s * F + f) * ln:(s * F + f + 1) * ln], fs)
+                assert status[s, f] == n
+                if n > 0:
+                    assert np.array_equal(pcm[s, f], want), (fs, ch, ln, s, f)

@@ -341,3 +341,57 @@ def test_packets_with_a_toc_frame_size_other_than_20ms_are_refused_without_touch
     assert n == -5
     ms.close()
     dec.close()
+
+
+@pytest.mark.parametrize("kind", ["silk_wb_mono", "silk_stereo", "hybrid_fb", "hybrid_swb_mono", "mode_walk_stereo"])
+def test_three_async_calls_in_flight_silk_hybrid_and_mode_walks(pkg, ref, kind):
+    """decode_many_async / dm_wait with THREE calls in flight (the side-stream SILK fork/join, double-buffered staging)
+    on SILK-only, hybrid and mode-switching streams: every frame equals the reference, and equals the blocking call."""
+    rng = np.random.default_rng(len(kind))
+    S, F, steps = 48, 6, 7
+    ch = 1 if "mono" in kind else 2
+    s4 = 4 if ch == 2 else 0
+    if kind == "mode_walk_stereo":
+        tocs = [0xFC, 0x4C, 0x7C, 0x0C, 0x6C, 0xDC]
+        plans = [[(int(rng.choice(tocs)), 0) for _ in range(F * steps)] for _ in range(S)]
+    else:
+        toc = {"silk_wb_mono": 0x48, "silk_stereo": 0x4C, "hybrid_fb": 0x7C, "hybrid_swb_mono": 0x68}[kind]
+        plans = [[(toc, 0) for _ in range(F * steps)] for _ in range(S)]
+    data, frames, pk = _pack(pkg, plans, 1000 + len(kind))
+    dec = pkg.BatchDecoder(S, F, channels=ch)
+    hb = pkg.api.PinnedArray(data.size, np.uint8)
+    hb.array[:] = data
+    hf = [pkg.api.PinnedArray((S, F), pkg.FRAME_DTYPE) for _ in range(steps)]
+    DEPTH = 3
+    outs = [(pkg.api.PinnedArray((S, F, 960, ch), np.int16), pkg.api.PinnedArray((S, F), np.int32)) for _ in range(DEPTH)]
+    got_pcm = np.zeros((S, F * steps, 960, ch), np.int16)
+    got_st = np.zeros((S, F * steps), np.int32)
+    pending = []
+
+    def retire():
+        k, ticket = pending.pop(0)
+        assert dec.wait(ticket) == 0
+        got_pcm[:, k * F:(k + 1) * F] = outs[k % DEPTH][0].array
+        got_st[:, k * F:(k + 1) * F] = outs[k % DEPTH][1].array
+
+    for k in range(steps):
+        hf[k].array[:] = frames[:, k * F:(k + 1) * F]
+        if len(pending) == DEPTH:
+            retire()
+        o = outs[k % DEPTH]
+        rc, ticket = dec.decode_many_async(hb.array, hf[k].array, o[0].array, o[1].array)
+        assert rc == 0
+        pending.append((k, ticket))
+    while pending:
+        retire()
+    dec.close()
+    for s in range(S):
+        o = ref.PacketDecoder(ch)
+        try:
+            for f in range(F * steps):
+                r, want = o.decode(pk[s][f])
+                assert got_st[s, f] == r, (s, f)
+                if r > 0:
+                    assert np.array_equal(got_pcm[s, f], want), "stream %d frame %d toc %#x" % (s, f, pk[s][f][0])
+        finally:
+            o.close()

@@ -50,6 +50,9 @@ def _worker(rank, world, port, n_global, n_frames, out):
 
     t = torch.from_numpy(hashes.view(np.int64).copy())
     dist.all_reduce(t, op=dist.ReduceOp.SUM)  # verification only: disjoint shards, so the sum is the union
+    # the gather bench.py uses for its cross-rank result check: per-rank hashes -> one array by global stream id
+    by_g = pkg.shard.gather_by_global_id(hashes[ids], rank, world, dist)
+    assert np.array_equal(by_g, t.numpy().view(np.uint64))
     slow = pkg.shard.max_over_ranks(1.0 + rank, dist)
     rate = pkg.shard.aggregate_rate(len(ids) * n_frames * 0.02, world, slow)
     if rank == 0:
