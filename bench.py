@@ -464,6 +464,7 @@ def main():
             # the two legs decode the same stream positions: their last step must agree bit for bit
             same = same and bool(np.array_equal(lp.reshape(-1), last_pcm_device[i]))
         dt_max = pkg.shard.max_over_ranks(dt, D, "cuda")
+        kernel_ms_last = sum(sum(d.stage_times().values()) for d in decs)  # (before the probe below re-uses the library's events)
         # the bare read-back of one step's PCM, all ranks at once: what PCIe and the host memory system allow
         barrier()
         d2h_ms = sum(decs[i].probe_d2h(outs[i][0][0], p.pcm_bytes_step, reps=5) for i, p in enumerate(parts))
@@ -474,7 +475,7 @@ def main():
                "h2d_bytes_per_step": int(nb_step + n_frames_step * 8), "d2h_bytes_per_step": int(pcm_bytes_step + n_frames_step * 4),
                "ms_per_step": 1e3 * dt_max / K, "matches_device_leg": same,
                "api": "decode_many_async + dm_wait, %d calls in flight, pinned host buffers" % DEPTH,
-               "kernel_ms_last_call": sum(sum(d.stage_times().values()) for d in decs),
+               "kernel_ms_last_call": kernel_ms_last,
                "d2h_gbs": achieved_d2h, "d2h_ceiling_gbs": ceiling, "frac_of_ceiling": achieved_d2h / ceiling,
                "d2h_ceiling_how": "bare cudaMemcpyAsync of one step's PCM per GPU (dm_probe_d2h), %d GPU(s) at once, aggregate" % world}
         for d in decs:
