@@ -223,6 +223,8 @@ def make_config(args, wl_desc, S):
            "sharding": "stream i -> GPU i mod N, no collective"}
     if len(WORKLOADS[args.workload][0]) > 1:
         cfg["mix_order"] = args.mix_order
+    if args.no_overlap:
+        cfg["device_leg"] = "dm_decode_device, calls not overlapped"
     cfg["l2"] = "no flush needed: every step decodes new packets, and a step's inputs plus intermediates exceed the 126 MB L2 many times over"
     return cfg
 
@@ -266,6 +268,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="device leg through dm_decode_device (one stream-ordered call after the other) instead of "
+                    "dm_decode_device_async (the tail of step k beside the head of step k+1)")
     ap.add_argument("--device-only", action="store_true", help="the device leg alone (what tools/ncu_capture.py profiles)")
     args = ap.parse_args()
     global METRIC
@@ -353,11 +357,22 @@ def main():
         def new_decoder(self):
             return pkg.BatchDecoder(self.n, self.F, channels=self.cc, device=local_rank)
 
-        def step_device(self, k, stream):
-            rc = self.dec.decode_device(self.d_bytes[k].data_ptr(), self.nb_step, self.d_frames[k].data_ptr(), self.F, self.d_pcm.data_ptr(),
-                                        self.d_status.data_ptr(), stream, **self.kw)
+        def step_device(self, k, stream, ready=None):
+            """One step with device-resident packets.  Steps overlap (dm_decode_device_async: the serial tail of step k runs
+            beside the parse and spectral stages of step k + 1) unless --no-overlap; the first timed step starts behind
+            `ready` (the start event of the timed region), finish_device() makes the timing stream wait for the last."""
+            if args.no_overlap:
+                rc = self.dec.decode_device(self.d_bytes[k].data_ptr(), self.nb_step, self.d_frames[k].data_ptr(), self.F, self.d_pcm.data_ptr(),
+                                            self.d_status.data_ptr(), stream, **self.kw)
+            else:
+                rc, _ = self.dec.decode_device_async(self.d_bytes[k].data_ptr(), self.nb_step, self.d_frames[k].data_ptr(), self.F, self.d_pcm.data_ptr(),
+                                                     self.d_status.data_ptr(), ready, **self.kw)
             if rc:
                 raise RuntimeError("dm_decode_device rc=%d" % rc)
+
+        def finish_device(self, stream):
+            if not args.no_overlap:
+                assert self.dec.stream_wait(stream) == 0
 
         def outs(self):
             return (pkg.api.PinnedArray((self.n, self.F, self.fs, self.cc), np.int16).array, pkg.api.PinnedArray((self.n, self.F), np.int32).array)
@@ -374,9 +389,13 @@ def main():
     algo_bytes_step = nb_step + toc_bytes_step + pcm_bytes_step  # packets in (payload + TOC) + int16 PCM out
     stream = torch.cuda.current_stream().cuda_stream
 
-    def step_device(k):
+    def step_device(k, ready=None):
         for p in parts:
-            p.step_device(k, stream)
+            p.step_device(k, stream, ready)
+
+    def finish_device():
+        for p in parts:
+            p.finish_device(stream)
 
     def barrier():
         if world > 1:
@@ -387,13 +406,15 @@ def main():
     sampler.load_begins()
     for k in range(W):
         step_device(k)
+    finish_device()
     barrier()
     launches0 = sum(p.dec.launch_count for p in parts)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.begin()
     ev0.record()
     for k in range(W, n_steps):
-        step_device(k)
+        step_device(k, ev0.cuda_event if k == W else None)  # the timed steps start behind ev0 ...
+    finish_device()                                          # ... and ev1 is behind the last kernel of the last step
     ev1.record()
     barrier()
     sampler.end()
@@ -402,17 +423,26 @@ def main():
     launches = sum(p.dec.launch_count for p in parts) - launches0
     for p in parts:
         assert (p.d_status.cpu().numpy() == p.fs).all(), "decode errors in the timed region"
-    # per-stage times of the last step (events recorded inside the library on the same stream), summed over the parts
-    stage_acc = {}
-    for p in parts:
-        for name, v in p.dec.stage_times().items():
-            stage_acc[name] = stage_acc.get(name, 0.0) + v
     device_bytes = sum(p.dec.device_bytes for p in parts)
     ms_max = pkg.shard.max_over_ranks(ms, D, "cuda")
     value = pkg.shard.aggregate_rate(K * audio_per_step, world, ms_max * 1e-3)
     last_pcm_device = [p.d_pcm.cpu().numpy() for p in parts]
     for p in parts:
         p.dec.close()
+    # per-stage times: the timed steps overlap (the tail of one beside the head of the next), where a stage has no time
+    # of its own; so once more, untimed, one stream-ordered call after the other (dm_decode_device) on fresh decoders:
+    # the last of W + 1 steps, CUDA events recorded inside the library on the streams the kernels run on, summed over the parts
+    stage_acc = {}
+    for p in parts:
+        d = p.new_decoder()
+        for k in range(W + 1):
+            rc = d.decode_device(p.d_bytes[k].data_ptr(), p.nb_step, p.d_frames[k].data_ptr(), p.F, p.d_pcm.data_ptr(), p.d_status.data_ptr(), stream, **p.kw)
+            assert rc == 0
+        torch.cuda.synchronize()
+        for name, v in d.stage_times().items():
+            stage_acc[name] = stage_acc.get(name, 0.0) + v
+        d.close()
+    staged_step_ms = stage_acc.pop("pipeline", None)
 
     # ---- e2e: C ABI with pinned host buffers (fresh decoders so that the same packets are legal input)
     e2e = None
@@ -464,7 +494,7 @@ def main():
             # the two legs decode the same stream positions: their last step must agree bit for bit
             same = same and bool(np.array_equal(lp.reshape(-1), last_pcm_device[i]))
         dt_max = pkg.shard.max_over_ranks(dt, D, "cuda")
-        kernel_ms_last = sum(sum(d.stage_times().values()) for d in decs)  # (before the probe below re-uses the library's events)
+        kernel_ms_last = sum(d.stage_times()["pipeline"] for d in decs)  # (before the probe below re-uses the library's events)
         # the bare read-back of one step's PCM, all ranks at once: what PCIe and the host memory system allow
         barrier()
         d2h_ms = sum(decs[i].probe_d2h(outs[i][0][0], p.pcm_bytes_step, reps=5) for i, p in enumerate(parts))
@@ -542,6 +572,8 @@ def main():
                 "issue_utilisation": (inst_step / step_s / (issue_peak / 32)) if inst_step else None,
                 "lanes_per_instruction": (sum(v["thread_inst"] for v in kern.values()) / sum(v["warp_inst"] for v in kern.values())) if nc else None,
                 "kernel": "k_" + str(top), "kernel_ms": top_ms, "stage_ms": stage_acc,
+                "stage_ms_how": "one untimed step on its own (dm_decode_device); the timed steps overlap the tail of one step with the head of the next",
+                "staged_step_ms": staged_step_ms,
                 "hbm": {"bound": "hbm", "kernel": "k_" + str(top), "achieved": achieved_hbm, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (achieved_hbm / hbm_peak) if achieved_hbm else None, "traffic": stage_sum(top, "dram_bytes"),
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_step,

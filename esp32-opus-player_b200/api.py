@@ -39,7 +39,7 @@ def lib():
         return _lib
     if not os.path.exists(LIB):
         build()
-    L = ctypes.CDLL(LIB)
+    L = ctypes.CDLL(os.environ.get("OPUSB_LIB") or LIB)  # OPUSB_LIB: a build variant of the same library (tuning sweeps)
     L.dm_create.argtypes = [ctypes.POINTER(_P), _I, _I, _I, _I]
     L.dm_destroy.argtypes = [_P]
     L.dm_reset.argtypes = [_P, _P, _I]
@@ -56,6 +56,9 @@ def lib():
     L.dm_launch_count.argtypes = [_P]
     L.dm_device_bytes.restype = ctypes.c_size_t
     L.dm_device_bytes.argtypes = [_P]
+    L.dm_decode_device_async.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), _P, ctypes.POINTER(_P)]
+    L.dm_stream_wait.argtypes = [_P, _P]
+    L.dm_debug_trace.argtypes = [_P, _I, _P]
     L.dm_stage_times.argtypes = [_P, _P, _I]
     L.dm_stage_name.restype = ctypes.c_char_p
     L.dm_stage_name.argtypes = [_I]
@@ -216,6 +219,28 @@ class BatchDecoder:
         if rc:
             raise RuntimeError("dm_probe_d2h rc=%d" % rc)
         return ms.value / reps
+
+    def decode_device_async(self, d_bytes, n_bytes, d_frames, n_frames, d_pcm, d_status, ready_event=None, mode=DM_MODE_OPUS, frame_size=960,
+                            coded_channels=2, start_band=0):
+        """Device pointers (ints); starts behind `ready_event` (a cudaEvent_t handle or None), returns (rc, done_event).
+        Consecutive calls overlap: the tail of one call runs beside the head of the next."""
+        b = self._batch(d_bytes, n_bytes, d_frames, n_frames, mode, frame_size, coded_channels, start_band)
+        o = _Out(d_pcm, d_status)
+        done = _P()
+        rc = lib().dm_decode_device_async(self._ctx, ctypes.byref(b), ctypes.byref(o), ready_event, ctypes.byref(done))
+        return rc, done.value
+
+    def stream_wait(self, cuda_stream=0):
+        """Make `cuda_stream` wait for every call enqueued on this context so far."""
+        return lib().dm_stream_wait(self._ctx, cuda_stream)
+
+    def trace(self, n):
+        """Stage boundaries (ms) of the last n pipelined calls, float32[n][9]; needs OPUSB_TRACE=1 at creation."""
+        out = np.zeros((n, 9), np.float32)
+        rc = lib().dm_debug_trace(self._ctx, n, out.ctypes.data)
+        if rc:
+            raise RuntimeError("dm_debug_trace rc=%d" % rc)
+        return out
 
     def stage_times(self):
         ms = (ctypes.c_float * 16)()

@@ -20,6 +20,7 @@ struct CeltStreamState {
     int32_t pf_gain, pf_gain_old;
     int32_t pf_tapset, pf_tapset_old;
     int32_t prev_mode;            // Opus layer: mode of the previous frame (ref st->prev_mode, src/opus_decoder.cpp:275)
+    int32_t pkt_failed;           // a frame of the multi-frame packet being decoded has failed: its remaining frames are dropped
     int32_t preemph_mem[2];       // de-emphasis IIR memory (ref :1972-1985)
     int32_t tail[2][kOverlap / 2];  // raw IMDCT tail awaiting the next frame's TDAC (ref :2349, 3281)
     int32_t hist[2][kCombHist];     // last post-filtered samples, oldest first (ref decode_mem)

@@ -14,7 +14,7 @@
 #pragma once
 #include <cuda_pipeline.h>
 
-#include "celt_synth.cuh"
+#include "celt_imdct_regs.cuh"
 #include "opus_frame.cuh"
 
 namespace opusb200 {
@@ -34,6 +34,13 @@ struct DevParams {
     int start_band;      // raw CELT only
     int CC;              // decoder (output) channels
     int first_stream, n_sel;  // stream range handled by this launch
+    int f0, nf;               // frame range [f0, f0 + nf) of every stream handled by this launch (a "frame group": the host
+                              // runs the groups of a call as a software pipeline, see launch_pipeline in opus_b200.cu)
+    // work item `local` of a frame-parallel launch -> stream, frame, frame index t
+    __device__ __forceinline__ int n_local() const { return n_sel * nf; }
+    __device__ __forceinline__ int stream_of(int local) const { return first_stream + local / nf; }
+    __device__ __forceinline__ int frame_of(int local) const { return f0 + local % nf; }
+    __device__ __forceinline__ size_t index_of(int local) const { return (size_t)stream_of(local) * n_frames + frame_of(local); }
 };
 
 #ifndef K1_THREADS
@@ -51,6 +58,12 @@ enum { KW_WARPS = 4 };
 #ifndef KI_WARPS
 #define KI_WARPS 4
 #endif
+#ifndef KI_GRID
+#define KI_GRID 8  // blocks per SM of the persistent grid of k_imdct_long
+#endif
+#ifndef KIL_BLOCKS
+#define KIL_BLOCKS 4  // resident blocks per SM the register allocation of k_imdct_long is held to (128 registers)
+#endif
 enum { FD_CONT = 1, FD_NULL = 2 };  // dm_frame.flags (include/opus_b200.h)
 
 __device__ __forceinline__ bool frame_skipped(int status) {
@@ -62,10 +75,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_BLOCKS)  // 80 registers: 24 wa
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
           BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
-    const bool in_range = local < P.n_sel * P.n_frames;
+    const bool in_range = local < P.n_local();
     const unsigned warp = __ballot_sync(0xffffffffu, in_range);  // the lanes of this warp that own a frame
     if (!in_range) return;
-    const size_t t = (size_t)P.first_stream * P.n_frames + local;
+    const size_t t = P.index_of(local);
     const FrameDesc d = fr[t];
     CeltFrameHdr& h = hdr[t];
     ParseCtx p;
@@ -83,8 +96,8 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
         oflags = OF_NO_CELT;
         celt = false;
     } else if (P.mode == 0) {
-        const int f = local % P.n_frames;
-        const int prev_mode = f > 0 ? opus_toc_mode(fr[t - 1].toc) : st[P.first_stream + local / P.n_frames].prev_mode;
+        const int f = P.frame_of(local);  // (the previous frame's TOC is call input, whichever group it belongs to)
+        const int prev_mode = f > 0 ? opus_toc_mode(fr[t - 1].toc) : st[P.stream_of(local)].prev_mode;
         oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade, silk_lanes);
     } else {
         rd_init(p.rd, bytes + d.offset, d.len);
@@ -131,8 +144,8 @@ k_leaf_count(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ op
     if (threadIdx.x < kLeafClasses) cnt[threadIdx.x] = 0;
     __syncthreads();
     const int local = blockIdx.x * KL_THREADS + threadIdx.x;
-    if (local < P.n_sel * P.n_frames) {
-        const size_t t = (size_t)P.first_stream * P.n_frames + local;
+    if (local < P.n_local()) {
+        const size_t t = P.index_of(local);
         const int n = hdr[t].n_leaves, spread = hdr[t].spread;
         const BandOp* last = ops + t * kMaxOps + (kMaxOps - 1);
 #pragma unroll 1
@@ -152,14 +165,14 @@ k_leaf_place(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ op
     int total = 0;
 #pragma unroll
     for (int c = 0; c < kLeafClasses; c++) total += ls->n[c];
-    if (total > cap || P.n_sel * P.n_frames > (1 << 21)) {  // the list is full, or a frame index does not fit an entry
+    if (total > cap || P.n_local() > (1 << 21)) {  // the list is full, or a frame index does not fit an entry
         if (blockIdx.x == 0 && threadIdx.x == 0) { ls->overflow = 1; ls->total = 0; }
         return;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) ls->total = total;
     const int local = blockIdx.x * KL_THREADS + threadIdx.x;
-    const bool in = local < P.n_sel * P.n_frames;
-    const size_t t = (size_t)P.first_stream * P.n_frames + (in ? local : 0);
+    const bool in = local < P.n_local();
+    const size_t t = P.index_of(in ? local : 0);
     const int n = in ? hdr[t].n_leaves : 0, spread = hdr[t].spread;
     const BandOp* last = ops + t * kMaxOps + (kMaxOps - 1);
 #pragma unroll 1
@@ -188,7 +201,7 @@ k_leaf_expand(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ o
 #pragma unroll 1
     for (int k = blockIdx.x * KL_THREADS + threadIdx.x; k < total; k += gridDim.x * KL_THREADS) {
         const uint32_t ent = order[k];
-        const size_t t = (size_t)P.first_stream * P.n_frames + (ent >> 11);
+        const size_t t = P.index_of((int)(ent >> 11));
         const BandOp o = ops[t * kMaxOps + (kMaxOps - 1) - (ent & 2047u)];
         leaf_expand(o, hdr[t].spread, y);
         int16_t* dst = X + t * (2 * kMaxFrame) + o.off;
@@ -218,9 +231,9 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ f
     if (lane < kNbEBands) b = S.band[lane];
     u32 rng = S.rng;
     int pfp = S.pf_period, pfpo = S.pf_period_old, pfg = S.pf_gain, pfgo = S.pf_gain_old, pft = S.pf_tapset, pfto = S.pf_tapset_old;
-    bool pkt_failed = false;
+    bool pkt_failed = S.pkt_failed != 0;  // a multi-frame packet may straddle two launches (frame groups of a call)
     int last_toc = -1;
-    for (int f = 0; f < P.n_frames; f++) {
+    for (int f = P.f0; f < P.f0 + P.nf; f++) {
         const size_t t = (size_t)s * P.n_frames + f;
         const CeltFrameHdr& h = hdr[t];
         FrameEnergy& o = fe[t];
@@ -259,6 +272,7 @@ k_sequence(const CeltFrameHdr* __restrict__ hdr, const FrameDesc* __restrict__ f
     if (lane < kNbEBands) S.band[lane] = b;
     if (lane == 0) {
         if (P.mode == 0 && last_toc >= 0) S.prev_mode = opus_toc_mode(last_toc);
+        S.pkt_failed = pkt_failed;
         S.rng = rng;
         S.pf_period = pfp; S.pf_period_old = pfpo; S.pf_gain = pfg; S.pf_gain_old = pfgo; S.pf_tapset = pft; S.pf_tapset_old = pfto;
     }
@@ -270,8 +284,8 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
         int16_t* __restrict__ X, const LeafSort* __restrict__ ls, DevParams P) {
     __shared__ __align__(16) int16_t Wsm[KB_WARPS][W_SIZE];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (local >= P.n_sel * P.n_frames) return;
-    const size_t t = (size_t)P.first_stream * P.n_frames + local;
+    if (local >= P.n_local()) return;
+    const size_t t = P.index_of(local);
     const CeltFrameHdr& h = hdr[t];
     const FrameEnergy& e = fe[t];
     if (e.skip & FS_NO_CELT) return;
@@ -295,18 +309,103 @@ k_bands(const CeltFrameHdr* __restrict__ hdr, const BandOp* __restrict__ ops, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// The long block of a 20 ms frame that is not transient (seven frames in eight of the headline workload) goes through the
+// register FFT of celt_imdct_regs.cuh: one warp per frame, the two channels side by side in pass A (30 lanes), one after
+// the other in pass B.  Blocks are persistent (grid-stride over the frames) so that the rotation and twiddle tables are
+// staged in shared memory once per block.  A kernel of its own: the straight-line butterfly code is long, and next to
+// the generic FFT (k_imdct, which takes every other frame) it would not stay in the instruction cache.
+enum {
+    kImdctWarpSmem = 2 * kMaxFrame * 2 + 2 * kImdctBuf * 4 + 2 * 24 * 4,          // spectrum + two transpose buffers + gains
+    kImdctLongSmem = KI_WARPS * kImdctWarpSmem + (960 + 3 * 480) * 2,            // + the tables
+};
+__device__ __forceinline__ bool imdct_is_long(const CeltFrameHdr& h) { return h.LM == 3 && !(h.flags & FF_TRANSIENT); }
+
+__global__ void __launch_bounds__(32 * KI_WARPS, KIL_BLOCKS)
+k_imdct_long(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int16_t* __restrict__ X,
+             int32_t* __restrict__ raw, DevParams P) {
+    // dynamic shared memory (kImdctLongSmem bytes, above the 48 KB static limit): per warp the frame's normalised spectrum
+    // (fetched one frame ahead), a transpose buffer per channel and the band gains; per block the tables
+    extern __shared__ __align__(16) unsigned char imdct_smem[];
+    Lanes L;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* mine_base = imdct_smem + (size_t)warp * kImdctWarpSmem;
+    int16_t* Xs = reinterpret_cast<int16_t*>(mine_base);
+    Cpx* T0 = reinterpret_cast<Cpx*>(mine_base + 2 * kMaxFrame * sizeof(int16_t));
+    Cpx* T1 = T0 + kImdctBuf / 2;
+    int32_t* gs0 = reinterpret_cast<int32_t*>(T1 + kImdctBuf / 2);
+    int32_t* gs1 = gs0 + 24;
+    int16_t* trig_s = reinterpret_cast<int16_t*>(imdct_smem + (size_t)KI_WARPS * kImdctWarpSmem);
+    int16_t* twr_s = trig_s + 960;
+    int16_t* twi_s = twr_s + 480;
+    int16_t* rev_s = twi_s + 480;
+    for (int i = threadIdx.x; i < 960; i += blockDim.x) trig_s[i] = kMdctTrig[i];
+    for (int i = threadIdx.x; i < 480; i += blockDim.x) { twr_s[i] = kFftTwRe[i]; twi_s[i] = kFftTwIm[i]; rev_s[i] = kBitrev480[i]; }
+    __syncthreads();
+    const int CC = P.CC, stride = gridDim.x * KI_WARPS, n_local = P.n_local();
+    auto fetch = [&](int local) {  // the X row of frame `local` -> Xs, 16 bytes per lane and copy
+        if (local < n_local) {
+            const int16_t* src = X + P.index_of(local) * (2 * kMaxFrame);
+            for (int i = 8 * L.lane; i < 2 * kMaxFrame; i += 256) __pipeline_memcpy_async(Xs + i, src + i, 16);
+        }
+        __pipeline_commit();
+    };
+    int local = blockIdx.x * KI_WARPS + warp;
+    fetch(local);
+#pragma unroll 1
+    for (; local < n_local; local += stride) {
+        const size_t t = P.index_of(local);
+        const CeltFrameHdr& h = hdr[t];
+        const FrameEnergy& e = fe[t];
+        const bool mine = !(e.skip & FS_NO_CELT) && imdct_is_long(h);
+        const int C = h.C, start = (h.flags & FF_SILENCE) ? 0 : h.start, end = (h.flags & FF_SILENCE) ? 0 : h.end;
+        if (mine && L.lane <= kNbEBands) {  // band gains (the lanes' loads of E run beside the wait for the spectrum)
+            gs0[L.lane] = band_gain_packed(L.lane, L.lane < kNbEBands ? e.E[0][L.lane] : (int16_t)0, start, end);
+            gs1[L.lane] = band_gain_packed(L.lane, L.lane < kNbEBands ? e.E[1][L.lane] : (int16_t)0, start, end);
+        }
+        __pipeline_wait_prior(0);
+        L.sync();
+        if (!mine) {
+            fetch(local + stride);
+            continue;
+        }
+        // spectra of the output channels (ref celt_synthesis :2085-2109)
+        const bool same = CC == 2 && C == 1;     // mono frame in a stereo decoder: one transform, stored twice
+        const bool downmix = CC == 1 && C == 2;  // stereo frame in a mono decoder: the average of the two spectra
+        const int nch = (CC == 2 && !same) ? 2 : 1;
+        imdct480_prerotate(L.lane, Xs, gs0, gs1, trig_s, rev_s, T0, downmix);
+        if (nch == 2) imdct480_prerotate(L.lane, Xs + kMaxFrame, gs1, gs1, trig_s, rev_s, T1, false);
+        L.sync();
+        fetch(local + stride);  // Xs is free: the next frame's spectrum arrives while this one is transformed
+        // pass A: lane = 15 * channel + block, each on its own row
+        {
+            const int ch = L.lane >= 15 ? 1 : 0, b = L.lane - 15 * ch;
+            if (L.lane < 15 * nch) imdct480_pass_a((ch ? T1 : T0) + kImdctRow * b);
+        }
+        L.sync();
+        int32_t* out0 = raw + (t * CC) * kMaxFrame;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) imdct480_pass_b(c ? T1 : T0, trig_s, twr_s, twi_s, L.lane, out0 + c * kMaxFrame);
+        if (same) {
+            L.sync();
+            for (int i = L.lane; i < kMaxFrame; i += 32) out0[kMaxFrame + i] = out0[i];
+        }
+    }
+    __pipeline_wait_prior(0);
+}
+
+// Every other frame (short blocks, the shorter frame sizes): the generic shared-memory FFT, one warp per (frame, channel).
 __global__ void __launch_bounds__(32 * KI_WARPS)
 k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int16_t* __restrict__ X,
         int32_t* __restrict__ raw, DevParams P) {
     __shared__ __align__(16) int32_t fsm[KI_WARPS][2][kMaxFrame];
     __shared__ int32_t gsm[KI_WARPS][kNbEBands + 1];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (local >= P.n_sel * P.n_frames * P.CC) return;
+    if (local >= P.n_local() * P.CC) return;
     const int c = local % P.CC;
-    const size_t t = (size_t)P.first_stream * P.n_frames + local / P.CC;
+    const size_t t = P.index_of(local / P.CC);
     const CeltFrameHdr& h = hdr[t];
     const FrameEnergy& e = fe[t];
-    if (e.skip & FS_NO_CELT) return;
+    if ((e.skip & FS_NO_CELT) || imdct_is_long(h)) return;
     Lanes L;
     int32_t* freq = fsm[threadIdx.x >> 5][0];
     int32_t* work = fsm[threadIdx.x >> 5][1];
@@ -358,8 +457,9 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
     const size_t t0 = (size_t)s * P.n_frames;
 
     // stage <- raw output of frame f (16 bytes per lane and copy), if that frame has a CELT layer
+    const int f_end = P.f0 + P.nf;
     auto fetch = [&](int f) {
-        if (f < P.n_frames) {
+        if (f < f_end) {
             const FrameEnergy& e = fe[t0 + f];
             if (!(e.skip & FS_NO_CELT)) {
                 const int n = e.celt_n;
@@ -369,8 +469,8 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
         }
         __pipeline_commit();
     };
-    fetch(0);
-    for (int f = 0; f < P.n_frames; f++) {
+    fetch(P.f0);
+    for (int f = P.f0; f < f_end; f++) {
         const size_t t = t0 + f;
         const FrameEnergy& e = fe[t];
         __pipeline_wait_prior(0);
@@ -423,12 +523,12 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     const int my_s = P.first_stream + (live ? my / CC : 0), my_c = live ? my % CC : 0;
     s32 mem = live ? st[my_s].preemph_mem[my_c] : 0;
     const int N = P.frame_size;
-    const int tpf = (N + DE_TW - 1) / DE_TW, T = tpf * P.n_frames;
+    const int tpf = (N + DE_TW - 1) / DE_TW, T = tpf * P.nf;
     const int32_t* row0 = syn + ((size_t)my_s * P.n_frames * CC + my_c) * kMaxFrame;  // frame f of this chain: + f * CC * kMaxFrame
     int16_t* out0 = pcm + (size_t)my_s * P.n_frames * N * CC;                            // frame f of this stream: + f * N * CC
 
     // prefetch cursor (tile index -> frame, offset) kept incrementally
-    int pf_q = 0, pf_f = 0, pf_j = 0, pf_n = 0;
+    int pf_q = 0, pf_f = P.f0, pf_j = 0, pf_n = 0;
     auto prefetch = [&]() {
         if (pf_q < T && live) {
             if (pf_j == 0) pf_n = fe[(size_t)my_s * P.n_frames + pf_f].celt_n;  // nothing to fetch for frames without a CELT layer
@@ -446,7 +546,7 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     };
     for (int q = 0; q < DE_STAGES - 1; q++) prefetch();
 
-    int f = 0, j0 = 0, my_n = 0;
+    int f = P.f0, j0 = 0, my_n = 0;
     bool silk_only = false;
     for (int q = 0; q < T; q++) {
         const int w = min(DE_TW, N - j0);

@@ -17,51 +17,64 @@ using namespace opusb200;
 static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
 static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
-enum { kStages = 8, kMaxChunks = 4, kRing = 4 };
-static const char* kStageNames[kStages] = {"entropy", "sequence", "leaves", "bands", "imdct", "postfilter", "deemph", "silk"};
+enum { kStages = 8, kMaxChunks = 4, kRing = 4, kTraceCalls = 16 };
+static const char* kStageNames[kStages + 1] = {"entropy", "sequence", "leaves", "bands", "imdct", "postfilter", "deemph", "silk", "pipeline"};
+
+// The per-frame intermediates that cross from the head of a call (parse, spectral stage) into its tail (post-filter,
+// de-emphasis) and its SILK stage.  There are two sets, used by consecutive calls in turn, so that the head of call k + 1
+// can run while the tail of call k still reads what the head of call k left.
+struct FrameSet {
+    CeltFrameHdr* hdr;
+    FrameEnergy* fe;
+    int32_t* raw;
+    int32_t* syn;            // post-filter -> de-emphasis
+    SilkFrame* silk;
+    SilkCtl* sctl;           // SILK stage hand-offs (silk_kernels.cuh)
+    SilkPost* spost;
+    int16_t* sxq;
+    int16_t* slr;
+    int16_t* sup;
+    FixEntry* sfix;          // LPC filters that failed their first stability check (two per SILK frame-channel at most)
+    int* any_silk;           // [kMaxChunks] a frame of that stream range of the call has a SILK layer
+    int* fix_count;          // [kMaxChunks] filters queued for k_silk_fix
+};
 
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
     int leaf_slots;  // capacity of the sorted leaf list per frame (OPUSB_LEAF_SLOTS lowers it: tests of the overflow path)
+    int tail_mode;   // pipelined calls: 2 = post-filter + de-emphasis on the tail stream, 1 = de-emphasis only, 0 = no tail stream (OPUSB_TAIL, for tuning)
     int silk_lanes;  // chains per warp of the SILK lane-per-chain kernels; 0 = silk_chain_lanes() (OPUSB_SILK_LANES overrides, for tuning)
     // per-stream state
     CeltStreamState* d_state;
     SilkStreamState* d_sstate;
-    // per-frame intermediates
-    CeltFrameHdr* d_hdr;
+    FrameSet set[2];         // set[1] is allocated by the first pipelined call
+    // per-frame intermediates of the head alone ...
     BandOp* d_ops;
-    SilkFrame* d_silk;
-    SilkCtl* d_sctl;         // SILK stage hand-offs (silk_kernels.cuh)
-    SilkPost* d_spost;
-    int16_t* d_sxq;
-    int16_t* d_slr;
-    int16_t* d_sup;
-    int* d_any_silk;         // [kMaxChunks] a frame of the stream range of the call has a SILK layer
-    int* d_fix_count;        // per stream range of a call (kMaxChunks): filters queued for k_silk_fix
-    FixEntry* d_sfix;        // LPC filters that failed their first stability check (two per SILK frame-channel at most)
     int16_t* d_X;
     LeafSort* d_leafsort;    // [kMaxChunks]: counting sort of the coded leaves of a launch by cost class
     uint32_t* d_leaf_order;  // the sorted leaf list, kLeafSlotsPerFrame entries per frame of the context
-    FrameEnergy* d_fe;
-    int32_t* d_raw;
-    int32_t* d_syn;
-    // staging for the host-buffer path
-    uint8_t* d_bytes[2];     // packet bytes, double buffered so that call n+1 can upload while call n still parses
+    // staging for the host-buffer path: double buffered so that call n+1 can upload while call n still parses
+    uint8_t* d_bytes[2];
     size_t d_bytes_cap[2];
-    FrameDesc* d_frames;
+    FrameDesc* d_frames[2];
     int16_t* d_pcm;
     int32_t* d_status;
     int16_t* d_pcm2;         // second output buffer, allocated on the first decode_many_async
     int32_t* d_status2;
-    cudaStream_t streams[kMaxChunks];
+    cudaStream_t streams[kMaxChunks];     // blocking decode_many: one per stream range; pipelined calls: [0] head, [1] read-back, [2] upload
+    cudaStream_t tail;                    // pipelined calls: post-filter, de-emphasis, final SILK sum
     cudaStream_t side[kMaxChunks];        // per stream range: the SILK kernels of a call run beside its CELT kernels
     cudaEvent_t fork_ev[kMaxChunks], join_ev[kMaxChunks];
     cudaEvent_t bytes_ready;
-    // calls in flight (decode_many_async): per chunk stream, "packets parsed" and "results in host memory"
-    cudaEvent_t parsed[kRing][kMaxChunks], done[kRing][kMaxChunks];
-    cudaEvent_t uploaded[kRing], kernels_done[kRing];
+    // pipelined calls (dm_decode_device, dm_decode_device_async, decode_many_async), a ring over the call number
+    long long calls;
+    cudaEvent_t ready_ev[kRing], seq_ev[kRing], head_ev[kRing], x_ev[kRing], done_ev[kRing];
+    // decode_many_async: "packets parsed", "results in host memory", "packets uploaded"
+    cudaEvent_t parsed[kRing], host_done[kRing], uploaded[kRing];
     long long next_ticket;
     cudaEvent_t ev[kStages + 1];
+    cudaEvent_t probe_ev[2];
+    cudaEvent_t* trace;      // OPUSB_TRACE=1: kTraceCalls x (kStages + 1) timing events, one row per pipelined call (dm_debug_trace)
     long long launches;
     size_t dev_bytes;
     int last_cuda_error;
@@ -90,9 +103,32 @@ static void init_state_host(CeltStreamState& s) {
         for (int c = 0; c < 2; c++) s.band[i].logE[c] = s.band[i].logE2[c] = -(28 << 10);  // ref src/celt.cpp:2496
 }
 
-extern "C" {
-
-}  // extern "C"
+static int alloc_set(dm_ctx* c, FrameSet& F) {
+    if (F.hdr) return 0;
+    const size_t nfr = (size_t)c->n_streams * c->max_frames;
+    int r;
+    if ((r = dev_alloc(c, &F.hdr, nfr))) return r;
+    if ((r = dev_alloc(c, &F.fe, nfr))) return r;
+    if ((r = dev_alloc(c, &F.raw, nfr * c->channels * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &F.syn, nfr * c->channels * kMaxFrame))) return r;
+    if ((r = dev_alloc(c, &F.silk, nfr))) return r;
+    if ((r = dev_alloc(c, &F.sctl, nfr * 2))) return r;
+    if ((r = dev_alloc(c, &F.spost, nfr))) return r;
+    if ((r = dev_alloc(c, &F.sxq, nfr * 2 * kXqRow))) return r;
+    if ((r = dev_alloc(c, &F.slr, nfr * 2 * kXqRow))) return r;
+    if ((r = dev_alloc(c, &F.sup, nfr * 2 * kUpRow))) return r;
+    if ((r = dev_alloc(c, &F.sfix, nfr * 4))) return r;
+    if ((r = dev_alloc(c, &F.any_silk, kMaxChunks))) return r;
+    if ((r = dev_alloc(c, &F.fix_count, kMaxChunks))) return r;
+    CU_TRY(c, cudaMemset(F.spost, 0, nfr * sizeof(SilkPost)));  // has_out of frames no SILK kernel has visited yet
+    CU_TRY(c, cudaMemset(F.any_silk, 0, kMaxChunks * sizeof(int)));
+    return 0;
+}
+static void free_set(FrameSet& F) {
+    cudaFree(F.hdr); cudaFree(F.fe); cudaFree(F.raw); cudaFree(F.syn); cudaFree(F.silk); cudaFree(F.sctl); cudaFree(F.spost); cudaFree(F.sxq); cudaFree(F.slr);
+    cudaFree(F.sup); cudaFree(F.sfix); cudaFree(F.any_silk); cudaFree(F.fix_count);
+    memset(&F, 0, sizeof(F));
+}
 
 // Everything dm_create allocates; on failure the caller tears the half-built context down with dm_destroy.
 static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, int device) {
@@ -100,6 +136,8 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     c->leaf_slots = kLeafSlotsPerFrame;  // (the context was just zeroed)
     if (const char* e = getenv("OPUSB_LEAF_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= kLeafSlotsPerFrame) c->leaf_slots = v; }
+    c->tail_mode = 2;
+    if (const char* e = getenv("OPUSB_TAIL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tail_mode = v; }
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // The entropy kernel keeps its per-thread allocation arrays and the explicit partition stack in local memory.  The
     // stack limit is a DEVICE-wide setting shared with every other CUDA user of the process (torch): it is only ever
@@ -116,49 +154,40 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     int r;
     if ((r = dev_alloc(c, &c->d_state, (size_t)n_streams))) return r;
     if ((r = dev_alloc(c, &c->d_sstate, (size_t)n_streams))) return r;
-    if ((r = dev_alloc(c, &c->d_silk, nfr))) return r;
-    if ((r = dev_alloc(c, &c->d_sctl, nfr * 2))) return r;
-    if ((r = dev_alloc(c, &c->d_spost, nfr))) return r;
-    if ((r = dev_alloc(c, &c->d_sxq, nfr * 2 * kXqRow))) return r;
-    if ((r = dev_alloc(c, &c->d_slr, nfr * 2 * kXqRow))) return r;
-    if ((r = dev_alloc(c, &c->d_sup, nfr * 2 * kUpRow))) return r;
-    if ((r = dev_alloc(c, &c->d_any_silk, kMaxChunks))) return r;
-    if ((r = dev_alloc(c, &c->d_fix_count, kMaxChunks))) return r;
-    if ((r = dev_alloc(c, &c->d_sfix, nfr * 4))) return r;
+    if ((r = alloc_set(c, c->set[0]))) return r;
     CU_TRY(c, cudaFuncSetAttribute(k_silk_core<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, silk_core_smem(32)));
-    if ((r = dev_alloc(c, &c->d_hdr, nfr))) return r;
+    CU_TRY(c, cudaFuncSetAttribute(k_imdct_long, cudaFuncAttributeMaxDynamicSharedMemorySize, kImdctLongSmem));
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_leafsort, (size_t)kMaxChunks))) return r;
     if ((r = dev_alloc(c, &c->d_leaf_order, nfr * kLeafSlotsPerFrame))) return r;
-    if ((r = dev_alloc(c, &c->d_fe, nfr))) return r;
-    if ((r = dev_alloc(c, &c->d_raw, nfr * channels * kMaxFrame))) return r;
-    if ((r = dev_alloc(c, &c->d_syn, nfr * channels * kMaxFrame))) return r;
-    if ((r = dev_alloc(c, &c->d_frames, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_frames[0], nfr))) return r;
     if ((r = dev_alloc(c, &c->d_pcm, nfr * channels * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_status, nfr))) return r;
+    // the streams that carry few, long-running warps (the serial tail, the SILK recurrences) get the first free slots
+    int prio_lo = 0, prio_hi = 0;
+    CU_TRY(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int i = 0; i < kMaxChunks; i++) CU_TRY(c, cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    CU_TRY(c, cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < kMaxChunks; i++) {
-        // the side stream carries few, long-running warps: give its blocks the first free slots
-        int prio_lo = 0, prio_hi = 0;
-        CU_TRY(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CU_TRY(c, cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio_hi));
         CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
         CU_TRY(c, cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
     }
     CU_TRY(c, cudaEventCreateWithFlags(&c->bytes_ready, cudaEventDisableTiming));
-    for (int r = 0; r < kRing; r++)
-        for (int k = 0; k < kMaxChunks; k++) {
-            CU_TRY(c, cudaEventCreateWithFlags(&c->parsed[r][k], cudaEventDisableTiming));
-            CU_TRY(c, cudaEventCreateWithFlags(&c->done[r][k], cudaEventDisableTiming));
-        }
     for (int r = 0; r < kRing; r++) {
-        CU_TRY(c, cudaEventCreateWithFlags(&c->uploaded[r], cudaEventDisableTiming));
-        CU_TRY(c, cudaEventCreateWithFlags(&c->kernels_done[r], cudaEventDisableTiming));
+        cudaEvent_t* evs[] = {&c->ready_ev[r], &c->seq_ev[r], &c->head_ev[r], &c->x_ev[r], &c->done_ev[r], &c->parsed[r], &c->host_done[r], &c->uploaded[r]};
+        for (cudaEvent_t* e : evs) CU_TRY(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     for (int i = 0; i <= kStages; i++) CU_TRY(c, cudaEventCreate(&c->ev[i]));
-    CU_TRY(c, cudaMemset(c->d_spost, 0, nfr * sizeof(SilkPost)));  // has_out of frames no SILK kernel has visited yet
-    CU_TRY(c, cudaMemset(c->d_any_silk, 0, kMaxChunks * sizeof(int)));
+    for (int i = 0; i < 2; i++) CU_TRY(c, cudaEventCreate(&c->probe_ev[i]));
+    if (const char* e = getenv("OPUSB_TRACE")) {
+        if (atoi(e) > 0) {
+            c->trace = (cudaEvent_t*)calloc((size_t)kTraceCalls * (kStages + 1), sizeof(cudaEvent_t));
+            if (!c->trace) return DM_ERR_NOMEM;
+            for (int i = 0; i < kTraceCalls * (kStages + 1); i++) CU_TRY(c, cudaEventCreate(&c->trace[i]));
+        }
+    }
     return dm_reset(c, nullptr, 0);
 }
 
@@ -189,34 +218,36 @@ void dm_destroy(dm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_state); cudaFree(c->d_sstate); cudaFree(c->d_silk); cudaFree(c->d_sctl); cudaFree(c->d_spost); cudaFree(c->d_sxq); cudaFree(c->d_slr);
-    cudaFree(c->d_sup); cudaFree(c->d_any_silk); cudaFree(c->d_sfix); cudaFree(c->d_fix_count); cudaFree(c->d_hdr); cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_fe);
-    cudaFree(c->d_raw); cudaFree(c->d_syn); cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames); cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status2);
-    cudaFree(c->d_status);
+    cudaFree(c->d_state); cudaFree(c->d_sstate);
+    free_set(c->set[0]); free_set(c->set[1]);
+    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order);
+    cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames[0]); cudaFree(c->d_frames[1]);
+    cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status); cudaFree(c->d_status2);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->tail) cudaStreamDestroy(c->tail);
     for (int i = 0; i < kMaxChunks; i++) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->fork_ev[i]) cudaEventDestroy(c->fork_ev[i]);
         if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
     }
     if (c->bytes_ready) cudaEventDestroy(c->bytes_ready);
-    for (int r = 0; r < kRing; r++)
-        for (int k = 0; k < kMaxChunks; k++) {
-            if (c->parsed[r][k]) cudaEventDestroy(c->parsed[r][k]);
-            if (c->done[r][k]) cudaEventDestroy(c->done[r][k]);
-        }
     for (int r = 0; r < kRing; r++) {
-        if (c->uploaded[r]) cudaEventDestroy(c->uploaded[r]);
-        if (c->kernels_done[r]) cudaEventDestroy(c->kernels_done[r]);
+        cudaEvent_t evs[] = {c->ready_ev[r], c->seq_ev[r], c->head_ev[r], c->x_ev[r], c->done_ev[r], c->parsed[r], c->host_done[r], c->uploaded[r]};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     }
     for (int i = 0; i <= kStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; i++) if (c->probe_ev[i]) cudaEventDestroy(c->probe_ev[i]);
+    if (c->trace) {
+        for (int i = 0; i < kTraceCalls * (kStages + 1); i++) if (c->trace[i]) cudaEventDestroy(c->trace[i]);
+        free(c->trace);
+    }
     delete c;
 }
 
 int dm_reset(dm_ctx* c, const int32_t* ids, int n) {
     if (!c) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaDeviceSynchronize());  // calls in flight (decode_many_async) finish first
+    CU_TRY(c, cudaDeviceSynchronize());  // calls in flight finish first
     CeltStreamState* init = (CeltStreamState*)malloc(sizeof(CeltStreamState));
     if (!init) return DM_ERR_NOMEM;
     init_state_host(*init);
@@ -299,75 +330,153 @@ static int reserve_bytes(dm_ctx* c, int bi, size_t n) {
     return 0;
 }
 
-// Enqueue the kernels of one call for streams [first, first+n_sel) on `s`.  Pointers are device pointers.
+// Where the kernels of one call go.  Blocking calls put everything on one stream (H == T); pipelined calls give the head
+// (parse + spectral stage) and the tail (post-filter, de-emphasis, final SILK sum) a stream each, so that the tail of
+// call k -- a handful of long-running warps that leave the SMs almost empty -- runs beside the head of call k + 1.
+struct CallPlan {
+    cudaStream_t H, T, X;     // head, tail, SILK side stream
+    FrameSet* F;
+    int chunk;
+    cudaEvent_t seq_ev;       // recorded on H behind k_sequence: the SILK stage may start
+    cudaEvent_t head_ev;      // recorded on H behind k_imdct: the tail may start (unused when H == T)
+    cudaEvent_t x_ev;         // recorded on X behind the SILK stage: the final sum may run
+    cudaEvent_t parsed;       // optional, recorded on H once the packet bytes and frame descriptors have been read
+    bool timed;
+};
+
+// Enqueue the kernels of one call for streams [first, first+n_sel).  Pointers are device pointers.
 static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm,
-                           int32_t* d_status, int first, int n_sel, cudaStream_t s, bool timed, cudaEvent_t parsed = nullptr, int chunk = 0) {
+                           int32_t* d_status, int first, int n_sel, const CallPlan& pl) {
     DevParams P;
     P.n_streams = c->n_streams; P.n_frames = in->n_frames; P.mode = in->mode;
     P.frame_size = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
     P.coded_channels = in->coded_channels; P.start_band = in->start_band; P.CC = c->channels;
     P.first_stream = first; P.n_sel = n_sel;
+    P.f0 = 0; P.nf = in->n_frames;
+    const FrameSet& F = *pl.F;
+    const cudaStream_t H = pl.H, T = pl.T, X = pl.X;
+    const bool timed = pl.timed;
+    const int chunk = pl.chunk;
+    cudaEvent_t* tr = (c->trace && timed) ? c->trace + (size_t)(c->calls % kTraceCalls) * (kStages + 1) : nullptr;
+    auto mark = [&](int i, cudaStream_t st) {
+        cudaEventRecord(c->ev[i], st);
+        if (tr) cudaEventRecord(tr[i], st);
+    };
     const int nfr = n_sel * in->n_frames;
     const int wb = 32 * KW_WARPS;
-    if (timed) cudaEventRecord(c->ev[0], s);
-    int* any_silk = c->d_any_silk + chunk;  // per stream range: ranges of one call run concurrently on their own streams
-    cudaMemsetAsync(any_silk, 0, sizeof(int), s);
-    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, s>>>(d_bytes, d_frames, P, c->d_hdr, c->d_ops, c->d_silk, c->d_state, any_silk);
-    if (timed) cudaEventRecord(c->ev[1], s);
-    if (parsed) cudaEventRecord(parsed, s);
-    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, s>>>(c->d_hdr, d_frames, c->d_fe, c->d_state, P);
-    if (timed) cudaEventRecord(c->ev[2], s);
+    if (timed) mark(0, H);
+    int* any_silk = F.any_silk + chunk;  // per stream range: ranges of one call run concurrently on their own streams
+    cudaMemsetAsync(any_silk, 0, sizeof(int), H);
+    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk);
+    if (timed) mark(1, H);
+    k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, H>>>(F.hdr, d_frames, F.fe, c->d_state, P);
+    if (timed) mark(2, H);
+    if (pl.parsed) cudaEventRecord(pl.parsed, H);
     // The SILK layer of a call needs nothing from its CELT layer until the final sum, and its two long kernels (LTP/LPC
     // synthesis, up-sampler) are single-wave recurrences that leave most issue slots idle: they run on a side stream
     // beside the issue-bound CELT kernels and meet them again in front of k_silk_fir.  Every one of these returns at
     // once unless k_entropy saw a frame with a SILK layer.
     const bool silk = in->mode == DM_MODE_OPUS;
-    SilkBufs B = {c->d_silk, c->d_sctl, c->d_spost, c->d_sxq, c->d_slr, c->d_sup, c->d_sstate, any_silk};
+    SilkBufs B = {F.silk, F.sctl, F.spost, F.sxq, F.slr, F.sup, c->d_sstate, any_silk};
     const int wide = c->n_sm * 8;  // grid-stride kernels: a fixed grid, so an idle call costs a few empty launches
     if (silk) {
-        cudaStream_t ss = c->side[chunk];
-        cudaEventRecord(c->fork_ev[chunk], s);
-        cudaStreamWaitEvent(ss, c->fork_ev[chunk], 0);
+        cudaEventRecord(pl.seq_ev, H);
+        cudaStreamWaitEvent(X, pl.seq_ev, 0);
         const int chains = n_sel * P.CC;
         // the stream range's own slice of the fix queue (at most two filters per frame and channel) and its own counter
-        FixEntry* fq = c->d_sfix + (size_t)first * in->n_frames * 4;
-        cudaMemsetAsync(c->d_fix_count + chunk, 0, sizeof(int), ss);
-        k_silk_params<<<c->n_sm * 12, 128, 0, ss>>>(c->d_hdr, c->d_fe, B, P, fq, c->d_fix_count + chunk);
-        k_silk_fix<<<c->n_sm * 8, 128, 0, ss>>>(any_silk, fq, c->d_fix_count + chunk);
+        FixEntry* fq = F.sfix + (size_t)first * in->n_frames * 4;
+        cudaMemsetAsync(F.fix_count + chunk, 0, sizeof(int), X);
+        k_silk_params<<<c->n_sm * 12, 128, 0, X>>>(F.hdr, F.fe, B, P, fq, F.fix_count + chunk);
+        k_silk_fix<<<c->n_sm * 8, 128, 0, X>>>(any_silk, fq, F.fix_count + chunk);
         const int lanes = c->silk_lanes > 0 ? c->silk_lanes : silk_chain_lanes(chains, c->n_sm);
-        if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), ss>>>(c->d_hdr, c->d_fe, B, P);
-        else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), ss>>>(c->d_hdr, c->d_fe, B, P);
-        else k_silk_core<32><<<(chains + 31) / 32, 32, silk_core_smem(32), ss>>>(c->d_hdr, c->d_fe, B, P);
-        k_silk_unmix<<<wide, 256, 0, ss>>>(B, P);
-        if (lanes == 8) k_silk_up2<8><<<(chains + 7) / 8, 32, 0, ss>>>(B, P);
-        else if (lanes == 16) k_silk_up2<16><<<(chains + 15) / 16, 32, 0, ss>>>(B, P);
-        else k_silk_up2<32><<<(chains + 31) / 32, 32, 0, ss>>>(B, P);
-        cudaEventRecord(c->join_ev[chunk], ss);
+        if (lanes == 8) k_silk_core<8><<<(chains + 7) / 8, 32, silk_core_smem(8), X>>>(F.hdr, F.fe, B, P);
+        else if (lanes == 16) k_silk_core<16><<<(chains + 15) / 16, 32, silk_core_smem(16), X>>>(F.hdr, F.fe, B, P);
+        else k_silk_core<32><<<(chains + 31) / 32, 32, silk_core_smem(32), X>>>(F.hdr, F.fe, B, P);
+        k_silk_unmix<<<wide, 256, 0, X>>>(B, P);
+        if (lanes == 8) k_silk_up2<8><<<(chains + 7) / 8, 32, 0, X>>>(B, P);
+        else if (lanes == 16) k_silk_up2<16><<<(chains + 15) / 16, 32, 0, X>>>(B, P);
+        else k_silk_up2<32><<<(chains + 31) / 32, 32, 0, X>>>(B, P);
+        cudaEventRecord(pl.x_ev, X);
     }
     // coded leaves: sort by cost class, expand one per thread
     LeafSort* ls = c->d_leafsort + chunk;
     uint32_t* order = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
-    cudaMemsetAsync(ls, 0, sizeof(LeafSort), s);
-    k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, P);
-    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, nfr * c->leaf_slots, P);
-    k_leaf_expand<<<c->n_sm * KL_GRID, KL_THREADS, 0, s>>>(c->d_hdr, c->d_ops, ls, order, c->d_X, P);
-    if (timed) cudaEventRecord(c->ev[3], s);
-    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, s>>>(c->d_hdr, c->d_ops, c->d_fe, c->d_X, ls, P);
-    if (timed) cudaEventRecord(c->ev[4], s);
-    k_imdct<<<(nfr * P.CC + KI_WARPS - 1) / KI_WARPS, 32 * KI_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_X, c->d_raw, P);
-    if (timed) cudaEventRecord(c->ev[5], s);
-    k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, s>>>(c->d_hdr, c->d_fe, c->d_raw, c->d_syn, c->d_state, P);
-    if (timed) cudaEventRecord(c->ev[6], s);
-    k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, s>>>(c->d_fe, c->d_hdr, c->d_syn, d_pcm, d_status, c->d_state, P);
-    if (timed) cudaEventRecord(c->ev[7], s);
+    cudaMemsetAsync(ls, 0, sizeof(LeafSort), H);
+    k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, P);
+    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, order, nfr * c->leaf_slots, P);
+    k_leaf_expand<<<c->n_sm * KL_GRID, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, order, c->d_X, P);
+    if (timed) mark(3, H);
+    k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, H>>>(F.hdr, c->d_ops, F.fe, c->d_X, ls, P);
+    if (timed) mark(4, H);
+    if (P.frame_size == 960) {  // long blocks: persistent blocks, a warp per frame (both channels), grid-stride over the frames
+        const int want = (nfr + KI_WARPS - 1) / KI_WARPS, cap = c->n_sm * KI_GRID;
+        k_imdct_long<<<want < cap ? want : cap, 32 * KI_WARPS, kImdctLongSmem, H>>>(F.hdr, F.fe, c->d_X, F.raw, P);
+        c->launches++;
+    }
+    k_imdct<<<(nfr * P.CC + KI_WARPS - 1) / KI_WARPS, 32 * KI_WARPS, 0, H>>>(F.hdr, F.fe, c->d_X, F.raw, P);  // everything else
+    if (timed) mark(5, H);
+    const cudaStream_t Tp = (T != H && c->tail_mode == 1) ? H : T;  // the post-filter's stream
+    if (T != H && Tp == T) {
+        cudaEventRecord(pl.head_ev, H);
+        cudaStreamWaitEvent(T, pl.head_ev, 0);
+    }
+    k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, Tp>>>(F.hdr, F.fe, F.raw, F.syn, c->d_state, P);
+    if (timed) mark(6, Tp);
+    if (T != H && Tp == H) {
+        cudaEventRecord(pl.head_ev, H);
+        cudaStreamWaitEvent(T, pl.head_ev, 0);
+    }
+    k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, T>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, P);
+    if (timed) mark(7, T);
     if (silk) {  // "silk" stage time: what is left of the SILK layer once the CELT kernels are done, plus the final sum
-        cudaStreamWaitEvent(s, c->join_ev[chunk], 0);
-        k_silk_fir<<<wide, 32 * FIR_WARPS, 0, s>>>(B, c->d_fe, d_pcm, P);
+        cudaStreamWaitEvent(T, pl.x_ev, 0);
+        k_silk_fir<<<wide, 32 * FIR_WARPS, 0, T>>>(B, F.fe, d_pcm, P);
         c->launches += 6;
     }
-    if (timed) cudaEventRecord(c->ev[8], s);
+    if (timed) mark(8, T);
     c->launches += 9;  // entropy, sequence, 3 leaf kernels, bands, imdct, postfilter, deemph
     CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+// One pipelined call over all streams: the head on streams[0] behind `ready`, the tail on c->tail, the SILK stage on
+// side[0]; *done fires when PCM and status are complete.  Consecutive calls alternate between the two frame sets.
+static int enqueue_pipelined(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes, const FrameDesc* d_frames, int16_t* d_pcm, int32_t* d_status,
+                             cudaEvent_t ready, cudaEvent_t parsed, cudaEvent_t* done) {
+    const long long q = c->calls;
+    const int r = (int)(q % kRing);
+    FrameSet& F = c->set[q & 1];
+    int rc = alloc_set(c, F);
+    if (rc) return rc;
+    const cudaStream_t H = c->streams[0];
+    if (ready) CU_TRY(c, cudaStreamWaitEvent(H, ready, 0));
+    // this frame set was last read by the tail and the SILK stage of the call before the previous one
+    if (q >= 2) CU_TRY(c, cudaStreamWaitEvent(H, c->done_ev[(q - 2) % kRing], 0));
+    CallPlan pl = {H, c->tail_mode ? c->tail : H, c->side[0], &F, 0, c->seq_ev[r], c->head_ev[r], c->x_ev[r], parsed, true};
+    rc = launch_pipeline(c, in, d_bytes, d_frames, d_pcm, d_status, 0, c->n_streams, pl);
+    if (rc) return rc;
+    CU_TRY(c, cudaEventRecord(c->done_ev[r], pl.T));
+    c->calls = q + 1;
+    if (done) *done = c->done_ev[r];
+    return 0;
+}
+
+int dm_decode_device_async(dm_ctx* c, const dm_batch* in, dm_out* out, void* ready_event, void** done_event) {
+    int r = check_batch(c, in);
+    if (r) return r;
+    if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaEvent_t done = nullptr;
+    r = enqueue_pipelined(c, in, in->bytes, (const FrameDesc*)in->frames, out->pcm, out->status, (cudaEvent_t)ready_event, nullptr, &done);
+    if (done_event) *done_event = (void*)done;
+    return r;
+}
+
+int dm_stream_wait(dm_ctx* c, void* cuda_stream) {
+    if (!c) return OPUSB_BAD_ARG;
+    if (c->calls == 0) return 0;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamWaitEvent((cudaStream_t)cuda_stream, c->done_ev[(c->calls - 1) % kRing], 0));
     return 0;
 }
 
@@ -376,8 +485,16 @@ int dm_decode_device(dm_ctx* c, const dm_batch* in, dm_out* out, void* cuda_stre
     if (r) return r;
     if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    return launch_pipeline(c, in, in->bytes, (const FrameDesc*)in->frames, out->pcm, out->status, 0, c->n_streams,
-                           (cudaStream_t)cuda_stream, true);
+    // one stream-ordered operation on the caller's stream: the internal streams start behind what that stream holds so
+    // far, and it waits for the call's last kernel
+    const cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int rr = (int)(c->calls % kRing);
+    CU_TRY(c, cudaEventRecord(c->ready_ev[rr], s));
+    cudaEvent_t done = nullptr;
+    r = enqueue_pipelined(c, in, in->bytes, (const FrameDesc*)in->frames, out->pcm, out->status, c->ready_ev[rr], nullptr, &done);
+    if (r) return r;
+    CU_TRY(c, cudaStreamWaitEvent(s, done, 0));
+    return 0;
 }
 
 // Blocking call: per stream range (chunk) frames H2D -> kernels -> PCM/status D2H, each chunk on its own CUDA stream so
@@ -387,7 +504,7 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
     if (r) return r;
     if (!out || !out->pcm || !out->status) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    if (c->next_ticket) CU_TRY(c, cudaDeviceSynchronize());  // asynchronous calls in flight finish first
+    if (c->next_ticket || c->calls) CU_TRY(c, cudaDeviceSynchronize());  // pipelined calls in flight finish first
     r = reserve_bytes(c, 0, in->n_bytes);
     if (r) return r;
     const int nf = in->n_frames, CC = c->channels;
@@ -402,8 +519,9 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
         cudaStream_t s = c->streams[k];
         const size_t f0 = (size_t)first * nf, fn = (size_t)n_sel * nf;
         if (k) CU_TRY(c, cudaStreamWaitEvent(s, c->bytes_ready, 0));
-        CU_TRY(c, cudaMemcpyAsync(c->d_frames + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
-        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames, c->d_pcm, c->d_status, first, n_sel, s, false, nullptr, k);
+        CU_TRY(c, cudaMemcpyAsync(c->d_frames[0] + f0, in->frames + f0, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, s));
+        CallPlan pl = {s, s, c->side[k], &c->set[0], k, c->fork_ev[k], nullptr, c->join_ev[k], nullptr, false};
+        r = launch_pipeline(c, in, c->d_bytes[0], c->d_frames[0], c->d_pcm, c->d_status, first, n_sel, pl);
         if (r) return r;
         CU_TRY(c, cudaMemcpyAsync(out->pcm + f0 * fs * CC, c->d_pcm + f0 * fs * CC, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(out->status + f0, c->d_status + f0, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -412,10 +530,11 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
     return 0;
 }
 
-// Pipelined call: upload, kernels and read-back each have their own CUDA stream and every buffer that crosses a
-// stage is double buffered, so with two calls in flight the GPU decodes call n+1 while call n's PCM crosses PCIe and
-// call n+2's packets arrive.  The kernels run over ALL streams at once: the stages that walk a stream's frames in
-// order (sequence, post-filter, de-emphasis, SILK) take as long for 1024 streams as for 4096.
+// Pipelined call with host buffers: upload, head, tail and read-back each have their own CUDA stream and every buffer
+// that crosses a stage is double buffered, so with calls in flight the GPU runs the head of call n+1 beside the tail of
+// call n while call n-1's PCM crosses PCIe and call n+2's packets arrive.  The kernels run over ALL streams at once: the
+// stages that walk a stream's frames in order (sequence, post-filter, de-emphasis, SILK) take as long for 1024 streams
+// as for 4096.
 int decode_many_async(dm_ctx* c, const dm_batch* in, dm_out* out, long long* ticket_out) {
     int r = check_batch(c, in);
     if (r) return r;
@@ -425,37 +544,35 @@ int decode_many_async(dm_ctx* c, const dm_batch* in, dm_out* out, long long* tic
     if (!c->d_pcm2) {
         if ((r = dev_alloc(c, &c->d_pcm2, nfr_cap * c->channels * kMaxFrame))) return r;
         if ((r = dev_alloc(c, &c->d_status2, nfr_cap))) return r;
+        if ((r = dev_alloc(c, &c->d_frames[1], nfr_cap))) return r;
     }
     const long long ticket = c->next_ticket;
     const int slot = (int)(ticket % kRing), bi = (int)(ticket & 1);
-    if (ticket >= kRing) CU_TRY(c, cudaEventSynchronize(c->done[slot][0]));  // the slot's previous call is over
+    if (ticket >= kRing) CU_TRY(c, cudaEventSynchronize(c->host_done[slot]));  // the slot's previous call is over
     if (in->n_bytes > c->d_bytes_cap[bi]) CU_TRY(c, cudaDeviceSynchronize());
     r = reserve_bytes(c, bi, in->n_bytes);
     if (r) return r;
     const int nf = in->n_frames, CC = c->channels;
     const int fs = in->mode == DM_MODE_CELT_RAW ? in->frame_size : 960;
     const size_t fn = (size_t)c->n_streams * nf;
-    cudaStream_t up = c->streams[2], run = c->streams[0], down = c->streams[1];
+    cudaStream_t up = c->streams[2], down = c->streams[1];
     int16_t* d_pcm = bi ? c->d_pcm2 : c->d_pcm;
     int32_t* d_status = bi ? c->d_status2 : c->d_status;
-    FrameDesc* d_frames = c->d_frames;
-    // upload: this byte buffer was last parsed two calls ago; the frame descriptors by the previous call
-    if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(up, c->parsed[(ticket - 2) % kRing][0], 0));
+    // upload: these input buffers were last read (entropy, sequence) two calls ago
+    if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(up, c->parsed[(ticket - 2) % kRing], 0));
     CU_TRY(c, cudaMemcpyAsync(c->d_bytes[bi], in->bytes, in->n_bytes, cudaMemcpyHostToDevice, up));
-    if (ticket >= 1) CU_TRY(c, cudaStreamWaitEvent(up, c->kernels_done[(ticket - 1) % kRing], 0));
-    CU_TRY(c, cudaMemcpyAsync(d_frames, in->frames, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, up));
+    CU_TRY(c, cudaMemcpyAsync(c->d_frames[bi], in->frames, fn * sizeof(dm_frame), cudaMemcpyHostToDevice, up));
     CU_TRY(c, cudaEventRecord(c->uploaded[slot], up));
     // kernels: the output buffer of this parity was last read back two calls ago
-    CU_TRY(c, cudaStreamWaitEvent(run, c->uploaded[slot], 0));
-    if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(run, c->done[(ticket - 2) % kRing][0], 0));
-    r = launch_pipeline(c, in, c->d_bytes[bi], d_frames, d_pcm, d_status, 0, c->n_streams, run, true, c->parsed[slot][0]);
+    if (ticket >= 2) CU_TRY(c, cudaStreamWaitEvent(c->streams[0], c->host_done[(ticket - 2) % kRing], 0));
+    cudaEvent_t done = nullptr;
+    r = enqueue_pipelined(c, in, c->d_bytes[bi], c->d_frames[bi], d_pcm, d_status, c->uploaded[slot], c->parsed[slot], &done);
     if (r) return r;
-    CU_TRY(c, cudaEventRecord(c->kernels_done[slot], run));
     // read-back
-    CU_TRY(c, cudaStreamWaitEvent(down, c->kernels_done[slot], 0));
+    CU_TRY(c, cudaStreamWaitEvent(down, done, 0));
     CU_TRY(c, cudaMemcpyAsync(out->pcm, d_pcm, fn * fs * CC * sizeof(int16_t), cudaMemcpyDeviceToHost, down));
     CU_TRY(c, cudaMemcpyAsync(out->status, d_status, fn * sizeof(int32_t), cudaMemcpyDeviceToHost, down));
-    CU_TRY(c, cudaEventRecord(c->done[slot][0], down));
+    CU_TRY(c, cudaEventRecord(c->host_done[slot], down));
     c->next_ticket = ticket + 1;
     if (ticket_out) *ticket_out = ticket;
     return 0;
@@ -465,7 +582,7 @@ int dm_wait(dm_ctx* c, long long ticket) {
     if (!c) return OPUSB_BAD_ARG;
     if (ticket < 0 || ticket >= c->next_ticket) return OPUSB_BAD_ARG;
     if (ticket + kRing <= c->next_ticket - 1) return 0;  // long finished: its ring slot was recycled after a synchronise
-    CU_TRY(c, cudaEventSynchronize(c->done[(int)(ticket % kRing)][0]));
+    CU_TRY(c, cudaEventSynchronize(c->host_done[(int)(ticket % kRing)]));
     return 0;
 }
 
@@ -479,11 +596,11 @@ int dm_probe_d2h(dm_ctx* c, void* host, size_t bytes, int reps, float* ms_total)
     CU_TRY(c, cudaDeviceSynchronize());
     cudaStream_t down = c->streams[1];
     CU_TRY(c, cudaMemcpyAsync(host, c->d_pcm, bytes, cudaMemcpyDeviceToHost, down));  // warm-up
-    CU_TRY(c, cudaEventRecord(c->ev[0], down));
+    CU_TRY(c, cudaEventRecord(c->probe_ev[0], down));
     for (int i = 0; i < reps; i++) CU_TRY(c, cudaMemcpyAsync(host, c->d_pcm, bytes, cudaMemcpyDeviceToHost, down));
-    CU_TRY(c, cudaEventRecord(c->ev[1], down));
+    CU_TRY(c, cudaEventRecord(c->probe_ev[1], down));
     CU_TRY(c, cudaStreamSynchronize(down));
-    CU_TRY(c, cudaEventElapsedTime(ms_total, c->ev[0], c->ev[1]));
+    CU_TRY(c, cudaEventElapsedTime(ms_total, c->probe_ev[0], c->probe_ev[1]));
     return 0;
 }
 
@@ -496,16 +613,32 @@ void dm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 long long dm_launch_count(const dm_ctx* c) { return c ? c->launches : 0; }
 size_t dm_device_bytes(const dm_ctx* c) { return c ? c->dev_bytes : 0; }
-const char* dm_stage_name(int i) { return (i >= 0 && i < kStages) ? kStageNames[i] : ""; }
+const char* dm_stage_name(int i) { return (i >= 0 && i <= kStages) ? kStageNames[i] : ""; }
 int dm_stage_times(dm_ctx* c, float* ms, int cap) {
     if (!c || !ms) return 0;
-    int n = cap < kStages ? cap : kStages;
+    int n = cap < kStages + 1 ? cap : kStages + 1;
     for (int i = 0; i < n; i++) {
         ms[i] = 0.f;
-        if (cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]) != cudaSuccess) ms[i] = -1.f;
+        const cudaEvent_t a = i == kStages ? c->ev[0] : c->ev[i], b = i == kStages ? c->ev[kStages] : c->ev[i + 1];
+        if (cudaEventElapsedTime(&ms[i], a, b) != cudaSuccess) ms[i] = -1.f;
     }
     return n;
 }
+// OPUSB_TRACE=1: the stage boundaries of the last n pipelined calls (n <= 16) in ms since the first boundary of the oldest
+// of them, out[call][kStages + 1]: head start, entropy, sequence, leaves, bands, imdct (head end), postfilter, deemph, end.
+int dm_debug_trace(dm_ctx* c, int n, float* out) {
+    if (!c || !c->trace || !out || n < 1 || n > kTraceCalls || n > c->calls) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    const long long q0 = c->calls - n;
+    const cudaEvent_t base = c->trace[(size_t)(q0 % kTraceCalls) * (kStages + 1)];
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i <= kStages; i++)
+            if (cudaEventElapsedTime(&out[k * (kStages + 1) + i], base, c->trace[(size_t)((q0 + k) % kTraceCalls) * (kStages + 1) + i]) != cudaSuccess)
+                out[k * (kStages + 1) + i] = -1.f;
+    return 0;
+}
+
 int dm_debug_leaf_overflow(dm_ctx* c) {
     if (!c) return OPUSB_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));

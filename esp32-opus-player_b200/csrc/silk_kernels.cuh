@@ -75,11 +75,11 @@ k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restric
               int* fix_count) {
     if (*B.any_silk == 0) return;
     const GlobalFixQueue queue{fix_ents, fix_count};
-    const int total = P.n_sel * P.n_frames * 2;
+    const int total = P.n_local() * 2;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int local = idx >> 1, n = idx & 1;
         if (n >= P.CC) continue;
-        const int f = local % P.n_frames, s = P.first_stream + local / P.n_frames;
+        const int f = P.frame_of(local), s = P.stream_of(local);
         const size_t t = (size_t)s * P.n_frames + f;
         if (!silk_frame_live(hdr, fe, t)) continue;
         const SilkFrame& F = B.frames[t];
@@ -89,9 +89,9 @@ k_silk_params(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restric
         int16_t prev[kSilkMaxOrder];
         bool have_prev = false;
         if (!(hdr[t].oflags & OF_SILK_REINIT)) {
-            int u = f - 1;
-            while (u >= 0 && !silk_frame_live(hdr, fe, t - (size_t)(f - u))) u--;
-            if (u >= 0) {
+            int u = f - 1;  // look back inside this launch's frame group only: in front of it the carried state speaks
+            while (u >= P.f0 && !silk_frame_live(hdr, fe, t - (size_t)(f - u))) u--;
+            if (u >= P.f0) {
                 const SilkFrame& Q = B.frames[t - (size_t)(f - u)];
                 if (Q.fs_kHz == fs && !(n == 1 && Q.mid_only)) {
                     silk_nlsf_decode(prev, Q.idx[n].nlsf, silk_cb(fs));
@@ -251,7 +251,7 @@ k_silk_core(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict_
     bool hist_zero = false;  // a re-init happened in this call and no frame has produced output since
     const size_t t0 = (size_t)s * P.n_frames;
 #pragma unroll 1
-    for (int f = 0; f < P.n_frames; f++) {
+    for (int f = P.f0; f < P.f0 + P.nf; f++) {
         const size_t t = t0 + f;
         SilkPost& post = B.post[t];
         const bool live = alive && silk_frame_live(hdr, fe, t);
@@ -339,11 +339,11 @@ k_silk_unmix(SilkBufs B, DevParams P) {
     if (*B.any_silk == 0) return;
     // one warp per frame: the frames are independent and each is a few hundred samples, a block per frame would spend
     // its time waiting for the handful of dependent loads in front of every frame
-    const int nfr = P.n_sel * P.n_frames;
+    const int nfr = P.n_local();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int local = blockIdx.x * wpb + (threadIdx.x >> 5); local < nfr; local += gridDim.x * wpb) {
-        const int s = P.first_stream + local / P.n_frames;
-        const size_t t = (size_t)P.first_stream * P.n_frames + local;
+        const int s = P.stream_of(local);
+        const size_t t = P.index_of(local);
         const SilkPost& post = B.post[t];
         if (!post.has_out) continue;
         const int fs = post.fs_kHz, L = 20 * fs;
@@ -389,7 +389,7 @@ k_silk_up2(SilkBufs B, DevParams P) {
     for (int i = 0; i < 4; i++) fh[i] = (uint32_t)(uint16_t)Rs.sFIR[2 * i] | (uint32_t)(uint16_t)Rs.sFIR[2 * i + 1] << 16;
     const size_t t0 = (size_t)s * P.n_frames;
     int last_out_f = -1;
-    for (int f = 0; f < P.n_frames; f++) {
+    for (int f = P.f0; f < P.f0 + P.nf; f++) {
         const size_t t = t0 + f;
         const SilkPost& post = B.post[t];
         if (!post.has_out) continue;
@@ -449,12 +449,12 @@ k_silk_fir(SilkBufs B, const FrameEnergy* __restrict__ fe, int16_t* __restrict__
     // one warp per frame; the up-sampled rows of the frame are staged in shared memory (every output reads 8
     // neighbouring taps of them), warps run independently of each other
     __shared__ __align__(16) int16_t rows[FIR_WARPS][2][kUpRow];
-    const int nfr = P.n_sel * P.n_frames;
+    const int nfr = P.n_local();
     const int CC = P.CC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int16_t(*my)[kUpRow] = rows[warp];
     for (int local = blockIdx.x * FIR_WARPS + warp; local < nfr; local += gridDim.x * FIR_WARPS) {
-        const size_t t = (size_t)P.first_stream * P.n_frames + local;
+        const size_t t = P.index_of(local);
         const SilkPost& post = B.post[t];
         if (!post.has_out) continue;
         const int fs = post.fs_kHz;

@@ -97,9 +97,19 @@ int decode_many(dm_ctx* ctx, const dm_batch* in, dm_out* out);
 int decode_many_async(dm_ctx* ctx, const dm_batch* in, dm_out* out, long long* ticket);
 int dm_wait(dm_ctx* ctx, long long ticket);
 
-/* Same with every pointer in DEVICE memory, enqueued on `cuda_stream` (a cudaStream_t, NULL = the
- * legacy default stream), no synchronisation: the kernel-only path. */
+/* Same with every pointer in DEVICE memory, as ONE stream-ordered operation on `cuda_stream` (a cudaStream_t, NULL =
+ * the legacy default stream), no host synchronisation: the kernel-only path.  The kernels run on the library's own
+ * streams behind everything `cuda_stream` holds when the call is made; `cuda_stream` continues once they are done. */
 int dm_decode_device(dm_ctx* ctx, const dm_batch* in_dev, dm_out* out_dev, void* cuda_stream);
+/* The same with explicit dependencies instead of a stream, so that consecutive calls overlap: the call starts once
+ * `ready_event` (a cudaEvent_t; NULL: the inputs are ready now) has fired and *done_event (a cudaEvent_t owned by the
+ * library, valid until four more calls have been made) fires when PCM and status are complete.  Calls on a context are
+ * ordered among themselves, and the serial tail of call k (post-filter, de-emphasis: few long-running warps) runs
+ * beside the parse and spectral stages of call k + 1; the inputs of a call may be reused once its done event has fired,
+ * and a consumer must have finished with an output buffer before a later call is given the same one.
+ * dm_stream_wait makes a stream wait for everything enqueued so far. */
+int dm_decode_device_async(dm_ctx* ctx, const dm_batch* in_dev, dm_out* out_dev, void* ready_event, void** done_event);
+int dm_stream_wait(dm_ctx* ctx, void* cuda_stream);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void* dm_host_alloc(size_t bytes);
@@ -112,14 +122,19 @@ int dm_probe_d2h(dm_ctx* ctx, void* host, size_t bytes, int reps, float* ms_tota
 long long dm_launch_count(const dm_ctx* ctx);
 /* Bytes of device memory held by the context. */
 size_t dm_device_bytes(const dm_ctx* ctx);
-/* Device time in ms of each pipeline stage of the most recent dm_decode_device call, measured with
- * CUDA events on the launching stream; valid after that stream was synchronised.  Returns the number
- * of stages written (names via dm_stage_name). */
+/* Device time in ms of each pipeline stage of the most recent pipelined call (dm_decode_device, dm_decode_device_async,
+ * decode_many_async), measured with CUDA events on the streams the kernels run on; valid once that call has completed.
+ * Returns the number of entries written (names via dm_stage_name): the eight stages, then "pipeline" = first kernel to
+ * last.  With calls in flight a stage's span includes whatever ran beside it: for a breakdown use dm_decode_device. */
 int dm_stage_times(dm_ctx* ctx, float* ms, int cap);
 const char* dm_stage_name(int i);
 /* Debug/test access: 1 if the most recent call had more coded PVQ leaves than the sorted leaf list holds and the band
  * kernel expanded its own leaves instead (slower, same result), 0 if not, < 0 on error.  Synchronises the device. */
 int dm_debug_leaf_overflow(dm_ctx* ctx);
+/* Debug access (contexts created with OPUSB_TRACE=1 in the environment): stage boundaries of the last n <= 16 pipelined
+ * calls in ms since the oldest one's start, out[n][9]: head start, end of entropy, sequence, leaves, bands, imdct, then
+ * on the tail stream end of postfilter, deemph, final SILK sum.  Shows which calls overlapped.  Synchronises the device. */
+int dm_debug_trace(dm_ctx* ctx, int n, float* out);
 /* Debug/test access: copies one stream's CELT state blob to host (checkpoint). */
 int dm_get_stream_state(dm_ctx* ctx, int stream, void* dst, size_t cap);
 size_t dm_stream_state_size(void);

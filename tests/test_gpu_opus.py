@@ -395,3 +395,39 @@ def test_three_async_calls_in_flight_silk_hybrid_and_mode_walks(pkg, ref, kind):
                     assert np.array_equal(got_pcm[s, f], want), "stream %d frame %d toc %#x" % (s, f, pk[s][f][0])
         finally:
             o.close()
+
+
+@pytest.mark.parametrize("kind", ["celt", "mode_walk"])
+def test_device_calls_overlapping_head_and_tail(pkg, kind):
+    """dm_decode_device_async: consecutive calls with explicit events, the tail of call k beside the head of call k + 1
+    (two alternating sets of intermediates): same PCM as the blocking host-buffer calls, for CELT and for streams that
+    walk through SILK / hybrid / CELT (SILK stage on its side stream)."""
+    import torch
+
+    rng = np.random.default_rng(5 + len(kind))
+    S, F, steps = 192, 8, 7
+    tocs = [0xFC] if kind == "celt" else [0xFC, 0x4C, 0x7C, 0x0C, 0x6C, 0xDC]
+    plans = [[(int(rng.choice(tocs)), 0) for _ in range(F * steps)] for _ in range(S)]
+    data, frames, _ = _pack(pkg, plans, 31)
+    a = pkg.BatchDecoder(S, F, channels=2)
+    want = []
+    for k in range(steps):
+        rc, pcm, st = a.decode_many(data, np.ascontiguousarray(frames[:, k * F:(k + 1) * F]))
+        assert rc == 0
+        want.append((pcm.copy(), st.copy()))
+    a.close()
+    b = pkg.BatchDecoder(S, F, channels=2)
+    d_bytes = torch.from_numpy(data).cuda()
+    d_frames = [torch.from_numpy(np.ascontiguousarray(frames[:, k * F:(k + 1) * F]).view(np.uint8).reshape(-1)).cuda() for k in range(steps)]
+    d_pcm = [torch.empty(S * F * 960 * 2, dtype=torch.int16, device="cuda") for _ in range(steps)]
+    d_st = [torch.empty(S * F, dtype=torch.int32, device="cuda") for _ in range(steps)]
+    torch.cuda.synchronize()
+    for k in range(steps):
+        rc, done = b.decode_device_async(d_bytes.data_ptr(), data.size, d_frames[k].data_ptr(), F, d_pcm[k].data_ptr(), d_st[k].data_ptr())
+        assert rc == 0 and done
+    assert b.stream_wait(torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    for k in range(steps):
+        assert np.array_equal(d_st[k].cpu().numpy().reshape(S, F), want[k][1]), k
+        assert np.array_equal(d_pcm[k].cpu().numpy().reshape(S, F, 960, 2), want[k][0]), k
+    b.close()

@@ -61,7 +61,7 @@ def launches_per_step(workload):
 
 def cmd(args):
     n = launches_per_step(args.workload)
-    base = "python bench.py --device-only --steps 1 --warmup 3 --workload %s" % args.workload
+    base = "python bench.py --device-only --no-overlap --steps 1 --warmup 3 --workload %s" % args.workload
     if args.streams:
         base += " --streams %d" % args.streams
     tag = "ncu_" + args.workload
