@@ -14,6 +14,44 @@
 
 namespace opusb200 {
 
+// The parser's per-band work arrays live in the thread's local memory, 24 warps of them per SM: their footprint decides
+// whether they stay in L1 / L2.  They are kept in the narrowest type that holds their values (the arithmetic stays
+// 32-bit); the host build of these bodies (tests/hostsim, -DOPUS_CHECK_NARROW) aborts if a stored value does not fit.
+template <class T>
+OPUS_HD T narrow(s32 v) {
+#if !defined(__CUDA_ARCH__) && defined(OPUS_CHECK_NARROW)
+    if ((s32)(T)v != v) { fprintf(stderr, "narrow: %d does not fit %d bytes\n", (int)v, (int)sizeof(T)); abort(); }
+#endif
+    return (T)v;
+}
+
+#ifndef PARSE_TF_T
+#define PARSE_TF_T int8_t      // tf_res: -3 .. 3
+#endif
+#ifndef PARSE_CAP_T
+#define PARSE_CAP_T int16_t    // cap, dynalloc offsets: <= 9792 + 352
+#endif
+#ifndef PARSE_FINE_T
+#define PARSE_FINE_T int8_t    // fine_quant 0 .. 8, fine_priority 0 / 1
+#endif
+#ifndef PARSE_BITS_T
+#define PARSE_BITS_T int32_t   // bits1, bits2 of the allocation search: 0 .. 34784.  Would fit uint16_t, and the host build is
+                               // bit-exact with it, but the sm_100a build (nvcc 12.9) then decodes wrongly -- with int16_t too, not
+                               // with uint32_t; cause not found (compute-sanitizer is closed on this pool), so they stay 32-bit
+#endif
+#ifndef PARSE_THR_T
+#define PARSE_THR_T int16_t    // thresh <= 264, trim_offset within +-7040
+#endif
+#ifndef PARSE_FACC_T
+#define PARSE_FACC_T int16_t   // fine energy sums, kept mod 2^16
+#endif
+typedef PARSE_TF_T tf_t;
+typedef PARSE_CAP_T cap_t;
+typedef PARSE_FINE_T fineq_t;
+typedef PARSE_BITS_T abits_t;
+typedef PARSE_THR_T thr_t;
+typedef PARSE_FACC_T facc_t;
+
 struct ParseCtx {
     RangeDec rd;
     // frame constants
@@ -273,12 +311,13 @@ OPUS_HD u32 band_n1(ParseCtx& p, int xoff, int yoff, int out) {
 // The reference recurses (a band splits into up to 16 leaves); here the tree is walked with an explicit
 // stack so that all lanes of a warp run the same loop whatever their depth -- recursion would leave
 // every lane in its own call frame and the warp would never reconverge.
-struct PartNode { int xoff, N, b, B, lowband, LM, fill; s16 gain; };
+struct PartNode { s32 b, fill; uint16_t xoff, N; s16 lowband, gain; uint8_t B; int8_t LM; };
 struct PartFrame {
     PartNode second;     // the child decoded second (its b is adjusted by the rebalance)
-    int first_bits, rebalance, itheta, shift;
+    s32 first_bits, rebalance;
     u32 cm;
-    uint8_t first_is_mid, phase;
+    s16 itheta;
+    uint8_t shift, first_is_mid, phase;
 };
 
 // Every lane of p.wmask calls this once per band job (`active` false: nothing to decode) and all of them step
@@ -289,7 +328,8 @@ OPUS_HD u32 partition(ParseCtx& p, bool active, int xoff, int N, int b, int B, i
     PartFrame st[5];
     int sp = 0;
     PartNode cur;
-    cur.xoff = xoff; cur.N = N; cur.b = b; cur.B = B; cur.lowband = lowband; cur.LM = LM; cur.fill = fill; cur.gain = gain;
+    cur.xoff = narrow<uint16_t>(xoff); cur.N = narrow<uint16_t>(N); cur.b = b; cur.B = narrow<uint8_t>(B); cur.lowband = narrow<s16>(lowband);
+    cur.LM = narrow<int8_t>(LM); cur.fill = fill; cur.gain = gain;
     u32 ret = 0;
     bool descend = true, done = !active;
 #pragma unroll 1
@@ -314,13 +354,15 @@ OPUS_HD u32 partition(ParseCtx& p, bool active, int xoff, int N, int b, int B, i
                 const int sbits = bb - mbits;
                 p.remaining_bits -= t.qalloc;
                 PartNode mid, side;
-                mid.xoff = cur.xoff; mid.N = Nh; mid.b = mbits; mid.B = Bh; mid.lowband = cur.lowband; mid.LM = LMh; mid.fill = fl;
+                mid.xoff = cur.xoff; mid.N = narrow<uint16_t>(Nh); mid.b = mbits; mid.B = narrow<uint8_t>(Bh); mid.lowband = cur.lowband;
+                mid.LM = narrow<int8_t>(LMh); mid.fill = fl;
                 mid.gain = (s16)mul16_p15(cur.gain, (s16)t.imid);
-                side.xoff = cur.xoff + Nh; side.N = Nh; side.b = sbits; side.B = Bh; side.lowband = cur.lowband >= 0 ? cur.lowband + Nh : -1;
-                side.LM = LMh; side.fill = fl >> Bh;
+                side.xoff = narrow<uint16_t>(cur.xoff + Nh); side.N = narrow<uint16_t>(Nh); side.b = sbits; side.B = narrow<uint8_t>(Bh);
+                side.lowband = cur.lowband >= 0 ? narrow<s16>(cur.lowband + Nh) : (s16)-1;
+                side.LM = narrow<int8_t>(LMh); side.fill = fl >> Bh;
                 side.gain = (s16)mul16_p15(cur.gain, (s16)t.iside);
                 PartFrame& f = st[sp++];
-                f.rebalance = p.remaining_bits; f.itheta = itheta; f.shift = B0 >> 1; f.cm = 0; f.phase = 0;
+                f.rebalance = p.remaining_bits; f.itheta = narrow<s16>(itheta); f.shift = narrow<uint8_t>(B0 >> 1); f.cm = 0; f.phase = 0;
                 if (mbits >= sbits) { f.first_is_mid = 1; f.first_bits = mbits; f.second = side; cur = mid; }
                 else { f.first_is_mid = 0; f.first_bits = sbits; f.second = mid; cur = side; }
             } else {
@@ -448,7 +490,7 @@ OPUS_HD u32 band_mono_post(ParseCtx& p, const MonoCtx& m, u32 cm) {
 struct BandJob { int xoff, b, lowband, out, scratch, fill; s16 gain; };
 
 OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int shortBlocks, int dual_stereo, int intensity,
-                       const int* tf_res, int total_bits, int balance, int codedBands) {
+                       const tf_t* tf_res, int total_bits, int balance, int codedBands) {
     const int LM = p.LM, C = p.C, start = p.start, end = p.end;
     const int M = 1 << LM;
     const int N = M * kShortMdct;
@@ -610,10 +652,10 @@ OPUS_HD void all_bands(ParseCtx& p, uint8_t* cmask, const int* pulses, int short
 }
 
 // ref interp_bits2pulses (src/celt.cpp:3298), decoder side
-OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start, const int* bits1, const int* bits2,
-                               const int* thresh, const int* cap, int total, int* balance_out, int skip_rsv, int* intensity,
-                               int intensity_rsv, int* dual_stereo, int dual_stereo_rsv, int* bits, int* ebits,
-                               int* fine_priority, int C, int LM) {
+OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start, const abits_t* bits1, const abits_t* bits2,
+                               const thr_t* thresh, const cap_t* cap, int total, int* balance_out, int skip_rsv, int* intensity,
+                               int intensity_rsv, int* dual_stereo, int dual_stereo_rsv, int* bits, fineq_t* ebits,
+                               fineq_t* fine_priority, int C, int LM) {
     const int alloc_floor = C << 3;
     const int stereo = C > 1;
     const int logM = LM << 3;
@@ -695,12 +737,13 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
             if (N == 2) offset += den << 3 >> 2;
             if (bits[j] + offset < den * 2 << 3) offset += NClogN >> 2;
             else if (bits[j] + offset < den * 3 << 3) offset += NClogN >> 3;
-            ebits[j] = imax(0, bits[j] + offset + (den << 2));
-            ebits[j] = (int)((u32)ebits[j] / (u32)den) >> 3;
-            if (C * ebits[j] > (bits[j] >> 3)) ebits[j] = bits[j] >> stereo >> 3;
-            ebits[j] = imin(ebits[j], 8);
-            fine_priority[j] = ebits[j] * (den << 3) >= bits[j] + offset;
-            bits[j] -= C * ebits[j] << 3;
+            int eb = imax(0, bits[j] + offset + (den << 2));
+            eb = (int)((u32)eb / (u32)den) >> 3;
+            if (C * eb > (bits[j] >> 3)) eb = bits[j] >> stereo >> 3;
+            eb = imin(eb, 8);
+            ebits[j] = narrow<fineq_t>(eb);
+            fine_priority[j] = eb * (den << 3) >= bits[j] + offset;
+            bits[j] -= C * eb << 3;
         } else {
             excess = imax(0, bit - (C << 3));
             bits[j] = bit - excess;
@@ -709,7 +752,7 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
         }
         if (excess > 0) {
             int extra_fine = imin(excess >> (stereo + 3), 8 - ebits[j]);
-            ebits[j] += extra_fine;
+            ebits[j] = narrow<fineq_t>(ebits[j] + extra_fine);
             int extra_bits = extra_fine * C << 3;
             fine_priority[j] = extra_bits >= excess - balance;
             excess -= extra_bits;
@@ -719,17 +762,18 @@ OPUS_HD int interp_bits2pulses(RangeDec& rd, int start, int end, int skip_start,
     *balance_out = balance;
 #pragma unroll 1
     for (; j < end; j++) {
-        ebits[j] = bits[j] >> stereo >> 3;
+        const int eb = bits[j] >> stereo >> 3;
+        ebits[j] = narrow<fineq_t>(eb);
         bits[j] = 0;
-        fine_priority[j] = ebits[j] < 1;
+        fine_priority[j] = eb < 1;
     }
     return codedBands;
 }
 
 // ref clt_compute_allocation (src/celt.cpp:3523), decoder side
-OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offsets, const int* cap, int alloc_trim,
-                               int* intensity, int* dual_stereo, int total, int* balance, int* pulses, int* ebits,
-                               int* fine_priority, int C, int LM) {
+OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const cap_t* offsets, const cap_t* cap, int alloc_trim,
+                               int* intensity, int* dual_stereo, int total, int* balance, int* pulses, fineq_t* ebits,
+                               fineq_t* fine_priority, int C, int LM) {
     total = imax(total, 0);
     const int len = kNbEBands;
     int skip_start = start;
@@ -745,13 +789,15 @@ OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offs
             total -= dual_stereo_rsv;
         }
     }
-    int bits1[kNbEBands], bits2[kNbEBands], thresh[kNbEBands], trim_offset[kNbEBands];
+    abits_t bits1[kNbEBands], bits2[kNbEBands];
+    thr_t thresh[kNbEBands], trim_offset[kNbEBands];
 #pragma unroll 1
     for (int j = start; j < end; j++) {
         int w = kEBands[j + 1] - kEBands[j];
-        thresh[j] = imax(C << 3, (3 * w << LM << 3) >> 4);
-        trim_offset[j] = C * w * (alloc_trim - 5 - LM) * (end - j - 1) * (1 << (LM + 3)) >> 6;
-        if (w << LM == 1) trim_offset[j] -= C << 3;
+        thresh[j] = narrow<thr_t>(imax(C << 3, (3 * w << LM << 3) >> 4));
+        int tr = C * w * (alloc_trim - 5 - LM) * (end - j - 1) * (1 << (LM + 3)) >> 6;
+        if (w << LM == 1) tr -= C << 3;
+        trim_offset[j] = narrow<thr_t>(tr);
     }
     int lo = 1, hi = 11 - 1;
 #pragma unroll 1
@@ -781,8 +827,8 @@ OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const int* offs
         bits2j += offsets[j];
         if (offsets[j] > 0) skip_start = j;
         bits2j = imax(0, bits2j - bits1j);
-        bits1[j] = bits1j;
-        bits2[j] = bits2j;
+        bits1[j] = narrow<abits_t>(bits1j);
+        bits2[j] = narrow<abits_t>(bits2j);
     }
     return interp_bits2pulses(rd, start, end, skip_start, bits1, bits2, thresh, cap, total, balance, skip_rsv, intensity,
                               intensity_rsv, dual_stereo, dual_stereo_rsv, pulses, ebits, fine_priority, C, LM);
@@ -873,7 +919,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     }
 
     // ---- tf_decode (ref :2128)
-    int tf_res[kNbEBands];
+    tf_t tf_res[kNbEBands];
     {
         u32 budget = rd.storage * 8;
         u32 t = (u32)rd_tell(rd);
@@ -888,7 +934,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
                 t = (u32)rd_tell(rd);
                 tf_changed |= curr;
             }
-            tf_res[i] = curr;
+            tf_res[i] = (tf_t)curr;
             logp = isTransient ? 4 : 5;
         }
         int tf_select = 0;
@@ -904,11 +950,11 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     p.spread = spread;
 
     // ---- caps + dynalloc (ref :911, :2301-2328)
-    int cap[kNbEBands], offsets[kNbEBands];
+    cap_t cap[kNbEBands], offsets[kNbEBands];
 #pragma unroll 1
     for (int i = 0; i < kNbEBands; i++) {
         int N = (kEBands[i + 1] - kEBands[i]) << LM;
-        cap[i] = (kCacheCaps[kNbEBands * (2 * LM + C - 1) + i] + 64) * C * N >> 2;
+        cap[i] = narrow<cap_t>((kCacheCaps[kNbEBands * (2 * LM + C - 1) + i] + 64) * C * N >> 2);
         offsets[i] = 0;
     }
     int dynalloc_logp = 6;
@@ -931,7 +977,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
             total_bits -= quanta;
             loop_logp = 1;
         }
-        offsets[i] = boost;
+        offsets[i] = narrow<cap_t>(boost);
         if (boost > 0) dynalloc_logp = imax(2, dynalloc_logp - 1);
     }
     const int alloc_trim = tell + (6 << 3) <= total_bits ? rd_icdf(rd, kTrimIcdf, 7) : 5;
@@ -940,7 +986,8 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     const int anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << 3) ? (1 << 3) : 0;
     bits -= anti_collapse_rsv;
 
-    int pulses[kNbEBands], fine_quant[kNbEBands], fine_priority[kNbEBands];
+    int pulses[kNbEBands];
+    fineq_t fine_quant[kNbEBands], fine_priority[kNbEBands];
 #pragma unroll 1
     for (int i = 0; i < kNbEBands; i++) { pulses[i] = 0; fine_quant[i] = 0; fine_priority[i] = 0; }
     int intensity = 0, dual_stereo = 0, balance = 0;
@@ -948,7 +995,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
                                               pulses, fine_quant, fine_priority, C, LM);
 
     // ---- fine energy (ref unquant_fine_energy :3664)
-    s32 fine_acc[2][kNbEBands];
+    facc_t fine_acc[2][kNbEBands];  // sums mod 2^16, which is all the header keeps
 #pragma unroll 1
     for (int c = 0; c < 2; c++) for (int i = 0; i < kNbEBands; i++) fine_acc[c][i] = 0;
 #pragma unroll 1
@@ -959,7 +1006,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
         for (int c = 0; c < C; c++) {
             s32 q2 = (s32)rd_bits(rd, (u32)fine_quant[i]);
             s32 offset = sub16((shl32(q2, 10) + 512) >> fine_quant[i], 512);
-            fine_acc[c][i] += (s16)offset;
+            fine_acc[c][i] = (facc_t)(fine_acc[c][i] + offset);
         }
     }
 
@@ -985,7 +1032,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
                 for (int c = 0; c < C; c++) {
                     s32 q2 = (s32)rd_bits(rd, 1);
                     s32 offset = ((s32)shl16(q2, 10) - 512) >> (fine_quant[i] + 1);
-                    fine_acc[c][i] += (s16)offset;
+                    fine_acc[c][i] = (facc_t)(fine_acc[c][i] + offset);
                     bits_left--;
                 }
             }

@@ -16,6 +16,8 @@
 #endif
 
 #if !defined(__CUDACC__)
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 struct uint2 { uint32_t x, y; };
 #endif

@@ -42,7 +42,9 @@ struct FrameSet {
 struct dm_ctx {
     int n_streams, max_frames, channels, device, n_sm;
     int leaf_slots;  // capacity of the sorted leaf list per frame (OPUSB_LEAF_SLOTS lowers it: tests of the overflow path)
-    int tail_mode;   // pipelined calls: 2 = post-filter + de-emphasis on the tail stream, 1 = de-emphasis only, 0 = no tail stream (OPUSB_TAIL, for tuning)
+    int tail_mode;   // pipelined calls: 0 = one stream (default: overlapping the tail of call k with the head of call k + 1 was measured
+                     // and wins nothing, profiles/r02_call_overlap_trace.txt), 2 = post-filter + de-emphasis on a tail stream beside the next
+                     // call's head (two alternating frame sets), 1 = de-emphasis only (OPUSB_TAIL, to repeat the measurement)
     int silk_lanes;  // chains per warp of the SILK lane-per-chain kernels; 0 = silk_chain_lanes() (OPUSB_SILK_LANES overrides, for tuning)
     // per-stream state
     CeltStreamState* d_state;
@@ -136,7 +138,7 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     CU_TRY(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
     c->leaf_slots = kLeafSlotsPerFrame;  // (the context was just zeroed)
     if (const char* e = getenv("OPUSB_LEAF_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= kLeafSlotsPerFrame) c->leaf_slots = v; }
-    c->tail_mode = 2;
+    c->tail_mode = 0;
     if (const char* e = getenv("OPUSB_TAIL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tail_mode = v; }
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // The entropy kernel keeps its per-thread allocation arrays and the explicit partition stack in local memory.  The
@@ -445,13 +447,13 @@ static int enqueue_pipelined(dm_ctx* c, const dm_batch* in, const uint8_t* d_byt
                              cudaEvent_t ready, cudaEvent_t parsed, cudaEvent_t* done) {
     const long long q = c->calls;
     const int r = (int)(q % kRing);
-    FrameSet& F = c->set[q & 1];
+    FrameSet& F = c->set[c->tail_mode ? (q & 1) : 0];
     int rc = alloc_set(c, F);
     if (rc) return rc;
     const cudaStream_t H = c->streams[0];
     if (ready) CU_TRY(c, cudaStreamWaitEvent(H, ready, 0));
     // this frame set was last read by the tail and the SILK stage of the call before the previous one
-    if (q >= 2) CU_TRY(c, cudaStreamWaitEvent(H, c->done_ev[(q - 2) % kRing], 0));
+    if (c->tail_mode && q >= 2) CU_TRY(c, cudaStreamWaitEvent(H, c->done_ev[(q - 2) % kRing], 0));
     CallPlan pl = {H, c->tail_mode ? c->tail : H, c->side[0], &F, 0, c->seq_ev[r], c->head_ev[r], c->x_ev[r], parsed, true};
     rc = launch_pipeline(c, in, d_bytes, d_frames, d_pcm, d_status, 0, c->n_streams, pl);
     if (rc) return rc;

@@ -104,9 +104,11 @@ int dm_decode_device(dm_ctx* ctx, const dm_batch* in_dev, dm_out* out_dev, void*
 /* The same with explicit dependencies instead of a stream, so that consecutive calls overlap: the call starts once
  * `ready_event` (a cudaEvent_t; NULL: the inputs are ready now) has fired and *done_event (a cudaEvent_t owned by the
  * library, valid until four more calls have been made) fires when PCM and status are complete.  Calls on a context are
- * ordered among themselves, and the serial tail of call k (post-filter, de-emphasis: few long-running warps) runs
- * beside the parse and spectral stages of call k + 1; the inputs of a call may be reused once its done event has fired,
- * and a consumer must have finished with an output buffer before a later call is given the same one.
+ * ordered among themselves; calls on different contexts run beside each other (a mixed workload has one context per
+ * channel count and call mode).  With OPUSB_TAIL=2 in the environment the serial tail of call k (post-filter,
+ * de-emphasis) also runs beside the head of call k + 1 -- measured, and off by default because it wins nothing.  The
+ * inputs of a call may be reused once its done event has fired, and a consumer must have finished with an output buffer
+ * before a later call is given the same one.
  * dm_stream_wait makes a stream wait for everything enqueued so far. */
 int dm_decode_device_async(dm_ctx* ctx, const dm_batch* in_dev, dm_out* out_dev, void* ready_event, void** done_event);
 int dm_stream_wait(dm_ctx* ctx, void* cuda_stream);

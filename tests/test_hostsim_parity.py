@@ -79,3 +79,25 @@ def test_opus_mode_switching_bit_exact(hostsim, ref, ch):
             (0x68 | s, 100, 5), (0xF8 | s, 100, 4), (0x78 | s, 120, 4), (0xD8 | s, 90, 4), (0x48 | s, 0, 8), (0x78 | s, 0, 8),
             (0x08 | s, 0, 6), (0xF8 | s, 0, 6)]
     _opus_run(hostsim, ref, ch, plan, 77 + ch)
+
+
+def test_narrowed_parser_arrays_hold_their_values(hostsim):
+    """The parser's per-band work arrays are int8 / int16 / uint16 (celt_parse.cuh `narrow`); the host build aborts the
+    process if a value does not fit.  Parse-only stress over the extremes: maximum and minimum frame sizes, every frame
+    size, mono and stereo, hybrid start band, random payloads (so boosts, trims and skip decisions of every kind occur)."""
+    rng = np.random.default_rng(2024)
+    hdr = np.zeros(512, np.uint8)
+    ops = np.zeros(1360 * 16, np.uint8)
+    X = np.zeros(1920, np.int16)
+    n = 0
+    for LM in range(4):
+        for C in (1, 2):
+            for start in (0, 17):
+                for L in (1275, 1000, 640, 320, 160, 60, 20, 9, 3, 2):
+                    for _ in range(40 if L >= 640 else 15):
+                        frame = rng.integers(0, 256, L, dtype=np.uint8)
+                        if rng.integers(0, 4) == 0:  # bias towards all-ones / all-zeros runs: long boosts, extreme trims
+                            frame[: int(rng.integers(1, L + 1))] = int(rng.choice([0, 255]))
+                        hostsim.hs_celt_parse(frame.ctypes.data, L, C, LM, start, 0, hdr.ctypes.data, ops.ctypes.data, X.ctypes.data)
+                        n += 1
+    assert n >= 3000

@@ -5,6 +5,7 @@ import os
 import sys
 
 os.environ["OPUSB_TRACE"] = "1"
+os.environ.setdefault("OPUSB_TAIL", "2")
 import numpy as np
 import torch
 
