@@ -65,21 +65,74 @@ enum { KW_WARPS = 4 };
 #define KIL_BLOCKS 4  // resident blocks per SM the register allocation of k_imdct_long is held to (128 registers)
 #endif
 enum { FD_CONT = 1, FD_NULL = 2 };  // dm_frame.flags (include/opus_b200.h)
+#ifndef OPUSB_STAGE_PACKETS
+#define OPUSB_STAGE_PACKETS 0  // k_entropy: 1 = packets through shared memory (one TMA bulk copy per packet) instead of byte loads from
+                               // global memory.  Bit-exact and measured 3-9 % slower (profiles/r02_packet_staging.txt): the parser needs
+                               // the shared-memory space as L1 for its work arrays more than it needs the packet bytes closer
+#endif
+enum { kStageBytes = 176 };  // per packet: covers a 160-byte packet at any alignment (11 x 16 bytes)
 
 __device__ __forceinline__ bool frame_skipped(int status) {
     return status == OPUSB_CELT_BAD_ARG || status == OPUSB_UNIMPLEMENTED || status == OPUSB_BAD_ARG;
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two instantiations share the frames of a call between them by TOC: kSilk = false takes the frames without a SILK layer
+// (CELT-only TOCs, raw CELT frames, fillers), kSilk = true the SILK-only and hybrid frames.  The CELT-only kernel -- the
+// whole of the headline workload -- then carries neither the SILK parser's code nor its registers; a warp of the other
+// kernel that finds no frame of its kind returns at once.
+template <bool kSilk>
 __global__ void __launch_bounds__(K1_THREADS, K1_BLOCKS)  // 80 registers: 24 warps per SM measured faster than 16 (128 regs) or 32 (64 regs, spills)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
           BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk) {
     const int local = blockIdx.x * K1_THREADS + threadIdx.x;
-    const bool in_range = local < P.n_local();
+    bool in_range = local < P.n_local();
+    const size_t t = P.index_of(in_range ? local : 0);
+    const FrameDesc d = fr[t];
+    // which of the two kernels owns the frame
+    const bool silk_kind = P.mode == 0 && !(d.flags & FD_NULL) && !(d.toc & 0x80);
+    in_range = in_range && (silk_kind == kSilk);
     const unsigned warp = __ballot_sync(0xffffffffu, in_range);  // the lanes of this warp that own a frame
     if (!in_range) return;
-    const size_t t = P.index_of(local);
-    const FrameDesc d = fr[t];
+    // ---- packet staging: the first kStageBytes of every packet of the warp go to shared memory, one bulk copy
+    // (cp.async.bulk, the TMA unit) per packet, all completing on one mbarrier per warp.  A bulk copy moves whole 16-byte
+    // units between 16-byte aligned addresses, so a lane copies the aligned span around its packet and remembers where
+    // payload byte 0 landed.  (The span never leaves the allocation the packet lies in: allocations are 256-byte units.)
+    u32 sbase = 0, staged = 0;
+#if OPUSB_STAGE_PACKETS
+    {
+        __shared__ __align__(16) uint8_t stage_sm[K1_THREADS][kStageBytes];
+        __shared__ __align__(8) unsigned long long stage_bar[K1_THREADS / 32];
+        const u32 bar = (u32)__cvta_generic_to_shared(&stage_bar[threadIdx.x >> 5]);
+        const int leader = __ffs(warp) - 1;
+        if ((int)(threadIdx.x & 31) == leader) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(__popc(warp)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp(warp);
+        const bool has_bytes = !(d.flags & FD_NULL) && d.len > 0;
+        const uintptr_t src = reinterpret_cast<uintptr_t>(bytes + d.offset);
+        const u32 pre = (u32)(src & 15);
+        u32 span = has_bytes ? ((pre + d.len + 15u) & ~15u) : 0u;
+        if (span > (u32)kStageBytes) span = kStageBytes;
+        const u32 dst = (u32)__cvta_generic_to_shared(&stage_sm[threadIdx.x][0]);
+        unsigned long long token;
+        if (span) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(token) : "r"(bar), "r"(span) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src - pre), "r"(span), "r"(bar)
+                         : "memory");
+            sbase = dst + pre;
+            staged = span - pre < d.len ? span - pre : d.len;
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(token) : "r"(bar) : "memory");
+        }
+        (void)token;
+        u32 ready = 0;
+        while (!ready)  // phase 0 of the barrier: every lane has arrived and every byte has landed
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ready) : "r"(bar) : "memory");
+    }
+#endif
     CeltFrameHdr& h = hdr[t];
     ParseCtx p;
     p.end = kNbEBands; p.disable_inv = (P.CC == 1);
@@ -88,8 +141,6 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     p.C = 1; p.LM = 3; p.start = 0; p.prep_on = 0;
     int oflags = 0;
     bool celt = true, fade = false;
-    // the lanes with a SILK layer go through its parser in lock step (silk_parse_frame)
-    const unsigned silk_lanes = __ballot_sync(warp, P.mode == 0 && !(d.flags & FD_NULL) && opus_has_silk_layer(d.toc, P.CC));
     if (d.flags & FD_NULL) {  // filler behind the last frame of a stream: no output, no state change
         h.status = OPUSB_FRAME_SKIPPED; h.flags = 0; h.n_ops = 0; h.n_leaves = 0; h.LM = 3; h.C = 1;
         h.start = 0; h.end = kNbEBands;
@@ -98,9 +149,15 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
     } else if (P.mode == 0) {
         const int f = P.frame_of(local);  // (the previous frame's TOC is call input, whichever group it belongs to)
         const int prev_mode = f > 0 ? opus_toc_mode(fr[t - 1].toc) : st[P.stream_of(local)].prev_mode;
-        oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade, silk_lanes);
+        if constexpr (kSilk) {
+            // the lanes with a SILK layer that this decoder can play go through its parser in lock step (silk_parse_frame)
+            const unsigned silk_lanes = __ballot_sync(warp, opus_has_silk_layer(d.toc, P.CC));
+            oflags = opus_parse_prologue(p, bytes + d.offset, d.len, d.toc, prev_mode, P.CC, h, silk[t], &celt, &fade, silk_lanes, sbase, staged);
+        } else {
+            oflags = opus_parse_prologue_celt(p, bytes + d.offset, d.len, d.toc, prev_mode, h, sbase, staged);
+        }
     } else {
-        rd_init(p.rd, bytes + d.offset, d.len);
+        rd_init(p.rd, bytes + d.offset, d.len, sbase, staged);
         p.C = P.coded_channels;
         p.LM = P.frame_size == 120 ? 0 : P.frame_size == 240 ? 1 : P.frame_size == 480 ? 2 : 3;
         p.start = P.start_band;
@@ -117,7 +174,7 @@ k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, D
         }
     }
     h.oflags = (uint8_t)oflags;
-    if (oflags & OF_HAS_SILK) *any_silk = 1;  // the SILK kernels of this call have work
+    if (kSilk && (oflags & OF_HAS_SILK)) *any_silk = 1;  // the SILK kernels of this call have work
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -146,7 +146,7 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     // raised, and only as far as this library's largest frame needs (no recursion anywhere, so ptxas knows the size).
     {
         cudaFuncAttributes fa;
-        CU_TRY(c, cudaFuncGetAttributes(&fa, k_entropy));
+        CU_TRY(c, cudaFuncGetAttributes(&fa, k_entropy<true>));
         size_t cur = 0;
         CU_TRY(c, cudaDeviceGetLimit(&cur, cudaLimitStackSize));
         const size_t need = (fa.localSizeBytes + 255) / 256 * 256;
@@ -369,7 +369,11 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) mark(0, H);
     int* any_silk = F.any_silk + chunk;  // per stream range: ranges of one call run concurrently on their own streams
     cudaMemsetAsync(any_silk, 0, sizeof(int), H);
-    k_entropy<<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk);
+    k_entropy<false><<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk);
+    if (in->mode == DM_MODE_OPUS) {  // the frames with a SILK layer
+        k_entropy<true><<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk);
+        c->launches++;
+    }
     if (timed) mark(1, H);
     k_sequence<<<(n_sel + KW_WARPS - 1) / KW_WARPS, wb, 0, H>>>(F.hdr, d_frames, F.fe, c->d_state, P);
     if (timed) mark(2, H);

@@ -30,7 +30,7 @@ OPUS_HD int opus_toc_mode(int toc) { return (toc & 0x80) ? MODE_CELT_ONLY : ((to
 // whether a CELT frame follows, *fade that it is the 120-sample hybrid -> SILK fade-out frame whose status
 // the reference ignores (ref :263-268).
 OPUS_HD int opus_parse_prologue(ParseCtx& p, const uint8_t* payload, int len, int toc, int prev_mode, int CC, CeltFrameHdr& hdr,
-                                SilkFrame& sf, bool* celt, bool* fade, unsigned silk_lanes) {
+                                SilkFrame& sf, bool* celt, bool* fade, unsigned silk_lanes, u32 sbase = 0, u32 staged = 0) {
     const int mode = opus_toc_mode(toc);
     const int C = (toc & 0x4) ? 2 : 1;
     int oflags = 0;
@@ -43,7 +43,7 @@ OPUS_HD int opus_parse_prologue(ParseCtx& p, const uint8_t* payload, int len, in
         *celt = false;
         return OF_NO_CELT;
     }
-    rd_init(p.rd, payload, (u32)len);
+    rd_init(p.rd, payload, (u32)len, sbase, staged);
     p.C = C; p.LM = 3; p.start = 0;
     if (mode != MODE_CELT_ONLY) {
         oflags |= OF_HAS_SILK;
@@ -69,6 +69,18 @@ OPUS_HD int opus_parse_prologue(ParseCtx& p, const uint8_t* payload, int len, in
         oflags |= OF_NO_CELT;
     }
     return oflags;
+}
+
+// The same for a frame with a CELT-only TOC (ref src/opus_decoder.cpp:154-278 with mode == MODE_CELT_ONLY): no SILK
+// layer, bands from 0, 20 ms; OPUS_RESET_STATE when the previous frame had another mode.
+OPUS_HD int opus_parse_prologue_celt(ParseCtx& p, const uint8_t* payload, int len, int toc, int prev_mode, CeltFrameHdr& hdr, u32 sbase = 0,
+                                     u32 staged = 0) {
+    const int C = (toc & 0x4) ? 2 : 1;
+    hdr.flags = 0; hdr.oflags = 0; hdr.n_ops = 0; hdr.n_leaves = 0; hdr.LM = 3; hdr.C = (uint8_t)C; hdr.start = 0; hdr.end = kNbEBands;
+    hdr.final_rng = 0; hdr.spread = 2; hdr.pf_pitch = 0; hdr.pf_gain = 0; hdr.pf_tapset = 0; hdr.lcg_steps = 0;
+    rd_init(p.rd, payload, (u32)len, sbase, staged);
+    p.C = C; p.LM = 3; p.start = 0;
+    return (prev_mode != MODE_CELT_ONLY && prev_mode > 0) ? OF_RESET_CELT : 0;
 }
 
 }  // namespace opusb200

@@ -11,6 +11,8 @@ namespace opusb200 {
 
 struct RangeDec {
     const uint8_t* buf;
+    u32 sbase;        // shared-memory address of payload byte 0 when the packet was staged there (k_entropy), else unused
+    u32 staged;       // payload bytes [0, staged) are in shared memory; 0: everything is read from global memory
     u32 storage;      // packet length in bytes
     u32 end_offs;     // bytes consumed from the back
     u32 end_window;   // raw-bit window
@@ -22,8 +24,20 @@ struct RangeDec {
     int error;
 };
 
-OPUS_HD int rd_read_byte(RangeDec& d) { return d.offs < d.storage ? d.buf[d.offs++] : 0; }
-OPUS_HD int rd_read_byte_end(RangeDec& d) { return d.end_offs < d.storage ? d.buf[d.storage - ++d.end_offs] : 0; }
+// Byte i of the payload: from the thread's staging window in shared memory if it holds it (k_entropy copies the first
+// kStageBytes of every packet there with one bulk copy per packet), else from global memory.
+OPUS_HD int rd_byte_at(const RangeDec& d, u32 i) {
+#if defined(__CUDA_ARCH__)
+    if (i < d.staged) {
+        u32 v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(d.sbase + i));
+        return (int)v;
+    }
+#endif
+    return d.buf[i];
+}
+OPUS_HD int rd_read_byte(RangeDec& d) { return d.offs < d.storage ? rd_byte_at(d, d.offs++) : 0; }
+OPUS_HD int rd_read_byte_end(RangeDec& d) { return d.end_offs < d.storage ? rd_byte_at(d, d.storage - ++d.end_offs) : 0; }
 
 // ref ec_dec_normalize (src/celt.cpp:2649)
 OPUS_HD void rd_normalize(RangeDec& d) {
@@ -39,8 +53,10 @@ OPUS_HD void rd_normalize(RangeDec& d) {
 }
 
 // ref ec_dec_init (src/celt.cpp:2666)
-OPUS_HD void rd_init(RangeDec& d, const uint8_t* buf, u32 len) {
+OPUS_HD void rd_init(RangeDec& d, const uint8_t* buf, u32 len, u32 sbase = 0, u32 staged = 0) {
     d.buf = buf;
+    d.sbase = sbase;
+    d.staged = staged;
     d.storage = len;
     d.end_offs = 0;
     d.end_window = 0;

@@ -1,3 +1,11 @@
-python tools/pcie_probe.py > gpurun_out/r02e_probe1.json 2> gpurun_out/r02e_probe1.err; echo "probe rc=$?"; cat gpurun_out/r02e_probe1.json | cut -c1-900; tail -3 gpurun_out/r02e_probe1.err
-python bench.py --workload mix --streams 512 --steps 3 --frames 20 > gpurun_out/r02e_mixsmall.json 2> gpurun_out/r02e_mixsmall.err; echo "mix rc=$?"; tail -c 300 gpurun_out/r02e_mixsmall.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 1 --streams 512 --steps 3 --frames 20 --scaling strong > gpurun_out/r02e_tr1.json 2> gpurun_out/r02e_tr1.err; echo "torchrun rc=$?"; tail -c 300 gpurun_out/r02e_tr1.err
+python -m pytest tests/test_gpu_celt.py tests/test_gpu_opus.py -m gpu -x -q 2>&1 | tail -2
+for i in 1 2; do
+python tools/stage_times.py celt
+OPUSB_LIB=esp32-opus-player_b200/lib/variants/nostage.so python tools/stage_times.py celt
+done
+python tools/stage_times.py silk
+OPUSB_LIB=esp32-opus-player_b200/lib/variants/nostage.so python tools/stage_times.py silk
+python bench.py --device-only --no-overlap --steps 5 --payload 639 | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('640B staged', d['ms_per_step'], d['roofline']['stage_ms']['entropy'])"
+OPUSB_LIB=esp32-opus-player_b200/lib/variants/nostage.so python bench.py --device-only --no-overlap --steps 5 --payload 639 | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('640B nostage', d['ms_per_step'], d['roofline']['stage_ms']['entropy'])"
