@@ -103,12 +103,17 @@ def parse(args):
         k["dram_read"] += num(r, col["dram_read"])
         k["dram_write"] += num(r, col["dram_write"])
         k["dram_bytes"] = k["dram_read"] + k["dram_write"]
-        k["time_us"] += num(r, col["time_ns"]) / 1e3
-        k["registers"] = num(r, col["registers"])
-        k["issue_active_pct"] = num(r, col["issue_active_pct"])
-        k["warps_active_pct"] = num(r, col["warps_active_pct"])
+        t_us = num(r, col["time_ns"]) / 1e3
+        k["time_us"] += t_us
         k["smem_bank_conflicts"] = k.get("smem_bank_conflicts", 0.0) + num(r, col["smem_bank_conflicts"])
-        k["stalls_per_issue"] = {n: round(num(r, i), 3) for n, i in stall_cols if num(r, i) >= 0.05}
+        if t_us >= k.get("_longest", -1.0):  # rates and stalls: those of the kernel's longest launch (template instantiations share a name)
+            k["_longest"] = t_us
+            k["registers"] = num(r, col["registers"])
+            k["issue_active_pct"] = num(r, col["issue_active_pct"])
+            k["warps_active_pct"] = num(r, col["warps_active_pct"])
+            k["stalls_per_issue"] = {n: round(num(r, i), 3) for n, i in stall_cols if num(r, i) >= 0.05}
+    for k in kernels.values():
+        k.pop("_longest", None)
     plain = os.path.join(os.path.dirname(os.path.abspath(args.report)), "ncu_%s_plain.json" % args.workload)
     src_hash, frames, value = None, args.frames_per_step, None
     if os.path.exists(plain):
