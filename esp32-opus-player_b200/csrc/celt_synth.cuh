@@ -382,6 +382,16 @@ OPUS_HD void comb_filter_inplace(const Lanes& L, View x, int T0, int T1, int N, 
 // The memory update MULT16_32_Q15(27853, tmp) = floor(27853 * tmp / 2^15) is written as tmp + floor(-4915 * tmp / 2^15)
 // (27853 = 2^15 - 4915; exact for every int32 tmp): the second term is ONE multiply-high by -4915 << 17, and the next
 // sample's tmp = x + tmp + hi is one three-input add behind it -- the dependent chain per sample is two instructions.
+// The same without the final clamp (the caller saturates two samples at once): PSHR32(tmp, 12), ref sig2word16 :413.
+OPUS_HD s32 deemph_round(s32 x, s32& mem) {
+    s32 tmp = (s32)((u32)x + (u32)mem);
+#if defined(__CUDA_ARCH__)
+    mem = (s32)((u32)tmp + (u32)__mulhi(tmp, -(4915 << 17)));
+#else
+    mem = mul16x32_q15(27853, tmp);
+#endif
+    return pshr32(tmp, 12);
+}
 OPUS_HD s32 deemph_sample(s32 x, s32& mem) {
     s32 tmp = (s32)((u32)x + (u32)mem);
 #if defined(__CUDA_ARCH__)

@@ -487,74 +487,99 @@ k_imdct(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe
 
 // ------------------------------------------------------------------------------------------------
 // One warp walks the frames of one (stream, channel) in order.  The signal history the comb filter reaches back
-// into (<= 1026 samples) and the frame being filtered live in a 2048-entry ring in shared memory, so nothing is
-// moved between frames; the next frame's raw IMDCT output is fetched with cp.async into a staging row while the
-// current frame is being filtered (the warp has nothing else to overlap a global-memory round trip with).
+// into (<= 1026 samples) and the frame being filtered live side by side in one linear shared-memory buffer --
+// [history | frame] -- so that every access of the filter is a plain offset; after a frame the newest 1028 samples are
+// moved down to the front (33 loads + 33 stores per lane, cheaper than masking every index of a ring: 18 % of the
+// kernel's instructions went into that).  The next frame's raw IMDCT output is fetched with cp.async into a staging row
+// while the current frame is being filtered (the warp has nothing else to overlap a global-memory round trip with).
 #ifndef PF_WARPS
 #define PF_WARPS 4
 #endif
+enum { kPfLin = kCombHist + kMaxFrame, kPfMove = 352 };  // kPfMove: samples moved per step of the history shift (11 per lane)
 
 __global__ void __launch_bounds__(32 * PF_WARPS)
 k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ raw,
              int32_t* __restrict__ syn, CeltStreamState* __restrict__ st, DevParams P) {
-    __shared__ __align__(16) int32_t rsm[PF_WARPS][kRingSize];
+    __shared__ __align__(16) int32_t lsm[PF_WARPS][kPfLin];
     __shared__ __align__(16) int32_t ssm[PF_WARPS][kMaxFrame];
     __shared__ int32_t tsm[PF_WARPS][kOverlap / 2];
     const int local = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (local >= P.n_sel * P.CC) return;
     const int c = local % P.CC, s = P.first_stream + local / P.CC;
     Lanes L;
-    int32_t* ring = rsm[threadIdx.x >> 5];
+    int32_t* lin = lsm[threadIdx.x >> 5];
     int32_t* stage = ssm[threadIdx.x >> 5];
     int32_t* tail = tsm[threadIdx.x >> 5];
     CeltStreamState& S = st[s];
-    for (int i = L.lane; i < kCombHist; i += 32) ring[i] = S.hist[c][i];
+    for (int i = L.lane; i < kCombHist; i += 32) lin[i] = S.hist[c][i];
     for (int i = L.lane; i < kOverlap / 2; i += 32) tail[i] = S.tail[c][i];
-    int pos = kCombHist;  // ring index of the first sample of the next frame
+    const LinView x{lin + kCombHist};  // the frame being filtered; x[-1] is the newest sample of the history
     const size_t t0 = (size_t)s * P.n_frames;
-
-    // stage <- raw output of frame f (16 bytes per lane and copy), if that frame has a CELT layer
     const int f_end = P.f0 + P.nf;
-    auto fetch = [&](int f) {
+
+    // What the warp needs to know about a frame is read one frame ahead (every lane the same words): loaded in front of
+    // the frame it would cost a DRAM round trip per frame with nothing to hide it behind.
+    struct Info { int skip, celt_n, LM, flags, T0, T1, T2, g0, g1, g2, tap0, tap1, tap2; };
+    auto load_info = [&](int f) {
+        Info v = {FS_NO_CELT, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (f < f_end) {
             const FrameEnergy& e = fe[t0 + f];
-            if (!(e.skip & FS_NO_CELT)) {
-                const int n = e.celt_n;
-                const int32_t* src = raw + ((t0 + f) * P.CC + c) * kMaxFrame;
-                for (int i = 4 * L.lane; i < n; i += 128) __pipeline_memcpy_async(stage + i, src + i, 16);
-            }
+            const CeltFrameHdr& h = hdr[t0 + f];
+            v.skip = e.skip; v.celt_n = e.celt_n; v.LM = h.LM; v.flags = h.flags;
+            v.T0 = e.pf_period_old; v.T1 = e.pf_period; v.T2 = h.pf_pitch;
+            v.g0 = e.pf_gain_old; v.g1 = e.pf_gain; v.g2 = h.pf_gain;
+            v.tap0 = e.pf_tapset_old; v.tap1 = e.pf_tapset; v.tap2 = h.pf_tapset;
+        }
+        return v;
+    };
+    // stage <- raw output of frame f (16 bytes per lane and copy), if that frame has a CELT layer
+    auto fetch = [&](int f, const Info& v) {
+        if (f < f_end && !(v.skip & FS_NO_CELT)) {
+            const int32_t* src = raw + ((t0 + f) * P.CC + c) * kMaxFrame;
+            for (int i = 4 * L.lane; i < v.celt_n; i += 128) __pipeline_memcpy_async(stage + i, src + i, 16);
         }
         __pipeline_commit();
     };
-    fetch(P.f0);
-    for (int f = P.f0; f < f_end; f++) {
+    Info cur = load_info(P.f0), nxt = load_info(P.f0 + 1);
+    fetch(P.f0, cur);
+    for (int f = P.f0; f < f_end; f++, cur = nxt, nxt = load_info(f + 1)) {
         const size_t t = t0 + f;
-        const FrameEnergy& e = fe[t];
         __pipeline_wait_prior(0);
         L.sync();
-        if (e.skip & FS_NO_CELT) {
-            fetch(f + 1);
+        if (cur.skip & FS_NO_CELT) {
+            fetch(f + 1, nxt);
             continue;
         }
-        const CeltFrameHdr& h = hdr[t];
-        const int LM = h.LM, N = kShortMdct << LM;
-        const int nblk = (h.flags & FF_TRANSIENT) ? (1 << LM) : 1;
-        const RingView x{ring, pos};
+        const int LM = cur.LM, N = kShortMdct << LM;
+        const int nblk = (cur.flags & FF_TRANSIENT) ? (1 << LM) : 1;
         tdac_frame(L, stage, tail, x, N / nblk, nblk);  // ends with a warp barrier: the staging row is free again
-        fetch(f + 1);
-        comb_filter_inplace(L, x, e.pf_period_old, e.pf_period, kShortMdct, e.pf_gain_old, e.pf_gain, e.pf_tapset_old, e.pf_tapset);
-        if (LM != 0)
-            comb_filter_inplace(L, x + kShortMdct, e.pf_period, h.pf_pitch, N - kShortMdct, e.pf_gain, h.pf_gain, e.pf_tapset,
-                                h.pf_tapset);
+        fetch(f + 1, nxt);
+        comb_filter_inplace(L, x, cur.T0, cur.T1, kShortMdct, (s16)cur.g0, (s16)cur.g1, cur.tap0, cur.tap1);
+        if (LM != 0) comb_filter_inplace(L, x + kShortMdct, cur.T1, cur.T2, N - kShortMdct, (s16)cur.g1, (s16)cur.g2, cur.tap1, cur.tap2);
         L.sync();
         int32_t* out = syn + (t * P.CC + c) * kMaxFrame;
         for (int i = L.lane; i < N; i += 32) out[i] = x[i];
-        pos = (pos + N) & (kRingSize - 1);
+        // the newest kCombHist samples become the history: shift down by N, front to back, each step's loads before its stores
+#pragma unroll 1
+        for (int base = 0; base < kCombHist; base += kPfMove) {
+            int32_t v[kPfMove / 32];
+#pragma unroll
+            for (int k = 0; k < kPfMove / 32; k++) {
+                const int i = base + 32 * k + L.lane;
+                v[k] = i < kCombHist ? lin[i + N] : 0;
+            }
+            L.sync();
+#pragma unroll
+            for (int k = 0; k < kPfMove / 32; k++) {
+                const int i = base + 32 * k + L.lane;
+                if (i < kCombHist) lin[i] = v[k];
+            }
+            L.sync();
+        }
     }
     __pipeline_wait_prior(0);
     L.sync();
-    const RingView endv{ring, pos};
-    for (int i = L.lane; i < kCombHist; i += 32) S.hist[c][i] = endv[i - kCombHist];
+    for (int i = L.lane; i < kCombHist; i += 32) S.hist[c][i] = lin[i];
     for (int i = L.lane; i < kOverlap / 2; i += 32) S.tail[c][i] = tail[i];
 }
 
@@ -584,11 +609,25 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     const int32_t* row0 = syn + ((size_t)my_s * P.n_frames * CC + my_c) * kMaxFrame;  // frame f of this chain: + f * CC * kMaxFrame
     int16_t* out0 = pcm + (size_t)my_s * P.n_frames * N * CC;                            // frame f of this stream: + f * N * CC
 
-    // prefetch cursor (tile index -> frame, offset) kept incrementally
+    // What the chain needs to know about a frame -- samples with CELT output, flags, status -- is read one frame ahead:
+    // a load in front of every frame would cost the warp a DRAM round trip 50 times per call with nothing to hide it behind.
+    const int f_end = P.f0 + P.nf;
+    int cur_n = 0, cur_sk = 0, cur_st = 0, nxt_n = 0, nxt_sk = 0, nxt_st = 0;
+    auto load_frame = [&](int ff, int& n, int& sk, int& stt) {
+        n = 0; sk = 0; stt = 0;
+        if (live && ff < f_end) {
+            const size_t tt = (size_t)my_s * P.n_frames + ff;
+            n = fe[tt].celt_n; sk = fe[tt].skip; stt = hdr[tt].status;
+        }
+    };
+    load_frame(P.f0, cur_n, cur_sk, cur_st);
+    load_frame(P.f0 + 1, nxt_n, nxt_sk, nxt_st);
+    int f = P.f0;  // the frame the recurrence is in
+    // prefetch cursor (tile index -> frame, offset) kept incrementally; it runs at most one frame ahead of f
     int pf_q = 0, pf_f = P.f0, pf_j = 0, pf_n = 0;
     auto prefetch = [&]() {
         if (pf_q < T && live) {
-            if (pf_j == 0) pf_n = fe[(size_t)my_s * P.n_frames + pf_f].celt_n;  // nothing to fetch for frames without a CELT layer
+            if (pf_j == 0) pf_n = pf_f == f ? cur_n : nxt_n;  // nothing to fetch for frames without a CELT layer
             const int w = min(DE_TW, pf_n - pf_j);
             const int32_t* src = row0 + (size_t)pf_f * CC * kMaxFrame + pf_j;
             int32_t* dst = &ring[pf_q % DE_STAGES][lane * DE_ROW];
@@ -603,17 +642,16 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     };
     for (int q = 0; q < DE_STAGES - 1; q++) prefetch();
 
-    int f = P.f0, j0 = 0, my_n = 0;
+    int j0 = 0, my_n = 0;
     bool silk_only = false;
     for (int q = 0; q < T; q++) {
         const int w = min(DE_TW, N - j0);
         if (j0 == 0) {
             const size_t my_t = (size_t)my_s * P.n_frames + f;
-            my_n = live ? fe[my_t].celt_n : 0;  // samples of this frame that carry CELT output (0, or 120 for a fade-out frame)
+            my_n = cur_n;  // samples of this frame that carry CELT output (0, or 120 for a fade-out frame)
             // a frame with no CELT layer whose SILK layer is decoded gets its PCM from k_silk_fir alone: nothing to store here
-            const int sk = live ? fe[my_t].skip : 0;
-            silk_only = live && my_n == 0 && (sk & FS_HAS_SILK) && !(sk & FS_DROPPED);
-            if (live && my_c == 0) status[my_t] = (fe[my_t].skip & FS_DROPPED) ? OPUSB_FRAME_SKIPPED : hdr[my_t].status;
+            silk_only = live && my_n == 0 && (cur_sk & FS_HAS_SILK) && !(cur_sk & FS_DROPPED);
+            if (live && my_c == 0) status[my_t] = (cur_sk & FS_DROPPED) ? OPUSB_FRAME_SKIPPED : cur_st;
         }
         prefetch();
         __pipeline_wait_prior(DE_STAGES - 1);
@@ -625,15 +663,27 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
             const int4 v = src[k];
             xv[4 * k] = v.x; xv[4 * k + 1] = v.y; xv[4 * k + 2] = v.z; xv[4 * k + 3] = v.w;
         }
-        // the recurrence; two samples per 32-bit word
+        // the recurrence; two samples per 32-bit word.  A tile is either all signal (the common case: no test per sample,
+        // and the two saturations + pack of a pair are ONE cvt.pack.sat), all silence, or the ragged end of a short frame.
         const int live_n = my_n - j0;
         uint32_t pk[DE_TW / 2];
+        if (live_n >= DE_TW) {
 #pragma unroll
-        for (int j = 0; j < DE_TW; j += 2) {
-            s32 a = 0, b = 0;
-            if (j < live_n) a = deemph_sample(xv[j], mem);
-            if (j + 1 < live_n) b = deemph_sample(xv[j + 1], mem);
-            pk[j >> 1] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+            for (int j = 0; j < DE_TW; j += 2) {
+                const s32 a = deemph_round(xv[j], mem), b = deemph_round(xv[j + 1], mem);
+                asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(pk[j >> 1]) : "r"(b), "r"(a));  // (sat16(b) << 16) | sat16(a)
+            }
+        } else if (live_n <= 0) {
+#pragma unroll
+            for (int j = 0; j < DE_TW / 2; j++) pk[j] = 0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < DE_TW; j += 2) {
+                s32 a = 0, b = 0;
+                if (j < live_n) a = deemph_sample(xv[j], mem);
+                if (j + 1 < live_n) b = deemph_sample(xv[j + 1], mem);
+                pk[j >> 1] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+            }
         }
         if (CC == 2) {
             // lanes 2k (left) and 2k+1 (right): the left lane keeps frames 0..15 of the tile, the right lane 16..31
@@ -677,7 +727,11 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
             }
         }
         j0 += DE_TW;
-        if (j0 >= N) { j0 = 0; f++; }
+        if (j0 >= N) {
+            j0 = 0; f++;
+            cur_n = nxt_n; cur_sk = nxt_sk; cur_st = nxt_st;
+            load_frame(f + 1, nxt_n, nxt_sk, nxt_st);
+        }
     }
     if (live) st[my_s].preemph_mem[my_c] = mem;
 }

@@ -17,7 +17,7 @@ using namespace opusb200;
 static_assert(sizeof(FrameDesc) == sizeof(dm_frame), "dm_frame layout");
 static_assert(sizeof(BandOp) == 16, "BandOp layout");
 
-enum { kStages = 8, kMaxChunks = 4, kRing = 4, kTraceCalls = 16 };
+enum { kStages = 8, kMaxChunks = 4, kRing = 4, kTraceCalls = 16, kMaxPieces = 8 };
 static const char* kStageNames[kStages + 1] = {"entropy", "sequence", "leaves", "bands", "imdct", "postfilter", "deemph", "silk", "pipeline"};
 
 // The per-frame intermediates that cross from the head of a call (parse, spectral stage) into its tail (post-filter,
@@ -66,6 +66,9 @@ struct dm_ctx {
     cudaStream_t streams[kMaxChunks];     // blocking decode_many: one per stream range; pipelined calls: [0] head, [1] read-back, [2] upload
     cudaStream_t tail;                    // pipelined calls: post-filter, de-emphasis, final SILK sum
     cudaStream_t side[kMaxChunks];        // per stream range: the SILK kernels of a call run beside its CELT kernels
+    cudaStream_t de_s[kMaxChunks];        // per stream range: the de-emphasis of one run of frames beside the post-filter of the next
+    cudaEvent_t pf_ev[kMaxChunks][kMaxPieces], de_ev[kMaxChunks];
+    int tail_pieces;                      // runs of frames the tail of a call is cut into (OPUSB_TAIL_PIECES; 1 = no overlap)
     cudaEvent_t fork_ev[kMaxChunks], join_ev[kMaxChunks];
     cudaEvent_t bytes_ready;
     // pipelined calls (dm_decode_device, dm_decode_device_async, decode_many_async), a ring over the call number
@@ -139,6 +142,8 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     c->leaf_slots = kLeafSlotsPerFrame;  // (the context was just zeroed)
     if (const char* e = getenv("OPUSB_LEAF_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= kLeafSlotsPerFrame) c->leaf_slots = v; }
     c->tail_mode = 0;
+    c->tail_pieces = 1;  // measured: 2 / 4 / 8 runs make the tail 0.1 - 0.7 ms slower (the two kernels slow each other down side by side)
+    if (const char* e = getenv("OPUSB_TAIL_PIECES")) { const int v = atoi(e); if (v >= 1 && v <= kMaxPieces) c->tail_pieces = v; }
     if (const char* e = getenv("OPUSB_TAIL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tail_mode = v; }
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // The entropy kernel keeps its per-thread allocation arrays and the explicit partition stack in local memory.  The
@@ -173,6 +178,9 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     CU_TRY(c, cudaStreamCreateWithPriority(&c->tail, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < kMaxChunks; i++) {
         CU_TRY(c, cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio_hi));
+        CU_TRY(c, cudaStreamCreateWithPriority(&c->de_s[i], cudaStreamNonBlocking, prio_hi));
+        CU_TRY(c, cudaEventCreateWithFlags(&c->de_ev[i], cudaEventDisableTiming));
+        for (int g = 0; g < kMaxPieces; g++) CU_TRY(c, cudaEventCreateWithFlags(&c->pf_ev[i][g], cudaEventDisableTiming));
         CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
         CU_TRY(c, cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
     }
@@ -229,6 +237,9 @@ void dm_destroy(dm_ctx* c) {
     if (c->tail) cudaStreamDestroy(c->tail);
     for (int i = 0; i < kMaxChunks; i++) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->de_s[i]) cudaStreamDestroy(c->de_s[i]);
+        if (c->de_ev[i]) cudaEventDestroy(c->de_ev[i]);
+        for (int g = 0; g < kMaxPieces; g++) if (c->pf_ev[i][g]) cudaEventDestroy(c->pf_ev[i][g]);
         if (c->fork_ev[i]) cudaEventDestroy(c->fork_ev[i]);
         if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
     }
@@ -426,13 +437,34 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
         cudaEventRecord(pl.head_ev, H);
         cudaStreamWaitEvent(T, pl.head_ev, 0);
     }
-    k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, Tp>>>(F.hdr, F.fe, F.raw, F.syn, c->d_state, P);
-    if (timed) mark(6, Tp);
-    if (T != H && Tp == H) {
-        cudaEventRecord(pl.head_ev, H);
-        cudaStreamWaitEvent(T, pl.head_ev, 0);
+    // The two serial kernels of the tail cost per frame in order, not per stream: the post-filter (16 warps per SM, bound by
+    // its shared-memory rings) and the de-emphasis (one warp per 32 chains: 256 warps on the whole GPU).  The frames of the
+    // call are cut into runs, and the de-emphasis of one run goes to a stream of its own beside the post-filter of the next.
+    {
+        int pieces = c->tail_pieces;
+        if (pieces > in->n_frames / 4) pieces = in->n_frames / 4;
+        if (pieces < 1) pieces = 1;
+        const int per = (in->n_frames + pieces - 1) / pieces;
+        const cudaStream_t D = pieces > 1 ? c->de_s[chunk] : T;
+        DevParams Q = P;
+        for (int g = 0; g < pieces; g++) {
+            Q.f0 = g * per;
+            Q.nf = in->n_frames - Q.f0 < per ? in->n_frames - Q.f0 : per;
+            if (Q.nf <= 0) break;
+            k_postfilter<<<(n_sel * P.CC + PF_WARPS - 1) / PF_WARPS, 32 * PF_WARPS, 0, Tp>>>(F.hdr, F.fe, F.raw, F.syn, c->d_state, Q);
+            if (D != Tp) {
+                cudaEventRecord(c->pf_ev[chunk][g], Tp);
+                cudaStreamWaitEvent(D, c->pf_ev[chunk][g], 0);
+            }
+            if (timed && Q.f0 + Q.nf >= in->n_frames) mark(6, Tp);
+            k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q);
+            c->launches += g ? 2 : 0;
+        }
+        if (D != T) {
+            cudaEventRecord(c->de_ev[chunk], D);
+            cudaStreamWaitEvent(T, c->de_ev[chunk], 0);
+        }
     }
-    k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, T>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, P);
     if (timed) mark(7, T);
     if (silk) {  // "silk" stage time: what is left of the SILK layer once the CELT kernels are done, plus the final sum
         cudaStreamWaitEvent(T, pl.x_ev, 0);
