@@ -399,30 +399,43 @@ k_imdct_long(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
     for (int i = threadIdx.x; i < 480; i += blockDim.x) { twr_s[i] = kFftTwRe[i]; twi_s[i] = kFftTwIm[i]; rev_s[i] = kBitrev480[i]; }
     __syncthreads();
     const int CC = P.CC, stride = gridDim.x * KI_WARPS, n_local = P.n_local();
-    auto fetch = [&](int local) {  // the X row of frame `local` -> Xs, 16 bytes per lane and copy
-        if (local < n_local) {
+    auto fetch = [&](int local, bool wanted) {  // the X row of frame `local` -> Xs, 16 bytes per lane and copy
+        if (wanted && local < n_local) {
             const int16_t* src = X + P.index_of(local) * (2 * kMaxFrame);
             for (int i = 8 * L.lane; i < 2 * kMaxFrame; i += 256) __pipeline_memcpy_async(Xs + i, src + i, 16);
         }
         __pipeline_commit();
     };
+    // what the warp needs to know about a frame (and lane b its band energies) is read one frame ahead, like the spectrum
+    struct Info { int skip, LM, flags, C, start, end; int16_t E0, E1; };
+    auto load_info = [&](int loc) {
+        Info v = {FS_NO_CELT, 0, 0, 1, 0, 0, 0, 0};
+        if (loc < n_local) {
+            const size_t tt = P.index_of(loc);
+            const CeltFrameHdr& h = hdr[tt];
+            const FrameEnergy& e = fe[tt];
+            v.skip = e.skip; v.LM = h.LM; v.flags = h.flags; v.C = h.C; v.start = h.start; v.end = h.end;
+            if (L.lane < kNbEBands) { v.E0 = e.E[0][L.lane]; v.E1 = e.E[1][L.lane]; }
+        }
+        return v;
+    };
+    auto is_mine = [](const Info& v) { return !(v.skip & FS_NO_CELT) && v.LM == 3 && !(v.flags & FF_TRANSIENT); };
     int local = blockIdx.x * KI_WARPS + warp;
-    fetch(local);
+    Info cur = load_info(local), nxt = load_info(local + stride);
+    fetch(local, is_mine(cur));
 #pragma unroll 1
-    for (; local < n_local; local += stride) {
+    for (; local < n_local; local += stride, cur = nxt, nxt = load_info(local + stride)) {
         const size_t t = P.index_of(local);
-        const CeltFrameHdr& h = hdr[t];
-        const FrameEnergy& e = fe[t];
-        const bool mine = !(e.skip & FS_NO_CELT) && imdct_is_long(h);
-        const int C = h.C, start = (h.flags & FF_SILENCE) ? 0 : h.start, end = (h.flags & FF_SILENCE) ? 0 : h.end;
-        if (mine && L.lane <= kNbEBands) {  // band gains (the lanes' loads of E run beside the wait for the spectrum)
-            gs0[L.lane] = band_gain_packed(L.lane, L.lane < kNbEBands ? e.E[0][L.lane] : (int16_t)0, start, end);
-            gs1[L.lane] = band_gain_packed(L.lane, L.lane < kNbEBands ? e.E[1][L.lane] : (int16_t)0, start, end);
+        const bool mine = is_mine(cur);
+        const int C = cur.C, start = (cur.flags & FF_SILENCE) ? 0 : cur.start, end = (cur.flags & FF_SILENCE) ? 0 : cur.end;
+        if (mine && L.lane <= kNbEBands) {  // band gains
+            gs0[L.lane] = band_gain_packed(L.lane, cur.E0, start, end);
+            gs1[L.lane] = band_gain_packed(L.lane, cur.E1, start, end);
         }
         __pipeline_wait_prior(0);
         L.sync();
         if (!mine) {
-            fetch(local + stride);
+            fetch(local + stride, is_mine(nxt));
             continue;
         }
         // spectra of the output channels (ref celt_synthesis :2085-2109)
@@ -432,7 +445,7 @@ k_imdct_long(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
         imdct480_prerotate(L.lane, Xs, gs0, gs1, trig_s, rev_s, T0, downmix);
         if (nch == 2) imdct480_prerotate(L.lane, Xs + kMaxFrame, gs1, gs1, trig_s, rev_s, T1, false);
         L.sync();
-        fetch(local + stride);  // Xs is free: the next frame's spectrum arrives while this one is transformed
+        fetch(local + stride, is_mine(nxt));  // Xs is free: the next frame's spectrum arrives while this one is transformed
         // pass A: lane = 15 * channel + block, each on its own row
         {
             const int ch = L.lane >= 15 ? 1 : 0, b = L.lane - 15 * ch;

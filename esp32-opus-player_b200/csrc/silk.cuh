@@ -20,8 +20,16 @@ namespace opusb200 {
 // ---- fixed-point helpers with the reference macro each one reproduces (src/silk.h:52-156, 446-486) ----
 OPUS_HD s32 smulbb(s32 a, s32 b) { return (s32)(s16)a * (s32)(s16)b; }                       // silk_SMULBB
 OPUS_HD s32 smlabb(s32 a, s32 b, s32 c) { return (s32)((u32)a + (u32)smulbb(b, c)); }          // silk_SMLABB (/_ovflw)
+// silk_SMULWB / silk_SMLAWB: floor(a * (int16)b / 2^16) is the high word of a * ((int16)b << 16), exactly, for every
+// int32 a -- one multiply-high on the device (and with a constant b the shift folds away) instead of a 64-bit product
+// and a funnel shift; the accumulate wraps like the reference's 32-bit add.
+#if defined(__CUDA_ARCH__)
+OPUS_HD s32 smulwb(s32 a, s32 b) { return __mulhi(a, (s32)((u32)(uint16_t)b << 16)); }
+OPUS_HD s32 smlawb(s32 a, s32 b, s32 c) { return (s32)((u32)a + (u32)__mulhi(b, (s32)((u32)(uint16_t)c << 16))); }
+#else
 OPUS_HD s32 smulwb(s32 a, s32 b) { return (s32)(((s64)a * (s64)(s16)b) >> 16); }              // silk_SMULWB
 OPUS_HD s32 smlawb(s32 a, s32 b, s32 c) { return (s32)((s64)a + (((s64)b * (s64)(s16)c) >> 16)); }  // silk_SMLAWB
+#endif
 OPUS_HD s32 smulww(s32 a, s32 b) { return (s32)(((s64)a * (s64)b) >> 16); }                   // silk_SMULWW
 OPUS_HD s32 smlaww(s32 a, s32 b, s32 c) { return (s32)((s64)a + (((s64)b * (s64)c) >> 16)); } // silk_SMLAWW
 OPUS_HD s32 smmul(s32 a, s32 b) { return (s32)(((s64)a * (s64)b) >> 32); }                    // silk_SMMUL
