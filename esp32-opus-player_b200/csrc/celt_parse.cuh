@@ -35,9 +35,7 @@ OPUS_HD T narrow(s32 v) {
 #define PARSE_FINE_T int8_t    // fine_quant 0 .. 8, fine_priority 0 / 1
 #endif
 #ifndef PARSE_BITS_T
-#define PARSE_BITS_T int32_t   // bits1, bits2 of the allocation search: 0 .. 34784.  Would fit uint16_t, and the host build is
-                               // bit-exact with it, but the sm_100a build (nvcc 12.9) then decodes wrongly -- with int16_t too, not
-                               // with uint32_t; cause not found (compute-sanitizer is closed on this pool), so they stay 32-bit
+#define PARSE_BITS_T uint16_t  // bits1, bits2 of the allocation search: 0 .. 34784
 #endif
 #ifndef PARSE_THR_T
 #define PARSE_THR_T int16_t    // thresh <= 264, trim_offset within +-7040
@@ -208,9 +206,13 @@ OPUS_HD u32 leaf_unquant(ParseCtx& p, int xoff, int N, int K, int B, s16 gain) {
 
 struct ThetaOut { int inv, imid, iside, delta, itheta, qalloc; };
 
+OPUS_LOCAL_TABLE s16 kExp2Table8[8] = {16384, 17866, 19483, 21247, 23170, 25267, 27554, 30048};               // ref :1216
+OPUS_LOCAL_TABLE uint8_t kBitInterleave[16] = {0, 1, 1, 1, 2, 3, 3, 3, 2, 3, 3, 3, 2, 3, 3, 3};              // ref :1560
+OPUS_LOCAL_TABLE uint8_t kBitDeinterleave[16] = {0x00, 0x03, 0x0C, 0x0F, 0x30, 0x33, 0x3C, 0x3F,            // ref :1606
+                                                 0xC0, 0xC3, 0xCC, 0xCF, 0xF0, 0xF3, 0xFC, 0xFF};
+
 // ref compute_qn (src/celt.cpp:1215)
 OPUS_HD int compute_qn(int N, int b, int offset, int pulse_cap, int stereo) {
-    const s16 exp2_table8[8] = {16384, 17866, 19483, 21247, 23170, 25267, 27554, 30048};
     int N2 = 2 * N - 1;
     if (stereo && N == 2) N2--;
     int qb = (b + N2 * offset) / N2;
@@ -219,7 +221,7 @@ OPUS_HD int compute_qn(int N, int b, int offset, int pulse_cap, int stereo) {
     int qn;
     if (qb < (1 << 3 >> 1)) qn = 1;
     else {
-        qn = exp2_table8[qb & 0x7] >> (14 - (qb >> 3));
+        qn = kExp2Table8[qb & 0x7] >> (14 - (qb >> 3));
         qn = (qn + 1) >> 1 << 1;
     }
     return qn;
@@ -439,8 +441,7 @@ OPUS_HD bool band_mono_pre(ParseCtx& p, MonoCtx& m, int xoff, int N, int B, int 
     if (scratch >= 0 && lowband >= 0 && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) lowband = scratch;
 #pragma unroll 1
     for (int k = 0; k < recombine; k++) {
-        const uint8_t bit_interleave[16] = {0, 1, 1, 1, 2, 3, 3, 3, 2, 3, 3, 3, 2, 3, 3, 3};
-        fill = bit_interleave[fill & 0xF] | bit_interleave[fill >> 4] << 2;
+        fill = kBitInterleave[fill & 0xF] | kBitInterleave[fill >> 4] << 2;
     }
     B >>= recombine;
     N_B <<= recombine;
@@ -472,9 +473,7 @@ OPUS_HD u32 band_mono_post(ParseCtx& p, const MonoCtx& m, u32 cm) {
     }
 #pragma unroll 1
     for (int k = 0; k < recombine; k++) {
-        const uint8_t bit_deinterleave[16] = {0x00, 0x03, 0x0C, 0x0F, 0x30, 0x33, 0x3C, 0x3F,
-                                              0xC0, 0xC3, 0xCC, 0xCF, 0xF0, 0xF3, 0xFC, 0xFF};
-        cm = bit_deinterleave[cm];
+        cm = kBitDeinterleave[cm];
         emit_op(p, OP_HAAR, 1 << k, xoff, 0, m.N0 >> k, 0, 0);
     }
     B <<= recombine;
@@ -834,6 +833,40 @@ OPUS_HD int compute_allocation(RangeDec& rd, int start, int end, const cap_t* of
                               intensity_rsv, dual_stereo, dual_stereo_rsv, pulses, ebits, fine_priority, C, LM);
 }
 
+// The first symbols of a CELT frame: silence flag, post-filter parameters, transient flag (ref src/celt.cpp:2239-2276).
+// Shared by the parser proper and by k_classify, which reads just these to sort the frames of a launch by kind.
+struct CeltHead { int silence, pf_gain, pf_pitch, pf_tapset, postfilter, transient, tell; };
+OPUS_HD CeltHead celt_parse_head(RangeDec& rd, int start, int LM) {
+    CeltHead h = {0, 0, 0, 0, 0, 0, 0};
+    const int total_bits = (int)rd.storage * 8;
+    int tell = rd_tell(rd);
+    if (tell >= total_bits) h.silence = 1;
+    else if (tell == 1) h.silence = rd_bit_logp(rd, 15);
+    if (h.silence) {
+        tell = (int)rd.storage * 8;
+        rd.nbits_total += tell - rd_tell(rd);
+    }
+    if (start == 0 && tell + 16 <= total_bits) {
+        if (rd_bit_logp(rd, 1)) {
+            int octave = (int)rd_uint(rd, 6);
+            h.pf_pitch = (16 << octave) + (int)rd_bits(rd, 4 + (u32)octave) - 1;
+            int qg = (int)rd_bits(rd, 3);
+            if (rd_tell(rd) + 2 <= total_bits) {
+                h.pf_tapset = rd_icdf(rd, kIcdf210, 2);
+            }
+            h.pf_gain = 3072 * (qg + 1);  // QCONST16(.09375, 15)
+            h.postfilter = 1;
+        }
+        tell = rd_tell(rd);
+    }
+    if (LM > 0 && tell + 3 <= total_bits) {
+        h.transient = rd_bit_logp(rd, 3);
+        tell = rd_tell(rd);
+    }
+    h.tell = tell;
+    return h;
+}
+
 // One CELT frame: every symbol of celt_decode_with_ec (ref src/celt.cpp:2239-2367) in bitstream order.
 // `p.rd` must already be initialised on the frame (and, for hybrid, advanced past the SILK layer).
 // frame_size = 120 << LM.  Returns the status also stored in hdr.
@@ -852,35 +885,11 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
     const int start0 = warp_min(p.wmask, start);  // common first band of the lanes that parse together
 
     int total_bits = (int)rd.storage * 8;
-    int tell = rd_tell(rd);
-    int silence;
-    if (tell >= total_bits) silence = 1;
-    else if (tell == 1) silence = rd_bit_logp(rd, 15);
-    else silence = 0;
-    if (silence) {
-        tell = (int)rd.storage * 8;
-        rd.nbits_total += tell - rd_tell(rd);
-    }
-    int pf_gain = 0, pf_pitch = 0, pf_tapset = 0, flags = 0;
-    if (start == 0 && tell + 16 <= total_bits) {
-        if (rd_bit_logp(rd, 1)) {
-            int octave = (int)rd_uint(rd, 6);
-            pf_pitch = (16 << octave) + (int)rd_bits(rd, 4 + (u32)octave) - 1;
-            int qg = (int)rd_bits(rd, 3);
-            if (rd_tell(rd) + 2 <= total_bits) {
-                const uint8_t tapset_icdf[3] = {2, 1, 0};
-                pf_tapset = rd_icdf(rd, tapset_icdf, 2);
-            }
-            pf_gain = 3072 * (qg + 1);  // QCONST16(.09375, 15)
-            flags |= FF_POSTFILTER;
-        }
-        tell = rd_tell(rd);
-    }
-    int isTransient = 0;
-    if (LM > 0 && tell + 3 <= total_bits) {
-        isTransient = rd_bit_logp(rd, 3);
-        tell = rd_tell(rd);
-    }
+    const CeltHead head = celt_parse_head(rd, start, LM);
+    const int silence = head.silence, pf_gain = head.pf_gain, pf_pitch = head.pf_pitch, pf_tapset = head.pf_tapset;
+    const int isTransient = head.transient;
+    int tell = head.tell;
+    int flags = head.postfilter ? FF_POSTFILTER : 0;
     const int shortBlocks = isTransient ? M : 0;
     const int intra = tell + 3 <= total_bits ? rd_bit_logp(rd, 3) : 0;
 
@@ -903,8 +912,7 @@ OPUS_HD int celt_parse_frame(ParseCtx& p, CeltFrameHdr& hdr) {
                     int pi = 2 * imin(i, 20);
                     qi = rd_laplace(rd, (u32)prob[pi] << 7, (int)prob[pi + 1] << 6);
                 } else if (budget - t >= 2) {
-                    const uint8_t small_icdf[3] = {2, 1, 0};
-                    qi = rd_icdf(rd, small_icdf, 2);
+                    qi = rd_icdf(rd, kIcdf210, 2);
                     qi = (qi >> 1) ^ -(qi & 1);
                 } else if (budget - t >= 1) {
                     qi = -rd_bit_logp(rd, 1);

@@ -330,20 +330,21 @@ OPUS_HD void tdac_frame(const Lanes& L, const int32_t* raw, int32_t* tail, View 
     L.sync();
 }
 
-// ---- comb post-filter (ref comb_filter :848, comb_filter_const_c :830), in place on a history ring ----
+OPUS_LOCAL_TABLE s16 kCombGains[3][3] = {{10048, 7112, 4248}, {15200, 8784, 0}, {26208, 3280, 0}};  // ref gains[3][3], :854-857
+
+// ---- comb post-filter (ref comb_filter :848, comb_filter_const_c :830), in place on a history buffer ----
 // x points at the first sample to filter inside a buffer that holds >= T+2 valid earlier samples.
 // In-place IIR: y[i] depends on y[i-T+2 .. i-T-2], T >= 15, so `chunk` = min(T0,T1)-2 >= 13 samples
 // are independent and are computed by the lanes in parallel.
 template <class View>
 OPUS_HD void comb_filter_inplace(const Lanes& L, View x, int T0, int T1, int N, s16 g0, s16 g1, int tapset0, int tapset1) {
     if (g0 == 0 && g1 == 0) return;
-    const s16 gains[3][3] = {{10048, 7112, 4248}, {15200, 8784, 0}, {26208, 3280, 0}};
     T0 = imax(T0, 15);
     T1 = imax(T1, 15);
-    const s16 g00 = (s16)mul16_p15(g0, gains[tapset0][0]), g01 = (s16)mul16_p15(g0, gains[tapset0][1]),
-              g02 = (s16)mul16_p15(g0, gains[tapset0][2]);
-    const s16 g10 = (s16)mul16_p15(g1, gains[tapset1][0]), g11 = (s16)mul16_p15(g1, gains[tapset1][1]),
-              g12 = (s16)mul16_p15(g1, gains[tapset1][2]);
+    const s16 g00 = (s16)mul16_p15(g0, kCombGains[tapset0][0]), g01 = (s16)mul16_p15(g0, kCombGains[tapset0][1]),
+              g02 = (s16)mul16_p15(g0, kCombGains[tapset0][2]);
+    const s16 g10 = (s16)mul16_p15(g1, kCombGains[tapset1][0]), g11 = (s16)mul16_p15(g1, kCombGains[tapset1][1]),
+              g12 = (s16)mul16_p15(g1, kCombGains[tapset1][2]);
     int overlap = kOverlap;
     if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
     if (overlap > N) overlap = N;

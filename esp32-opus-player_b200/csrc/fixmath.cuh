@@ -15,6 +15,16 @@
 #define OPUS_HD inline
 #endif
 
+// Small constant tables live at namespace scope, never as function-local arrays: a local `const T x[] = {...}` that is
+// indexed at run time is rebuilt on the thread's stack at every call, and nvcc 12.9 for sm_100a was caught sharing that
+// stack slot with a LIVE array of the caller (the parser's collapse masks came back holding the eight words of the
+// ec_tell_frac correction table; found with dm_debug_frame_script + tools/debug_script.py).
+#if defined(__CUDACC__)
+#define OPUS_LOCAL_TABLE static __device__ const
+#else
+#define OPUS_LOCAL_TABLE static const
+#endif
+
 #if !defined(__CUDACC__)
 #include <stdio.h>
 #include <stdlib.h>

@@ -80,6 +80,42 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Frames of one kind side by side.  In a thread-per-frame parser the lanes of a warp only work together while their frames
+// go the same way, and the one decision that changes the way most is the transient flag: short blocks (B = 8) mean other
+// transforms per band and a collapse-mask walk for every coded leaf, which 7 lanes in 8 then sit out.  k_classify reads
+// just the first symbols of every CELT frame (celt_parse_head) and writes the work order of the parser kernel: the
+// transient frames of the launch first (the longest first), then the others.  Two counters, one atomic per warp and class;
+// which slot a frame gets inside its class is left to chance -- frames are independent, the results do not depend on it.
+__global__ void __launch_bounds__(256)
+k_classify(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, uint32_t* __restrict__ order, int* __restrict__ counters) {
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = P.n_local();
+    const bool in_range = local < n;
+    bool transient = false;
+    if (in_range) {
+        const FrameDesc d = fr[P.index_of(local)];
+        const bool celt_kind = P.mode != 0 || (!(d.flags & FD_NULL) && (d.toc & 0x80));
+        if (celt_kind && !(P.mode == 0 && (d.flags & FD_NULL)) && d.len > 1 && d.len <= kMaxPacket) {
+            RangeDec rd;
+            rd_init(rd, bytes + d.offset, d.len);
+            const int LM = P.mode == 0 ? 3 : (P.frame_size == 120 ? 0 : P.frame_size == 240 ? 1 : P.frame_size == 480 ? 2 : 3);
+            transient = celt_parse_head(rd, P.mode == 0 ? 0 : P.start_band, LM).transient != 0;
+        }
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, in_range);
+    const unsigned tr = __ballot_sync(0xffffffffu, in_range && transient);
+    if (!in_range) return;
+    const unsigned lane = threadIdx.x & 31, below = (1u << lane) - 1u;
+    const unsigned mine = transient ? tr : (active & ~tr);
+    const int leader = __ffs(mine) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&counters[transient ? 1 : 0], __popc(mine));
+    base = __shfl_sync(mine, base, leader);
+    const int rank = base + __popc(mine & below);
+    // transient frames fill the order from the front, the others from the back
+    order[transient ? rank : n - 1 - rank] = (uint32_t)local;
+}
+
 // Two instantiations share the frames of a call between them by TOC: kSilk = false takes the frames without a SILK layer
 // (CELT-only TOCs, raw CELT frames, fillers), kSilk = true the SILK-only and hybrid frames.  The CELT-only kernel -- the
 // whole of the headline workload -- then carries neither the SILK parser's code nor its registers; a warp of the other
@@ -87,9 +123,11 @@ __device__ __forceinline__ bool frame_skipped(int status) {
 template <bool kSilk>
 __global__ void __launch_bounds__(K1_THREADS, K1_BLOCKS)  // 80 registers: 24 warps per SM measured faster than 16 (128 regs) or 32 (64 regs, spills)
 k_entropy(const uint8_t* __restrict__ bytes, const FrameDesc* __restrict__ fr, DevParams P, CeltFrameHdr* __restrict__ hdr,
-          BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk) {
-    const int local = blockIdx.x * K1_THREADS + threadIdx.x;
-    bool in_range = local < P.n_local();
+          BandOp* __restrict__ ops, SilkFrame* __restrict__ silk, const CeltStreamState* __restrict__ st, int* __restrict__ any_silk,
+          const uint32_t* __restrict__ order) {
+    const int slot = blockIdx.x * K1_THREADS + threadIdx.x;
+    bool in_range = slot < P.n_local();
+    const int local = (order && in_range) ? (int)order[slot] : slot;  // the work order of k_classify, or frame order
     const size_t t = P.index_of(in_range ? local : 0);
     const FrameDesc d = fr[t];
     // which of the two kernels owns the frame

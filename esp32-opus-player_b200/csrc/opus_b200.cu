@@ -53,6 +53,9 @@ struct dm_ctx {
     // per-frame intermediates of the head alone ...
     BandOp* d_ops;
     int16_t* d_X;
+    uint32_t* d_parse_order; // work order of the CELT-only parser kernel (k_classify), one entry per frame of the context
+    int* d_parse_count;      // [kMaxChunks][2]: frames per class of a launch
+    int sort_frames;         // 1: the parser takes its frames sorted by kind (OPUSB_SORT_FRAMES=1; off by default)
     LeafSort* d_leafsort;    // [kMaxChunks]: counting sort of the coded leaves of a launch by cost class
     uint32_t* d_leaf_order;  // the sorted leaf list, kLeafSlotsPerFrame entries per frame of the context
     // staging for the host-buffer path: double buffered so that call n+1 can upload while call n still parses
@@ -167,6 +170,10 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_leafsort, (size_t)kMaxChunks))) return r;
+    if ((r = dev_alloc(c, &c->d_parse_order, nfr))) return r;
+    if ((r = dev_alloc(c, &c->d_parse_count, (size_t)kMaxChunks * 2))) return r;
+    c->sort_frames = 0;  // measured: 3.85 ms without, 3.91 ms with (the classification pass costs what the fuller warps win)
+    if (const char* e = getenv("OPUSB_SORT_FRAMES")) c->sort_frames = atoi(e) != 0;
     if ((r = dev_alloc(c, &c->d_leaf_order, nfr * kLeafSlotsPerFrame))) return r;
     if ((r = dev_alloc(c, &c->d_frames[0], nfr))) return r;
     if ((r = dev_alloc(c, &c->d_pcm, nfr * channels * kMaxFrame))) return r;
@@ -230,7 +237,7 @@ void dm_destroy(dm_ctx* c) {
     cudaDeviceSynchronize();
     cudaFree(c->d_state); cudaFree(c->d_sstate);
     free_set(c->set[0]); free_set(c->set[1]);
-    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order);
+    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_parse_order); cudaFree(c->d_parse_count);
     cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames[0]); cudaFree(c->d_frames[1]);
     cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status); cudaFree(c->d_status2);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -380,9 +387,17 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     if (timed) mark(0, H);
     int* any_silk = F.any_silk + chunk;  // per stream range: ranges of one call run concurrently on their own streams
     cudaMemsetAsync(any_silk, 0, sizeof(int), H);
-    k_entropy<false><<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk);
+    const uint32_t* order = nullptr;
+    if (c->sort_frames && nfr >= 4096) {  // (a small launch has too few transient frames to fill warps with)
+        uint32_t* ord = c->d_parse_order + (size_t)first * in->n_frames;
+        cudaMemsetAsync(c->d_parse_count + 2 * chunk, 0, 2 * sizeof(int), H);
+        k_classify<<<(nfr + 255) / 256, 256, 0, H>>>(d_bytes, d_frames, P, ord, c->d_parse_count + 2 * chunk);
+        c->launches++;
+        order = ord;
+    }
+    k_entropy<false><<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk, order);
     if (in->mode == DM_MODE_OPUS) {  // the frames with a SILK layer
-        k_entropy<true><<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk);
+        k_entropy<true><<<(nfr + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, H>>>(d_bytes, d_frames, P, F.hdr, c->d_ops, F.silk, c->d_state, any_silk, nullptr);
         c->launches++;
     }
     if (timed) mark(1, H);
@@ -417,11 +432,11 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
     }
     // coded leaves: sort by cost class, expand one per thread
     LeafSort* ls = c->d_leafsort + chunk;
-    uint32_t* order = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
+    uint32_t* lorder = c->d_leaf_order + (size_t)first * in->n_frames * kLeafSlotsPerFrame;
     cudaMemsetAsync(ls, 0, sizeof(LeafSort), H);
     k_leaf_count<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, P);
-    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, order, nfr * c->leaf_slots, P);
-    k_leaf_expand<<<c->n_sm * KL_GRID, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, order, c->d_X, P);
+    k_leaf_place<<<(nfr + KL_THREADS - 1) / KL_THREADS, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, lorder, nfr * c->leaf_slots, P);
+    k_leaf_expand<<<c->n_sm * KL_GRID, KL_THREADS, 0, H>>>(F.hdr, c->d_ops, ls, lorder, c->d_X, P);
     if (timed) mark(3, H);
     k_bands<<<(nfr + KB_WARPS - 1) / KB_WARPS, 32 * KB_WARPS, 0, H>>>(F.hdr, c->d_ops, F.fe, c->d_X, ls, P);
     if (timed) mark(4, H);
@@ -674,6 +689,16 @@ int dm_debug_trace(dm_ctx* c, int n, float* out) {
         for (int i = 0; i <= kStages; i++)
             if (cudaEventElapsedTime(&out[k * (kStages + 1) + i], base, c->trace[(size_t)((q0 + k) % kTraceCalls) * (kStages + 1) + i]) != cudaSuccess)
                 out[k * (kStages + 1) + i] = -1.f;
+    return 0;
+}
+
+// Debug access: the script of frame t of the most recent call (header and op buffer) as the parser left it.
+int dm_debug_frame_script(dm_ctx* c, long long t, void* hdr_out, size_t hdr_cap, void* ops_out, size_t ops_cap) {
+    if (!c || t < 0 || t >= (long long)c->n_streams * c->max_frames) return OPUSB_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    if (hdr_out && hdr_cap >= sizeof(CeltFrameHdr)) CU_TRY(c, cudaMemcpy(hdr_out, c->set[0].hdr + t, sizeof(CeltFrameHdr), cudaMemcpyDeviceToHost));
+    if (ops_out && ops_cap >= sizeof(BandOp) * kMaxOps) CU_TRY(c, cudaMemcpy(ops_out, c->d_ops + t * kMaxOps, sizeof(BandOp) * kMaxOps, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -71,15 +71,17 @@ OPUS_HD void rd_init(RangeDec& d, const uint8_t* buf, u32 len, u32 sbase = 0, u3
     rd_normalize(d);
 }
 
+OPUS_LOCAL_TABLE u32 kTellFracCorr[8] = {35733, 38967, 42495, 46340, 50535, 55109, 60097, 65535};  // ref correction[8], :2628
+OPUS_LOCAL_TABLE uint8_t kIcdf210[3] = {2, 1, 0};                                                   // tapset_icdf :587, small_energy_icdf :579
+
 // ref ec_tell (src/celt.h:420), ec_tell_frac (src/celt.cpp:2627)
 OPUS_HD int rd_tell(const RangeDec& d) { return d.nbits_total - ilog32(d.rng); }
 OPUS_HD u32 rd_tell_frac(const RangeDec& d) {
-    const u32 corr[8] = {35733, 38967, 42495, 46340, 50535, 55109, 60097, 65535};
     u32 nbits = (u32)d.nbits_total << 3;
     int l = ilog32(d.rng);
     u32 r = d.rng >> (l - 16);
     u32 b = (r >> 12) - 8;
-    b += r > corr[b];
+    b += r > kTellFracCorr[b];
     return nbits - (u32)((l << 3) + (int)b);
 }
 

@@ -158,25 +158,33 @@ OPUS_HD void nlsf_unpack(int16_t* ec_ix, uint8_t* pred_Q8, const SilkCb& cb, int
 // lanes drift apart for good, as they did in the CELT parser.
 enum { kSilkMaxBlocks = kSilkMaxFrame / 16 };
 
+// uniform and small iCDF tables of the side information (ref src/silk.cpp:37-142); at namespace scope, see rangedec.cuh
+OPUS_LOCAL_TABLE uint8_t kUni3[3] = {171, 85, 0}, kUni4[4] = {192, 128, 64, 0}, kUni5[5] = {205, 154, 102, 51, 0},
+                         kUni6[6] = {213, 171, 128, 85, 43, 0}, kUni8[8] = {224, 192, 160, 128, 96, 64, 32, 0};
+OPUS_LOCAL_TABLE uint8_t kNlsfExtIcdf[7] = {100, 40, 16, 7, 3, 1, 0};
+OPUS_LOCAL_TABLE uint8_t kTypeVadIcdf[4] = {232, 158, 10, 0};
+OPUS_LOCAL_TABLE uint8_t kNlsfInterpIcdf[5] = {243, 221, 192, 181, 0};
+OPUS_LOCAL_TABLE uint8_t kLtpPerIcdf[3] = {179, 99, 0};
+OPUS_LOCAL_TABLE uint8_t kLtpScaleIcdf[3] = {128, 64, 0};
+OPUS_LOCAL_TABLE uint8_t kNlsf2aOrder16[16] = {0, 15, 8, 7, 4, 11, 12, 3, 2, 13, 10, 5, 6, 9, 14, 1};
+OPUS_LOCAL_TABLE uint8_t kNlsf2aOrder10[10] = {0, 9, 6, 3, 4, 5, 8, 1, 2, 7};
+
 // ref silk_decode_indices (src/silk.cpp:708) with condCoding == CODE_INDEPENDENTLY
 OPUS_HD void silk_parse_indices(RangeDec& rd, SilkIdx& ix, int fs_kHz, int vad_or_lbrr, bool on, unsigned m) {
-    const uint8_t uni4[4] = {192, 128, 64, 0}, uni6[6] = {213, 171, 128, 85, 43, 0}, uni8[8] = {224, 192, 160, 128, 96, 64, 32, 0};
-    const uint8_t ext[7] = {100, 40, 16, 7, 3, 1, 0};
     const SilkCb cb = silk_cb(fs_kHz);
     int16_t ec_ix[kSilkMaxOrder];
     uint8_t pred_Q8[kSilkMaxOrder];
     int Ix;
     if (on) {
         if (vad_or_lbrr) {
-            const uint8_t t[4] = {232, 158, 10, 0};
-            Ix = rd_icdf(rd, t, 8) + 2;
+            Ix = rd_icdf(rd, kTypeVadIcdf, 8) + 2;
         } else {
             Ix = rd_icdf2(rd, 230, 8);
         }
         ix.signalType = (int8_t)(Ix >> 1);
         ix.quantOffsetType = (int8_t)(Ix & 1);
         ix.gains[0] = (int8_t)(rd_icdf_tab(rd, kGainIcdf + ix.signalType * 8, 8) << 3);
-        ix.gains[0] += (int8_t)rd_icdf(rd, uni8, 8);
+        ix.gains[0] += (int8_t)rd_icdf(rd, kUni8, 8);
         for (int i = 1; i < 4; i++) ix.gains[i] = (int8_t)rd_icdf_tab(rd, kDeltaGainIcdf, 8);
         ix.nlsf[0] = (int8_t)rd_icdf_tab(rd, cb.cb1_icdf + (ix.signalType >> 1) * 32, 8);
         nlsf_unpack(ec_ix, pred_Q8, cb, ix.nlsf[0]);
@@ -186,29 +194,26 @@ OPUS_HD void silk_parse_indices(RangeDec& rd, SilkIdx& ix, int fs_kHz, int vad_o
         warp_converge(m);
         if (on && i < cb.order) {
             Ix = rd_icdf_tab(rd, cb.ec_icdf + ec_ix[i], 8);
-            if (Ix == 0) Ix -= rd_icdf(rd, ext, 8);
-            else if (Ix == 8) Ix += rd_icdf(rd, ext, 8);
+            if (Ix == 0) Ix -= rd_icdf(rd, kNlsfExtIcdf, 8);
+            else if (Ix == 8) Ix += rd_icdf(rd, kNlsfExtIcdf, 8);
             ix.nlsf[i + 1] = (int8_t)(Ix - 4);
         }
     }
     warp_converge(m);
     if (on) {
-        const uint8_t t[5] = {243, 221, 192, 181, 0};
-        ix.interpQ2 = (int8_t)rd_icdf(rd, t, 8);
+        ix.interpQ2 = (int8_t)rd_icdf(rd, kNlsfInterpIcdf, 8);
         ix.lagIndex = 0; ix.contour = 0; ix.perIndex = 0; ix.ltpScaleIndex = 0;
         for (int k = 0; k < 4; k++) ix.ltp[k] = 0;
         if (ix.signalType == 2) {
             ix.lagIndex = (int16_t)((int16_t)rd_icdf_tab(rd, kPitchLagIcdf, 8) * (fs_kHz >> 1));
-            ix.lagIndex += (int16_t)rd_icdf(rd, fs_kHz == 16 ? uni8 : fs_kHz == 12 ? uni6 : uni4, 8);
+            ix.lagIndex += (int16_t)rd_icdf(rd, fs_kHz == 16 ? kUni8 : fs_kHz == 12 ? kUni6 : kUni4, 8);
             ix.contour = (int8_t)rd_icdf_tab(rd, fs_kHz == 8 ? kPitchContourNbIcdf : kPitchContourIcdf, 8);
-            const uint8_t per[3] = {179, 99, 0};
-            ix.perIndex = (int8_t)rd_icdf(rd, per, 8);
+            ix.perIndex = (int8_t)rd_icdf(rd, kLtpPerIcdf, 8);
             const uint8_t* g = ix.perIndex == 0 ? kLtpGainIcdf0 : ix.perIndex == 1 ? kLtpGainIcdf1 : kLtpGainIcdf2;
             for (int k = 0; k < 4; k++) ix.ltp[k] = (int8_t)rd_icdf_tab(rd, g, 8);
-            const uint8_t sc[3] = {128, 64, 0};
-            ix.ltpScaleIndex = (int8_t)rd_icdf(rd, sc, 8);
+            ix.ltpScaleIndex = (int8_t)rd_icdf(rd, kLtpScaleIcdf, 8);
         }
-        ix.seed = (int8_t)rd_icdf(rd, uni4, 8);
+        ix.seed = (int8_t)rd_icdf(rd, kUni4, 8);
     }
 }
 
@@ -309,14 +314,13 @@ OPUS_HD void silk_parse_pulses(RangeDec& rd, int16_t* pulses, int signalType, in
 
 // ref silk_stereo_decode_pred (src/silk.cpp:592)
 OPUS_HD void silk_parse_stereo_pred(RangeDec& rd, int32_t* pred_Q13) {
-    const uint8_t uni3[3] = {171, 85, 0}, uni5[5] = {205, 154, 102, 51, 0};
     int ix[2][3];
     int n = rd_icdf_tab(rd, kStereoJointIcdf, 8);
     ix[0][2] = n / 5;
     ix[1][2] = n - 5 * ix[0][2];
     for (n = 0; n < 2; n++) {
-        ix[n][0] = rd_icdf(rd, uni3, 8);
-        ix[n][1] = rd_icdf(rd, uni5, 8);
+        ix[n][0] = rd_icdf(rd, kUni3, 8);
+        ix[n][1] = rd_icdf(rd, kUni5, 8);
     }
     for (n = 0; n < 2; n++) {
         ix[n][0] += 3 * ix[n][2];
@@ -577,9 +581,7 @@ OPUS_HD void silk_nlsf2a_find_poly(s32* out, const s32* cLSF, int dd) {
 // while the rest of their warp waits, so the params kernel queues them and a second kernel runs the loop one failed
 // filter per thread (k_silk_fix).  Returns whether the filter is stable as it is.
 OPUS_HD bool silk_nlsf2a_first(int16_t* a_Q12, s32* a32_QA1, const int16_t* NLSF, int d) {
-    const uint8_t ordering16[16] = {0, 15, 8, 7, 4, 11, 12, 3, 2, 13, 10, 5, 6, 9, 14, 1};
-    const uint8_t ordering10[10] = {0, 9, 6, 3, 4, 5, 8, 1, 2, 7};
-    const uint8_t* ordering = d == 16 ? ordering16 : ordering10;
+    const uint8_t* ordering = d == 16 ? kNlsf2aOrder16 : kNlsf2aOrder10;
     s32 cos_LSF_QA[kSilkMaxOrder], P[kSilkMaxOrder / 2 + 1], Q[kSilkMaxOrder / 2 + 1];
     for (int k = 0; k < d; k++) {
         s32 f_int = NLSF[k] >> 8;

@@ -208,13 +208,13 @@ struct SerialCoop {
 // code is written for the latency of one instruction stream: the 16-tap sums are split over four accumulators (the
 // reference's 32-bit wrapping adds are associative), the next block's pulses are loaded before the current block is
 // computed, ring addresses are formed once per block of four samples.
+OPUS_LOCAL_TABLE s32 kQuantOffsets[2][2] = {{100, 240}, {32, 100}};  // ref silk_Quantization_Offsets_Q10, src/silk.cpp
 template <class LtpRing, class Coop>
 OPUS_HD void silk_core_frame(SilkChainRegs& R, ChainHistory hist, LtpRing ltp, const int16_t* pulses, const SilkCtl* ctl, const s32* Gains_Q16,
                              int signalType, int quantOffsetType, int seed, int fs_kHz, int16_t* xq, bool active, const Coop& coop) {
     const int order = fs_kHz == 16 ? 16 : 10;
     const int subfr = 5 * fs_kHz;
-    const s32 offs[2][2] = {{100, 240}, {32, 100}};
-    const s32 offset_Q14 = active ? offs[signalType >> 1][quantOffsetType] << 4 : 0;
+    const s32 offset_Q14 = active ? kQuantOffsets[signalType >> 1][quantOffsetType] << 4 : 0;
     u32 rand_seed = (u32)(s32)seed;
     int lag = 0;
     const uint2* p4 = reinterpret_cast<const uint2*>(pulses);  // four pulses per load (rows are 16-byte aligned)

@@ -137,6 +137,9 @@ int dm_debug_leaf_overflow(dm_ctx* ctx);
  * calls in ms since the oldest one's start, out[n][9]: head start, end of entropy, sequence, leaves, bands, imdct, then
  * on the tail stream end of postfilter, deemph, final SILK sum.  Shows which calls overlapped.  Synchronises the device. */
 int dm_debug_trace(dm_ctx* ctx, int n, float* out);
+/* Debug access: header (CeltFrameHdr, 364 bytes) and op buffer (1360 x 16 bytes) of frame t = stream * n_frames + frame
+ * of the most recent call, as the parser kernel left them.  Synchronises the device. */
+int dm_debug_frame_script(dm_ctx* ctx, long long t, void* hdr_out, size_t hdr_cap, void* ops_out, size_t ops_cap);
 /* Debug/test access: copies one stream's CELT state blob to host (checkpoint). */
 int dm_get_stream_state(dm_ctx* ctx, int stream, void* dst, size_t cap);
 size_t dm_stream_state_size(void);
