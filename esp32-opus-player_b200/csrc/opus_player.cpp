@@ -352,8 +352,14 @@ private:
                 if (pend_.empty()) continue;  // end trimming removed every packet of the first page
                 return make_decode_ready();
             }
+            // kStreamSet is only left over when a LATER link's headers parsed but its first audio page was refused
+            // (find_initial_pcm_offset < 0 above): the reference then makes the decoder ready for that link's head on
+            // the next page it sees and carries on (src/opusfile.cpp:949-952) -- found by tools/fuzz_demux.py
+            if (ready_ == kStreamSet) {
+                const int ret = make_decode_ready();
+                if (ret < 0) return ret;
+            }
             pk_.page_in(og);
-            if (ready_ < kInitSet) continue;
             bool hole = false;
             int32_t total = collect();
             if (total < 0) {

@@ -257,3 +257,55 @@ def test_synthetic_ogg_writer_is_read_like_by_the_reference(pkg, ref):
     assert predicted_returns(ev) == want
     _, direct, err = ref.decode_synth_stream(0xFC, 160, 2, 37)
     assert err == 0 and np.array_equal(pcm.reshape(-1, 2), direct)
+
+
+def test_error_in_a_later_link_then_foreign_bos(pkg, ref):
+    """A chain whose second link is refused (its only page claims fewer samples than its pre-skip: OP_EBADTIMESTAMP) is left in
+    the reference's OP_STREAMSET state: on the next page it makes the decoder ready for that link's head and carries on, so the
+    BOS page of a multiplexed foreign stream then costs one OP_ENOTFORMAT per remaining page (src/opusfile.cpp:862-870,
+    949-952).  Found by tools/fuzz_demux.py (seed 33555108)."""
+    rng = np.random.default_rng(21)
+    a = og.simple_file(og.rand_packets(rng, 0xFC, 5), per_page=2, serial=0x1000)
+    w = og.OggWriter(0x1001)
+    w.headers(2, 900)
+    w.write_page(og.rand_packets(rng, 0xFC, 3), 500, eos=True)  # granule position below the pre-skip
+    b = w.blob()
+    w = og.OggWriter(0x1002)
+    w.write_page([og.opus_head(2, 0)], 0, bos=True)
+    other = og.OggWriter(0x99)
+    other.write_page([b"\x80theora-ish" + bytes(20)], 0, bos=True)
+    w.out += other.out
+    w.write_page([og.opus_tags()], 0)
+    pk = og.rand_packets(rng, 0xFC, 6)
+    w.write_page(pk[:3], 3 * 960)
+    w.write_page(pk[3:], 6 * 960, eos=True)
+    blob = a + b + w.blob()
+    want, _ = ref_returns(ref, blob)
+    res, ev = pkg.demux_events(blob)
+    assert res == 0
+    assert -139 in want and want.count(-132) == 3
+    assert predicted_returns(ev) == want
+
+
+def test_demux_fuzz_smoke(pkg, ref):
+    """A short run of the differential demux fuzzer (tools/fuzz_demux.py): random layouts against the reference player."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--wild"]):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_demux.py"), "--cases", "120", "--seed", "77"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_hostsim_fuzz_smoke(hostsim, ref):
+    """A short run of the differential decoder fuzzer (tools/fuzz_hostsim.py): random mode walks with biased payloads, the
+    kernels' stage bodies compiled for the host against the reference."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_hostsim.py"), "--seconds", "8", "--jobs", "2", "--seed", "9"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
