@@ -108,6 +108,22 @@ def ncu_constants(workload):
     return d.get("workloads", {}).get(workload)
 
 
+def ncu_provenance(nc):
+    """Which capture the instruction / DRAM-byte counts come from, and whether it is of the running kernels: either the
+    kernel sources hash to the capture's, or tools/sass_equiv.py recorded that every kernel's SASS is the capture's
+    instruction for instruction (a change that moved data or touched host code only)."""
+    if not nc:
+        return None
+    cur = source_hash()
+    out = {"file": os.path.relpath(NCU_CONSTANTS, ROOT), "git": nc.get("git"), "source_hash": nc.get("source_hash"),
+           "matches_this_source": nc.get("source_hash") == cur}
+    if not out["matches_this_source"]:
+        for e in nc.get("sass_equivalent", []):
+            if e.get("source_hash") == cur:
+                out.update(matches_this_source=True, matched_by="sass_equivalent: " + e.get("why", ""), evidence=e.get("evidence"))
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi takes up to a
     second to produce its first line, so the sampler is started early (start) and only the lines read between begin() and
@@ -579,8 +595,7 @@ def main():
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_step,
                         "step_traffic_gbs": (dram_step / step_s / 1e9) if dram_step else None,
                         "step_traffic_frac_of_peak": (dram_step / step_s / 1e9 / hbm_peak) if dram_step else None},
-                "ncu_constants": ({"file": os.path.relpath(NCU_CONSTANTS, ROOT), "git": nc.get("git"), "source_hash": nc.get("source_hash"),
-                                   "matches_this_source": nc.get("source_hash") == source_hash()} if nc else None)}
+                "ncu_constants": ncu_provenance(nc)}
         cfg = make_config(args, wl_desc, S)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int16/int32 fixed-point", "data": "synthetic",

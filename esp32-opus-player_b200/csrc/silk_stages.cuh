@@ -295,7 +295,7 @@ OPUS_HD void silk_core_frame(SilkChainRegs& R, ChainHistory hist, LtpRing ltp, c
                     const s32 v = (u - 1 - j >= 0) ? nw[(u - 1 - j) & 3] : R.h[(j - u) & (kSilkMaxOrder - 1)];
                     acc[j & 3] = smlawt(acc[j & 3], v, A[j]);
                 }
-                const s32 pred = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                const s32 pred = add_w(add_w(acc[0], acc[1]), add_w(acc[2], acc[3]));  // wraps like the reference's running sum (:1925-1960)
                 const s32 s = add_sat32(res, lshift_sat32(pred, 4));
                 nw[u] = s;
                 yq[u] = sat16(rshift_round(smulww(s, Gain_Q10), 8));

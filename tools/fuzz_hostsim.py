@@ -23,7 +23,9 @@ sys.path.insert(0, ROOT)
 
 
 def load_hostsim():
-    so = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
+    # HOSTSIM_SO: another build of tests/hostsim/hostsim.cpp, e.g. with -fsanitize=address,undefined (run with
+    # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
+    so = os.environ.get("HOSTSIM_SO") or os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
     H = ctypes.CDLL(so)
     P, I = ctypes.c_void_p, ctypes.c_int
     H.hs_celt_new.restype = P
