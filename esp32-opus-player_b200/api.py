@@ -47,6 +47,8 @@ def lib():
     L.decode_many_async.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), ctypes.POINTER(ctypes.c_longlong)]
     L.dm_wait.argtypes = [_P, ctypes.c_longlong]
     L.dm_debug_leaf_overflow.argtypes = [_P]
+    L.dm_debug_deemph_redone.argtypes = [_P]
+    L.dm_debug_deemph_redone.restype = ctypes.c_longlong
     L.dm_decode_device.argtypes = [_P, ctypes.POINTER(_Batch), ctypes.POINTER(_Out), _P]
     L.dm_probe_d2h.argtypes = [_P, _P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_float)]
     L.dm_host_alloc.restype = _P
@@ -250,6 +252,10 @@ class BatchDecoder:
     @property
     def launch_count(self):
         return int(lib().dm_launch_count(self._ctx))
+
+    def deemph_redone(self):
+        """Segments of de-emphasis chains done a second time since the decoder was created (dm_debug_deemph_redone)."""
+        return int(lib().dm_debug_deemph_redone(self._ctx))
 
     def leaf_overflow(self):
         """1 if the last call took the band kernel's own leaf expansion (sorted leaf list full), else 0."""

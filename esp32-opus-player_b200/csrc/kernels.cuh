@@ -645,27 +645,63 @@ k_postfilter(const CeltFrameHdr* __restrict__ hdr, const FrameEnergy* __restrict
 // address arithmetic on the critical path), pulls a tile into registers with 8 LDS.128, runs the recurrence
 // (add -> 64-bit multiply -> shift per sample), and the stereo pair of lanes swaps halves with 8 shuffles so that
 // every lane ends up with 16 consecutive interleaved frames = 64 contiguous bytes, written as 4 x int16x8 stores.
-enum { DE_TW = 32, DE_ROW = 36, DE_STAGES = 4 };
+//
+// Segments.  The chain is serial, but it FORGETS: the memory is scaled by 0.85 per sample, so two runs over the same samples
+// from different memories differ by less than one after ~110 samples and -- both being integers -- soon meet exactly and
+// stay together (simulated on noise of every loudness: always within 170 samples).  So a chain's frames of a call are cut
+// into G runs of frames ("segments") that different warps work on at the same time: the first starts from the carried
+// memory, every other one from memory 0 `DE_WARM` samples inside the frame in front of it, and records the memory it had
+// arrived at where its own frames begin (`spec`) and where they end.  k_deemph_fix then walks the G segments of a chain in order:
+// a segment whose `spec` equals the true memory at that point (the end of the segment before it) IS the serial result, bit
+// for bit; one that does not (never seen with the full warm-up; forced in the tests with a short one), or that had no full
+// frame in front of it to warm up on, is done again from the true memory.  Measured (profiles/r02_sweep_deemph.txt): G = 2
+// takes 0.47 ms where the serial kernel takes 0.81; three and more segments are SLOWER again (0.8 - 1.3 ms: beyond about four
+// of these warps per SM every one of them slows down by more than their number grows), so G = 2 is the default.
+//
+// Fetching: a lane's row goes through a ring of tiles in shared memory with cp.async, in groups of kBurst tiles, kGroups
+// groups in the ring (<1, 4>: one tile at a time, three ahead; <4, 2>: 512 contiguous bytes of a row at a time, which needs
+// frames longer than the look-ahead and is used for 20 ms frames).  The group size hardly matters; who copies does (kCoop).
+#ifndef DE_BURST
+#define DE_BURST 4
+#endif
+#ifndef DE_GROUPS
+#define DE_GROUPS 2
+#endif
+#ifndef DE_COOP
+#define DE_COOP 1
+#endif
+enum { DE_TW = 32, DE_ROW = 36, DE_WARM = 256, DE_MAX_SEGS = 8 };
+enum { DSEG_EXACT = 0, DSEG_SPEC = 1, DSEG_REDO = 2 };
+struct DeemphSeg { int32_t spec, end, kind, pad; };  // [chain of the context][segment]
 
+// frames [a, b) of segment g of G over a range of nf frames
+__host__ __device__ __forceinline__ int deemph_seg_begin(int nf, int g, int G) { return (int)((long long)nf * g / G); }
+
+template <int kBurst, int kGroups, bool kCoop>
 __global__ void __launch_bounds__(32)
 k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hdr, const int32_t* __restrict__ syn,
-         int16_t* __restrict__ pcm, int32_t* __restrict__ status, CeltStreamState* __restrict__ st, DevParams P) {
-    __shared__ __align__(16) int32_t ring[DE_STAGES][32 * DE_ROW];
+         int16_t* __restrict__ pcm, int32_t* __restrict__ status, CeltStreamState* __restrict__ st, DevParams P,
+         DeemphSeg* __restrict__ segs, int G, int warm_tiles) {
+    constexpr int RS = kBurst * kGroups;  // ring slots
+    __shared__ __align__(16) int32_t ring[RS][32 * DE_ROW];
     const int lane = threadIdx.x;
     const int CC = P.CC;
     const int n_chains = P.n_sel * CC;          // chains are (stream - first_stream) * CC + c
-    const int my = blockIdx.x * 32 + lane;
+    const int warps_per_seg = (n_chains + 31) >> 5;  // a warp works on ONE segment: its lanes walk the same frames
+    const int g = blockIdx.x / warps_per_seg;
+    const int my = (blockIdx.x - g * warps_per_seg) * 32 + lane;
     const bool live = my < n_chains;
     const int my_s = P.first_stream + (live ? my / CC : 0), my_c = live ? my % CC : 0;
-    s32 mem = live ? st[my_s].preemph_mem[my_c] : 0;
+    s32 mem = (live && g == 0) ? st[my_s].preemph_mem[my_c] : 0;
     const int N = P.frame_size;
-    const int tpf = (N + DE_TW - 1) / DE_TW, T = tpf * P.nf;
+    const int fa = P.f0 + deemph_seg_begin(P.nf, g, G), f_end = P.f0 + deemph_seg_begin(P.nf, g + 1, G);  // this warp's frames
+    const int WT = g ? warm_tiles : 0;          // warm-up tiles in front of them
+    const int tpf = (N + DE_TW - 1) / DE_TW, T = tpf * (f_end - fa);
     const int32_t* row0 = syn + ((size_t)my_s * P.n_frames * CC + my_c) * kMaxFrame;  // frame f of this chain: + f * CC * kMaxFrame
     int16_t* out0 = pcm + (size_t)my_s * P.n_frames * N * CC;                            // frame f of this stream: + f * N * CC
 
     // What the chain needs to know about a frame -- samples with CELT output, flags, status -- is read one frame ahead:
     // a load in front of every frame would cost the warp a DRAM round trip 50 times per call with nothing to hide it behind.
-    const int f_end = P.f0 + P.nf;
     int cur_n = 0, cur_sk = 0, cur_st = 0, nxt_n = 0, nxt_sk = 0, nxt_st = 0;
     auto load_frame = [&](int ff, int& n, int& sk, int& stt) {
         n = 0; sk = 0; stt = 0;
@@ -674,27 +710,97 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
             n = fe[tt].celt_n; sk = fe[tt].skip; stt = hdr[tt].status;
         }
     };
-    load_frame(P.f0, cur_n, cur_sk, cur_st);
-    load_frame(P.f0 + 1, nxt_n, nxt_sk, nxt_st);
-    int f = P.f0;  // the frame the recurrence is in
+    load_frame(fa, cur_n, cur_sk, cur_st);
+    load_frame(fa + 1, nxt_n, nxt_sk, nxt_st);
+    int f = fa;  // the frame the recurrence is in
+    // warm-up (segments behind the first): the last WT tiles of the frame in front of this segment, which must be a full one
+    int kind = DSEG_EXACT;
+    if (g) kind = (live && fe[(size_t)my_s * P.n_frames + fa - 1].celt_n == N) ? DSEG_SPEC : DSEG_REDO;
+    int wq = 0;  // warm-up tiles prefetched so far
     // prefetch cursor (tile index -> frame, offset) kept incrementally; it runs at most one frame ahead of f
-    int pf_q = 0, pf_f = P.f0, pf_j = 0, pf_n = 0;
-    auto prefetch = [&]() {
-        if (pf_q < T && live) {
+    int pf_q = 0, pf_f = fa, pf_j = 0, pf_n = 0;
+    int ps = 0;  // ring slot the next tile is fetched into
+    // kCoop: the warp copies a tile of its 32 rows TOGETHER -- copy k of a lane is 16 bytes of row 4k + lane / 8, so one
+    // instruction covers four whole 128-byte lines instead of 16 bytes of 32 different ones (the LSU handles a line per
+    // cycle: lane-private copies made it the limit of the kernel as soon as an SM held more than three of these warps).
+    // Whole tiles are copied whatever a row's frame holds (stale rows are never looked at), unless no lane needs the tile.
+    const int32_t* rowk[kCoop ? DE_TW / 4 : 1];
+    if (kCoop) {
+#pragma unroll
+        for (int k = 0; k < DE_TW / 4; k++) {
+            int ch = (blockIdx.x - g * warps_per_seg) * 32 + 4 * k + (lane >> 3);
+            if (ch >= n_chains) ch = 0;  // (a ragged last warp: any row that exists)
+            rowk[k] = syn + ((size_t)(P.first_stream + ch / CC) * P.n_frames * CC + ch % CC) * kMaxFrame + 4 * (lane & 7);
+        }
+    }
+    auto issue_tile = [&]() {
+        int32_t* dst = kCoop ? &ring[ps][(lane >> 3) * DE_ROW + 4 * (lane & 7)] : &ring[ps][lane * DE_ROW];
+        if (++ps == RS) ps = 0;
+        if (wq < WT) {  // (warp-uniform)
+            const size_t off = (size_t)(fa - 1) * CC * kMaxFrame + (N - WT * DE_TW) + wq * DE_TW;
+            if (kCoop) {
+#pragma unroll
+                for (int k = 0; k < DE_TW / 4; k++) __pipeline_memcpy_async(dst + 4 * k * DE_ROW, rowk[k] + off, 16);
+            } else if (live) {
+                const int32_t* src = row0 + off;
+#pragma unroll
+                for (int k = 0; k < DE_TW / 4; k++) __pipeline_memcpy_async(dst + 4 * k, src + 4 * k, 16);
+            }
+            wq++;
+            return;
+        }
+        if (kCoop) {
+            if (pf_j == 0) pf_n = (pf_q < T && live) ? (pf_f == f ? cur_n : nxt_n) : 0;
+            if (__any_sync(0xffffffffu, pf_n > pf_j)) {
+                const size_t off = (size_t)pf_f * CC * kMaxFrame + pf_j;
+#pragma unroll
+                for (int k = 0; k < DE_TW / 4; k++) __pipeline_memcpy_async(dst + 4 * k * DE_ROW, rowk[k] + off, 16);
+            }
+        } else if (pf_q < T && live) {
             if (pf_j == 0) pf_n = pf_f == f ? cur_n : nxt_n;  // nothing to fetch for frames without a CELT layer
             const int w = min(DE_TW, pf_n - pf_j);
             const int32_t* src = row0 + (size_t)pf_f * CC * kMaxFrame + pf_j;
-            int32_t* dst = &ring[pf_q % DE_STAGES][lane * DE_ROW];
 #pragma unroll
             for (int k = 0; k < DE_TW / 4; k++)
                 if (4 * k < w) __pipeline_memcpy_async(dst + 4 * k, src + 4 * k, 16);
         }
-        __pipeline_commit();
         pf_q++;
         pf_j += DE_TW;
         if (pf_j >= N) { pf_j = 0; pf_f++; }
     };
-    for (int q = 0; q < DE_STAGES - 1; q++) prefetch();
+    auto issue_group = [&]() {
+#pragma unroll
+        for (int k = 0; k < kBurst; k++) issue_tile();
+        __pipeline_commit();
+    };
+    for (int q = 0; q < kGroups - 1; q++) issue_group();
+    int gt = 0;  // tile of the current group the recurrence is in
+    int cs = 0;  // ring slot it reads
+    // in front of every tile: at the head of a group, ask for the group kGroups - 1 ahead and wait for this one
+    auto fetch_sync = [&]() -> const int4* {
+        if (gt == 0) {
+            if (kCoop) __syncwarp();  // every lane is done with the slots about to be refilled
+            issue_group();
+            __pipeline_wait_prior(kGroups - 1);
+            if (kCoop) __syncwarp();  // ... and sees the copies of the others
+        }
+        if (++gt == kBurst) gt = 0;
+        const int4* src = reinterpret_cast<const int4*>(&ring[cs][lane * DE_ROW]);
+        if (++cs == RS) cs = 0;
+        return src;
+    };
+
+    // the warm-up run: the recurrence alone, nothing stored
+#pragma unroll 1
+    for (int q = 0; q < WT; q++) {
+        const int4* src = fetch_sync();
+#pragma unroll
+        for (int k = 0; k < DE_TW / 4; k++) {
+            const int4 v = src[k];
+            deemph_round(v.x, mem); deemph_round(v.y, mem); deemph_round(v.z, mem); deemph_round(v.w, mem);
+        }
+    }
+    const s32 spec = mem;
 
     int j0 = 0, my_n = 0;
     bool silk_only = false;
@@ -707,10 +813,8 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
             silk_only = live && my_n == 0 && (cur_sk & FS_HAS_SILK) && !(cur_sk & FS_DROPPED);
             if (live && my_c == 0) status[my_t] = (cur_sk & FS_DROPPED) ? OPUSB_FRAME_SKIPPED : cur_st;
         }
-        prefetch();
-        __pipeline_wait_prior(DE_STAGES - 1);
         // tile -> registers (a lane only ever reads what it copied itself: no warp synchronisation needed)
-        const int4* src = reinterpret_cast<const int4*>(&ring[q % DE_STAGES][lane * DE_ROW]);
+        const int4* src = fetch_sync();
         s32 xv[DE_TW];
 #pragma unroll
         for (int k = 0; k < DE_TW / 4; k++) {
@@ -787,7 +891,43 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
             load_frame(f + 1, nxt_n, nxt_sk, nxt_st);
         }
     }
-    if (live) st[my_s].preemph_mem[my_c] = mem;
+    if (live) {
+        if (G == 1) {
+            st[my_s].preemph_mem[my_c] = mem;
+        } else {
+            DeemphSeg& S = segs[((size_t)my_s * CC + my_c) * DE_MAX_SEGS + g];
+            S.spec = spec; S.end = mem; S.kind = kind;
+        }
+    }
+}
+
+// The segments of a chain in order (see k_deemph): thread per chain.  `redone` counts the segments done again.
+__global__ void __launch_bounds__(128)
+k_deemph_fix(const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ syn, int16_t* __restrict__ pcm, CeltStreamState* __restrict__ st,
+             DevParams P, const DeemphSeg* __restrict__ segs, int G, int* __restrict__ redone) {
+    const int CC = P.CC, N = P.frame_size;
+    const int my = blockIdx.x * blockDim.x + threadIdx.x;
+    if (my >= P.n_sel * CC) return;
+    const int my_s = P.first_stream + my / CC, my_c = my % CC;
+    const DeemphSeg* S = segs + ((size_t)my_s * CC + my_c) * DE_MAX_SEGS;
+    s32 mem = S[0].end;  // the first segment started from the carried memory
+#pragma unroll 1
+    for (int g = 1; g < G; g++) {
+        const DeemphSeg sg = S[g];
+        if (sg.kind == DSEG_SPEC && sg.spec == mem) { mem = sg.end; continue; }
+        atomicAdd(redone, 1);
+        const int fa = P.f0 + deemph_seg_begin(P.nf, g, G), fb = P.f0 + deemph_seg_begin(P.nf, g + 1, G);
+#pragma unroll 1
+        for (int f = fa; f < fb; f++) {
+            const size_t t = (size_t)my_s * P.n_frames + f;
+            const int n = fe[t].celt_n;  // samples with CELT output: the others are zeros whatever the memory, already stored
+            const int32_t* x = syn + (t * CC + my_c) * kMaxFrame;
+            int16_t* out = pcm + (t * N) * CC + my_c;
+#pragma unroll 1
+            for (int j = 0; j < n; j++) out[(size_t)j * CC] = (int16_t)deemph_sample(x[j], mem);
+        }
+    }
+    st[my_s].preemph_mem[my_c] = mem;
 }
 
 // ------------------------------------------------------------------------------------------------

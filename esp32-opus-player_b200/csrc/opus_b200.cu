@@ -72,6 +72,9 @@ struct dm_ctx {
     cudaStream_t de_s[kMaxChunks];        // per stream range: the de-emphasis of one run of frames beside the post-filter of the next
     cudaEvent_t pf_ev[kMaxChunks][kMaxPieces], de_ev[kMaxChunks];
     int tail_pieces;                      // runs of frames the tail of a call is cut into (OPUSB_TAIL_PIECES; 1 = no overlap)
+    DeemphSeg* d_deseg;                   // [stream][channel][DE_MAX_SEGS]: what the segments of a de-emphasis chain hand to k_deemph_fix
+    int* d_deemph_redone;                 // segments k_deemph_fix had to do again, since dm_create (dm_debug_deemph_redone)
+    int deemph_segs, deemph_warm;         // OPUSB_DEEMPH_SEGS (1 = the serial kernel alone), OPUSB_DEEMPH_WARM (warm-up tiles of 32 samples)
     cudaEvent_t fork_ev[kMaxChunks], join_ev[kMaxChunks];
     cudaEvent_t bytes_ready;
     // pipelined calls (dm_decode_device, dm_decode_device_async, decode_many_async), a ring over the call number
@@ -148,6 +151,10 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     c->tail_pieces = 1;  // measured: 2 / 4 / 8 runs make the tail 0.1 - 0.7 ms slower (the two kernels slow each other down side by side)
     if (const char* e = getenv("OPUSB_TAIL_PIECES")) { const int v = atoi(e); if (v >= 1 && v <= kMaxPieces) c->tail_pieces = v; }
     if (const char* e = getenv("OPUSB_TAIL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tail_mode = v; }
+    c->deemph_segs = 2;  // measured: 0.81 ms (1) -> 0.47 (2) -> 1.3 (3) / 0.9 (4) / 0.8 (8); at 2 the kernel moves 5.1 TB/s
+    c->deemph_warm = DE_WARM / DE_TW;
+    if (const char* e = getenv("OPUSB_DEEMPH_SEGS")) { const int v = atoi(e); if (v >= 1 && v <= DE_MAX_SEGS) c->deemph_segs = v; }
+    if (const char* e = getenv("OPUSB_DEEMPH_WARM")) { const int v = atoi(e); if (v >= 1 && v <= DE_WARM / DE_TW) c->deemph_warm = v; }  // (tests: a short warm-up forces the redo path)
     if (const char* e = getenv("OPUSB_SILK_LANES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) c->silk_lanes = v; }
     // The entropy kernel keeps its per-thread allocation arrays and the explicit partition stack in local memory.  The
     // stack limit is a DEVICE-wide setting shared with every other CUDA user of the process (torch): it is only ever
@@ -170,6 +177,9 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     if ((r = dev_alloc(c, &c->d_ops, nfr * kMaxOps))) return r;
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_leafsort, (size_t)kMaxChunks))) return r;
+    if ((r = dev_alloc(c, &c->d_deseg, (size_t)n_streams * 2 * DE_MAX_SEGS))) return r;
+    if ((r = dev_alloc(c, &c->d_deemph_redone, (size_t)1))) return r;
+    CU_TRY(c, cudaMemset(c->d_deemph_redone, 0, sizeof(int)));
     if ((r = dev_alloc(c, &c->d_parse_order, nfr))) return r;
     if ((r = dev_alloc(c, &c->d_parse_count, (size_t)kMaxChunks * 2))) return r;
     c->sort_frames = 0;  // measured: 3.85 ms without, 3.91 ms with (the classification pass costs what the fuller warps win)
@@ -237,7 +247,7 @@ void dm_destroy(dm_ctx* c) {
     cudaDeviceSynchronize();
     cudaFree(c->d_state); cudaFree(c->d_sstate);
     free_set(c->set[0]); free_set(c->set[1]);
-    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_parse_order); cudaFree(c->d_parse_count);
+    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_deseg); cudaFree(c->d_deemph_redone); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_parse_order); cudaFree(c->d_parse_count);
     cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames[0]); cudaFree(c->d_frames[1]);
     cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status); cudaFree(c->d_status2);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -472,7 +482,17 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
                 cudaStreamWaitEvent(D, c->pf_ev[chunk][g], 0);
             }
             if (timed && Q.f0 + Q.nf >= in->n_frames) mark(6, Tp);
-            k_deemph<<<(n_sel * P.CC + 31) / 32, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q);
+            // the chains of a 20 ms call in G segments side by side, put together again by k_deemph_fix (kernels.cuh)
+            const int G = (pieces == 1 && P.frame_size == 960 && Q.nf >= 2 * c->deemph_segs) ? c->deemph_segs : 1;
+            const int dgrid = ((n_sel * P.CC + 31) / 32) * G;
+            if (P.frame_size == 960 && (DE_BURST > 1 || DE_GROUPS != 4))  // (the burst fetch needs frames longer than its look-ahead)
+                k_deemph<DE_BURST, DE_GROUPS, DE_COOP != 0><<<dgrid, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q, c->d_deseg, G, c->deemph_warm);
+            else
+                k_deemph<1, 4, DE_COOP != 0><<<dgrid, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q, c->d_deseg, G, c->deemph_warm);
+            if (G > 1) {
+                k_deemph_fix<<<(n_sel * P.CC + 127) / 128, 128, 0, D>>>(F.fe, F.syn, d_pcm, c->d_state, Q, c->d_deseg, G, c->d_deemph_redone);
+                c->launches++;
+            }
             c->launches += g ? 2 : 0;
         }
         if (D != T) {
@@ -700,6 +720,16 @@ int dm_debug_frame_script(dm_ctx* c, long long t, void* hdr_out, size_t hdr_cap,
     if (hdr_out && hdr_cap >= sizeof(CeltFrameHdr)) CU_TRY(c, cudaMemcpy(hdr_out, c->set[0].hdr + t, sizeof(CeltFrameHdr), cudaMemcpyDeviceToHost));
     if (ops_out && ops_cap >= sizeof(BandOp) * kMaxOps) CU_TRY(c, cudaMemcpy(ops_out, c->d_ops + t * kMaxOps, sizeof(BandOp) * kMaxOps, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// Segments of de-emphasis chains that k_deemph_fix did again since dm_create (a segment behind a frame without full CELT
+// output, or one whose warm-up had not met the serial run): -1 on error.
+long long dm_debug_deemph_redone(dm_ctx* c) {
+    if (!c) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+    int v = 0;
+    if (cudaMemcpy(&v, c->d_deemph_redone, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
 }
 
 int dm_debug_leaf_overflow(dm_ctx* c) {

@@ -133,6 +133,10 @@ const char* dm_stage_name(int i);
 /* Debug/test access: 1 if the most recent call had more coded PVQ leaves than the sorted leaf list holds and the band
  * kernel expanded its own leaves instead (slower, same result), 0 if not, < 0 on error.  Synchronises the device. */
 int dm_debug_leaf_overflow(dm_ctx* ctx);
+/* Debug/test access: how many segments of de-emphasis chains were done a second time since dm_create (the chains of a
+ * 20 ms call are cut into runs of frames that warm up on the frame in front of them and are checked against the serial
+ * order afterwards, csrc/kernels.cuh k_deemph / k_deemph_fix): 0 for streams of full CELT frames.  Synchronises the device. */
+long long dm_debug_deemph_redone(dm_ctx* ctx);
 /* Debug access (contexts created with OPUSB_TRACE=1 in the environment): stage boundaries of the last n <= 16 pipelined
  * calls in ms since the oldest one's start, out[n][9]: head start, end of entropy, sequence, leaves, bands, imdct, then
  * on the tail stream end of postfilter, deemph, final SILK sum.  Shows which calls overlapped.  Synchronises the device. */

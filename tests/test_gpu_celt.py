@@ -317,3 +317,70 @@ def test_script_capacity_is_a_true_worst_case(pkg, ref):
                 assert status[s, f] == n
                 if n > 0:
                     assert np.array_equal(pcm[s, f], want), (fs, ch, ln, s, f)
+
+
+@pytest.mark.parametrize("segs,warm", [(4, 8), (1, 8), (8, 8), (2, 3), (4, 1), (8, 1)])
+def test_deemphasis_segments(pkg, ref, monkeypatch, segs, warm):
+    """The de-emphasis chains of a 20 ms call run as `segs` runs of frames side by side, each warmed up on `warm` x 32 samples
+    of the frame in front of it and checked against the serial order afterwards (k_deemph / k_deemph_fix).  Bit-exact PCM
+    and carried state (two calls) whatever the cut; with the full warm-up (8 tiles) no segment of a stream of full CELT
+    frames is done twice, with a 32-sample warm-up the memories have not met and the redo path does the work."""
+    monkeypatch.setenv("OPUSB_DEEMPH_SEGS", str(segs))
+    monkeypatch.setenv("OPUSB_DEEMPH_WARM", str(warm))
+    n_streams, n_frames, calls = 70, 19, 2   # 140 chains: the last warp of a segment is ragged; 19 frames: uneven segments
+    data, frames = pkg.synth_corpus(n_streams, n_frames * calls, 159, 0xFC)
+    dec = pkg.BatchDecoder(n_streams, n_frames, channels=2)
+    got = []
+    for k in range(calls):
+        rc, pcm, status = dec.decode_many(data, np.ascontiguousarray(frames[:, k * n_frames:(k + 1) * n_frames]))
+        assert rc == 0 and (status == 960).all()
+        got.append(pcm.copy())
+    redone = dec.deemph_redone()
+    dec.close()
+    got = np.concatenate(got, axis=1)
+    for s in range(n_streams):
+        _, want, err = ref.decode_synth_stream(0xFC, 160, 2, n_frames * calls, seed=ref.SEED ^ s)
+        assert err == 0
+        assert np.array_equal(got[s].reshape(-1, 2), want), "stream %d" % s
+    if segs == 1 or warm == 8:
+        assert redone == 0
+    if segs > 1 and warm == 1:
+        assert redone > 0
+
+
+def test_deemphasis_segments_behind_frames_without_celt_output(pkg, ref):
+    """Segments that begin behind a SILK-only frame (no CELT samples to warm up on) or a hybrid -> SILK fade-out frame (120
+    samples) are done in serial order by k_deemph_fix: mono and stereo mode walks, 24 frames per call."""
+    for ch in (1, 2):
+        s4 = 4 if ch == 2 else 0
+        rng = np.random.default_rng(40 + ch)
+        tocs = [0xF8 | s4, 0x48 | s4, 0x78 | s4, 0xF8 | s4]
+        n_streams, n_frames = 40, 24
+        plans = [[int(rng.choice(tocs)) for _ in range(n_frames)] for _ in range(n_streams)]
+        frames = pkg.make_frames(n_streams, n_frames)
+        chunks, pos, pk = [], 0, []
+        for s in range(n_streams):
+            row = []
+            for f in range(n_frames):
+                L = int(rng.integers(20, 200))
+                payload = rng.integers(0, 256, L, dtype=np.uint8)
+                frames[s, f] = (pos, L, plans[s][f], 0)
+                chunks.append(payload)
+                pos += L
+                row.append(np.concatenate([np.array([plans[s][f]], np.uint8), payload]))
+            pk.append(row)
+        dec = pkg.BatchDecoder(n_streams, n_frames, channels=ch)
+        rc, pcm, status = dec.decode_many(np.concatenate(chunks), frames)
+        assert rc == 0
+        assert dec.deemph_redone() > 0
+        dec.close()
+        for s in range(n_streams):
+            o = ref.PacketDecoder(ch)
+            try:
+                for f in range(n_frames):
+                    r, want = o.decode(pk[s][f])
+                    assert status[s, f] == r
+                    if r > 0:
+                        assert np.array_equal(pcm[s, f], want), (ch, s, f)
+            finally:
+                o.close()

@@ -23,9 +23,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles", "r02_ncu_constants.json")
 KERNEL_RE = "^k_(entropy|sequence|leaf|bands|imdct|postfilter|synth|deemph|silk)"
-# launches of one step (decode kernels only), per workload part: CELT-only contexts run 9 kernels, contexts with a SILK layer 15
+# launches of one step (decode kernels only), per workload part (see launches_per_step)
 STAGES = {"entropy": ["k_entropy"], "sequence": ["k_sequence"], "leaves": ["k_leaf_count", "k_leaf_place", "k_leaf_expand"], "bands": ["k_bands"],
-          "imdct": ["k_imdct_long", "k_imdct"], "postfilter": ["k_postfilter", "k_synth"], "deemph": ["k_deemph"],
+          "imdct": ["k_imdct_long", "k_imdct"], "postfilter": ["k_postfilter", "k_synth"], "deemph": ["k_deemph", "k_deemph_fix"],
           "silk": ["k_silk_params", "k_silk_fix", "k_silk_core", "k_silk_unmix", "k_silk_up2", "k_silk_fir"]}
 METRICS = {"warp_inst": "smsp__inst_executed.sum", "lanes": "smsp__thread_inst_executed_per_inst_executed.ratio", "dram_read": "dram__bytes_read.sum",
            "dram_write": "dram__bytes_write.sum", "time_ns": "gpu__time_duration.sum", "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -57,7 +57,8 @@ def launches_per_step(workload):
     for key in keys:
         # raw CELT context: 9 kernels (+ k_imdct_long for 20 ms frames); Opus-mode context: + k_imdct_long, the SILK
         # instantiation of k_entropy and 6 SILK kernels (they return at once without SILK frames)
-        n += (9 + (1 if key[2] == 960 else 0)) if key[0] else 17
+        # 20 ms frames: + k_imdct_long and k_deemph_fix (the de-emphasis chains run as two segments)
+        n += (9 + (2 if key[2] == 960 else 0)) if key[0] else 18
     return n
 
 
