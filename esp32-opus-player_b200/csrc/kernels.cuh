@@ -681,7 +681,7 @@ template <int kBurst, int kGroups, bool kCoop>
 __global__ void __launch_bounds__(32)
 k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hdr, const int32_t* __restrict__ syn,
          int16_t* __restrict__ pcm, int32_t* __restrict__ status, CeltStreamState* __restrict__ st, DevParams P,
-         DeemphSeg* __restrict__ segs, int G, int warm_tiles) {
+         DeemphSeg* __restrict__ segs, int32_t* __restrict__ memf, int G, int warm_tiles) {
     constexpr int RS = kBurst * kGroups;  // ring slots
     __shared__ __align__(16) int32_t ring[RS][32 * DE_ROW];
     const int lane = threadIdx.x;
@@ -886,6 +886,8 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
         }
         j0 += DE_TW;
         if (j0 >= N) {
+            // (segments) the memory this run had at the end of the frame: where k_deemph_fix may stop doing a segment again
+            if (G > 1 && live) memf[((size_t)my_s * CC + my_c) * P.n_frames + f] = mem;
             j0 = 0; f++;
             cur_n = nxt_n; cur_sk = nxt_sk; cur_st = nxt_st;
             load_frame(f + 1, nxt_n, nxt_sk, nxt_st);
@@ -901,15 +903,20 @@ k_deemph(const FrameEnergy* __restrict__ fe, const CeltFrameHdr* __restrict__ hd
     }
 }
 
-// The segments of a chain in order (see k_deemph): thread per chain.  `redone` counts the segments done again.
+// The segments of a chain in order (see k_deemph): thread per chain.  A segment that has to be done again is done frame by
+// frame from the true memory, and only until the memory at the end of a frame equals the one the segment's own run had
+// there (`memf`): from that frame on its output stands.  That is one frame as a rule -- the case that does occur is a warm-up
+// over digital silence (a frame with the silence flag, 2^-15 of random frames): on zeros a negative memory settles at -1, the
+// warm-up from 0 stays at 0, and the two meet a few dozen samples into the next frame that has signal.  `redone` counts.
 __global__ void __launch_bounds__(128)
 k_deemph_fix(const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ syn, int16_t* __restrict__ pcm, CeltStreamState* __restrict__ st,
-             DevParams P, const DeemphSeg* __restrict__ segs, int G, int* __restrict__ redone) {
+             DevParams P, const DeemphSeg* __restrict__ segs, const int32_t* __restrict__ memf, int G, int* __restrict__ redone) {
     const int CC = P.CC, N = P.frame_size;
     const int my = blockIdx.x * blockDim.x + threadIdx.x;
     if (my >= P.n_sel * CC) return;
     const int my_s = P.first_stream + my / CC, my_c = my % CC;
     const DeemphSeg* S = segs + ((size_t)my_s * CC + my_c) * DE_MAX_SEGS;
+    const int32_t* mf = memf + ((size_t)my_s * CC + my_c) * P.n_frames;
     s32 mem = S[0].end;  // the first segment started from the carried memory
 #pragma unroll 1
     for (int g = 1; g < G; g++) {
@@ -920,11 +927,26 @@ k_deemph_fix(const FrameEnergy* __restrict__ fe, const int32_t* __restrict__ syn
 #pragma unroll 1
         for (int f = fa; f < fb; f++) {
             const size_t t = (size_t)my_s * P.n_frames + f;
-            const int n = fe[t].celt_n;  // samples with CELT output: the others are zeros whatever the memory, already stored
-            const int32_t* x = syn + (t * CC + my_c) * kMaxFrame;
+            const int n = fe[t].celt_n;  // samples with CELT output (a multiple of 8): the others are zeros whatever the memory
+            const int4* x = reinterpret_cast<const int4*>(syn + (t * CC + my_c) * kMaxFrame);
             int16_t* out = pcm + (t * N) * CC + my_c;
 #pragma unroll 1
-            for (int j = 0; j < n; j++) out[(size_t)j * CC] = (int16_t)deemph_sample(x[j], mem);
+            for (int j = 0; j < n; j += 32) {  // 32 samples at a time: eight independent loads, then the chain
+                int4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = (j + 4 * k < n) ? x[(j >> 2) + k] : make_int4(0, 0, 0, 0);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (j + 4 * k < n) {
+                        int16_t* o = out + (size_t)(j + 4 * k) * CC;
+                        o[0] = (int16_t)deemph_sample(v[k].x, mem);
+                        o[CC] = (int16_t)deemph_sample(v[k].y, mem);
+                        o[2 * CC] = (int16_t)deemph_sample(v[k].z, mem);
+                        o[3 * CC] = (int16_t)deemph_sample(v[k].w, mem);
+                    }
+                }
+            }
+            if (mem == mf[f]) { mem = sg.end; break; }  // met the segment's own run: the rest of it stands
         }
     }
     st[my_s].preemph_mem[my_c] = mem;

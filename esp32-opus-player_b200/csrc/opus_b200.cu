@@ -73,6 +73,7 @@ struct dm_ctx {
     cudaEvent_t pf_ev[kMaxChunks][kMaxPieces], de_ev[kMaxChunks];
     int tail_pieces;                      // runs of frames the tail of a call is cut into (OPUSB_TAIL_PIECES; 1 = no overlap)
     DeemphSeg* d_deseg;                   // [stream][channel][DE_MAX_SEGS]: what the segments of a de-emphasis chain hand to k_deemph_fix
+    int32_t* d_demem;                     // [stream][channel][frame]: memory of a segment's run at the end of every frame (k_deemph_fix stops there)
     int* d_deemph_redone;                 // segments k_deemph_fix had to do again, since dm_create (dm_debug_deemph_redone)
     int deemph_segs, deemph_warm;         // OPUSB_DEEMPH_SEGS (1 = the serial kernel alone), OPUSB_DEEMPH_WARM (warm-up tiles of 32 samples)
     cudaEvent_t fork_ev[kMaxChunks], join_ev[kMaxChunks];
@@ -178,6 +179,7 @@ static int create_impl(dm_ctx* c, int n_streams, int max_frames, int channels, i
     if ((r = dev_alloc(c, &c->d_X, nfr * 2 * kMaxFrame))) return r;
     if ((r = dev_alloc(c, &c->d_leafsort, (size_t)kMaxChunks))) return r;
     if ((r = dev_alloc(c, &c->d_deseg, (size_t)n_streams * 2 * DE_MAX_SEGS))) return r;
+    if ((r = dev_alloc(c, &c->d_demem, nfr * 2))) return r;
     if ((r = dev_alloc(c, &c->d_deemph_redone, (size_t)1))) return r;
     CU_TRY(c, cudaMemset(c->d_deemph_redone, 0, sizeof(int)));
     if ((r = dev_alloc(c, &c->d_parse_order, nfr))) return r;
@@ -247,7 +249,7 @@ void dm_destroy(dm_ctx* c) {
     cudaDeviceSynchronize();
     cudaFree(c->d_state); cudaFree(c->d_sstate);
     free_set(c->set[0]); free_set(c->set[1]);
-    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_deseg); cudaFree(c->d_deemph_redone); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_parse_order); cudaFree(c->d_parse_count);
+    cudaFree(c->d_ops); cudaFree(c->d_X); cudaFree(c->d_deseg); cudaFree(c->d_demem); cudaFree(c->d_deemph_redone); cudaFree(c->d_leafsort); cudaFree(c->d_leaf_order); cudaFree(c->d_parse_order); cudaFree(c->d_parse_count);
     cudaFree(c->d_bytes[0]); cudaFree(c->d_bytes[1]); cudaFree(c->d_frames[0]); cudaFree(c->d_frames[1]);
     cudaFree(c->d_pcm); cudaFree(c->d_pcm2); cudaFree(c->d_status); cudaFree(c->d_status2);
     for (int i = 0; i < kMaxChunks; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -486,11 +488,11 @@ static int launch_pipeline(dm_ctx* c, const dm_batch* in, const uint8_t* d_bytes
             const int G = (pieces == 1 && P.frame_size == 960 && Q.nf >= 2 * c->deemph_segs) ? c->deemph_segs : 1;
             const int dgrid = ((n_sel * P.CC + 31) / 32) * G;
             if (P.frame_size == 960 && (DE_BURST > 1 || DE_GROUPS != 4))  // (the burst fetch needs frames longer than its look-ahead)
-                k_deemph<DE_BURST, DE_GROUPS, DE_COOP != 0><<<dgrid, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q, c->d_deseg, G, c->deemph_warm);
+                k_deemph<DE_BURST, DE_GROUPS, DE_COOP != 0><<<dgrid, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q, c->d_deseg, c->d_demem, G, c->deemph_warm);
             else
-                k_deemph<1, 4, DE_COOP != 0><<<dgrid, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q, c->d_deseg, G, c->deemph_warm);
+                k_deemph<1, 4, DE_COOP != 0><<<dgrid, 32, 0, D>>>(F.fe, F.hdr, F.syn, d_pcm, d_status, c->d_state, Q, c->d_deseg, c->d_demem, G, c->deemph_warm);
             if (G > 1) {
-                k_deemph_fix<<<(n_sel * P.CC + 127) / 128, 128, 0, D>>>(F.fe, F.syn, d_pcm, c->d_state, Q, c->d_deseg, G, c->d_deemph_redone);
+                k_deemph_fix<<<(n_sel * P.CC + 127) / 128, 128, 0, D>>>(F.fe, F.syn, d_pcm, c->d_state, Q, c->d_deseg, c->d_demem, G, c->d_deemph_redone);
                 c->launches++;
             }
             c->launches += g ? 2 : 0;

@@ -15,7 +15,7 @@ import __graft_entry__ as ge
 
 pkg = ge.load_package()
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-F, steps = 50, 8
+F, steps = 50, int(sys.argv[3]) if len(sys.argv) > 3 else 8
 toc = 0xFC
 data, frames = pkg.synth_corpus(S, F * steps, 159, toc)
 dec = pkg.BatchDecoder(S, F, channels=2)
@@ -32,4 +32,4 @@ names = ["start", "entropy", "sequence", "leaves", "bands", "imdct", "postfilter
 print("call  " + "  ".join("%10s" % n for n in names))
 for k in range(steps):
     print("%4d  " % k + "  ".join("%10.3f" % v for v in t[k]))
-print("steady-state ms per call: %.3f" % ((t[-1, 8] - t[2, 8]) / (steps - 3)))
+print("steady-state ms per call: %.3f" % ((t[-1, 8] - t[2, 8]) / (steps - 3)), "| de-emphasis segments done again:", dec.deemph_redone())
