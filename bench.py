@@ -118,6 +118,10 @@ def ncu_provenance(nc):
     out = {"file": os.path.relpath(NCU_CONSTANTS, ROOT), "git": nc.get("git"), "source_hash": nc.get("source_hash"),
            "matches_this_source": nc.get("source_hash") == cur}
     if not out["matches_this_source"]:
+        sp = nc.get("sass_partial")
+        if sp and sp.get("source_hash") == cur:  # some kernels changed since the capture: say which (the others are SASS-identical)
+            out.update(kernels_identical_to_capture=sp.get("kernels_identical"), kernels_changed_since_capture=sp.get("kernels_changed"),
+                       evidence=sp.get("evidence"))
         for e in nc.get("sass_equivalent", []):
             if e.get("source_hash") == cur:
                 out.update(matches_this_source=True, matched_by="sass_equivalent: " + e.get("why", ""), evidence=e.get("evidence"))

@@ -88,10 +88,21 @@ def main():
     lines.append("")
     lines.append("every kernel identical: %s" % all_same)
     print("\n".join(lines))
+    if a.record and not all_same:
+        # some kernels changed: record WHICH, so that bench.py can say what part of the capture still describes the running code
+        changed = sorted({demangle(k).split("(")[0] for k in set(base) | set(cur) if k not in cur or k not in base or base[k] != cur[k]})
+        same = sorted({demangle(k).split("(")[0] for k in base if k in cur and base[k] == cur[k]})
+        open(OUT, "w").write("\n".join(lines) + "\n")
+        d = json.load(open(CONST))
+        for w in d["workloads"].values():
+            if w.get("source_hash") == cur_hash or not str(w.get("git", "")).startswith(a.base):
+                continue
+            w["sass_partial"] = {"source_hash": cur_hash, "base": a.base, "evidence": os.path.relpath(OUT, ROOT), "kernels_identical": len(same),
+                                 "kernels_changed": changed}
+        json.dump(d, open(CONST, "w"), indent=1)
+        print("recorded (partial) in", CONST)
+        return 0
     if a.record:
-        if not all_same:
-            print("not recorded: kernels differ", file=sys.stderr)
-            return 1
         open(OUT, "w").write("\n".join(lines) + "\n")
         d = json.load(open(CONST))
         for w in d["workloads"].values():
