@@ -84,8 +84,12 @@ public:
     OpusHeadB200 head;
     std::vector<uint8_t> arena;  // packet bytes of queued events
 
-    void set_callback(opusb_read_func fn, void* user) { read_ = fn; user_ = user; mem_ = nullptr; }
-    void set_memory(const uint8_t* p, size_t n, bool clean_eof) { mem_ = p; mem_len_ = n; mem_pos_ = 0; clean_eof_ = clean_eof; read_ = nullptr; }
+    void set_callback(opusb_read_func fn, void* user) { read_ = fn; user_ = user; mem_ = nullptr; fr_.attach(nullptr, 0); }
+    void set_memory(const uint8_t* p, size_t n, bool clean_eof) {
+        mem_ = p; mem_len_ = n; mem_pos_ = 0; clean_eof_ = clean_eof; read_ = nullptr;
+        fr_.attach(p, n);   // framed in place (ogg_demux.hpp): source_read() below then has nothing to copy
+        arena.reserve(n);   // the packets of the whole file fit: no regrowth while events are queued
+    }
 
     // ref opus_init_decoder -> op_open1 / op_open2 (src/opusfile.cpp:730-799)
     int open(std::deque<Event>* q) {
@@ -136,7 +140,7 @@ private:
         if (n == 0) return 0;
         if (mem_pos_ >= mem_len_) return clean_eof_ ? 0 : -1;
         const size_t k = std::min((size_t)n, mem_len_ - mem_pos_);
-        memcpy(dst, mem_ + mem_pos_, k);
+        if (dst != mem_ + mem_pos_) memcpy(dst, mem_ + mem_pos_, k);
         mem_pos_ += k;
         return (int)k;
     }

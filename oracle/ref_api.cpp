@@ -304,4 +304,54 @@ double ref_bench_fork_ids(int toc, int len, int channels, int frame_size, const 
     return wall;
 }
 
+/* ---- demux only: the reference's page framer + CRC, packetizer and time-stamp logic over one memory
+ * image, nothing decoded -- opus_init_decoder(), then op_fetch_and_process_page() (src/opusfile.cpp:835) page after page with
+ * the buffered packets marked as consumed.  Returns the audio packets seen (< 0: the file does not open). */
+} /* extern "C" */
+int op_fetch_and_process_page(ogg_page* _og, int64_t _page_offset, int _spanp, int _ignore_holes); /* src/opusfile.cpp:835 */
+extern OggOpusFile_t* m_OggOpusFile; /* src/opusfile.cpp:20 */
+extern "C" {
+
+long ref_ogg_demux_only(const uint8_t* data, size_t size, long long* packet_bytes) {
+    if (ref_ogg_open(data, size) != 0) return -1;
+    long n = 0;
+    long long nb = 0;
+    for (;;) {
+        for (int i = m_OggOpusFile->op_pos; i < m_OggOpusFile->op_count; i++) { n++; nb += m_OggOpusFile->op[i].bytes; }
+        m_OggOpusFile->op_pos = m_OggOpusFile->op_count;
+        if (op_fetch_and_process_page(NULL, -1, 1, 0) < 0) break; /* OP_EOF, or OP_EREAD at the end of the image */
+    }
+    if (packet_bytes) *packet_bytes = nb;
+    return n;
+}
+
+/* The same image `n_files` times, shared out over `jobs` forked workers (the reference's demux state is a process-wide
+ * singleton too): wall seconds, packets of one file in *packets. */
+double ref_demux_fork(const uint8_t* data, size_t size, int n_files, int jobs, long* packets) {
+    if (jobs < 1) jobs = 1;
+    if (jobs > n_files) jobs = n_files;
+    long* sh = (long*)mmap(nullptr, sizeof(long), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (sh == MAP_FAILED) return -1.0;
+    ref_setup();
+    double t0 = now_s();
+    pid_t* pids = (pid_t*)calloc(jobs, sizeof(pid_t));
+    for (int j = 0; j < jobs; j++) {
+        pid_t p = fork();
+        if (p == 0) {
+            int lo = (int)((int64_t)n_files * j / jobs), hi = (int)((int64_t)n_files * (j + 1) / jobs);
+            long n = 0;
+            for (int f = lo; f < hi; f++) n = ref_ogg_demux_only(data, size, nullptr);
+            if (j == 0) *sh = n;
+            _exit(0);
+        }
+        pids[j] = p;
+    }
+    for (int j = 0; j < jobs; j++) { int stt; if (pids[j] > 0) waitpid(pids[j], &stt, 0); }
+    double wall = now_s() - t0;
+    if (packets) *packets = *sh;
+    free(pids);
+    munmap(sh, sizeof(long));
+    return wall;
+}
+
 } /* extern "C" */
