@@ -66,6 +66,8 @@ int decode_many(dm_ctx* c, const dm_batch* in, dm_out* out) {
             if (c->failed[(size_t)s]) { st = -2004; continue; }
             if ((size_t)fr.offset + fr.len > in->n_bytes) return -2;
             const uint8_t* p = in->bytes + fr.offset;
+            static const bool fast = getenv("MOCK_DEVICE_FAST") != nullptr;  // benchmarks of the host side: every frame "decodes", no samples written
+            if (fast) { c->seq[(size_t)s]++; st = 960; continue; }
             if (fr.len > 0 && p[0] == 0xEE) { st = -4; c->failed[(size_t)s] = 1; continue; }
             uint32_t h = 2166136261u;
             auto mix = [&](uint32_t v) { h = (h ^ v) * 16777619u; };
