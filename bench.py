@@ -108,6 +108,21 @@ def ncu_constants(workload):
     return d.get("workloads", {}).get(workload)
 
 
+def stage_traffic_view(nc, scale, stage_ms, hbm_peak):
+    """Measured DRAM traffic (ncu capture) over the live device time of every stage: which stage moves how many GB/s, as a
+    fraction of the measured HBM peak.  The de-emphasis is the one stage of the path that is HBM bound."""
+    if not nc or not stage_ms or not hbm_peak:
+        return None
+    kern, sk = nc.get("kernels", {}), nc.get("stage_kernels", {})
+    out = {}
+    for stage, ms in stage_ms.items():
+        b = sum(kern[k]["dram_bytes"] for k in sk.get(stage, []) if k in kern) * (scale or 1.0)
+        if b > 0 and ms and ms > 0:
+            gbs = b / (ms * 1e-3) / 1e9
+            out[stage] = {"GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)}
+    return out or None
+
+
 def ncu_provenance(nc):
     """Which capture the instruction / DRAM-byte counts come from, and whether it is of the running kernels: either the
     kernel sources hash to the capture's, or tools/sass_equiv.py recorded that every kernel's SASS is the capture's
@@ -600,6 +615,10 @@ def main():
                         "step_traffic_gbs": (dram_step / step_s / 1e9) if dram_step else None,
                         "step_traffic_frac_of_peak": (dram_step / step_s / 1e9 / hbm_peak) if dram_step else None},
                 "ncu_constants": ncu_provenance(nc)}
+        try:  # (an extra view; nothing in the line depends on it)
+            roof["hbm"]["by_stage"] = stage_traffic_view(nc, scale, stage_acc, hbm_peak)
+        except Exception:
+            roof["hbm"]["by_stage"] = None
         cfg = make_config(args, wl_desc, S)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int16/int32 fixed-point", "data": "synthetic",
