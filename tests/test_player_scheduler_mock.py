@@ -201,3 +201,55 @@ def test_scheduler_delivers_every_frame_once_in_order(mock, seed, n_files, frame
             assert g.shape == want[i][0].shape and np.array_equal(g, want[i][0]), "file %d: samples" % i
     finally:
         L.opfb_set_destroy(st)
+
+
+@pytest.mark.parametrize("seed,allow_fail", [(11, False), (12, True)])
+def test_single_stream_player_over_a_read_callback(mock, seed, allow_fail):
+    """opus_init_decoder() + op_read_stereo() (opusb_init_decoder / opusb_read_stereo) over a read callback that hands out the
+    file in odd chunk sizes: the framer's own buffer (not the in-place path of memory images), one track per scheduler, the
+    decode-ahead loop inside the read call -- same samples and return codes as the model."""
+    L = mock
+    P, I = ctypes.c_void_p, ctypes.c_int
+    READ = ctypes.CFUNCTYPE(I, P, P, I)
+    L.opusb_init_decoder.restype = P
+    L.opusb_init_decoder.argtypes = [READ, P, I, ctypes.POINTER(I)]
+    L.opusb_read_stereo.argtypes = [P, P, I]
+    L.opusb_free_decoder.argtypes = [P]
+    rng = np.random.default_rng(seed)
+    for k in range(12):
+        blob, packets, ch = make_file(rng, k, allow_fail)
+        want_pcm, want_codes = model(L, blob, packets, ch)
+        pos = [0]
+        short = int(rng.integers(0, 2))
+
+        def cb(user, buf, n, blob=blob, pos=pos, short=short):
+            if n == 0:
+                return 0
+            m = min(n, len(blob) - pos[0])
+            if m <= 0:
+                return -1
+            if short:  # a source that returns less than asked for
+                m = max(1, min(m, 1 + (pos[0] * 7919) % 700))
+            ctypes.memmove(buf, blob[pos[0]:pos[0] + m], m)
+            pos[0] += m
+            return m
+
+        fn = READ(cb)
+        err = I(0)
+        of = L.opusb_init_decoder(fn, None, 0, ctypes.byref(err))
+        assert of and err.value == 0
+        buf = np.zeros(11520, np.int16)
+        bs = int(rng.choice([2048, 600, 11520, 64]))
+        got, codes = [], []
+        for _ in range(200000):
+            r = L.opusb_read_stereo(of, buf.ctypes.data, bs)
+            if r > 0:
+                got.append(buf[: 2 * r].copy())
+            else:
+                codes.append(r)
+                if r in (0, -128):
+                    break
+        L.opusb_free_decoder(of)
+        g = np.concatenate(got).reshape(-1, 2) if got else np.zeros((0, 2), np.int16)
+        assert codes == want_codes, "file %d" % k
+        assert g.shape == want_pcm.shape and np.array_equal(g, want_pcm), "file %d" % k
